@@ -1,0 +1,111 @@
+"""Pin the CPU oracle (oracle/) against (i) the reference's own golden vectors in DemoData
+(Features/*.mat: KeyPts + Features) and (ii) outputs of the UNMODIFIED reference functions run
+in the build container (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+import golden_data as G
+
+
+def _rows(a):
+    return set(map(tuple, np.round(np.asarray(a, np.float64), 4)))
+
+
+@pytest.mark.parametrize("tag", G.FRAMES)
+def test_keypoints_bit_identical_to_reference_run(oracle_mod, tag):
+    f, rr = G.frame(tag), G.refrun(tag)
+    resp = oracle_mod.respond_predict(f["ring3"][None])[0]
+    kp5, px5 = oracle_mod.select_keypoints(f["ring5"], f["counter"], resp)
+    kp3, px3 = oracle_mod.select_keypoints(f["ring3"], f["counter_i8"], resp)
+    # GetKeyPtsByAE (SphericalRing.py:113) run unmodified on the same response image
+    assert np.array_equal(px5, rr["keypix_ring5_i32"]) and np.array_equal(kp5, rr["keypts_ring5_i32"])
+    assert np.array_equal(px3, rr["keypix_ring3_i8"]) and np.array_equal(kp3, rr["keypts_ring3_i8"])
+    # DemoData golden KeyPts were produced by the 3-channel production path (quirk 3) with an older
+    # column mask (quirk 2): set agreement 1021..1023 of 1024
+    assert len(_rows(f["golden_KeyPts"]) & _rows(kp3)) >= 1021
+
+
+@pytest.mark.parametrize("tag", G.FRAMES[:2])
+def test_patches_and_descriptors_vs_golden(oracle_mod, tag):
+    f, rr = G.frame(tag), G.refrun(tag)
+    _, pl, tr = oracle_mod.get_patches_list(f["golden_KeyPts"], f["vox0"], f["vox1"], f["vox2"],
+                                            return_truncated=True)
+    ref = G.unpack_patches(rr["patches_packed"])  # GetPatchesList (Voxel.py:177) run unmodified
+    bad = 0
+    for s in range(3):
+        neq = (pl[s].reshape(1024, -1) != ref[s].reshape(1024, -1)).any(1)
+        assert not (neq & ~tr[s]).any()       # exact wherever the 496-NN cut cannot bite
+        bad += int(neq.sum())
+    assert bad <= 8                            # k-th-neighbour ties (quirk 5), implementation-defined
+    feat = oracle_mod.get_features_from_patches(pl)
+    err = np.abs(feat - f["golden_Features"]).max(1)
+    anytr = tr[0] | tr[1] | tr[2]
+    assert err[~anytr].max() < 1e-5            # golden Features: TF1.14 arithmetic, agreement ~1e-6
+    assert (err < 1e-5).sum() >= 1020
+
+
+@pytest.mark.parametrize("seq", ["00", "01"])
+def test_nn_match_bit_identical_to_scipy(oracle_mod, seq):
+    a, b = G.PAIRS[seq]
+    P = G.pose(seq)
+    idx = oracle_mod.nn_match(G.frame(a)["golden_Features"], G.frame(b)["golden_Features"])
+    assert np.array_equal(idx, P["pair_idx"])
+    u = G.usip(seq)
+    assert np.array_equal(oracle_mod.nn_match(u["d0"], u["d1"]), u["pair_idx"])
+
+
+def test_nn_match_ties_take_lowest_row(oracle_mod):
+    c0 = np.zeros((5, 7), np.float32)
+    c0[3] = 1
+    c1 = np.zeros((2, 7), np.float32)
+    c1[1] = 1
+    assert oracle_mod.nn_match(c0, c1).tolist() == [0, 3]
+
+
+@pytest.mark.parametrize("seq", ["00", "01"])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_solve_relative_pose_vs_reference_run(oracle_mod, seq, seed):
+    a, b = G.PAIRS[seq]
+    f0, f1, P = G.frame(a), G.frame(b), G.pose(seq)
+    np.random.seed(seed)
+    R, T, ok, i0, i1, thr = oracle_mod.solve_relative_pose(
+        f0["golden_KeyPts"], f0["golden_Features"], None, f1["golden_KeyPts"], f1["golden_Features"], None)
+    nxt = np.random.random()
+    assert ok == bool(P["ok_%d" % seed]) and thr == float(P["thr_%d" % seed])
+    assert np.array_equal(i0, P["idx0_%d" % seed]) and np.array_equal(i1, P["idx1_%d" % seed])
+    # [R|t] within 1e-4 relative (north_star tolerance); the reference is float32 LAPACK
+    assert np.abs(R - P["R_%d" % seed]).max() <= 1e-4
+    Tr = P["T_%d" % seed].reshape(-1)
+    assert np.abs(T.reshape(-1) - Tr).max() <= 1e-4 * max(1.0, np.abs(Tr).max())
+    assert nxt == float(P["next_random_%d" % seed])   # global RNG stream left where the reference leaves it
+
+
+def test_solve_rt_reflection_quirk(oracle_mod):
+    """det<0 -> the reference negates a COLUMN of Vh (Match.py:151-155): R = diag(1,1,-1) V U^T."""
+    rng = np.random.default_rng(3)
+    P1 = rng.standard_normal((40, 3)).astype(np.float32)
+    M = np.diag([1.0, 1.0, -1.0]).astype(np.float32)          # a reflection
+    P0 = (P1 @ M.T + np.float32([1, 2, 3])).astype(np.float32)
+    R, T, cred = oracle_mod.solve_rt(P0, P1)
+    H = (P1 - P1.mean(0)).astype(np.float64).T @ (P0 - P0.mean(0)).astype(np.float64)
+    U, S, Vh = np.linalg.svd(H)
+    Rref = Vh.T @ U.T
+    assert np.linalg.det(Rref) < 0 and cred == -1
+    Vh[:, 2] *= -1
+    assert np.abs(R - Vh.T @ U.T).max() < 1e-5
+
+
+def test_ransac_failure_ladder(oracle_mod):
+    """No hypothesis reaches leastInliers -> thresholds 0.4, 0.8, 1.6 then failure (Match.py:207-214)."""
+    rng = np.random.default_rng(0)
+    P0 = (rng.standard_normal((300, 3)) * 50).astype(np.float32)
+    P1 = (rng.standard_normal((300, 3)) * 50).astype(np.float32)
+    np.random.seed(5)
+    st = np.random.get_state()
+    R, T, ok, mask, thr = oracle_mod.ransac4rt(P0, P1)
+    assert not ok and thr == 1.6 and mask.sum() == 0
+    assert np.array_equal(R, np.eye(3)) and R.dtype == np.float64
+    after = np.random.random()
+    np.random.set_state(st)
+    np.random.random((3 * 500 * 4,))
+    assert after == np.random.random()         # three full rounds of 500 trials x 4 draws consumed
