@@ -1,0 +1,462 @@
+"""Host-side mirror of the reference's call surface for the odometry hot path.
+
+Same names, argument meaning and return values as the reference functions, numpy in / numpy
+out; underneath every call goes through the C ABI of libcaelo_b200.so (include/caelo.h) with
+torch tensors used only as device buffers.  There is no CPU fallback.
+
+    reference symbol (file:line)                          here
+    keras.models.load_model (Match.py:313,324)            load_model -> B200Model
+    model.predict (SphericalRing.py:407, Match.py:131)    B200Model.predict
+    GetKeyPtsByAE (SphericalRing.py:113)                  GetKeyPtsByAE
+    GetKeyPtsFromRawFileName (SphericalRing.py:389)       GetKeyPtsFromRawFileName
+    GetPatchesList (Voxel.py:177)                         GetPatchesList
+    GetFeaturesFromPatches (Match.py:130)                 GetFeaturesFromPatches
+    SolveRT / RANSAC4RT / SolveRelativePose (Match.py)    SolveRT / RANSAC4RT / SolveRelativePose
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .h5weights import layer_summary, read_keras_weights, read_model_config
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+WEIGHT_DIR = os.path.join(_HERE, "weights")
+
+# module-level constants the reference's drivers pull in with ``from X import *``
+# (SphericalRing.py:28-57, Voxel.py:15-52)
+nLines = 64
+ImgH = 69
+ImgW = 1800
+CropWidth_SphericalRing = 8
+Channels4AE = [0, 1, 2]
+PatchSize = 16
+Scales = 3
+VoxelSize = 0.02
+VoxelSizes = [VoxelSize, VoxelSize * 8, VoxelSize * 32]
+VisibleLength = 156 / 2 * 1.28
+VisibleWidth = 156 / 2 * 1.28
+VisibleHeight = 23 / 2 * 1.28
+nFixedKeyPts = 1024
+MAX_TRIALS = 500
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _np_ptr(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Context:
+    """One per GPU: owns the caelo_ctx, the network weights and the device scratch."""
+
+    def __init__(self, device: int = 0, respond_weights=None, encoder_weights=None):
+        if not torch.cuda.is_available():
+            raise _lib.CaeloError("no CUDA device: caelo_b200 has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)  # make torch own the primary context first
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.caelo_create(device, ctypes.byref(h)), None, "caelo_create")
+        self.h = h
+        self.has_respond = False
+        self.has_encoder = False
+        self.set_respond_weights(respond_weights or _default_weights("respond"))
+        self.set_encoder_weights(encoder_weights or _default_weights("encoder"))
+
+    def check(self, rc, what=""):
+        _lib.check(rc, self.h, what)
+
+    def set_respond_weights(self, w):
+        a = [np.ascontiguousarray(w[k], np.float32) for k in
+             ("conv2d_1/kernel:0", "conv2d_1/bias:0", "conv2d_2/kernel:0", "conv2d_2/bias:0")]
+        assert a[0].shape == (3, 3, 3, 32) and a[2].size == 256
+        self.check(self.lib.caelo_set_respond_weights(self.h, *[_np_ptr(x) for x in a]), "set_respond_weights")
+        self.has_respond = True
+
+    def set_encoder_weights(self, w):
+        keys = ("conv3d_1/kernel:0", "conv3d_1/bias:0", "conv3d_2/kernel:0", "conv3d_2/bias:0",
+                "conv3d_3/kernel:0", "conv3d_3/bias:0", "dense_1/kernel:0", "dense_1/bias:0",
+                "dense_2/kernel:0", "dense_2/bias:0")
+        a = [np.ascontiguousarray(w[k], np.float32) for k in keys]
+        assert a[0].shape == (3, 3, 3, 1, 8) and a[6].shape == (2048, 200) and a[8].shape == (200, 20)
+        self.check(self.lib.caelo_set_encoder_weights(self.h, *[_np_ptr(x) for x in a]), "set_encoder_weights")
+        self.has_encoder = True
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.caelo_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.caelo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- device-level wrappers (torch tensors in/out, asynchronous) ----------------------
+    def respond_forward(self, ring: torch.Tensor) -> torch.Tensor:
+        B, H, W, C = ring.shape
+        assert C == 3 and ring.dtype == torch.float32 and ring.is_contiguous()
+        out = torch.empty((B, H, W, 8), dtype=torch.float32, device=self.device)
+        self.check(self.lib.caelo_respond_forward(self.h, _ptr(ring), B, H, W, _ptr(out), _stream()),
+                   "caelo_respond_forward")
+        return out
+
+    def select_keypoints(self, ring: torch.Tensor, counter: torch.Tensor, resp: Optional[torch.Tensor],
+                         H: int = nLines, W: int = ImgW - CropWidth_SphericalRing, max_kpts: int = nFixedKeyPts):
+        """ring [B,rH,rW,C], counter [B,cH,cW] int8|int32, resp [B,H,W,8] or None (fused a1+a2)."""
+        B, rH, rW, rC = ring.shape
+        assert ring.dtype == torch.float32 and ring.is_contiguous() and counter.is_contiguous()
+        kind = {torch.int8: 0, torch.int32: 1}[counter.dtype]
+        kpts = torch.empty((B, max_kpts, 3), dtype=torch.float32, device=self.device)
+        kpix = torch.empty((B, max_kpts, 2), dtype=torch.int64, device=self.device)
+        n = torch.empty((B,), dtype=torch.int32, device=self.device)
+        if resp is None:
+            rc = self.lib.caelo_respond_select(self.h, _ptr(ring), rC, rH, rW, _ptr(counter), kind,
+                                               counter.shape[1], counter.shape[2], H, W, B, max_kpts,
+                                               _ptr(kpts), _ptr(kpix), _ptr(n), None, _stream())
+        else:
+            assert resp.shape == (B, H, W, 8) and resp.is_contiguous()
+            rc = self.lib.caelo_select_keypoints(self.h, _ptr(resp), H, W, _ptr(ring), rC, rH, rW,
+                                                 _ptr(counter), kind, counter.shape[1], counter.shape[2],
+                                                 B, max_kpts, _ptr(kpts), _ptr(kpix), _ptr(n), _stream())
+        self.check(rc, "caelo_select_keypoints")
+        return kpts, kpix, n
+
+    def gather_patches(self, kpts: torch.Tensor, vox: torch.Tensor, vox_offsets: np.ndarray,
+                       n_kpts: Optional[torch.Tensor] = None, want_f32: bool = False, want_trunc: bool = False):
+        """kpts [F,K,3] f32|f64; vox int16 [sumV,3]; vox_offsets host int64 [F*3+1] (rows)."""
+        F, K, _ = kpts.shape
+        assert kpts.is_contiguous() and vox.dtype == torch.int16 and vox.is_contiguous()
+        off = np.ascontiguousarray(vox_offsets, np.int64)
+        assert off.shape == (F * 3 + 1,)
+        packed = torch.empty((F, 3, K, 128), dtype=torch.int32, device=self.device)
+        f32 = torch.empty((F, 3, K, 16, 16, 16), dtype=torch.float32, device=self.device) if want_f32 else None
+        trunc = torch.empty((F, 3, K), dtype=torch.uint8, device=self.device) if want_trunc else None
+        rc = self.lib.caelo_gather_patches(self.h, _ptr(kpts), 1 if kpts.dtype == torch.float64 else 0,
+                                           _ptr(n_kpts), F, K, _ptr(vox),
+                                           off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                           _ptr(packed), _ptr(f32), _ptr(trunc), _stream())
+        self.check(rc, "caelo_gather_patches")
+        return packed, f32, trunc
+
+    def encode_frames(self, packed: torch.Tensor) -> torch.Tensor:
+        F, S, K, Wd = packed.shape
+        assert S == 3 and Wd == 128 and packed.is_contiguous()
+        feat = torch.empty((F, K, 60), dtype=torch.float32, device=self.device)
+        self.check(self.lib.caelo_encode_frames(self.h, _ptr(packed), F, K, _ptr(feat), _stream()),
+                   "caelo_encode_frames")
+        return feat
+
+    def encode_patches(self, patches: torch.Tensor) -> torch.Tensor:
+        P = patches.shape[0]
+        assert patches.dtype == torch.float32 and patches.is_contiguous() and patches[0].numel() == 4096
+        feat = torch.empty((P, 20), dtype=torch.float32, device=self.device)
+        status = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        self.check(self.lib.caelo_encode_patches(self.h, _ptr(patches), P, _ptr(feat), _ptr(status), _stream()),
+                   "caelo_encode_patches")
+        self.check(int(status.item()), "caelo_encode_patches(input check)")
+        return feat
+
+    def nn_match(self, codes0: torch.Tensor, codes1: torch.Tensor) -> torch.Tensor:
+        P, N, D = codes0.shape
+        M = codes1.shape[1]
+        assert codes1.shape[0] == P and codes1.shape[2] == D
+        assert codes0.dtype == torch.float32 and codes0.is_contiguous() and codes1.is_contiguous()
+        idx = torch.empty((P, M), dtype=torch.int64, device=self.device)
+        self.check(self.lib.caelo_nn_match(self.h, _ptr(codes0), _ptr(codes1), P, N, M, D, _ptr(idx), _stream()),
+                   "caelo_nn_match")
+        return idx
+
+    def ransac_round(self, pc0, pc1, pair_idx, sample_idx, thr, best_n_in=None, want_counts=False):
+        P, N0, _ = pc0.shape
+        N = pc1.shape[1]
+        T = sample_idx.shape[1]
+        result = torch.empty((P, 16), dtype=torch.float32, device=self.device)
+        mask = torch.empty((P, N), dtype=torch.uint8, device=self.device)
+        counts = torch.empty((P, T), dtype=torch.int32, device=self.device) if want_counts else None
+        rc = self.lib.caelo_ransac_round(self.h, _ptr(pc0), N0, _ptr(pc1), N, _ptr(pair_idx), _ptr(sample_idx),
+                                         T, _ptr(thr), _ptr(best_n_in), P, _ptr(result), _ptr(mask),
+                                         _ptr(counts), _stream())
+        self.check(rc, "caelo_ransac_round")
+        return result, mask, counts
+
+    def kabsch(self, pc0, pc1, pair_idx=None, mask=None):
+        P, N0, _ = pc0.shape
+        N = pc1.shape[1]
+        rt = torch.empty((P, 12), dtype=torch.float32, device=self.device)
+        cred = torch.empty((P,), dtype=torch.int32, device=self.device)
+        self.check(self.lib.caelo_kabsch(self.h, _ptr(pc0), N0, _ptr(pc1), N, _ptr(pair_idx), _ptr(mask), P,
+                                         _ptr(rt), _ptr(cred), _stream()), "caelo_kabsch")
+        return rt, cred
+
+
+def _default_weights(which: str):
+    z = np.load(os.path.join(WEIGHT_DIR, which + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        dev = int(os.environ.get("LOCAL_RANK", "0")) if torch.cuda.device_count() > 1 else 0
+        _default_ctx = Context(dev)
+    return _default_ctx
+
+
+def _dev(a: np.ndarray, dtype=None) -> torch.Tensor:
+    a = np.ascontiguousarray(a if dtype is None else np.asarray(a, dtype=dtype))
+    return torch.from_numpy(a).to(default_context().device, non_blocking=False)
+
+
+# ------------------------------------------------------------------------------------------
+# Keras stand-in
+# ------------------------------------------------------------------------------------------
+class B200Model:
+    """What ``keras.models.load_model`` returns here: ``predict(ndarray) -> ndarray``."""
+
+    def __init__(self, kind: str, weights: dict, ctx: Optional[Context] = None):
+        self.kind = kind
+        self.ctx = ctx or default_context()
+        if kind == "respond":
+            self.ctx.set_respond_weights(weights)
+        elif kind == "encoder":
+            self.ctx.set_encoder_weights(weights)
+        else:
+            raise ValueError(kind)
+
+    def predict(self, x, batch_size=None, verbose=0):
+        x = np.asarray(x, dtype=np.float32)
+        if self.kind == "respond":
+            if x.ndim != 4 or x.shape[3] != 3:
+                raise ValueError("expected input (B,H,W,3), got %r" % (x.shape,))
+            out = self.ctx.respond_forward(_dev(x))
+            return out.cpu().numpy()
+        if x.ndim == 5 and x.shape[1:] == (16, 16, 16, 1):
+            x = x.reshape(x.shape[0], 16, 16, 16)
+        if x.ndim != 4 or x.shape[1:] != (16, 16, 16):
+            raise ValueError("expected input (K,16,16,16,1), got %r" % (x.shape,))
+        if x.shape[0] == 0:
+            return np.zeros((0, 20), np.float32)
+        return self.ctx.encode_patches(_dev(x)).cpu().numpy()
+
+
+def load_model(path: str, ctx: Optional[Context] = None) -> B200Model:
+    """Drop-in for ``keras.models.load_model`` on the two inference networks CAE-LO ships
+    (TrainedModels/SphericalRingPCRespondLayer.h5, EncoderModel4VoxelPatch.h5)."""
+    if path.endswith(".npz"):
+        z = np.load(path)
+        w = {k: z[k] for k in z.files}
+        layers = None
+    else:
+        w, _sha = read_keras_weights(path)
+        layers = layer_summary(read_model_config(path))
+    if "conv2d_1/kernel:0" in w and "conv3d_1/kernel:0" not in w:
+        if layers is not None:
+            acts = [l[2] for l in layers if l[0] == "Conv2D"]
+            if acts != ["relu", "relu"]:
+                raise _lib.CaeloError("unsupported respond-layer activations %r" % acts)
+        return B200Model("respond", w, ctx)
+    if "conv3d_1/kernel:0" in w and "dense_2/kernel:0" in w:
+        if layers is not None:
+            acts = [l[2] for l in layers if l[0] in ("Conv3D", "Dense")]
+            if acts != ["tanh"] * 5:
+                raise _lib.CaeloError("unsupported encoder activations %r (the kernel implements the "
+                                      "shipped all-tanh EncoderModel4VoxelPatch.h5)" % acts)
+        return B200Model("encoder", w, ctx)
+    raise _lib.CaeloError("%s is neither the respond layer nor the voxel-patch encoder" % path)
+
+
+# ------------------------------------------------------------------------------------------
+# keypoints
+# ------------------------------------------------------------------------------------------
+def _select(SphericalRing, GridCounter, RespondImg):
+    ctx = default_context()
+    ring = np.asarray(SphericalRing, dtype=np.float32)
+    cnt = np.asarray(GridCounter)
+    if cnt.dtype != np.int8:
+        cnt = cnt.astype(np.int32, copy=False)
+    resp = None
+    if RespondImg is not None:
+        r = np.asarray(RespondImg, dtype=np.float32)
+        H, W = r.shape[0], r.shape[1]
+        resp = _dev(r[None])
+    else:
+        H, W = nLines, ImgW - CropWidth_SphericalRing
+    kpts, kpix, n = ctx.select_keypoints(_dev(ring[None]), _dev(cnt[None]), resp, H, W, nFixedKeyPts)
+    n = int(n.item())
+    KeyPts = kpts[0, :n].cpu().numpy()
+    KeyPixels = kpix[0, :n].cpu().numpy()
+    PlanarPts = np.array([], dtype=np.float32)
+    assert KeyPts.shape[0] > 50  # SphericalRing.py:286
+    return KeyPts, KeyPixels, PlanarPts
+
+
+def GetKeyPtsByAE(SphericalRing, GridCounter, RespondImg):
+    """SphericalRing.py:113 — (KeyPts (n,3) f32 ascending by score, KeyPixels (n,2) int64, PlanarPts)."""
+    return _select(SphericalRing, GridCounter, RespondImg)
+
+
+def GetKeyPtsFromRing(SphericalRing, GridCounter):
+    """Fused a1+a2: what GetKeyPtsFromRawFileName computes once the .mat is loaded."""
+    return _select(SphericalRing, GridCounter, None)
+
+
+def GetKeyPtsFromRawFileName(rawFileFullPath, RespondLayer=None):
+    """SphericalRing.py:389 — loads <seq>/SphericalRing/<name>.mat next to the raw file."""
+    from scipy import io
+    baseDir = os.path.dirname(os.path.dirname(rawFileFullPath))
+    mat = io.loadmat(os.path.join(baseDir, "SphericalRing", os.path.basename(rawFileFullPath) + ".mat"))
+    return GetKeyPtsFromRing(mat["SphericalRing"], mat["GridCounter"])
+
+
+# ------------------------------------------------------------------------------------------
+# patches + descriptors
+# ------------------------------------------------------------------------------------------
+def _vox_cat(AllVoxels0, AllVoxels1, AllVoxels2):
+    lists = [np.ascontiguousarray(np.asarray(v), np.int16).reshape(-1, 3) for v in (AllVoxels0, AllVoxels1, AllVoxels2)]
+    off = np.zeros(4, np.int64)
+    off[1:] = np.cumsum([l.shape[0] for l in lists])
+    if min(l.shape[0] for l in lists) < 496:
+        raise ValueError("Expected n_neighbors <= n_samples_fit")  # what sklearn raises (Voxel.py:195)
+    return np.concatenate(lists, 0), off
+
+
+def _gather(Pts, AllVoxels0, AllVoxels1, AllVoxels2, want_f32):
+    ctx = default_context()
+    P = np.asarray(Pts)
+    if P.dtype != np.float64:
+        P = P.astype(np.float32, copy=False)
+    vox, off = _vox_cat(AllVoxels0, AllVoxels1, AllVoxels2)
+    return ctx.gather_patches(_dev(P[None]), _dev(vox), off, None, want_f32=want_f32)
+
+
+def GetPatchesList(Pts, AllVoxels0, AllVoxels1, AllVoxels2):
+    """Voxel.py:177 — (Pts, [3 x (K,16,16,16,1) float32])."""
+    _packed, f32, _ = _gather(Pts, AllVoxels0, AllVoxels1, AllVoxels2, True)
+    K = np.asarray(Pts).shape[0]
+    out = f32[0].cpu().numpy().reshape(3, K, 16, 16, 16, 1)
+    return Pts, [out[0], out[1], out[2]]
+
+
+def GetFeaturesFromPatches(PatchEncoder, PatchesList):
+    """Match.py:130 — np.c_[predict(p0), predict(p1), predict(p2)]."""
+    return np.c_[PatchEncoder.predict(PatchesList[0]), PatchEncoder.predict(PatchesList[1]),
+                 PatchEncoder.predict(PatchesList[2])]
+
+
+def GetFeaturesAtKeyPts(Pts, AllVoxels0, AllVoxels1, AllVoxels2):
+    """a6+a3 without materialising float32 patches: GetFeaturesFromPatches(GetPatchesList(...))."""
+    ctx = default_context()
+    packed, _, _ = _gather(Pts, AllVoxels0, AllVoxels1, AllVoxels2, False)
+    return ctx.encode_frames(packed)[0].cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------
+# match + pose
+# ------------------------------------------------------------------------------------------
+def SolveRT(Pairs0, Pairs1):
+    """Match.py:138 — (R (3,3) f32, T (3,1) f32, isCredible)."""
+    ctx = default_context()
+    p0 = _dev(np.asarray(Pairs0, np.float32)[None])
+    p1 = _dev(np.asarray(Pairs1, np.float32)[None])
+    rt, cred = ctx.kabsch(p0, p1)
+    rt = rt.cpu().numpy()[0]
+    return rt[:9].reshape(3, 3).copy(), rt[9:].reshape(3, 1).copy(), int(cred.item())
+
+
+def _ransac(ctx, pc0, pc1, pair_idx, N, verbose=False):
+    """RANSAC4RT's threshold ladder around caelo_ransac_round; consumes np.random exactly like
+    the reference (Match.py:181-214): 4 doubles per trial actually run."""
+    thr = 0.4
+    best_n = 0
+    R_star = np.eye(3, dtype=np.float64)
+    T_star = np.zeros((3, 1), dtype=np.float64)
+    mask_star = None
+    ok = False
+    used = 0
+    while True:
+        state = np.random.get_state()
+        u = np.random.random((MAX_TRIALS, 4))
+        idx = np.array(u * N, dtype=np.int32)
+        res, mask, _ = ctx.ransac_round(pc0, pc1, pair_idx, _dev(idx[None]),
+                                        _dev(np.array([thr], np.float32)),
+                                        _dev(np.array([best_n], np.int32)))
+        r = res.cpu().numpy()[0]
+        used = int(r[13])
+        np.random.set_state(state)
+        np.random.random((used * 4,))
+        if int(r[15]) >= 0:
+            best_n = int(r[14])
+            R_star = r[:9].reshape(3, 3).copy()
+            T_star = r[9:12].reshape(3, 1).copy()
+            mask_star = mask
+        if r[12] != 0:
+            ok = True
+            break
+        thr = 2 * thr
+        if thr > 2.0:
+            if verbose:
+                print('failed when residual =', thr)
+            thr = thr / 2
+            break
+    if verbose:
+        print('cntItersRANSAC =', used)
+        print('residualThreshold =', thr)
+        print('nInliers/nFilteredKeyPts1 =', best_n, '/', N, '=', round(best_n / N, 3))
+    return R_star, T_star, ok, mask_star, thr
+
+
+def RANSAC4RT(Pairs0, Pairs1, Weights0=None, Weights1=None):
+    """Match.py:162 — (R*, T*, isSuccess, inlierMask bool (N,), residualThreshold)."""
+    ctx = default_context()
+    P0 = np.asarray(Pairs0, np.float32)
+    N = P0.shape[0]
+    R, T, ok, mask, thr = _ransac(ctx, _dev(P0[None]), _dev(np.asarray(Pairs1, np.float32)[None]), None, N)
+    m = np.zeros((N,), dtype=bool) if mask is None else mask[0].cpu().numpy().astype(bool)
+    return R, T, ok, m, thr
+
+
+def SolveRelativePose(OriPC0, OriCodes0, Weights0, OriPC1, OriCodes1, Weights1):
+    """Match.py:241 — (R, T, isSuccess, inliersIdx0, inliersIdx1, residualThreshold);
+    x0 ~= R x1 + T.  Weights are ignored, as in the reference (overwritten with ones, :265-266)."""
+    ctx = default_context()
+    pc0 = _dev(np.asarray(OriPC0, np.float32)[None])
+    pc1 = _dev(np.asarray(OriPC1, np.float32)[None])
+    c0 = _dev(np.asarray(OriCodes0, np.float32)[None])
+    c1 = _dev(np.asarray(OriCodes1, np.float32)[None])
+    N = pc1.shape[1]
+    pair_idx = ctx.nn_match(c0, c1)
+    R, T, ok, mask, thr = _ransac(ctx, pc0, pc1, pair_idx, N)
+    if mask is None:
+        e = np.zeros((0,), np.int64)
+        return R, T, ok, e, e.copy(), thr
+    m = mask[0].cpu().numpy().astype(bool)
+    pidx = pair_idx[0].cpu().numpy()
+    inliersIdx0 = pidx[m]
+    inliersIdx1 = np.arange(N)[m]
+    if inliersIdx0.shape[0] == 0:
+        return R, T, ok, inliersIdx0, inliersIdx1, thr
+    rt, _ = ctx.kabsch(pc0, pc1, pair_idx, mask)
+    rt = rt.cpu().numpy()[0]
+    return rt[:9].reshape(3, 3).copy(), rt[9:].reshape(3, 1).copy(), ok, inliersIdx0, inliersIdx1, thr

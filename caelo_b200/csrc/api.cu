@@ -1,0 +1,103 @@
+// api.cu — ctx lifetime, weights and error reporting for libcaelo_b200.so (include/caelo.h).
+#include <new>
+
+#include "common.cuh"
+
+int caelo_encoder_init(caelo_ctx *ctx);
+int caelo_match_init(caelo_ctx *ctx);
+int caelo_select_init(caelo_ctx *ctx);
+
+extern "C" int caelo_version(void) { return 100; }
+
+extern "C" const char *caelo_error_string(int code)
+{
+    switch (code) {
+    case CAELO_OK: return "ok";
+    case CAELO_ERR_CUDA: return "CUDA runtime error (see caelo_last_cuda_error)";
+    case CAELO_ERR_ARG: return "invalid argument";
+    case CAELO_ERR_NO_WEIGHTS: return "network weights not set on this ctx";
+    case CAELO_ERR_NONBINARY_PATCH: return "encoder input contains a value other than 0 or 1";
+    case CAELO_ERR_TOO_FEW_VOXELS: return "a voxel list has fewer than 496 entries (n_neighbors <= n_samples_fit)";
+    case CAELO_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+    case CAELO_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown error";
+    }
+}
+
+extern "C" const char *caelo_last_cuda_error(const caelo_ctx *ctx)
+{
+    return ctx ? cudaGetErrorString(ctx->last_err) : "null ctx";
+}
+
+extern "C" int caelo_create(int device_id, caelo_ctx **out)
+{
+    if (!out) return CAELO_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device_id < 0 || device_id >= n)
+        return CAELO_ERR_NO_DEVICE;
+    if (cudaSetDevice(device_id) != cudaSuccess) return CAELO_ERR_NO_DEVICE;
+    caelo_ctx *ctx = new (std::nothrow) caelo_ctx();
+    if (!ctx) return CAELO_ERR_ARG;
+    ctx->device = device_id;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) { delete ctx; return CAELO_ERR_NO_DEVICE; }
+    ctx->num_sms = prop.multiProcessorCount;
+    memset(&ctx->enc, 0, sizeof(ctx->enc));
+    int rc = caelo_encoder_init(ctx);
+    if (!rc) rc = caelo_match_init(ctx);
+    if (!rc) rc = caelo_select_init(ctx);
+    if (rc) { delete ctx; return rc; }
+    *out = ctx;
+    return CAELO_OK;
+}
+
+extern "C" int caelo_destroy(caelo_ctx *ctx)
+{
+    if (!ctx) return CAELO_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    Scratch *all[] = {&ctx->cand, &ctx->bricks, &ctx->enc_ws, &ctx->pose_ws, &ctx->misc};
+    for (Scratch *s : all)
+        if (s->ptr) cudaFree(s->ptr);
+    if (ctx->enc_blob) cudaFree(ctx->enc_blob);
+    delete ctx;
+    return CAELO_OK;
+}
+
+extern "C" int caelo_num_sms(const caelo_ctx *ctx) { return ctx ? ctx->num_sms : 0; }
+extern "C" int64_t caelo_launch_count(const caelo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int caelo_set_respond_weights(caelo_ctx *ctx, const float *w1, const float *b1,
+                                         const float *w2, const float *b2)
+{
+    if (!ctx || !w1 || !b1 || !w2 || !b2) return CAELO_ERR_ARG;
+    memcpy(ctx->respond_host.w1, w1, sizeof(ctx->respond_host.w1));
+    memcpy(ctx->respond_host.b1, b1, sizeof(ctx->respond_host.b1));
+    memcpy(ctx->respond_host.w2, w2, sizeof(ctx->respond_host.w2));
+    memcpy(ctx->respond_host.b2, b2, sizeof(ctx->respond_host.b2));
+    ctx->have_respond = true;
+    return CAELO_OK;
+}
+
+extern "C" int caelo_set_encoder_weights(caelo_ctx *ctx, const float *k1, const float *b1,
+                                         const float *k2, const float *b2, const float *k3,
+                                         const float *b3, const float *d1, const float *bd1,
+                                         const float *d2, const float *bd2)
+{
+    if (!ctx || !k1 || !b1 || !k2 || !b2 || !k3 || !b3 || !d1 || !bd1 || !d2 || !bd2) return CAELO_ERR_ARG;
+    const size_t n[10] = {27 * 8, 8, 27 * 8 * 16, 16, 27 * 16 * 32, 32, 2048 * 200, 200, 200 * 20, 20};
+    const float *src[10] = {k1, b1, k2, b2, k3, b3, d1, bd1, d2, bd2};
+    size_t total = 0, off[10];
+    for (int i = 0; i < 10; ++i) { off[i] = total; total += (n[i] + 63) / 64 * 64; }
+    CAELO_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->enc_blob) CAELO_CUDA(ctx, cudaMalloc(&ctx->enc_blob, total * 4));
+    for (int i = 0; i < 10; ++i)
+        CAELO_CUDA(ctx, cudaMemcpy(ctx->enc_blob + off[i], src[i], n[i] * 4, cudaMemcpyHostToDevice));
+    float *b = ctx->enc_blob;
+    ctx->enc.k1 = b + off[0]; ctx->enc.b1 = b + off[1]; ctx->enc.k2 = b + off[2]; ctx->enc.b2 = b + off[3];
+    ctx->enc.k3 = b + off[4]; ctx->enc.b3 = b + off[5]; ctx->enc.d1 = b + off[6]; ctx->enc.bd1 = b + off[7];
+    ctx->enc.d2 = b + off[8]; ctx->enc.bd2 = b + off[9];
+    ctx->have_encoder = true;
+    return CAELO_OK;
+}

@@ -1,0 +1,80 @@
+// common.cuh — ctx layout, scratch management and launch helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/caelo.h"
+
+struct RespondWeights {  // SphericalRingPCRespondLayer.h5, Keras layouts
+    float w1[27 * 32];   // (ky,kx,ci,co)
+    float b1[32];
+    float w2[32 * 8];    // (ci,co)
+    float b2[8];
+};
+
+struct EncoderWeightsDev {  // EncoderModel4VoxelPatch.h5 on the device
+    float *k1, *b1;         // (27,8)  tap-major, (8)
+    float *k2, *b2;         // (27,8,16), (16)
+    float *k3, *b3;         // (27,16,32), (32)
+    float *d1, *bd1;        // (2048,200), (200)
+    float *d2, *bd2;        // (200,20), (20)
+};
+
+struct Scratch {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct caelo_ctx {
+    int device = 0;
+    int num_sms = 0;
+    int64_t launches = 0;
+    cudaError_t last_err = cudaSuccess;
+    bool have_respond = false, have_encoder = false;
+    RespondWeights respond_host;
+    EncoderWeightsDev enc;
+    float *enc_blob = nullptr;
+    // scratch regions (grown on demand, never shrunk)
+    Scratch cand;      // select: candidate keys + counters
+    Scratch bricks;    // patches: hash tables
+    Scratch enc_ws;    // encoder activations
+    Scratch pose_ws;   // ransac: hypotheses
+    Scratch misc;
+};
+
+#define CAELO_CUDA(ctx, call)                         \
+    do {                                              \
+        cudaError_t e__ = (call);                     \
+        if (e__ != cudaSuccess) {                     \
+            (ctx)->last_err = e__;                    \
+            return CAELO_ERR_CUDA;                    \
+        }                                             \
+    } while (0)
+
+static inline int caelo_reserve(caelo_ctx *ctx, Scratch &s, size_t bytes)
+{
+    if (s.bytes >= bytes) return CAELO_OK;
+    if (s.ptr) {
+        // the old block may still be in use by work queued on a stream
+        CAELO_CUDA(ctx, cudaDeviceSynchronize());
+        CAELO_CUDA(ctx, cudaFree(s.ptr));
+        s.ptr = nullptr;
+        s.bytes = 0;
+    }
+    size_t want = bytes + bytes / 4;
+    CAELO_CUDA(ctx, cudaMalloc(&s.ptr, want));
+    s.bytes = want;
+    return CAELO_OK;
+}
+
+#define CAELO_LAUNCH_CHECK(ctx)                       \
+    do {                                              \
+        (ctx)->launches++;                            \
+        cudaError_t e__ = cudaGetLastError();         \
+        if (e__ != cudaSuccess) {                     \
+            (ctx)->last_err = e__;                    \
+            return CAELO_ERR_CUDA;                    \
+        }                                             \
+    } while (0)
+

@@ -1,0 +1,313 @@
+// patches.cu — a6: GetPatchesList (reference Voxel.py:177-216) for sm_100a.
+//
+// The reference fits an sklearn kNN index on each of the three occupied-voxel lists, asks for
+// the 496 nearest voxels of every key voxel, keeps those inside the [-8,8)^3 cube and scatters
+// 1.0 into a 16^3 patch using NEGATIVE indices (offset o lands at index o mod 16).  Here:
+//   1. brick_insert_kernel: every occupied voxel sets one bit of a 4x4x4 "brick" (64-bit mask)
+//      kept in an open-addressing hash table keyed by the brick coordinate (per frame, scale);
+//   2. gather_kernel: one warp per (frame, scale, keypoint) probes the <=8^3 bricks that meet
+//      the ball d^2 <= 192 around the key voxel, counts the ball and sets the cube bits of a
+//      512-byte bit-packed patch in shared memory; only if the ball holds more than 496 voxels
+//      (the kNN cut can bite) it re-runs with the exact rank rule (d^2, then x,y,z).
+// Integer-exact; HBM traffic = voxel lists in + 512 B per patch out.
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned long long EMPTY = ~0ull;
+constexpr int kWarps = 8;
+constexpr int NNB = 496;  // n_neighbors, Voxel.py:182
+
+struct Table {
+    unsigned long long *keys;
+    unsigned long long *masks;
+    unsigned cap_mask;  // capacity - 1 (power of two)
+};
+
+__device__ __forceinline__ unsigned hash64(unsigned long long k)
+{
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return (unsigned)k;
+}
+
+__device__ __forceinline__ unsigned long long brick_key(int bx, int by, int bz)
+{
+    return (unsigned long long)(bx + 8192) | ((unsigned long long)(by + 8192) << 14) |
+           ((unsigned long long)(bz + 8192) << 28);
+}
+
+struct BuildArgs {
+    const int16_t *vox;          // all lists concatenated, rows of 3
+    const long long *offsets;    // dev [F*3+1]
+    const Table *tables;         // dev [F*3]
+    int nlists;
+};
+
+__global__ void brick_insert_kernel(const BuildArgs a)
+{
+    const int list = blockIdx.y;
+    const long long beg = a.offsets[list], end = a.offsets[list + 1];
+    const Table t = a.tables[list];
+    for (long long i = beg + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < end;
+         i += (long long)gridDim.x * blockDim.x) {
+        int x = a.vox[i * 3 + 0], y = a.vox[i * 3 + 1], z = a.vox[i * 3 + 2];
+        unsigned long long key = brick_key(x >> 2, y >> 2, z >> 2);
+        unsigned long long bit = 1ull << (((x & 3) * 4 + (y & 3)) * 4 + (z & 3));
+        unsigned slot = hash64(key) & t.cap_mask;
+        while (true) {
+            unsigned long long old = atomicCAS(t.keys + slot, EMPTY, key);
+            if (old == EMPTY || old == key) {
+                atomicOr(t.masks + slot, bit);
+                break;
+            }
+            slot = (slot + 1) & t.cap_mask;
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned long long brick_lookup(const Table &t, unsigned long long key)
+{
+    unsigned slot = hash64(key) & t.cap_mask;
+    while (true) {
+        unsigned long long k = t.keys[slot];
+        if (k == key) return t.masks[slot];
+        if (k == EMPTY) return 0ull;
+        slot = (slot + 1) & t.cap_mask;
+    }
+}
+
+struct GatherArgs {
+    const void *kpts;            // [F,K,3] f32 or f64
+    const int *n_kpts;           // [F] or null
+    const Table *tables;         // [F*3]
+    unsigned *packed;            // [F,3,K,128]
+    unsigned char *trunc;        // [F,3,K] or null
+    double vis[3];               // VisibleLength/Width/Height (Voxel.py:50-52)
+    double vsize[3];             // VoxelSizes (Voxel.py:31)
+    int kpts_f64, F, K;
+};
+
+// visit every occupied voxel of the bricks meeting [-13,13]^3 around kv; f(dx,dy,dz)
+template <class Fn>
+__device__ __forceinline__ void for_ball_voxels(const Table &t, int kx, int ky, int kz, int lane, Fn f)
+{
+    const int bx0 = (kx - 13) >> 2, by0 = (ky - 13) >> 2, bz0 = (kz - 13) >> 2;
+    const int nx = ((kx + 13) >> 2) - bx0 + 1, ny = ((ky + 13) >> 2) - by0 + 1,
+              nz = ((kz + 13) >> 2) - bz0 + 1;
+    const int nb = nx * ny * nz;
+    for (int i = lane; i < nb; i += 32) {
+        int bz = bz0 + i % nz, by = by0 + (i / nz) % ny, bx = bx0 + i / (nz * ny);
+        if (bx < -8192 || by < -8192 || bz < -8192) continue;
+        unsigned long long m = brick_lookup(t, brick_key(bx, by, bz));
+        while (m) {
+            int bit = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            int dx = bx * 4 + (bit >> 4) - kx, dy = by * 4 + ((bit >> 2) & 3) - ky,
+                dz = bz * 4 + (bit & 3) - kz;
+            f(dx, dy, dz);
+        }
+    }
+}
+
+__device__ __forceinline__ bool in_cube(int dx, int dy, int dz)
+{
+    return dx >= -8 && dx < 8 && dy >= -8 && dy < 8 && dz >= -8 && dz < 8;
+}
+
+__device__ __forceinline__ void set_patch_bit(unsigned *patch, int dx, int dy, int dz)
+{
+    int idx = (((dx & 15) * 16) + (dy & 15)) * 16 + (dz & 15);  // o mod 16: the negative-index roll
+    atomicOr(patch + (idx >> 5), 1u << (idx & 31));
+}
+
+__global__ void __launch_bounds__(kWarps * 32) gather_kernel(const GatherArgs a)
+{
+    __shared__ unsigned s_patch[kWarps][128];
+    __shared__ int s_hist[kWarps][196];
+    __shared__ unsigned s_list[kWarps][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long total = (long long)a.F * 3 * a.K;
+    unsigned *patch = s_patch[warp];
+    for (long long w = (long long)blockIdx.x * kWarps + warp; w < total;
+         w += (long long)gridDim.x * kWarps) {
+        const int k = (int)(w % a.K);
+        const int s = (int)((w / a.K) % 3);
+        const int f = (int)(w / (3LL * a.K));
+        for (int i = lane; i < 128; i += 32) patch[i] = 0u;
+        __syncwarp();
+        const bool live = a.n_kpts == nullptr || k < a.n_kpts[f];
+        bool flagged = false;
+        if (live) {
+            double p[3];
+            for (int c = 0; c < 3; ++c)
+                p[c] = a.kpts_f64 ? reinterpret_cast<const double *>(a.kpts)[((size_t)f * a.K + k) * 3 + c]
+                                  : (double)reinterpret_cast<const float *>(a.kpts)[((size_t)f * a.K + k) * 3 + c];
+            // KeyVoxels = int32((Pts + Visible) / VoxelSizes[s])  — float64, truncation (Voxel.py:185,193)
+            const int kx = (int)__ddiv_rn(__dadd_rn(p[0], a.vis[0]), a.vsize[s]);
+            const int ky = (int)__ddiv_rn(__dadd_rn(p[1], a.vis[1]), a.vsize[s]);
+            const int kz = (int)__ddiv_rn(__dadd_rn(p[2], a.vis[2]), a.vsize[s]);
+            const Table t = a.tables[f * 3 + s];
+            int ball = 0;
+            for_ball_voxels(t, kx, ky, kz, lane, [&](int dx, int dy, int dz) {
+                int d2 = dx * dx + dy * dy + dz * dz;
+                if (d2 <= 192) {
+                    ++ball;
+                    if (in_cube(dx, dy, dz)) set_patch_bit(patch, dx, dy, dz);
+                }
+            });
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ball += __shfl_xor_sync(0xffffffffu, ball, o);
+            __syncwarp();
+            if (ball > NNB) {
+                // the 496-NN cut can bite: keep cube voxels whose rank by (d2, x, y, z) is < 496
+                flagged = true;
+                int *hist = s_hist[warp];
+                unsigned *list = s_list[warp];
+                for (int i = lane; i < 196; i += 32) hist[i] = 0;
+                for (int i = lane; i < 128; i += 32) patch[i] = 0u;
+                __syncwarp();
+                for_ball_voxels(t, kx, ky, kz, lane, [&](int dx, int dy, int dz) {
+                    int d2 = dx * dx + dy * dy + dz * dz;
+                    if (d2 <= 192) atomicAdd(hist + d2, 1);
+                });
+                __syncwarp();
+                // cut value q: smallest d2 with cumulative count >= 496 (every lane computes it)
+                int q = 0, before = 0;
+                for (; q <= 192; ++q) {
+                    if (before + hist[q] >= NNB) break;
+                    before += hist[q];
+                }
+                const int room = NNB - before;  // how many voxels at d2 == q survive
+                if (lane == 0) hist[193] = 0;
+                __syncwarp();
+                for_ball_voxels(t, kx, ky, kz, lane, [&](int dx, int dy, int dz) {
+                    int d2 = dx * dx + dy * dy + dz * dz;
+                    if (d2 < q) {
+                        if (in_cube(dx, dy, dz)) set_patch_bit(patch, dx, dy, dz);
+                    } else if (d2 == q) {
+                        int pos = atomicAdd(hist + 193, 1);
+                        if (pos < 256) list[pos] = ((unsigned)(dx + 16) << 12) | ((unsigned)(dy + 16) << 6) | (unsigned)(dz + 16);
+                    }
+                });
+                __syncwarp();
+                int m = hist[193];
+                if (m > 256) m = 256;  // r3(n) <= 168 for n <= 192: cannot happen
+                for (int i = lane; i < m; i += 32) {
+                    unsigned me = list[i];
+                    int rank = 0;
+                    for (int j = 0; j < m; ++j) rank += list[j] < me;
+                    if (rank < room) {
+                        int dx = (int)(me >> 12) - 16, dy = (int)((me >> 6) & 63) - 16, dz = (int)(me & 63) - 16;
+                        if (in_cube(dx, dy, dz)) set_patch_bit(patch, dx, dy, dz);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        unsigned *out = a.packed + (((size_t)f * 3 + s) * a.K + k) * 128;
+        for (int i = lane; i < 128; i += 32) out[i] = patch[i];
+        if (a.trunc && lane == 0) a.trunc[((size_t)f * 3 + s) * a.K + k] = flagged ? 1 : 0;
+        __syncwarp();
+    }
+}
+
+__global__ void unpack_kernel(const unsigned *__restrict__ packed, float *__restrict__ out, long long nwords)
+{
+    // one thread per packed word -> 32 floats (coalesced 128 B per thread pair of float4 x8)
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords;
+         w += (long long)gridDim.x * blockDim.x) {
+        unsigned v = packed[w];
+        float4 *o = reinterpret_cast<float4 *>(out + w * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            o[j] = make_float4((v >> (4 * j)) & 1u ? 1.f : 0.f, (v >> (4 * j + 1)) & 1u ? 1.f : 0.f,
+                               (v >> (4 * j + 2)) & 1u ? 1.f : 0.f, (v >> (4 * j + 3)) & 1u ? 1.f : 0.f);
+    }
+}
+
+}  // namespace
+
+extern "C" int caelo_gather_patches(caelo_ctx *ctx, const void *kpts, int kpts_f64,
+                                    const int32_t *n_kpts, int F, int K, const int16_t *vox,
+                                    const int64_t *vox_offsets, uint32_t *packed, float *patches_f32,
+                                    uint8_t *trunc, void *stream)
+{
+    if (!ctx || !kpts || !vox || !vox_offsets || !packed || F <= 0 || K <= 0) return CAELO_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nl = F * 3;
+    // table geometry from the (host) list sizes
+    size_t total_slots = 0;
+    long long maxlen = 0;
+    for (int l = 0; l < nl; ++l) {
+        long long len = vox_offsets[l + 1] - vox_offsets[l];
+        if (len < NNB) return CAELO_ERR_TOO_FEW_VOXELS;  // sklearn: n_neighbors <= n_samples_fit
+        if (len > maxlen) maxlen = len;
+        size_t cap = 1024;
+        while (cap < (size_t)len * 2) cap <<= 1;
+        total_slots += cap;
+    }
+    size_t head = ((size_t)nl * sizeof(Table) + (size_t)(nl + 1) * 8 + 255) / 256 * 256;
+    size_t need = head + total_slots * 16;
+    int rc = caelo_reserve(ctx, ctx->bricks, need);
+    if (rc) return rc;
+    char *base = reinterpret_cast<char *>(ctx->bricks.ptr);
+    Table *d_tables = reinterpret_cast<Table *>(base);
+    long long *d_off = reinterpret_cast<long long *>(base + (size_t)nl * sizeof(Table));
+    unsigned long long *d_keys = reinterpret_cast<unsigned long long *>(base + head);
+    unsigned long long *d_masks = d_keys + total_slots;
+    // host staging (small): tables + offsets
+    Table *h_tables = new Table[nl];
+    size_t cur = 0;
+    for (int l = 0; l < nl; ++l) {
+        long long len = vox_offsets[l + 1] - vox_offsets[l];
+        size_t cap = 1024;
+        while (cap < (size_t)len * 2) cap <<= 1;
+        h_tables[l].keys = d_keys + cur;
+        h_tables[l].masks = d_masks + cur;
+        h_tables[l].cap_mask = (unsigned)(cap - 1);
+        cur += cap;
+    }
+    cudaError_t e = cudaMemcpyAsync(d_tables, h_tables, (size_t)nl * sizeof(Table), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_off, vox_offsets, (size_t)(nl + 1) * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // h_tables is pageable and freed below
+    delete[] h_tables;
+    CAELO_CUDA(ctx, e);
+    CAELO_CUDA(ctx, cudaMemsetAsync(d_keys, 0xFF, total_slots * 8, st));
+    CAELO_CUDA(ctx, cudaMemsetAsync(d_masks, 0, total_slots * 8, st));
+
+    BuildArgs b;
+    b.vox = vox; b.offsets = d_off; b.tables = d_tables; b.nlists = nl;
+    int bx = (int)((maxlen + 255) / 256);
+    if (bx > 64) bx = 64;
+    brick_insert_kernel<<<dim3(bx, nl), 256, 0, st>>>(b);
+    CAELO_LAUNCH_CHECK(ctx);
+
+    GatherArgs g;
+    g.kpts = kpts; g.n_kpts = n_kpts; g.tables = d_tables; g.packed = packed; g.trunc = trunc;
+    // Voxel.py:40-52: nBlocksL = int(200/1.28) = 156, nBlocksH = int(30/1.28) = 23; Visible* = n/2*1.28
+    const double brs = 1.28;
+    g.vis[0] = 156 / 2.0 * brs; g.vis[1] = 156 / 2.0 * brs; g.vis[2] = 23 / 2.0 * brs;
+    const double vs = 0.02;
+    g.vsize[0] = vs; g.vsize[1] = vs * 8; g.vsize[2] = vs * 32;
+    g.kpts_f64 = kpts_f64; g.F = F; g.K = K;
+    long long warps = (long long)F * 3 * K;
+    long long blocks = (warps + kWarps - 1) / kWarps;
+    long long maxb = (long long)ctx->num_sms * 16;
+    if (blocks > maxb) blocks = maxb;
+    gather_kernel<<<(unsigned)blocks, kWarps * 32, 0, st>>>(g);
+    CAELO_LAUNCH_CHECK(ctx);
+
+    if (patches_f32) {
+        long long nwords = (long long)F * 3 * K * 128;
+        long long ub = (nwords + 255) / 256;
+        if (ub > (long long)ctx->num_sms * 32) ub = (long long)ctx->num_sms * 32;
+        unpack_kernel<<<(unsigned)ub, 256, 0, st>>>(packed, patches_f32, nwords);
+        CAELO_LAUNCH_CHECK(ctx);
+    }
+    return CAELO_OK;
+}

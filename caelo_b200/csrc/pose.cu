@@ -1,0 +1,407 @@
+// pose.cu — a5: RANSAC4RT / SolveRT (reference Match.py:138-218, 273-283) for sm_100a.
+//
+// COMPILED WITH -fmad=false: contract K1 (oracle/caelo_oracle.c) is written in plain float64
+// +,-,*,/,sqrt and must not be contracted into FMAs, so that gcc and nvcc agree bit-for-bit.
+// The float32 scoring contract D1 uses explicit __fmaf_rn where a fused op is specified.
+//
+//   hyp_score_kernel   one warp per hypothesis: Kabsch of the 4 sampled pairs (the reference's
+//                      reflection quirk included), then inlier count over all N pairs with
+//                      per-lane counters and a warp-shuffle reduction
+//   replay_mask_kernel one CTA per pair: the sequential accept/stop rule replayed over the
+//                      per-hypothesis counts, then the inlier mask of the accepted hypothesis
+//   kabsch_kernel      one warp per problem: masked refit over all inliers (Match.py:280-282)
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ double warp_tree(double v)
+{
+    // xor-butterfly 16,8,4,2,1: lane 0 ends with the fixed tree of contract K1 (lane_tree)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void cross3(const double a[3], const double b[3], double o[3])
+{
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+__device__ __forceinline__ double dot3(const double a[3], const double b[3])
+{
+    return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2];
+}
+
+__device__ __forceinline__ void ortho3(const double a[3], double o[3])
+{
+    double ax = fabs(a[0]), ay = fabs(a[1]), az = fabs(a[2]);
+    double e[3] = {0.0, 0.0, 0.0};
+    if (ax <= ay && ax <= az) e[0] = 1.0; else if (ay <= az) e[1] = 1.0; else e[2] = 1.0;
+    cross3(a, e, o);
+    double n = sqrt(dot3(o, o));
+    o[0] = o[0] / n; o[1] = o[1] / n; o[2] = o[2] / n;
+}
+
+__device__ void jacobi3(double S[3][3], double V[3][3])
+{
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        double off = fabs(S[0][1]) + fabs(S[0][2]) + fabs(S[1][2]);
+        if (off == 0.0) break;
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 3; ++q) {
+                double apq = S[p][q];
+                if (apq == 0.0) continue;
+                double theta = (S[q][q] - S[p][p]) / (2.0 * apq);
+                double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
+                if (theta < 0.0) t = -t;
+                double c = 1.0 / sqrt(t * t + 1.0);
+                double s = t * c;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    double skp = S[k][p], skq = S[k][q];
+                    S[k][p] = c * skp - s * skq;
+                    S[k][q] = s * skp + c * skq;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    double spk = S[p][k], sqk = S[q][k];
+                    S[p][k] = c * spk - s * sqk;
+                    S[q][k] = s * spk + c * sqk;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - s * vkq;
+                    V[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+}
+
+// contract K1 from H, m0, m1 -> float32 R (row-major), T; returns credible (+1 / -1)
+__device__ int kabsch_from_H(const double H[3][3], const double m0[3], const double m1[3],
+                             float R[9], float T[3])
+{
+    double S[3][3], V[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            S[i][j] = (H[0][i] * H[0][j] + H[1][i] * H[1][j]) + H[2][i] * H[2][j];
+    jacobi3(S, V);
+    double lam[3] = {S[0][0], S[1][1], S[2][2]};
+    int o0 = 0, o1 = 1, o2 = 2, tmp;
+    if (lam[o0] < lam[o1]) { tmp = o0; o0 = o1; o1 = tmp; }
+    if (lam[o1] < lam[o2]) { tmp = o1; o1 = o2; o2 = tmp; }
+    if (lam[o0] < lam[o1]) { tmp = o0; o0 = o1; o1 = tmp; }
+    const int ord[3] = {o0, o1, o2};
+    double v[3][3], u[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int k = 0; k < 3; ++k) {
+            // V[k][ord[i]] with a runtime column index, selected without local-memory indexing
+            int c = ord[i];
+            v[i][k] = c == 0 ? V[k][0] : (c == 1 ? V[k][1] : V[k][2]);
+        }
+    const double l1 = o0 == 0 ? lam[0] : (o0 == 1 ? lam[1] : lam[2]);
+    const double l2 = o1 == 0 ? lam[0] : (o1 == 1 ? lam[1] : lam[2]);
+    const double l3 = o2 == 0 ? lam[0] : (o2 == 1 ? lam[1] : lam[2]);
+    const double tiny = 1e-14;
+    if (!(l1 > 0.0)) {
+        for (int i = 0; i < 3; ++i)
+            for (int k = 0; k < 3; ++k) { v[i][k] = (i == k) ? 1.0 : 0.0; u[i][k] = (i == k) ? 1.0 : 0.0; }
+    } else {
+        double b[3];
+        for (int k = 0; k < 3; ++k) b[k] = (H[k][0] * v[0][0] + H[k][1] * v[0][1]) + H[k][2] * v[0][2];
+        double n = sqrt(dot3(b, b));
+        for (int k = 0; k < 3; ++k) u[0][k] = b[k] / n;
+        if (l2 > tiny * l1) {
+            for (int k = 0; k < 3; ++k) b[k] = (H[k][0] * v[1][0] + H[k][1] * v[1][1]) + H[k][2] * v[1][2];
+            double p = dot3(b, u[0]);
+            for (int k = 0; k < 3; ++k) b[k] = b[k] - p * u[0][k];
+            n = sqrt(dot3(b, b));
+            for (int k = 0; k < 3; ++k) u[1][k] = b[k] / n;
+        } else {
+            ortho3(u[0], u[1]);
+        }
+        if (l3 > tiny * l1 && l2 > tiny * l1) {
+            for (int k = 0; k < 3; ++k) b[k] = (H[k][0] * v[2][0] + H[k][1] * v[2][1]) + H[k][2] * v[2][2];
+            double p0 = dot3(b, u[0]);
+            for (int k = 0; k < 3; ++k) b[k] = b[k] - p0 * u[0][k];
+            double p1 = dot3(b, u[1]);
+            for (int k = 0; k < 3; ++k) b[k] = b[k] - p1 * u[1][k];
+            n = sqrt(dot3(b, b));
+            for (int k = 0; k < 3; ++k) u[2][k] = b[k] / n;
+        } else {
+            double cu[3], cv[3];
+            cross3(u[0], u[1], cu);
+            cross3(v[0], v[1], cv);
+            double sgn = dot3(cv, v[2]) < 0.0 ? -1.0 : 1.0;
+            for (int k = 0; k < 3; ++k) u[2][k] = sgn * cu[k];
+        }
+    }
+    double Q[3][3];
+    for (int a = 0; a < 3; ++a)
+        for (int c = 0; c < 3; ++c)
+            Q[a][c] = (v[0][a] * u[0][c] + v[1][a] * u[1][c]) + v[2][a] * u[2][c];
+    double det = (Q[0][0] * (Q[1][1] * Q[2][2] - Q[1][2] * Q[2][1]) -
+                  Q[0][1] * (Q[1][0] * Q[2][2] - Q[1][2] * Q[2][0])) +
+                 Q[0][2] * (Q[1][0] * Q[2][1] - Q[1][1] * Q[2][0]);
+    int cred = 1;
+    if (det < 0.0) {
+        cred = -1;
+        for (int c = 0; c < 3; ++c) Q[2][c] = -Q[2][c];  // quirk 4 (Match.py:151-155)
+    }
+    for (int a = 0; a < 3; ++a) {
+        double t = m0[a] - ((Q[a][0] * m1[0] + Q[a][1] * m1[1]) + Q[a][2] * m1[2]);
+        T[a] = (float)t;
+        for (int c = 0; c < 3; ++c) R[a * 3 + c] = (float)Q[a][c];
+    }
+    return cred;
+}
+
+// Kabsch over the points this warp's lanes hold: lane l contributes its own sequential partial
+// sums (s0/s1/cnt for the means, then h for H); combination is the K1 butterfly.
+struct LanePoint { float p0[3], p1[3]; };
+
+__device__ __forceinline__ bool inlier_d1(const float R[9], const float T[3], const float p0[3],
+                                          const float p1[3], float thr)
+{
+    float e[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float t = __fmul_rn(R[a * 3 + 0], p1[0]);
+        t = __fmaf_rn(R[a * 3 + 1], p1[1], t);
+        t = __fmaf_rn(R[a * 3 + 2], p1[2], t);
+        float q = __fadd_rn(t, T[a]);
+        e[a] = __fsub_rn(p0[a], q);
+    }
+    float d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(e[0], e[0]), __fmul_rn(e[1], e[1])), __fmul_rn(e[2], e[2])));
+    return d < thr;
+}
+
+struct PoseArgs {
+    const float *pc0, *pc1;       // [P,N0,3], [P,N,3]
+    const long long *pair_idx;    // [P,N] or null
+    const int *sample_idx;        // [P,T,4]
+    const float *thr;             // [P]
+    const int *best_n_in;         // [P] or null
+    int N0, N, T, P;
+    int *counts;                  // [P,T]
+    float *rt_hyp;                // [P,T,12]
+    float *result;                // [P,16]
+    unsigned char *mask;          // [P,N]
+};
+
+__device__ __forceinline__ void load_pair(const PoseArgs &a, int pair, int i, float p0[3], float p1[3])
+{
+    long long j = a.pair_idx ? a.pair_idx[(size_t)pair * a.N + i] : i;
+    const float *q0 = a.pc0 + ((size_t)pair * a.N0 + j) * 3;
+    const float *q1 = a.pc1 + ((size_t)pair * a.N + i) * 3;
+    p0[0] = q0[0]; p0[1] = q0[1]; p0[2] = q0[2];
+    p1[0] = q1[0]; p1[1] = q1[1]; p1[2] = q1[2];
+}
+
+constexpr int HS_WARPS = 8;
+
+__global__ void __launch_bounds__(HS_WARPS * 32) hyp_score_kernel(const PoseArgs a)
+{
+    const int pair = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * HS_WARPS + warp;
+    if (t >= a.T) return;
+    // Kabsch of the 4 samples: sample i sits in lane i of the K1 reduction
+    double s0[3] = {0, 0, 0}, s1[3] = {0, 0, 0};
+    float q0[3] = {0, 0, 0}, q1[3] = {0, 0, 0};
+    if (lane < 4) {
+        int si = a.sample_idx[((size_t)pair * a.T + t) * 4 + lane];
+        load_pair(a, pair, si, q0, q1);
+        for (int c = 0; c < 3; ++c) { s0[c] = 0.0 + (double)q0[c]; s1[c] = 0.0 + (double)q1[c]; }
+    }
+    double m0[3], m1[3];
+    for (int c = 0; c < 3; ++c) {
+        m0[c] = warp_tree(s0[c]) / 4.0;
+        m1[c] = warp_tree(s1[c]) / 4.0;
+    }
+    double H[3][3];
+    {
+        double a1[3], a0[3];
+        for (int c = 0; c < 3; ++c) { a1[c] = (double)q1[c] - m1[c]; a0[c] = (double)q0[c] - m0[c]; }
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+                double h = lane < 4 ? 0.0 + a1[r] * a0[c] : 0.0;
+                H[r][c] = warp_tree(h);
+            }
+    }
+    float R[9], T[3];
+    kabsch_from_H(H, m0, m1, R, T);
+    const float thr = a.thr[pair];
+    int cnt = 0;
+    for (int i = lane; i < a.N; i += 32) {
+        float p0[3], p1[3];
+        load_pair(a, pair, i, p0, p1);
+        cnt += inlier_d1(R, T, p0, p1, thr) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) a.counts[(size_t)pair * a.T + t] = cnt;
+    if (lane < 12) a.rt_hyp[((size_t)pair * a.T + t) * 12 + lane] = lane < 9 ? R[lane] : T[lane - 9];
+}
+
+__global__ void __launch_bounds__(256) replay_mask_kernel(const PoseArgs a)
+{
+    __shared__ int s_bt, s_bn, s_ok, s_it;
+    __shared__ float s_rt[12];
+    const int pair = blockIdx.x;
+    if (threadIdx.x == 0) {
+        // RANSAC4RT's loop (Match.py:181-206) over the pre-scored trials
+        const int N = a.N;
+        int least = (int)(0.2 * (double)N);
+        if (least > 100) least = 100;
+        const double succ = 0.25 * (double)N;
+        int it = 0, bn = a.best_n_in ? a.best_n_in[pair] : 0, bt = -1, ok = 0;
+        const int *cnt = a.counts + (size_t)pair * a.T;
+        while (it < a.T && ((it < 100) || (it < 500 && (double)bn < succ))) {
+            int n = cnt[it];
+            ++it;
+            if (n < least) continue;
+            if (n > bn) { bn = n; bt = it - 1; }
+            ok = 1;
+        }
+        s_bt = bt; s_bn = bn; s_ok = ok; s_it = it;
+    }
+    __syncthreads();
+    const int bt = s_bt;
+    if (threadIdx.x < 12) {
+        float v = (threadIdx.x == 0 || threadIdx.x == 4 || threadIdx.x == 8) ? 1.0f : 0.0f;  // R_star = I, T_star = 0
+        if (bt >= 0) v = a.rt_hyp[((size_t)pair * a.T + bt) * 12 + threadIdx.x];
+        s_rt[threadIdx.x] = v;
+        a.result[(size_t)pair * 16 + threadIdx.x] = v;
+    }
+    if (threadIdx.x == 12) a.result[(size_t)pair * 16 + 12] = (float)s_ok;
+    if (threadIdx.x == 13) a.result[(size_t)pair * 16 + 13] = (float)s_it;
+    if (threadIdx.x == 14) a.result[(size_t)pair * 16 + 14] = (float)s_bn;
+    if (threadIdx.x == 15) a.result[(size_t)pair * 16 + 15] = (float)bt;
+    __syncthreads();
+    float R[9], T[3];
+    for (int i = 0; i < 9; ++i) R[i] = s_rt[i];
+    for (int i = 0; i < 3; ++i) T[i] = s_rt[9 + i];
+    const float thr = a.thr[pair];
+    for (int i = threadIdx.x; i < a.N; i += blockDim.x) {
+        unsigned char m = 0;
+        if (bt >= 0) {
+            float p0[3], p1[3];
+            load_pair(a, pair, i, p0, p1);
+            m = inlier_d1(R, T, p0, p1, thr) ? 1 : 0;
+        }
+        a.mask[(size_t)pair * a.N + i] = m;
+    }
+}
+
+struct KabschArgs {
+    const float *pc0, *pc1;
+    const long long *pair_idx;
+    const unsigned char *mask;
+    int N0, N, P;
+    float *rt;      // [P,12]
+    int *credible;  // [P]
+};
+
+__global__ void __launch_bounds__(128) kabsch_kernel(const KabschArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (pair >= a.P) return;
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    int cnt = 0;
+    auto fetch = [&](int i, float p0[3], float p1[3]) {
+        long long j = a.pair_idx ? a.pair_idx[(size_t)pair * a.N + i] : i;
+        const float *q0 = a.pc0 + ((size_t)pair * a.N0 + j) * 3;
+        const float *q1 = a.pc1 + ((size_t)pair * a.N + i) * 3;
+        p0[0] = q0[0]; p0[1] = q0[1]; p0[2] = q0[2];
+        p1[0] = q1[0]; p1[1] = q1[1]; p1[2] = q1[2];
+    };
+    for (int i = lane; i < a.N; i += 32) {
+        if (a.mask && !a.mask[(size_t)pair * a.N + i]) continue;
+        float p0[3], p1[3];
+        fetch(i, p0, p1);
+        for (int c = 0; c < 3; ++c) { s[c] = s[c] + (double)p0[c]; s[3 + c] = s[3 + c] + (double)p1[c]; }
+        ++cnt;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (cnt == 0) {
+        if (lane < 12) a.rt[(size_t)pair * 12 + lane] = (lane == 0 || lane == 4 || lane == 8) ? 1.0f : 0.0f;
+        if (lane == 0) a.credible[pair] = 0;
+        return;
+    }
+    double m0[3], m1[3];
+    for (int c = 0; c < 3; ++c) {
+        m0[c] = warp_tree(s[c]) / (double)cnt;
+        m1[c] = warp_tree(s[3 + c]) / (double)cnt;
+    }
+    double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = lane; i < a.N; i += 32) {
+        if (a.mask && !a.mask[(size_t)pair * a.N + i]) continue;
+        float p0[3], p1[3];
+        fetch(i, p0, p1);
+        double a1[3], a0[3];
+        for (int c = 0; c < 3; ++c) { a1[c] = (double)p1[c] - m1[c]; a0[c] = (double)p0[c] - m0[c]; }
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) h[r * 3 + c] = h[r * 3 + c] + a1[r] * a0[c];
+    }
+    double H[3][3];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) H[r][c] = warp_tree(h[r * 3 + c]);
+    float R[9], T[3];
+    int cred = kabsch_from_H(H, m0, m1, R, T);
+    if (lane < 12) a.rt[(size_t)pair * 12 + lane] = lane < 9 ? R[lane] : T[lane - 9];
+    if (lane == 0) a.credible[pair] = cred;
+}
+
+}  // namespace
+
+extern "C" int caelo_ransac_round(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int N,
+                                  const int64_t *pair_idx, const int32_t *sample_idx, int T,
+                                  const float *thr, const int32_t *best_n_in, int P, float *result,
+                                  uint8_t *inlier_mask, int32_t *counts, void *stream)
+{
+    if (!ctx || !pc0 || !pc1 || !sample_idx || !thr || !result || !inlier_mask) return CAELO_ERR_ARG;
+    if (P <= 0 || N <= 0 || N0 <= 0 || T <= 0 || T > CAELO_MAX_TRIALS) return CAELO_ERR_ARG;
+    if (!pair_idx && N0 != N) return CAELO_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t need = (size_t)P * T * 12 * 4 + (size_t)P * T * 4;
+    int rc = caelo_reserve(ctx, ctx->pose_ws, need);
+    if (rc) return rc;
+    PoseArgs a;
+    a.pc0 = pc0; a.pc1 = pc1; a.pair_idx = reinterpret_cast<const long long *>(pair_idx);
+    a.sample_idx = sample_idx; a.thr = thr; a.best_n_in = best_n_in;
+    a.N0 = N0; a.N = N; a.T = T; a.P = P;
+    a.rt_hyp = reinterpret_cast<float *>(ctx->pose_ws.ptr);
+    a.counts = counts ? counts : reinterpret_cast<int *>(a.rt_hyp + (size_t)P * T * 12);
+    a.result = result; a.mask = inlier_mask;
+    dim3 grid((T + HS_WARPS - 1) / HS_WARPS, P);
+    hyp_score_kernel<<<grid, HS_WARPS * 32, 0, st>>>(a);
+    CAELO_LAUNCH_CHECK(ctx);
+    replay_mask_kernel<<<P, 256, 0, st>>>(a);
+    CAELO_LAUNCH_CHECK(ctx);
+    return CAELO_OK;
+}
+
+extern "C" int caelo_kabsch(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int N,
+                            const int64_t *pair_idx, const uint8_t *mask, int P, float *Rt,
+                            int32_t *credible, void *stream)
+{
+    if (!ctx || !pc0 || !pc1 || !Rt || !credible || P <= 0 || N <= 0 || N0 <= 0) return CAELO_ERR_ARG;
+    if (!pair_idx && N0 != N) return CAELO_ERR_ARG;
+    KabschArgs a;
+    a.pc0 = pc0; a.pc1 = pc1; a.pair_idx = reinterpret_cast<const long long *>(pair_idx);
+    a.mask = mask; a.N0 = N0; a.N = N; a.P = P; a.rt = Rt; a.credible = credible;
+    int blocks = (P * 32 + 127) / 128;
+    kabsch_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a);
+    CAELO_LAUNCH_CHECK(ctx);
+    return CAELO_OK;
+}

@@ -1,0 +1,414 @@
+// respond_select.cu — a1 (RespondLayer.predict) and a2 (GetKeyPtsByAE) for sm_100a.
+//
+// Reference: /root/reference/SphericalRing.py:113-291 (selection), :405-408 (predict call),
+// AE4SphericalRingPC.py:132-133 (the two conv layers).  Arithmetic contracts R1 and S1 are the
+// ones written out in oracle/caelo_oracle.c; every float op that decides a keypoint index is an
+// explicit round-to-nearest intrinsic so that no compiler flag can change the result.
+//
+// Kernels
+//   respond_kernel        a1 alone: ring NHWC -> 8-channel response (the predict() boundary)
+//   respond_score_kernel  <fused>: ring tile -> conv3x3+relu -> conv1x1+relu in shared memory
+//                         -> 5x5 window-min score -> candidate keys; the response never
+//                         reaches HBM.  <!fused>: same scoring from a response tile in HBM.
+//   topk_kernel           per frame: radix-select the (maxk+1) largest (score,index) keys,
+//                         bitonic-sort them, drop the best (quirk 1), emit points + pixels.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TH = 16, TW = 64, HALO = 2;
+constexpr int RH = TH + 2 * HALO, RW = TW + 2 * HALO;  // response region held per tile
+constexpr int IH = RH + 2, IW = RW + 2;                // conv input region
+constexpr int NPIX = RH * RW;
+constexpr int kThreads = 256;
+constexpr int EDGE = 8;  // Size4FilterTopEdge, SphericalRing.py:42
+
+// contract R1 for one pixel; x[27] in (ky,kx,ci) order, out[8]
+__device__ __forceinline__ void respond_pixel(const RespondWeights &w, const float (&x)[27],
+                                              float (&out)[8])
+{
+#pragma unroll
+    for (int c2 = 0; c2 < 8; ++c2) out[c2] = w.b2[c2];
+#pragma unroll 4
+    for (int co = 0; co < 32; ++co) {
+        float acc = w.b1[co];
+#pragma unroll
+        for (int t = 0; t < 27; ++t) acc = __fmaf_rn(x[t], w.w1[t * 32 + co], acc);
+        float h = fmaxf(acc, 0.0f);
+#pragma unroll
+        for (int c2 = 0; c2 < 8; ++c2) out[c2] = __fmaf_rn(h, w.w2[co * 8 + c2], out[c2]);
+    }
+#pragma unroll
+    for (int c2 = 0; c2 < 8; ++c2) out[c2] = fmaxf(out[c2], 0.0f);
+}
+
+__global__ void __launch_bounds__(kThreads)
+respond_kernel(const __grid_constant__ RespondWeights w, const float *__restrict__ ring, int B,
+               int H, int W, float *__restrict__ resp)
+{
+    const long long total = (long long)B * H * W;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+         p += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(p % W);
+        int r = (int)((p / W) % H);
+        const float *img = ring + (p / ((long long)H * W)) * (long long)H * W * 3;
+        float x[27];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                int rr = r + ky - 1, cc = c + kx - 1;
+                bool in = rr >= 0 && rr < H && cc >= 0 && cc < W;
+                const float *q = img + ((long long)rr * W + cc) * 3;
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) x[(ky * 3 + kx) * 3 + ci] = in ? __ldg(q + ci) : 0.0f;
+            }
+        float out[8];
+        respond_pixel(w, x, out);
+        float4 *o = reinterpret_cast<float4 *>(resp + p * 8);
+        o[0] = make_float4(out[0], out[1], out[2], out[3]);
+        o[1] = make_float4(out[4], out[5], out[6], out[7]);
+    }
+}
+
+struct SelectArgs {
+    const float *ring;   // [B,ring_H,ring_W,ring_C]
+    const void *counter; // [B,cnt_H,cnt_W]
+    const float *resp;   // [B,H,W,8] (unfused mode)
+    unsigned long long *keys;  // [B,H*W]
+    int *count;                // [B]
+    int ring_C, ring_H, ring_W, cnt_kind, cnt_H, cnt_W, H, W, B;
+};
+
+__device__ __forceinline__ bool occupied(const SelectArgs &a, int b, int r, int c)
+{
+    if (r < 0 || r >= a.cnt_H || c < 0 || c >= a.cnt_W) return false;
+    size_t i = ((size_t)b * a.cnt_H + r) * a.cnt_W + c;
+    return a.cnt_kind == CAELO_COUNTER_I8 ? (reinterpret_cast<const int8_t *>(a.counter)[i] > 0)
+                                          : (reinterpret_cast<const int32_t *>(a.counter)[i] > 0);
+}
+
+template <bool kFused>
+__global__ void __launch_bounds__(kThreads)
+respond_score_kernel(const __grid_constant__ RespondWeights w, const SelectArgs a)
+{
+    extern __shared__ float smem[];
+    float *resp_s = smem;                                   // [8][NPIX]
+    unsigned char *occ_s = reinterpret_cast<unsigned char *>(resp_s + 8 * NPIX);  // [NPIX]
+    float *in_s = reinterpret_cast<float *>(occ_s + ((NPIX + 15) / 16) * 16);      // [IH*IW*3]
+
+    const int b = blockIdx.z;
+    const int r0 = EDGE + blockIdx.y * TH - HALO;  // image row of region row 0
+    const int c0 = EDGE + blockIdx.x * TW - HALO;
+    const int H = a.H, W = a.W;
+    const float *ring_b = a.ring + (size_t)b * a.ring_H * a.ring_W * a.ring_C;
+
+    if (kFused) {
+        // stage the conv input (zero padded outside the H x W image)
+        for (int i = threadIdx.x; i < IH * IW; i += kThreads) {
+            int rr = r0 - 1 + i / IW, cc = c0 - 1 + i % IW;
+            bool in = rr >= 0 && rr < H && cc >= 0 && cc < W;
+            const float *q = ring_b + ((size_t)rr * a.ring_W + cc) * a.ring_C;
+            in_s[i * 3 + 0] = in ? __ldg(q + 0) : 0.0f;
+            in_s[i * 3 + 1] = in ? __ldg(q + 1) : 0.0f;
+            in_s[i * 3 + 2] = in ? __ldg(q + 2) : 0.0f;
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < NPIX; i += kThreads) {
+        int lr = i / RW, lc = i % RW;
+        int rr = r0 + lr, cc = c0 + lc;
+        bool in = rr >= 0 && rr < H && cc >= 0 && cc < W;
+        occ_s[i] = (in && occupied(a, b, rr, cc)) ? 1 : 0;
+        float out[8];
+        if (kFused) {
+            if (in) {
+                float x[27];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int ci = 0; ci < 3; ++ci)
+                            x[(ky * 3 + kx) * 3 + ci] = in_s[((lr + ky) * IW + (lc + kx)) * 3 + ci];
+                respond_pixel(w, x, out);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) out[k] = 0.0f;
+            }
+        } else {
+            if (in) {
+                const float4 *q = reinterpret_cast<const float4 *>(
+                    a.resp + (((size_t)b * H + rr) * W + cc) * 8);
+                float4 v0 = __ldg(q), v1 = __ldg(q + 1);
+                out[0] = v0.x; out[1] = v0.y; out[2] = v0.z; out[3] = v0.w;
+                out[4] = v1.x; out[5] = v1.y; out[6] = v1.z; out[7] = v1.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) out[k] = 0.0f;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) resp_s[k * NPIX + i] = out[k];
+    }
+    __syncthreads();
+
+    // ---- score the TH x TW interior (contract S1) ----
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < TH * TW; i += kThreads) {  // TH*TW is a multiple of kThreads
+        int lr = i / TW + HALO, lc = i % TW + HALO;
+        int r = r0 + lr, c = c0 + lc;
+        int li = lr * RW + lc;
+        bool keep = false;
+        float best = __int_as_float(0x7f800000);
+        // rows [8,H-8); cols [8,W-8) from the final filter; quirk 2 removes cols [H-8,H)
+        bool self_ok = occ_s[li] && r >= EDGE && r < H - EDGE && c >= EDGE && c < W - EDGE &&
+                       !(c >= H - EDGE && c < H);
+        if (self_ok) {
+            float ctr[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ctr[k] = resp_s[k * NPIX + li];
+            int count = 0;
+#pragma unroll
+            for (int dr = -2; dr <= 2; ++dr)
+#pragma unroll
+                for (int dc = -2; dc <= 2; ++dc) {
+                    if (dr == 0 && dc == 0) continue;
+                    int ni = li + dr * RW + dc;
+                    if (!occ_s[ni]) continue;
+                    float sq[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float d = __fsub_rn(resp_s[k * NPIX + ni], ctr[k]);
+                        sq[k] = __fmul_rn(d, d);
+                    }
+                    float s = __fadd_rn(__fadd_rn(__fadd_rn(sq[0], sq[1]), __fadd_rn(sq[2], sq[3])),
+                                        __fadd_rn(__fadd_rn(sq[4], sq[5]), __fadd_rn(sq[6], sq[7])));
+                    float n = __fsqrt_rn(s);
+                    best = fminf(best, n);
+                    ++count;
+                }
+            if (count >= 5 && (double)best > 0.2) {
+                const float *p = ring_b + ((size_t)r * a.ring_W + c) * a.ring_C;
+                float s = 0.0f;
+                for (int k = 0; k < a.ring_C; ++k) {
+                    float v = __ldg(p + k);
+                    s = __fadd_rn(s, __fmul_rn(v, v));
+                }
+                keep = __fsqrt_rn(s) >= 10.0f;  // VisibleBottom, SphericalRing.py:39,197-198
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+            int leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(a.count + b, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (keep) {
+                unsigned long long key =
+                    ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)(r * W + c);
+                a.keys[(size_t)b * H * W + base + __popc(m & ((1u << lane) - 1u))] = key;
+            }
+        }
+    }
+}
+
+// ---- top-k ------------------------------------------------------------------------------
+struct TopkArgs {
+    const unsigned long long *keys;  // [B,cap]
+    const int *count;                // [B]
+    const float *ring;
+    int ring_C, ring_H, ring_W, W, cap, maxk, sort_n;
+    float *kpts;        // [B,maxk,3]
+    long long *kpix;    // [B,maxk,2]
+    int *n_kpts;        // [B]
+};
+
+__global__ void __launch_bounds__(1024) topk_kernel(const TopkArgs a)
+{
+    extern __shared__ unsigned long long sk[];  // [sort_n]
+    __shared__ int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_krem, s_fill;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int n = a.count[b];
+    const unsigned long long *keys = a.keys + (size_t)b * a.cap;
+    const int want = a.maxk + 1;  // keep maxk+1 largest, then drop the best (quirk 1)
+    const int S = a.sort_n;
+
+    for (int i = tid; i < S; i += blockDim.x) sk[i] = 0ull;
+    if (tid == 0) s_fill = 0;
+    __syncthreads();
+
+    if (n <= want) {
+        for (int i = tid; i < n; i += blockDim.x) sk[i] = keys[i];
+    } else {
+        // MSB-first radix select of the want-th largest key (keys are unique)
+        if (tid == 0) { s_prefix = 0ull; s_krem = want; }
+        for (int pass = 0; pass < 8; ++pass) {
+            const int shift = 56 - 8 * pass;
+            if (tid < 256) hist[tid] = 0;
+            __syncthreads();
+            const unsigned long long prefix = s_prefix;
+            const unsigned long long hmask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+            for (int i = tid; i < n; i += blockDim.x) {
+                unsigned long long k = keys[i];
+                if ((k & hmask) == prefix) atomicAdd(&hist[(int)((k >> shift) & 0xff)], 1);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int krem = s_krem, d = 255, cum = 0;
+                for (; d > 0; --d) {
+                    if (cum + hist[d] >= krem) break;
+                    cum += hist[d];
+                }
+                s_krem = krem - cum;
+                s_prefix = prefix | ((unsigned long long)d << shift);
+            }
+            __syncthreads();
+        }
+        const unsigned long long kth = s_prefix;
+        for (int i = tid; i < n; i += blockDim.x) {
+            unsigned long long k = keys[i];
+            if (k >= kth) {
+                int pos = atomicAdd(&s_fill, 1);
+                if (pos < S) sk[pos] = k;
+            }
+        }
+    }
+    __syncthreads();
+
+    // bitonic sort ascending; zero padding sinks to the front
+    for (int k = 2; k <= S; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < S; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long x = sk[i], y = sk[ixj];
+                    bool up = (i & k) == 0;
+                    if ((x > y) == up) { sk[i] = y; sk[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+
+    const int have = n < want ? n : want;
+    const int nout = have > 0 ? have - 1 : 0;   // candidates[-maxk-1:-1]
+    const float *ring_b = a.ring + (size_t)b * a.ring_H * a.ring_W * a.ring_C;
+    for (int i = tid; i < a.maxk; i += blockDim.x) {
+        float x = 0.f, y = 0.f, z = 0.f;
+        long long r = 0, c = 0;
+        if (i < nout) {
+            unsigned idx = (unsigned)(sk[S - 1 - nout + i] & 0xffffffffu);
+            r = idx / (unsigned)a.W;
+            c = idx % (unsigned)a.W;
+            const float *p = ring_b + ((size_t)r * a.ring_W + c) * a.ring_C;
+            x = p[0]; y = p[1]; z = p[2];
+        }
+        float *o = a.kpts + ((size_t)b * a.maxk + i) * 3;
+        o[0] = x; o[1] = y; o[2] = z;
+        long long *q = a.kpix + ((size_t)b * a.maxk + i) * 2;
+        q[0] = r; q[1] = c;
+    }
+    if (tid == 0) a.n_kpts[b] = nout;
+}
+
+int launch_select(caelo_ctx *ctx, bool fused, const float *resp, int H, int W, const float *ring,
+                  int ring_C, int ring_H, int ring_W, const void *counter, int counter_dtype,
+                  int cnt_H, int cnt_W, int B, int max_kpts, float *kpts, int64_t *kpix,
+                  int32_t *n_kpts, cudaStream_t st)
+{
+    if (!ring || !counter || !kpts || !kpix || !n_kpts || B <= 0) return CAELO_ERR_ARG;
+    if (max_kpts <= 0 || max_kpts > 4095) return CAELO_ERR_ARG;
+    if (H < 2 * EDGE + 1 || W < 2 * EDGE + 1 || ring_H < H || ring_W < W || ring_C < 3 || ring_C > 8)
+        return CAELO_ERR_ARG;
+    if (counter_dtype != CAELO_COUNTER_I8 && counter_dtype != CAELO_COUNTER_I32) return CAELO_ERR_ARG;
+    if (fused && !ctx->have_respond) return CAELO_ERR_NO_WEIGHTS;
+    const size_t cap = (size_t)H * W;
+    size_t need = (size_t)B * cap * 8 + (size_t)B * 4 + 256;
+    int rc = caelo_reserve(ctx, ctx->cand, need);
+    if (rc) return rc;
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(ctx->cand.ptr);
+    int *count = reinterpret_cast<int *>(keys + (size_t)B * cap);
+    CAELO_CUDA(ctx, cudaMemsetAsync(count, 0, (size_t)B * 4, st));
+
+    SelectArgs a;
+    a.ring = ring; a.counter = counter; a.resp = resp; a.keys = keys; a.count = count;
+    a.ring_C = ring_C; a.ring_H = ring_H; a.ring_W = ring_W; a.cnt_kind = counter_dtype;
+    a.cnt_H = cnt_H; a.cnt_W = cnt_W; a.H = H; a.W = W; a.B = B;
+    dim3 grid((W - 2 * EDGE + TW - 1) / TW, (H - 2 * EDGE + TH - 1) / TH, B);
+    size_t smem = (size_t)8 * NPIX * 4 + ((NPIX + 15) / 16) * 16 + (fused ? (size_t)IH * IW * 3 * 4 : 0);
+    if (fused) {
+        respond_score_kernel<true><<<grid, kThreads, smem, st>>>(ctx->respond_host, a);
+    } else {
+        if (!resp) return CAELO_ERR_ARG;
+        respond_score_kernel<false><<<grid, kThreads, smem, st>>>(ctx->respond_host, a);
+    }
+    CAELO_LAUNCH_CHECK(ctx);
+
+    TopkArgs t;
+    t.keys = keys; t.count = count; t.ring = ring; t.ring_C = ring_C; t.ring_H = ring_H;
+    t.ring_W = ring_W; t.W = W; t.cap = (int)cap; t.maxk = max_kpts;
+    int S = 2;
+    while (S < max_kpts + 1) S <<= 1;
+    t.sort_n = S;
+    t.kpts = kpts; t.kpix = reinterpret_cast<long long *>(kpix); t.n_kpts = n_kpts;
+    topk_kernel<<<B, 1024, (size_t)S * 8, st>>>(t);
+    CAELO_LAUNCH_CHECK(ctx);
+    return CAELO_OK;
+}
+
+}  // namespace
+
+int caelo_select_init(caelo_ctx *ctx)
+{
+    const int smem = 8 * NPIX * 4 + ((NPIX + 15) / 16) * 16 + IH * IW * 3 * 4;
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(respond_score_kernel<true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return CAELO_OK;
+}
+
+extern "C" int caelo_respond_forward(caelo_ctx *ctx, const float *ring, int B, int H, int W,
+                                     float *resp, void *stream)
+{
+    if (!ctx || !ring || !resp || B <= 0 || H <= 0 || W <= 0) return CAELO_ERR_ARG;
+    if (!ctx->have_respond) return CAELO_ERR_NO_WEIGHTS;
+    long long total = (long long)B * H * W;
+    long long blocks = (total + kThreads - 1) / kThreads;
+    long long maxb = (long long)ctx->num_sms * 32;
+    if (blocks > maxb) blocks = maxb;
+    respond_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(ctx->respond_host, ring, B, H, W, resp);
+    CAELO_LAUNCH_CHECK(ctx);
+    return CAELO_OK;
+}
+
+extern "C" int caelo_select_keypoints(caelo_ctx *ctx, const float *resp, int H, int W,
+                                      const float *ring, int ring_C, int ring_H, int ring_W,
+                                      const void *counter, int counter_dtype, int cnt_H, int cnt_W,
+                                      int B, int max_kpts, float *kpts, int64_t *kpix,
+                                      int32_t *n_kpts, void *stream)
+{
+    if (!ctx) return CAELO_ERR_ARG;
+    return launch_select(ctx, false, resp, H, W, ring, ring_C, ring_H, ring_W, counter, counter_dtype,
+                         cnt_H, cnt_W, B, max_kpts, kpts, kpix, n_kpts, (cudaStream_t)stream);
+}
+
+extern "C" int caelo_respond_select(caelo_ctx *ctx, const float *ring, int ring_C, int ring_H,
+                                    int ring_W, const void *counter, int counter_dtype, int cnt_H,
+                                    int cnt_W, int H, int W, int B, int max_kpts, float *kpts,
+                                    int64_t *kpix, int32_t *n_kpts, float *resp_out, void *stream)
+{
+    if (!ctx) return CAELO_ERR_ARG;
+    if (resp_out) {
+        // the caller wants the response image as well: a1 to HBM, then score from it
+        if (ring_C != 3 || ring_H != H || ring_W != W) return CAELO_ERR_UNSUPPORTED;
+        int rc = caelo_respond_forward(ctx, ring, B, H, W, resp_out, stream);
+        if (rc) return rc;
+        return launch_select(ctx, false, resp_out, H, W, ring, ring_C, ring_H, ring_W, counter,
+                             counter_dtype, cnt_H, cnt_W, B, max_kpts, kpts, kpix, n_kpts,
+                             (cudaStream_t)stream);
+    }
+    return launch_select(ctx, true, nullptr, H, W, ring, ring_C, ring_H, ring_W, counter, counter_dtype,
+                         cnt_H, cnt_W, B, max_kpts, kpts, kpix, n_kpts, (cudaStream_t)stream);
+}

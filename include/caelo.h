@@ -1,0 +1,146 @@
+/* caelo.h — C ABI of libcaelo_b200.so: the CAE-LO odometry hot path on one B200 (sm_100a).
+ *
+ * The reference (SRainGit/CAE-LO) has no FFI layer: its boundary is a handful of Python
+ * functions plus duck-typed Keras ``model.predict``.  Each entry point
+ * below replaces one of those call sites; the reference file:line it stands in for is
+ * given with it.  The Python side (caelo_b200/api.py) keeps the reference's names and
+ * binds these symbols with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain C types only; every ``dev`` pointer is a DEVICE pointer (e.g. torch
+ *     ``Tensor.data_ptr()``), every ``host`` pointer is host memory;
+ *   - the last argument is the CUDA stream (``cudaStream_t`` passed as void*; NULL = default);
+ *     calls are asynchronous on that stream unless stated otherwise;
+ *   - return value: 0 = CAELO_OK, negative = error (caelo_error_string); never throws,
+ *     never allocates or frees caller memory; scratch lives in the ctx and grows on demand;
+ *   - one ctx per GPU; a ctx is not thread-safe; distinct ctxs are independent.
+ *   - there is NO CPU fallback: without a CUDA device caelo_create fails.
+ */
+#ifndef CAELO_H
+#define CAELO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct caelo_ctx caelo_ctx;
+
+enum {
+    CAELO_OK = 0,
+    CAELO_ERR_CUDA = -1,           /* a CUDA runtime call failed (see caelo_last_cuda_error) */
+    CAELO_ERR_ARG = -2,            /* bad argument (null pointer, size out of range) */
+    CAELO_ERR_NO_WEIGHTS = -3,     /* the network weights were not set on this ctx */
+    CAELO_ERR_NONBINARY_PATCH = -4,/* encoder input has a value other than 0 or 1 */
+    CAELO_ERR_TOO_FEW_VOXELS = -5, /* a voxel list has < 496 entries (sklearn raises too) */
+    CAELO_ERR_NO_DEVICE = -6,      /* no usable CUDA device */
+    CAELO_ERR_UNSUPPORTED = -7
+};
+
+#define CAELO_COUNTER_I8 0
+#define CAELO_COUNTER_I32 1
+#define CAELO_MAX_TRIALS 500       /* RANSAC4RT maxTrails, Match.py:168 */
+
+int caelo_version(void);
+const char *caelo_error_string(int code);
+const char *caelo_last_cuda_error(const caelo_ctx *ctx);
+
+int caelo_create(int device_id, caelo_ctx **out);
+int caelo_destroy(caelo_ctx *ctx);
+int caelo_num_sms(const caelo_ctx *ctx);
+/* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
+int64_t caelo_launch_count(const caelo_ctx *ctx);
+
+/* Weights of SphericalRingPCRespondLayer.h5 (HOST pointers, Keras layouts):
+ * w1 (3,3,3,32) HWIO, b1 (32), w2 (1,1,32,8), b2 (8).  Replaces keras load_model at
+ * Match.py:324, BatchPreprocess.py:168.  Synchronous. */
+int caelo_set_respond_weights(caelo_ctx *ctx, const float *w1, const float *b1, const float *w2,
+                              const float *b2);
+
+/* Weights of EncoderModel4VoxelPatch.h5 (HOST pointers, Keras layouts): conv kernels DHWIO
+ * (3,3,3,1,8) (3,3,3,8,16) (3,3,3,16,32), dense (2048,200) (200,20), all activations tanh.
+ * Replaces keras load_model at Match.py:313, PoseEstimation.py:73.  Synchronous. */
+int caelo_set_encoder_weights(caelo_ctx *ctx, const float *k1, const float *b1, const float *k2,
+                              const float *b2, const float *k3, const float *b3, const float *d1,
+                              const float *bd1, const float *d2, const float *bd2);
+
+/* a1 — RespondLayer.predict (SphericalRing.py:405-408, BatchPreprocess.py:110):
+ * relu(conv1x1(relu(conv3x3_same(x)+b1))+b2).  ring: dev [B,H,W,3] f32 NHWC; resp: dev [B,H,W,8]. */
+int caelo_respond_forward(caelo_ctx *ctx, const float *ring, int B, int H, int W, float *resp,
+                          void *stream);
+
+/* a2 — GetKeyPtsByAE (SphericalRing.py:113-291).  resp: dev [B,H,W,8]; ring: dev
+ * [B,ring_H,ring_W,ring_C] (ring_C = 3 or 5; the range test norms ALL channels, quirk 3);
+ * counter: dev [B,cnt_H,cnt_W] int8 or int32.  All three share the pixel origin.
+ * Outputs: kpts dev [B,max_kpts,3] f32 (ascending score), kpix dev [B,max_kpts,2] int64
+ * (row,col), n_kpts dev [B] int32 (<= max_kpts; rows beyond it are zero).  max_kpts <= 4095. */
+int caelo_select_keypoints(caelo_ctx *ctx, const float *resp, int H, int W, const float *ring,
+                           int ring_C, int ring_H, int ring_W, const void *counter,
+                           int counter_dtype, int cnt_H, int cnt_W, int B, int max_kpts,
+                           float *kpts, int64_t *kpix, int32_t *n_kpts, void *stream);
+
+/* a1+a2 fused — GetKeyPtsFromRawFileName (SphericalRing.py:389-416) without the file I/O:
+ * the response image is computed tile by tile in shared memory and never written to HBM.
+ * The CNN input is ring[:, 0:H, 0:W, 0:3].  resp_out may be NULL. */
+int caelo_respond_select(caelo_ctx *ctx, const float *ring, int ring_C, int ring_H, int ring_W,
+                         const void *counter, int counter_dtype, int cnt_H, int cnt_W, int H, int W,
+                         int B, int max_kpts, float *kpts, int64_t *kpix, int32_t *n_kpts,
+                         float *resp_out, void *stream);
+
+/* a6 — GetPatchesList (Voxel.py:177-216) for F frames at once.  kpts: dev [F,K,3] f32 or
+ * f64 (kpts_f64 != 0); n_kpts: dev [F] int32 or NULL (= K everywhere); vox: dev, the three
+ * int16 (V,3) lists of every frame concatenated; vox_offsets: HOST [F*3+1] int64 element
+ * (row) offsets into vox, frame-major then scale.  Outputs: packed dev [F,3,K,128] uint32
+ * (bit i of the patch = flattened index (x*16+y)*16+z, stored rolled by 8 exactly as the
+ * reference's negative-index scatter does); patches_f32 dev [F,3,K,16,16,16] or NULL;
+ * trunc dev [F,3,K] uint8 or NULL (1 where the 496-neighbour cut removed a voxel). */
+int caelo_gather_patches(caelo_ctx *ctx, const void *kpts, int kpts_f64, const int32_t *n_kpts,
+                         int F, int K, const int16_t *vox, const int64_t *vox_offsets,
+                         uint32_t *packed, float *patches_f32, uint8_t *trunc, void *stream);
+
+/* a3 — PatchEncoder.predict (Match.py:131-133): dev [P,16,16,16(,1)] f32 in {0,1} -> dev [P,20].
+ * status: dev int32[1] or NULL; set to CAELO_ERR_NONBINARY_PATCH if an input is not 0/1. */
+int caelo_encode_patches(caelo_ctx *ctx, const float *patches, int P, float *feat, int32_t *status,
+                         void *stream);
+/* a3 on the bit-packed form: packed dev [P,128] uint32 -> feat dev, row p written at
+ * feat + p*feat_stride (+ feat_col0), 20 floats.  GetFeaturesFromPatches (Match.py:130-135)
+ * is three such calls with feat_stride=60, col0=0/20/40, or one call over [3K] with
+ * scale-major packing via caelo_encode_frames. */
+int caelo_encode_packed(caelo_ctx *ctx, const uint32_t *packed, int P, float *feat,
+                        int feat_stride, int feat_col0, void *stream);
+/* packed dev [F,3,K,128] -> feat dev [F,K,60] (np.c_[f0,f1,f2], Match.py:134) */
+int caelo_encode_frames(caelo_ctx *ctx, const uint32_t *packed, int F, int K, float *feat,
+                        void *stream);
+
+/* a4 — cdist(Codes0,Codes1,'euclidean') + argmin(axis=0) (Match.py:257-258) for P pairs:
+ * codes0 dev [P,N,D], codes1 dev [P,M,D] -> pair_idx dev [P,M] int64 (ties -> lowest row,
+ * decided on float64 distances as scipy computes them). */
+int caelo_nn_match(caelo_ctx *ctx, const float *codes0, const float *codes1, int P, int N, int M,
+                   int D, int64_t *pair_idx, void *stream);
+
+/* a5 — one threshold round of RANSAC4RT (Match.py:181-206) for P pairs, all hypotheses in
+ * parallel, then the sequential accept/stop rule replayed on the device.
+ * pc0 dev [P,N0,3], pc1 dev [P,N,3], pair_idx dev [P,N] int64 (Pairs0 = pc0[pair_idx]) or
+ * NULL (then N0 == N and Pairs0 = pc0); sample_idx dev [P,T,4] int32 drawn by the caller
+ * from np.random exactly as Match.py:182-184 does; thr dev [P] f32; best_n_in dev [P]
+ * int32 (curNumInliers carried across ladder rounds) or NULL (= 0).
+ * Outputs (dev): result [P,16] f32 = R(9) T(3) isSuccess trials nInliers bestTrial — R,T of
+ * the accepted hypothesis (identity/0 if none); inlier_mask [P,N] uint8 of that hypothesis;
+ * counts [P,T] int32 per-hypothesis inlier counts or NULL. */
+int caelo_ransac_round(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int N,
+                       const int64_t *pair_idx, const int32_t *sample_idx, int T, const float *thr,
+                       const int32_t *best_n_in, int P, float *result, uint8_t *inlier_mask,
+                       int32_t *counts, void *stream);
+
+/* a5 — SolveRT (Match.py:138-158) for P independent problems: p0 = pc0[pair_idx] (or pc0),
+ * p1 = pc1, restricted to mask != 0 (mask dev [P,N] or NULL = all).  Rt dev [P,12] (R row-major
+ * then T), credible dev [P] int32 (+1, -1 = reflection quirk applied, 0 = no points). */
+int caelo_kabsch(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int N,
+                 const int64_t *pair_idx, const uint8_t *mask, int P, float *Rt, int32_t *credible,
+                 void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAELO_H */

@@ -1,0 +1,301 @@
+"""GPU parity: every stage of the hot path, called through the C ABI (caelo_b200.api), against
+the CPU oracle on the same inputs and against the committed golden / reference-run fixtures.
+
+Bars: keypoint pixels, patch bits, nn-match indices, RANSAC inlier sets, trial counts and the
+hypothesis/refit [R|t] are BIT-EXACT vs the oracle; descriptors within 1e-4 relative fp32
+(measured: ~1e-6).  Run with ``pytest -m gpu`` on the B200 box."""
+import numpy as np
+import pytest
+
+import golden_data as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from caelo_b200 import api as a
+    a.default_context()
+    return a
+
+
+def _bits_from_f32(p):
+    return (np.asarray(p).reshape(p.shape[0], -1) > 0)
+
+
+# ---- a1 ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", G.FRAMES[:2])
+def test_respond_predict_bit_exact(api, oracle_mod, tag):
+    f = G.frame(tag)
+    model = api.load_model(api.WEIGHT_DIR + "/respond.npz")
+    got = model.predict(f["ring3"][None])
+    want = oracle_mod.respond_predict(f["ring3"][None])
+    assert got.shape == (1, 64, 1792, 8) and got.dtype == np.float32
+    assert np.array_equal(got, want)
+
+
+def test_respond_predict_batch_and_odd_shape(api, oracle_mod):
+    rng = np.random.default_rng(7)
+    x = (rng.standard_normal((3, 11, 37, 3)) * 20).astype(np.float32)
+    x[rng.random(x.shape[:3]) < 0.3] = 0
+    model = api.load_model(api.WEIGHT_DIR + "/respond.npz")
+    assert np.array_equal(model.predict(x), oracle_mod.respond_predict(x))
+
+
+# ---- a2 ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", G.FRAMES)
+def test_keypoints_bit_exact(api, oracle_mod, tag):
+    f, rr = G.frame(tag), G.refrun(tag)
+    resp = oracle_mod.respond_predict(f["ring3"][None])[0]
+    # unfused: reference signature GetKeyPtsByAE(SphericalRing, GridCounter, RespondImg)
+    kp5, px5, planar = api.GetKeyPtsByAE(f["ring5"], f["counter"], resp)
+    assert np.array_equal(px5, rr["keypix_ring5_i32"]) and np.array_equal(kp5, rr["keypts_ring5_i32"])
+    assert px5.dtype == np.int64 and kp5.dtype == np.float32 and planar.shape == (0,)
+    kp3, px3, _ = api.GetKeyPtsByAE(f["ring3"], f["counter_i8"], resp)
+    assert np.array_equal(px3, rr["keypix_ring3_i8"]) and np.array_equal(kp3, rr["keypts_ring3_i8"])
+    # fused a1+a2: response computed in shared memory, never stored
+    kpf, pxf, _ = api.GetKeyPtsFromRing(f["ring5"], f["counter"])
+    assert np.array_equal(pxf, rr["keypix_ring5_i32"]) and np.array_equal(kpf, rr["keypts_ring5_i32"])
+    kpf3, pxf3, _ = api.GetKeyPtsFromRing(f["ring3"], f["counter_i8"])
+    assert np.array_equal(pxf3, rr["keypix_ring3_i8"])
+    # the reference's own golden keypoints (set agreement)
+    g = set(map(tuple, np.round(f["golden_KeyPts"].astype(np.float64), 4)))
+    assert len(g & set(map(tuple, np.round(kpf3.astype(np.float64), 4)))) >= 1021
+
+
+def test_keypoints_few_candidates_and_ties(api, oracle_mod):
+    """< 1025 candidates (slice [-1025:-1] keeps all but the best) and exact score ties."""
+    import torch
+    rng = np.random.default_rng(11)
+    H, W = 64, 1792
+    ring = np.zeros((H, W, 3), np.float32)
+    cnt = np.zeros((69, 1800), np.int32)
+    rr, cc = np.meshgrid(np.arange(10, 50), np.arange(100, 160), indexing="ij")
+    ring[rr, cc] = (rng.standard_normal(rr.shape + (3,)) * 3 + [20, 5, -1]).astype(np.float32)
+    cnt[rr, cc] = 1
+    resp = (rng.integers(0, 4, (H, W, 8))).astype(np.float32)  # few distinct values -> many exact ties
+    want_k, want_p = oracle_mod.select_keypoints(ring, cnt, resp)
+    ctx = api.default_context()
+    kpts, kpix, n = ctx.select_keypoints(api._dev(ring[None]), api._dev(cnt[None]), api._dev(resp[None]))
+    n = int(n.item())
+    assert 50 < n < 1024 and n == want_p.shape[0]
+    assert np.array_equal(kpix[0, :n].cpu().numpy(), want_p)
+    assert np.array_equal(kpts[0, :n].cpu().numpy(), want_k)
+    assert torch.count_nonzero(kpix[0, n:]).item() == 0
+
+
+def test_keypoints_batched_frames(api):
+    """B=4 frames in one launch == the four single-frame results."""
+    ctx = api.default_context()
+    ring = np.stack([G.frame(t)["ring3"] for t in G.FRAMES])
+    cnt = np.stack([G.frame(t)["counter_i8"] for t in G.FRAMES])
+    kpts, kpix, n = ctx.select_keypoints(api._dev(ring), api._dev(cnt), None)
+    for b, t in enumerate(G.FRAMES):
+        assert int(n[b].item()) == 1024
+        assert np.array_equal(kpix[b].cpu().numpy(), G.refrun(t)["keypix_ring3_i8"])
+
+
+# ---- a6 ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", G.FRAMES[:2])
+def test_patches_exact(api, oracle_mod, tag):
+    f, rr = G.frame(tag), G.refrun(tag)
+    pts, pl = api.GetPatchesList(f["golden_KeyPts"], f["vox0"], f["vox1"], f["vox2"])
+    assert pts is f["golden_KeyPts"] and len(pl) == 3
+    _, want, tr = oracle_mod.get_patches_list(f["golden_KeyPts"], f["vox0"], f["vox1"], f["vox2"],
+                                              return_truncated=True)
+    ref = G.unpack_patches(rr["patches_packed"])
+    for s in range(3):
+        assert pl[s].shape == (1024, 16, 16, 16, 1) and pl[s].dtype == np.float32
+        assert np.array_equal(pl[s], want[s])                       # incl. the 496-NN cut rule
+        neq = (_bits_from_f32(pl[s]) != _bits_from_f32(ref[s])).any(1)
+        assert not (neq & ~tr[s]).any()                             # == unmodified reference run
+
+
+def test_patches_float64_keypoints_and_edges(api, oracle_mod):
+    f = G.frame(G.FRAMES[0])
+    rng = np.random.default_rng(5)
+    pts = f["golden_KeyPts"][:64].astype(np.float64) + rng.normal(0, 0.3, (64, 3))
+    pts[0] = [-99.8, -99.8, -14.7]     # cube pokes outside the voxel grid (negative coordinates)
+    pts[1] = [99.8, 99.8, 14.7]
+    _, pl = api.GetPatchesList(pts, f["vox0"], f["vox1"], f["vox2"])
+    _, want = oracle_mod.get_patches_list(pts, f["vox0"], f["vox1"], f["vox2"])
+    for s in range(3):
+        assert np.array_equal(pl[s], want[s])
+
+
+def test_patches_too_few_voxels_raises(api):
+    f = G.frame(G.FRAMES[0])
+    with pytest.raises(ValueError):
+        api.GetPatchesList(f["golden_KeyPts"][:4], f["vox0"][:100], f["vox1"], f["vox2"])
+
+
+# ---- a3 ------------------------------------------------------------------------------------
+DESC_RTOL = 1e-4  # north_star: descriptors within 1e-4 relative fp32 (|err| <= rtol * max|ref|, max|ref| ~ 1)
+
+
+@pytest.mark.parametrize("tag", G.FRAMES[:2])
+def test_descriptors_vs_oracle_and_golden(api, oracle_mod, tag):
+    f, rr = G.frame(tag), G.refrun(tag)
+    enc = api.load_model(api.WEIGHT_DIR + "/encoder.npz")
+    ref_patches = G.unpack_patches(rr["patches_packed"])       # from the unmodified reference
+    feat = api.GetFeaturesFromPatches(enc, ref_patches)          # predict() boundary: float32 patches
+    want = oracle_mod.get_features_from_patches(ref_patches)
+    assert feat.shape == (1024, 60) and feat.dtype == np.float32
+    assert np.abs(feat - want).max() <= DESC_RTOL * np.abs(want).max()
+    # golden Features/*.mat (TF 1.14): <1e-5 except rows whose patch hit a k-th-neighbour tie
+    err = np.abs(feat - f["golden_Features"]).max(1)
+    assert (err < 1e-5).sum() >= 1022
+    # packed path (a6+a3 fused through device memory) gives the same numbers
+    feat2 = api.GetFeaturesAtKeyPts(f["golden_KeyPts"], f["vox0"], f["vox1"], f["vox2"])
+    _, mine = api.GetPatchesList(f["golden_KeyPts"], f["vox0"], f["vox1"], f["vox2"])
+    assert np.array_equal(feat2, api.GetFeaturesFromPatches(enc, mine))
+
+
+def test_encoder_dense_random_patches(api, oracle_mod):
+    rng = np.random.default_rng(3)
+    x = (rng.random((70, 16, 16, 16, 1)) < 0.3).astype(np.float32)   # far denser than real patches
+    x[0] = 0
+    x[1] = 1
+    enc = api.load_model(api.WEIGHT_DIR + "/encoder.npz")
+    got, want = enc.predict(x), oracle_mod.encoder_predict(x)
+    assert np.abs(got - want).max() <= DESC_RTOL * np.abs(want).max()
+    assert enc.predict(x[:0]).shape == (0, 20)
+
+
+def test_encoder_rejects_non_binary(api):
+    from caelo_b200._lib import CaeloError
+    x = np.zeros((2, 16, 16, 16, 1), np.float32)
+    x[1, 3, 3, 3, 0] = 0.5
+    enc = api.load_model(api.WEIGHT_DIR + "/encoder.npz")
+    with pytest.raises(CaeloError):
+        enc.predict(x)
+
+
+# ---- a4 ------------------------------------------------------------------------------------
+def _nn(api, c0, c1):
+    ctx = api.default_context()
+    return ctx.nn_match(api._dev(c0[None]), api._dev(c1[None]))[0].cpu().numpy()
+
+
+@pytest.mark.parametrize("seq", ["00", "01"])
+def test_nn_match_golden(api, seq):
+    a, b = G.PAIRS[seq]
+    assert np.array_equal(_nn(api, G.frame(a)["golden_Features"], G.frame(b)["golden_Features"]),
+                          G.pose(seq)["pair_idx"])            # scipy cdist + argmin (Match.py:257-258)
+    u = G.usip(seq)
+    assert np.array_equal(_nn(api, u["d0"], u["d1"]), u["pair_idx"])
+
+
+@pytest.mark.parametrize("N,M,D", [(1, 1, 1), (5, 3, 60), (1000, 1031, 60), (2048, 2048, 128), (777, 64, 33)])
+def test_nn_match_synthetic_and_ties(api, oracle_mod, N, M, D):
+    rng = np.random.default_rng(N + M + D)
+    c0 = np.tanh(rng.standard_normal((N, D))).astype(np.float32)
+    c1 = np.tanh(rng.standard_normal((M, D))).astype(np.float32)
+    if N > 4:
+        c0[N // 2] = c0[1]                    # duplicate rows: ties -> lowest row index
+        c1[0] = c0[1]
+        c1[M // 2] = c0[N // 3] + np.float32(1e-7)
+    assert np.array_equal(_nn(api, c0, c1), oracle_mod.nn_match(c0, c1))
+
+
+def test_nn_match_quantised_descriptors_many_ties(api, oracle_mod):
+    rng = np.random.default_rng(0)
+    c0 = rng.integers(-2, 3, (600, 60)).astype(np.float32) / 4
+    c1 = rng.integers(-2, 3, (500, 60)).astype(np.float32) / 4
+    c0[300:] = c0[:300]
+    assert np.array_equal(_nn(api, c0, c1), oracle_mod.nn_match(c0, c1))
+
+
+# ---- a5 ------------------------------------------------------------------------------------
+def test_solve_rt_bit_exact(api, oracle_mod):
+    rng = np.random.default_rng(1)
+    for n in (1, 2, 3, 4, 5, 33, 400, 1024):
+        P1 = (rng.standard_normal((n, 3)) * 20).astype(np.float32)
+        P0 = (P1 + rng.standard_normal((n, 3)) * 0.05 + [0.7, 0, 0]).astype(np.float32)
+        R, T, c = api.SolveRT(P0, P1)
+        Ro, To, co = oracle_mod.solve_rt(P0, P1)
+        assert np.array_equal(R, Ro) and np.array_equal(T, To) and c == co, n
+    # reflection quirk + coplanar (rank-2) input
+    P1 = (rng.standard_normal((50, 3))).astype(np.float32)
+    P0 = (P1 * np.float32([1, 1, -1])).astype(np.float32)
+    R, T, c = api.SolveRT(P0, P1)
+    Ro, To, co = oracle_mod.solve_rt(P0, P1)
+    assert c == -1 and co == -1 and np.array_equal(R, Ro)
+    P1[:, 2] = 0
+    P0 = P1[:, [1, 0, 2]].copy()
+    R, T, c = api.SolveRT(P0, P1)
+    Ro, To, co = oracle_mod.solve_rt(P0, P1)
+    assert np.array_equal(R, Ro) and np.array_equal(T, To) and c == co
+
+
+def test_ransac_hypotheses_bit_exact(api, oracle_mod):
+    a, b = G.PAIRS["00"]
+    f0, f1 = G.frame(a), G.frame(b)
+    pidx = G.pose("00")["pair_idx"]
+    P0 = f0["golden_KeyPts"][pidx]
+    P1 = f1["golden_KeyPts"]
+    rng = np.random.default_rng(2)
+    idx = rng.integers(0, 1024, (500, 4)).astype(np.int32)
+    idx[7] = [5, 5, 9, 11]       # degenerate samples (duplicates): rank-deficient H
+    idx[8] = [3, 3, 3, 3]
+    idx[9] = [1, 1, 2, 2]
+    ctx = api.default_context()
+    res, mask, counts = ctx.ransac_round(api._dev(P0[None]), api._dev(P1[None]), None, api._dev(idx[None]),
+                                         api._dev(np.array([0.4], np.float32)), None, want_counts=True)
+    want_counts, want_rt = oracle_mod.ransac_score(P0, P1, idx, 0.4)
+    assert np.array_equal(counts[0].cpu().numpy(), want_counts)
+
+
+@pytest.mark.parametrize("seq", ["00", "01"])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_solve_relative_pose(api, oracle_mod, seq, seed):
+    a, b = G.PAIRS[seq]
+    f0, f1, P = G.frame(a), G.frame(b), G.pose(seq)
+    args = (f0["golden_KeyPts"], f0["golden_Features"], None, f1["golden_KeyPts"], f1["golden_Features"], None)
+    np.random.seed(seed)
+    R, T, ok, i0, i1, thr = api.SolveRelativePose(*args)
+    nxt = np.random.random()
+    np.random.seed(seed)
+    Ro, To, oko, j0, j1, thro = oracle_mod.solve_relative_pose(*args)
+    # bit-exact vs the oracle
+    assert np.array_equal(R, Ro) and np.array_equal(T, To) and ok == oko and thr == thro
+    assert np.array_equal(i0, j0) and np.array_equal(i1, j1)
+    assert R.shape == (3, 3) and T.shape == (3, 1) and R.dtype == np.float32
+    # vs the unmodified reference run (fixtures): same inliers, [R|t] within 1e-4, same RNG position
+    assert np.array_equal(i0, P["idx0_%d" % seed]) and np.array_equal(i1, P["idx1_%d" % seed])
+    assert np.abs(R - P["R_%d" % seed]).max() <= 1e-4
+    Tr = P["T_%d" % seed].reshape(-1)
+    assert np.abs(T.reshape(-1) - Tr).max() <= 1e-4 * max(1.0, np.abs(Tr).max())
+    assert nxt == float(P["next_random_%d" % seed])
+
+
+def test_ransac_failure_ladder(api, oracle_mod):
+    rng = np.random.default_rng(0)
+    P0 = (rng.standard_normal((300, 3)) * 50).astype(np.float32)
+    P1 = (rng.standard_normal((300, 3)) * 50).astype(np.float32)
+    np.random.seed(5)
+    R, T, ok, mask, thr = api.RANSAC4RT(P0, P1, None, None)
+    after = np.random.random()
+    np.random.seed(5)
+    Ro, To, oko, masko, thro = oracle_mod.ransac4rt(P0, P1)
+    assert not ok and thr == 1.6 == thro and mask.sum() == 0 and mask.dtype == bool
+    assert np.array_equal(R, np.eye(3)) and R.dtype == np.float64 and T.shape == (3, 1)
+    assert after == np.random.random()
+
+
+def test_ransac_small_n(api, oracle_mod):
+    """N < 500: leastInliers = int(0.2 N); indices int32(u*N)."""
+    rng = np.random.default_rng(4)
+    P1 = (rng.standard_normal((37, 3)) * 10).astype(np.float32)
+    P0 = (P1 + [1, 2, 3] + rng.standard_normal((37, 3)) * 0.01).astype(np.float32)
+    P0[::3] += 5
+    np.random.seed(9)
+    R, T, ok, mask, thr = api.RANSAC4RT(P0, P1)
+    np.random.seed(9)
+    Ro, To, oko, masko, thro = oracle_mod.ransac4rt(P0, P1)
+    assert ok == oko and thr == thro and np.array_equal(mask, masko)
+    assert np.array_equal(np.asarray(R, np.float32), np.asarray(Ro, np.float32))
+    assert np.array_equal(np.asarray(T, np.float32), np.asarray(To, np.float32))
