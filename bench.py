@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — frame-pairs/s of the CAE-LO odometry hot path (keypts + desc + match + pose).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1)
+
+One step = one pass of the hot path over one batch of P consecutive synthetic frame pairs
+(P+1 KITTI-seq-00-shaped frames: 64x1792x3 ring, 1024 keypoints, 3 x 16^3 voxel patches per
+keypoint, 60-D descriptors, nn match + RANSAC + refit per pair) on every rank.  Frame pairs
+shard across ranks with no data-path collective; one NCCL gather brings the per-pair poses to
+rank 0 (inside the timed region).  Prints ONE JSON line on rank 0.
+
+``--impl reference`` times the CPU restatement of the reference path (oracle/, the reference's
+own .py cannot travel to the GPU box and Keras/TF/CuPy are not installable) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frame-pairs/sec (keypts+desc+match+pose), KITTI-00 shape"
+UNIT = "frame-pairs/s"
+K_PTS = 1024
+# algorithmic work per unit
+FLOP_CONV_STACK_PER_PATCH = 2 * (4096 * 27 * 8 + 512 * 216 * 16 + 64 * 432 * 32)   # 7,077,888
+FLOP_DENSE_PER_PATCH = 2 * (2048 * 200 + 200 * 20)                                  # 827,200
+BYTES_RESPOND_SELECT_PER_FRAME = 64 * 1792 * 3 * 4 + 69 * 1800 + 1024 * (12 + 16)   # fused: resp stays on chip
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            busy = [s for s in sm if s >= 0.5 * max(sm)] or sm
+            out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference path)
+# ------------------------------------------------------------------------------------------
+def _cpu_frame(args):
+    ring3, counter, v0, v1, v2 = args
+    from oracle import oracle
+    resp = oracle.respond_predict(ring3[None])[0]
+    kp, _px = oracle.select_keypoints(ring3, counter, resp)
+    _, pl = oracle.get_patches_list(kp, v0, v1, v2)
+    return kp, pl
+
+
+def _cpu_pair(args):
+    pid, k0, c0, k1, c1 = args
+    from oracle import oracle
+    np.random.seed(pid)
+    R, T, ok, i0, i1, thr = oracle.solve_relative_pose(k0, c0, None, k1, c1, None)
+    return np.r_[np.asarray(R, np.float32).ravel(), np.asarray(T, np.float32).ravel(), float(ok), len(i0), thr, 0]
+
+
+def cpu_pass(data, n_frames, pool, threads):
+    """Steady-state CPU pass over n_frames frames / n_frames-1 pairs; returns seconds."""
+    import torch
+    from oracle import oracle
+    torch.set_num_threads(threads)
+    off = data["vox_offsets"]
+    jobs = []
+    for f in range(n_frames):
+        v = [data["vox"][off[3 * f + s]:off[3 * f + s + 1]] for s in range(3)]
+        jobs.append((data["ring3"][f], data["counter"][f], *v))
+    t0 = time.perf_counter()
+    frames = pool.map(_cpu_frame, jobs) if pool else [_cpu_frame(j) for j in jobs]
+    feats = [oracle.get_features_from_patches(pl) for _, pl in frames]   # torch-CPU, all threads (Keras stand-in)
+    pj = [(p, frames[p][0], feats[p], frames[p + 1][0], feats[p + 1]) for p in range(n_frames - 1)]
+    _poses = pool.map(_cpu_pair, pj) if pool else [_cpu_pair(j) for j in pj]
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation (oracle port) on the host cores."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from caelo_b200 import synth
+    from oracle import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    n_frames = min(args.pairs, 4) + 1            # bounded sample: 4 pairs of the P-pair step
+    data = synth.make_frames(n_frames, seed=0)
+    workers = min(cores, n_frames)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        for _ in range(args.warmup):
+            cpu_pass(data, n_frames, pool, cores)
+        t = [cpu_pass(data, n_frames, pool, cores) for _ in range(args.steps)]
+    total = sum(t)
+    value = (n_frames - 1) * args.steps / total
+    sample = ("%d of the step's %d pairs (%d synthetic frames) per step; oracle port of the reference path "
+              "(C respond/select/match/RANSAC, scipy k-d tree patches, torch-CPU encoder), %d worker processes "
+              "+ %d torch threads" % (n_frames - 1, args.pairs, n_frames, workers, cores))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": _config(args, 1),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def _config(args, world):
+    return {"workload": "configs[1] scaled to a batch: seq-00-shaped synthetic odometry, %d consecutive frame pairs "
+                        "per step per GPU (%d frames; 64x1792x3 ring, 1024 keypts/frame, 3x16^3 voxel patches, "
+                        "60-D descriptors, 500-trial RANSAC)" % (args.pairs, args.pairs + 1),
+            "pairs_per_step_per_gpu": args.pairs, "keypoints": K_PTS, "parallelism": "pairs sharded x%d" % world,
+            "l2": "256 MiB write between timed steps (untimed); per-step intermediates (~0.8 GB) exceed L2"}
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: caelo_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from caelo_b200 import api, pipeline, synth
+
+    ctx = api.Context(local_rank)
+    pipe = pipeline.OdometryPipeline(ctx, K_PTS)
+    P = args.pairs
+    F = P + 1
+    # pair ids of this rank inside a notional sequence: rank r owns pairs [r*P, (r+1)*P)
+    pair_ids = list(range(rank * P, (rank + 1) * P))
+    data = synth.make_frames(F, seed=1 + rank, first_frame=rank * P)
+    host = dict(ring=torch.from_numpy(data["ring3"]).pin_memory(),
+                counter=torch.from_numpy(data["counter"]).pin_memory(),
+                vox=torch.from_numpy(data["vox"]).pin_memory())
+    voff = data["vox_offsets"]
+    d_ring, d_counter, d_vox = (host[k].to(dev) for k in ("ring", "counter", "vox"))
+    samples_h = pipeline.draw_samples(pair_ids, K_PTS)
+    d_samples = torch.from_numpy(samples_h).to(dev)
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        poses = pipe.run_device(d_ring, d_counter, d_vox, voff, d_samples, pair_ids)
+        return pipeline.gather_poses(poses, dev)
+
+    def step_host():
+        poses = pipe.run_host(host["ring"], host["counter"], host["vox"], voff, pair_ids)
+        return pipeline.gather_poses(poses, dev)
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        poses = step_device()
+    ok_pairs = None
+    if rank == 0 and poses is not None:
+        ok_pairs = int((poses[:, 12] != 0).sum())
+
+    # ---- timed region: K steps, CUDA events on the launch stream, L2 flushed between steps ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ctx.profile(True)
+    ctx.profile_fetch()
+    launches0 = ctx.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev:
+        flush.zero_()
+        torch.cuda.synchronize()
+        a.record()
+        step_device()
+        b.record()
+    barrier()
+    launches = ctx.launches - launches0
+    prof = ctx.profile_fetch()
+    ctx.profile(False)
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+
+    # ---- end to end: host (pinned) inputs, H2D + sample drawing + kernels + D2H every step ----
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        peaks = _peaks()
+        n_patches = F * 3 * K_PTS
+
+        def kern(name, work, peak, unit, scale):
+            if name not in prof:
+                return None
+            n, tot = prof[name]
+            sec = tot / n * 1e-3
+            ach = work / sec / scale
+            return {"kernel": name, "launches_per_step": n // args.steps, "avg_ms": tot / n,
+                    "share_of_step": tot / ms if ms else None, "achieved": ach, "peak": peak, "unit": unit,
+                    "frac": ach / peak}
+
+        kernels = [k for k in (
+            kern("conv_stack_kernel", FLOP_CONV_STACK_PER_PATCH * n_patches, peaks["tf_sustained"], "TFLOP/s", 1e12),
+            kern("dense_kernel", FLOP_DENSE_PER_PATCH * n_patches, peaks["tf_sustained"], "TFLOP/s", 1e12),
+            kern("respond_score_kernel<fused>", BYTES_RESPOND_SELECT_PER_FRAME * F, peaks["hbm"], "GB/s", 1e9),
+            kern("gather_kernel", (n_patches * 512 + F * 3 * 4), peaks["hbm"], "GB/s", 1e9),
+            kern("nn_tile_kernel", 2.0 * P * K_PTS * K_PTS * 60, peaks["tf_sustained"], "TFLOP/s", 1e12),
+        ) if k]
+        top = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
+        dom = next((k for k in kernels if k["kernel"] == top), kernels[0] if kernels else None)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if dom and os.path.isfile(tp):
+            traffic = json.load(open(tp)).get(dom["kernel"])
+        roofline = None
+        if dom:
+            roofline = {"bound": "tensor" if dom["unit"] == "TFLOP/s" else "hbm", "achieved": dom["achieved"],
+                        "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic,
+                        "kernel": dom["kernel"], "avg_launch_ms": dom["avg_ms"], "share_of_step": dom["share_of_step"],
+                        "peak_source": peaks["source"] + (" bf16 sustained" if dom["unit"] == "TFLOP/s" else " copy"),
+                        "all_kernels": kernels,
+                        "time_by_kernel_ms_per_step": {k: v[1] / args.steps for k, v in prof.items()}}
+        h2d = sum(host[k].numel() * host[k].element_size() for k in host) + samples_h.nbytes + voff.nbytes
+        d2h = P * (16 + 12 + 1) * 4
+        line = {"metric": METRIC, "value": world * P * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": _config(args, world), "clocks": clocks,
+                "e2e": {"value": world * P * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(launches), "roofline": roofline,
+                "pairs_with_model": ok_pairs}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(data)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(data):
+    """Oracle port of the reference path on the host cores, bounded sample (3 frames / 2 pairs)."""
+    import multiprocessing as mp
+    from oracle import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    n_frames = 3
+    with mp.get_context("fork").Pool(min(cores, n_frames)) as pool:
+        cpu_pass(data, n_frames, pool, cores)
+        sec = cpu_pass(data, n_frames, pool, cores)
+    return {"value": (n_frames - 1) / sec, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "2 pairs (3 frames) of the same synthetic workload, steady-state accounting "
+                      "(each frame processed once); oracle port, %d worker processes + %d torch threads; "
+                      "1 warm-up pass" % (min(cores, n_frames), cores)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=32, help="frame pairs per step per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

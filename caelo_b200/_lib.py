@@ -23,6 +23,8 @@ SIGNATURES = {
     "caelo_destroy": (c_int, [c_void_p]),
     "caelo_num_sms": (c_int, [c_void_p]),
     "caelo_launch_count": (c_int64, [c_void_p]),
+    "caelo_profile_enable": (c_int, [c_void_p, c_int]),
+    "caelo_profile_fetch": (c_int, [c_void_p, c_char_p, c_int]),
     "caelo_set_respond_weights": (c_int, [c_void_p] + [c_void_p] * 4),
     "caelo_set_encoder_weights": (c_int, [c_void_p] + [c_void_p] * 10),
     "caelo_respond_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

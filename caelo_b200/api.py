@@ -99,6 +99,19 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.caelo_launch_count(self.h))
 
+    def profile(self, on: bool):
+        self.check(self.lib.caelo_profile_enable(self.h, 1 if on else 0), "caelo_profile_enable")
+
+    def profile_fetch(self):
+        """{kernel name: (launches, total_ms)} since the last fetch (synchronises)."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        self.check(self.lib.caelo_profile_fetch(self.h, buf, len(buf)), "caelo_profile_fetch")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.rsplit(" ", 2)
+            out[name] = (int(n), float(ms))
+        return out
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.caelo_destroy(self.h)

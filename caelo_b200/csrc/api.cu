@@ -1,4 +1,6 @@
 // api.cu — ctx lifetime, weights and error reporting for libcaelo_b200.so (include/caelo.h).
+#include <stdio.h>
+
 #include <new>
 
 #include "common.cuh"
@@ -62,6 +64,44 @@ extern "C" int caelo_destroy(caelo_ctx *ctx)
         if (s->ptr) cudaFree(s->ptr);
     if (ctx->enc_blob) cudaFree(ctx->enc_blob);
     delete ctx;
+    return CAELO_OK;
+}
+
+extern "C" int caelo_profile_enable(caelo_ctx *ctx, int on)
+{
+    if (!ctx) return CAELO_ERR_ARG;
+    ctx->prof_on = on != 0;
+    return CAELO_OK;
+}
+
+// Writes "name count total_ms\n" lines (aggregated per kernel name, launch order of first use)
+// into buf, clears the records.  Synchronises the device.
+extern "C" int caelo_profile_fetch(caelo_ctx *ctx, char *buf, int buflen)
+{
+    if (!ctx || !buf || buflen <= 0) return CAELO_ERR_ARG;
+    CAELO_CUDA(ctx, cudaDeviceSynchronize());
+    struct Agg { const char *name; int n; double ms; };
+    std::vector<Agg> agg;
+    for (ProfRec &r : ctx->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        size_t i = 0;
+        for (; i < agg.size(); ++i)
+            if (!strcmp(agg[i].name, r.name)) break;
+        if (i == agg.size()) agg.push_back({r.name, 0, 0.0});
+        agg[i].n++;
+        agg[i].ms += ms;
+        ctx->prof_pool.push_back(r.a);
+        ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof.clear();
+    int pos = 0;
+    buf[0] = 0;
+    for (Agg &a : agg) {
+        int w = snprintf(buf + pos, buflen - pos, "%s %d %.6f\n", a.name, a.n, a.ms);
+        if (w < 0 || w >= buflen - pos) break;
+        pos += w;
+    }
     return CAELO_OK;
 }
 

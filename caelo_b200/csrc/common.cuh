@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/caelo.h"
 
 struct RespondWeights {  // SphericalRingPCRespondLayer.h5, Keras layouts
@@ -26,7 +28,15 @@ struct Scratch {
     size_t bytes = 0;
 };
 
+struct ProfRec {
+    const char *name;
+    cudaEvent_t a, b;
+};
+
 struct caelo_ctx {
+    bool prof_on = false;
+    std::vector<ProfRec> prof;          // one record per launch while profiling is enabled
+    std::vector<cudaEvent_t> prof_pool; // recycled events
     int device = 0;
     int num_sms = 0;
     int64_t launches = 0;
@@ -78,3 +88,27 @@ static inline int caelo_reserve(caelo_ctx *ctx, Scratch &s, size_t bytes)
         }                                             \
     } while (0)
 
+
+// Per-launch device timing (caelo_profile_enable): events on the launch stream around one kernel.
+struct ProfScope {
+    caelo_ctx *c;
+    cudaStream_t st;
+    int idx = -1;
+    ProfScope(caelo_ctx *ctx, const char *name, cudaStream_t stream) : c(ctx), st(stream)
+    {
+        if (!c->prof_on) return;
+        ProfRec r;
+        r.name = name;
+        for (cudaEvent_t *e : {&r.a, &r.b}) {
+            if (!c->prof_pool.empty()) { *e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+            else if (cudaEventCreate(e) != cudaSuccess) return;
+        }
+        cudaEventRecord(r.a, st);
+        c->prof.push_back(r);
+        idx = (int)c->prof.size() - 1;
+    }
+    ~ProfScope()
+    {
+        if (idx >= 0) cudaEventRecord(c->prof[idx].b, st);
+    }
+};

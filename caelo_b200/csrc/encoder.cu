@@ -340,13 +340,13 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
     c.packed = packed; c.k1 = ctx->enc.k1; c.b1 = ctx->enc.b1; c.k2 = ctx->enc.k2; c.b2 = ctx->enc.b2;
     c.k3 = ctx->enc.k3; c.b3 = ctx->enc.b3; c.act3 = act3; c.P = P;
     int grid = ctx->num_sms < P ? ctx->num_sms : P;
-    conv_stack_kernel<<<grid, CS_THREADS, CS_SMEM_FLOATS * 4, st>>>(c);
+    { ProfScope ps_(ctx, "conv_stack_kernel", st); conv_stack_kernel<<<grid, CS_THREADS, CS_SMEM_FLOATS * 4, st>>>(c); }
     CAELO_LAUNCH_CHECK(ctx);
     DenseArgs d;
     d.act3 = act3; d.d1 = ctx->enc.d1; d.bd1 = ctx->enc.bd1; d.d2 = ctx->enc.d2; d.bd2 = ctx->enc.bd2;
     d.feat = feat; d.P = P; d.feat_stride = feat_stride; d.feat_col0 = feat_col0;
     d.frame_mode = frame_mode; d.K = K;
-    dense_kernel<<<(P + DT_ROWS - 1) / DT_ROWS, 256, DT_SMEM, st>>>(d);
+    { ProfScope ps_(ctx, "dense_kernel", st); dense_kernel<<<(P + DT_ROWS - 1) / DT_ROWS, 256, DT_SMEM, st>>>(d); }
     CAELO_LAUNCH_CHECK(ctx);
     return CAELO_OK;
 }
@@ -388,7 +388,7 @@ extern "C" int caelo_encode_patches(caelo_ctx *ctx, const float *patches, int P,
     long long nwords = (long long)P * 128;
     long long blocks = (nwords * 32 + 255) / 256;
     if (blocks > (long long)ctx->num_sms * 32) blocks = (long long)ctx->num_sms * 32;
-    pack_kernel<<<(unsigned)blocks, 256, 0, st>>>(patches, packed, nwords, status);
+    { ProfScope ps_(ctx, "pack_kernel", st); pack_kernel<<<(unsigned)blocks, 256, 0, st>>>(patches, packed, nwords, status); }
     CAELO_LAUNCH_CHECK(ctx);
     return run_encoder(ctx, packed, P, feat, 20, 0, 0, 1, st);
 }

@@ -176,10 +176,10 @@ extern "C" int caelo_nn_match(caelo_ctx *ctx, const float *codes0, const float *
     a.out = reinterpret_cast<long long *>(pair_idx);
     dim3 grid((M + TILE - 1) / TILE, P);
     size_t smem = (size_t)2 * a.Dp * TILE * 4;
-    nn_tile_kernel<<<grid, MT_THREADS, smem, st>>>(a);
+    { ProfScope ps_(ctx, "nn_tile_kernel", st); nn_tile_kernel<<<grid, MT_THREADS, smem, st>>>(a); }
     CAELO_LAUNCH_CHECK(ctx);
     long long threads = (long long)cols * 32;
-    nn_exact_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a, P);
+    { ProfScope ps_(ctx, "nn_exact_kernel", st); nn_exact_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a, P); }
     CAELO_LAUNCH_CHECK(ctx);
     return CAELO_OK;
 }

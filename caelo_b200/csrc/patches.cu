@@ -284,7 +284,7 @@ extern "C" int caelo_gather_patches(caelo_ctx *ctx, const void *kpts, int kpts_f
     b.vox = vox; b.offsets = d_off; b.tables = d_tables; b.nlists = nl;
     int bx = (int)((maxlen + 255) / 256);
     if (bx > 64) bx = 64;
-    brick_insert_kernel<<<dim3(bx, nl), 256, 0, st>>>(b);
+    { ProfScope ps_(ctx, "brick_insert_kernel", st); brick_insert_kernel<<<dim3(bx, nl), 256, 0, st>>>(b); }
     CAELO_LAUNCH_CHECK(ctx);
 
     GatherArgs g;
@@ -299,14 +299,14 @@ extern "C" int caelo_gather_patches(caelo_ctx *ctx, const void *kpts, int kpts_f
     long long blocks = (warps + kWarps - 1) / kWarps;
     long long maxb = (long long)ctx->num_sms * 16;
     if (blocks > maxb) blocks = maxb;
-    gather_kernel<<<(unsigned)blocks, kWarps * 32, 0, st>>>(g);
+    { ProfScope ps_(ctx, "gather_kernel", st); gather_kernel<<<(unsigned)blocks, kWarps * 32, 0, st>>>(g); }
     CAELO_LAUNCH_CHECK(ctx);
 
     if (patches_f32) {
         long long nwords = (long long)F * 3 * K * 128;
         long long ub = (nwords + 255) / 256;
         if (ub > (long long)ctx->num_sms * 32) ub = (long long)ctx->num_sms * 32;
-        unpack_kernel<<<(unsigned)ub, 256, 0, st>>>(packed, patches_f32, nwords);
+        { ProfScope ps_(ctx, "unpack_kernel", st); unpack_kernel<<<(unsigned)ub, 256, 0, st>>>(packed, patches_f32, nwords); }
         CAELO_LAUNCH_CHECK(ctx);
     }
     return CAELO_OK;

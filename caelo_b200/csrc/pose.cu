@@ -384,9 +384,9 @@ extern "C" int caelo_ransac_round(caelo_ctx *ctx, const float *pc0, int N0, cons
     a.counts = counts ? counts : reinterpret_cast<int *>(a.rt_hyp + (size_t)P * T * 12);
     a.result = result; a.mask = inlier_mask;
     dim3 grid((T + HS_WARPS - 1) / HS_WARPS, P);
-    hyp_score_kernel<<<grid, HS_WARPS * 32, 0, st>>>(a);
+    { ProfScope ps_(ctx, "hyp_score_kernel", st); hyp_score_kernel<<<grid, HS_WARPS * 32, 0, st>>>(a); }
     CAELO_LAUNCH_CHECK(ctx);
-    replay_mask_kernel<<<P, 256, 0, st>>>(a);
+    { ProfScope ps_(ctx, "replay_mask_kernel", st); replay_mask_kernel<<<P, 256, 0, st>>>(a); }
     CAELO_LAUNCH_CHECK(ctx);
     return CAELO_OK;
 }
@@ -401,7 +401,7 @@ extern "C" int caelo_kabsch(caelo_ctx *ctx, const float *pc0, int N0, const floa
     a.pc0 = pc0; a.pc1 = pc1; a.pair_idx = reinterpret_cast<const long long *>(pair_idx);
     a.mask = mask; a.N0 = N0; a.N = N; a.P = P; a.rt = Rt; a.credible = credible;
     int blocks = (P * 32 + 127) / 128;
-    kabsch_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a);
+    { ProfScope ps_(ctx, "kabsch_kernel", (cudaStream_t)stream); kabsch_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a); }
     CAELO_LAUNCH_CHECK(ctx);
     return CAELO_OK;
 }

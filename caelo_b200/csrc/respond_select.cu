@@ -340,10 +340,10 @@ int launch_select(caelo_ctx *ctx, bool fused, const float *resp, int H, int W, c
     dim3 grid((W - 2 * EDGE + TW - 1) / TW, (H - 2 * EDGE + TH - 1) / TH, B);
     size_t smem = (size_t)8 * NPIX * 4 + ((NPIX + 15) / 16) * 16 + (fused ? (size_t)IH * IW * 3 * 4 : 0);
     if (fused) {
-        respond_score_kernel<true><<<grid, kThreads, smem, st>>>(ctx->respond_host, a);
+        { ProfScope ps_(ctx, "respond_score_kernel<fused>", st); respond_score_kernel<true><<<grid, kThreads, smem, st>>>(ctx->respond_host, a); }
     } else {
         if (!resp) return CAELO_ERR_ARG;
-        respond_score_kernel<false><<<grid, kThreads, smem, st>>>(ctx->respond_host, a);
+        { ProfScope ps_(ctx, "respond_score_kernel<from_resp>", st); respond_score_kernel<false><<<grid, kThreads, smem, st>>>(ctx->respond_host, a); }
     }
     CAELO_LAUNCH_CHECK(ctx);
 
@@ -354,7 +354,7 @@ int launch_select(caelo_ctx *ctx, bool fused, const float *resp, int H, int W, c
     while (S < max_kpts + 1) S <<= 1;
     t.sort_n = S;
     t.kpts = kpts; t.kpix = reinterpret_cast<long long *>(kpix); t.n_kpts = n_kpts;
-    topk_kernel<<<B, 1024, (size_t)S * 8, st>>>(t);
+    { ProfScope ps_(ctx, "topk_kernel", st); topk_kernel<<<B, 1024, (size_t)S * 8, st>>>(t); }
     CAELO_LAUNCH_CHECK(ctx);
     return CAELO_OK;
 }
@@ -378,7 +378,7 @@ extern "C" int caelo_respond_forward(caelo_ctx *ctx, const float *ring, int B, i
     long long blocks = (total + kThreads - 1) / kThreads;
     long long maxb = (long long)ctx->num_sms * 32;
     if (blocks > maxb) blocks = maxb;
-    respond_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(ctx->respond_host, ring, B, H, W, resp);
+    { ProfScope ps_(ctx, "respond_kernel", (cudaStream_t)stream); respond_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(ctx->respond_host, ring, B, H, W, resp); }
     CAELO_LAUNCH_CHECK(ctx);
     return CAELO_OK;
 }

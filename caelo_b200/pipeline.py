@@ -1,0 +1,173 @@
+"""Batched odometry pipeline: F consecutive frames -> F-1 relative poses on one GPU, and the
+frame-pair sharding across ranks.
+
+This is what replaces the reference's producer/consumer fan-out in PoseEstimation.py:48-150,
+241-267 (four loader processes + one Keras process + a CPU RANSAC loop): every stage is batched
+over frames (a1/a2/a6/a3) or frame pairs (a4/a5) and runs as a handful of kernel launches.
+Per pair the arithmetic is exactly that of ``api.SolveRelativePose`` with ``np.random.seed(pair_id)``
+called before it (the harness convention of SURVEY §8d)."""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import api
+
+MAX_TRIALS = api.MAX_TRIALS
+
+
+def shard_pairs(n_pairs: int, rank: int, world: int):
+    """Contiguous pair range [lo, hi) of this rank; it needs frames [lo, hi] (one-frame halo
+    recomputed, not exchanged)."""
+    base, rem = divmod(n_pairs, world)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def draw_samples(pair_ids: Sequence[int], n_points: int, rounds_done: int = 0) -> np.ndarray:
+    """Round ``rounds_done`` sample indices [P,500,4] int32, drawn exactly as RANSAC4RT does
+    after ``np.random.seed(pair_id)`` (Match.py:182-184: 4 doubles per trial, int32(u*N))."""
+    out = np.empty((len(pair_ids), MAX_TRIALS, 4), np.int32)
+    for i, pid in enumerate(pair_ids):
+        rs = np.random.RandomState(int(pid))
+        if rounds_done:
+            rs.random_sample((rounds_done * MAX_TRIALS * 4,))
+        out[i] = np.array(rs.random_sample((MAX_TRIALS, 4)) * n_points, dtype=np.int32)
+    return out
+
+
+class OdometryPipeline:
+    def __init__(self, ctx: Optional[api.Context] = None, n_keypoints: int = api.nFixedKeyPts):
+        self.ctx = ctx or api.default_context()
+        self.K = n_keypoints
+        self.dev = self.ctx.device
+
+    # ---- device-resident stages ---------------------------------------------------------
+    def frames_to_descriptors(self, ring: torch.Tensor, counter: torch.Tensor, vox: torch.Tensor,
+                              vox_offsets: np.ndarray):
+        """ring [F,64,1792,3] (or [F,69,1800,5]), counter [F,69,1800] i8/i32, voxel lists ->
+        kpts [F,K,3], feat [F,K,60], n_kpts [F]."""
+        kpts, _kpix, n = self.ctx.select_keypoints(ring, counter, None, max_kpts=self.K)
+        packed, _, _ = self.ctx.gather_patches(kpts, vox, vox_offsets, n)
+        feat = self.ctx.encode_frames(packed)
+        return kpts, feat, n
+
+    def pairs_to_poses(self, kpts: torch.Tensor, feat: torch.Tensor, samples: torch.Tensor,
+                       thr: torch.Tensor):
+        """Consecutive pairs (f, f+1): returns result [P,16], refit Rt [P,12], mask, pair_idx."""
+        pc0, pc1 = kpts[:-1], kpts[1:]
+        pair_idx = self.ctx.nn_match(feat[:-1], feat[1:])
+        result, mask, _ = self.ctx.ransac_round(pc0, pc1, pair_idx, samples, thr)
+        rt, _cred = self.ctx.kabsch(pc0, pc1, pair_idx, mask)
+        return result, rt, mask, pair_idx
+
+    # ---- whole batch ------------------------------------------------------------------------
+    def run_device(self, ring, counter, vox, vox_offsets, samples, pair_ids):
+        """Inputs already in HBM.  Returns poses [P,16] float32 (host): refit R(9) T(3), isSuccess,
+        nInliers, residualThreshold, trials — rows follow ``pair_ids``."""
+        P = ring.shape[0] - 1
+        kpts, feat, n = self.frames_to_descriptors(ring, counter, vox, vox_offsets)
+        thr = torch.full((P,), 0.4, dtype=torch.float32, device=self.dev)
+        result, rt, mask, pair_idx = self.pairs_to_poses(kpts, feat, samples, thr)
+        res = result.cpu().numpy()                      # sync point: tiny D2H of the per-pair results
+        rt_h = rt.cpu().numpy()
+        n_h = n.cpu().numpy()
+        if (n_h != self.K).any():
+            raise api._lib.CaeloError("a frame yielded fewer than %d keypoints; use the per-pair API" % self.K)
+        poses = np.zeros((P, 16), np.float32)
+        poses[:, :12] = rt_h
+        poses[:, 12] = res[:, 12]
+        poses[:, 13] = res[:, 14]
+        poses[:, 14] = 0.4
+        poses[:, 15] = res[:, 13]
+        failed = np.flatnonzero(res[:, 12] == 0)
+        if failed.size:
+            self._ladder(failed, kpts, pair_idx, pair_ids, poses)
+        return poses
+
+    def _ladder(self, failed, kpts, pair_idx, pair_ids, poses):
+        """Threshold ladder 0.8, 1.6 for the pairs whose first round found no model (Match.py:207-214)."""
+        thr_val = 0.4
+        rounds = 0
+        while failed.size:
+            thr_val *= 2
+            rounds += 1
+            if thr_val > 2.0:
+                for p in failed:                        # total failure: R=I, T=0 (Match.py:277-278)
+                    poses[p, :12] = [1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]
+                    poses[p, 12:] = [0, 0, thr_val / 2, MAX_TRIALS]
+                return
+            sel = torch.as_tensor(failed, device=self.dev)
+            pc0 = kpts[:-1][sel].contiguous()
+            pc1 = kpts[1:][sel].contiguous()
+            pidx = pair_idx[sel].contiguous()
+            smp = torch.from_numpy(draw_samples([pair_ids[p] for p in failed], self.K, rounds)).to(self.dev)
+            thr = torch.full((failed.size,), thr_val, dtype=torch.float32, device=self.dev)
+            result, mask, _ = self.ctx.ransac_round(pc0, pc1, pidx, smp, thr)
+            rt, _ = self.ctx.kabsch(pc0, pc1, pidx, mask)
+            res, rt_h = result.cpu().numpy(), rt.cpu().numpy()
+            still = []
+            for i, p in enumerate(failed):
+                if res[i, 12] != 0:
+                    poses[p, :12] = rt_h[i]
+                    poses[p, 12:] = [1, res[i, 14], thr_val, res[i, 13]]
+                else:
+                    still.append(p)
+            failed = np.asarray(still, np.int64)
+
+    def run_host(self, ring_h: torch.Tensor, counter_h: torch.Tensor, vox_h: torch.Tensor,
+                 vox_offsets: np.ndarray, pair_ids: Sequence[int]):
+        """End-to-end call with HOST (pinned) buffers: H2D of the inputs, RANSAC sample drawing,
+        all kernels, D2H of the poses."""
+        ring = ring_h.to(self.dev, non_blocking=True)
+        counter = counter_h.to(self.dev, non_blocking=True)
+        vox = vox_h.to(self.dev, non_blocking=True)
+        smp = torch.from_numpy(draw_samples(pair_ids, self.K)).to(self.dev, non_blocking=True)
+        return self.run_device(ring, counter, vox, vox_offsets, smp, pair_ids)
+
+
+def gather_poses(poses: np.ndarray, device: torch.device):
+    """NCCL gather of the per-rank [P_local,16] pose rows to rank 0 (the only collective on the
+    path; PoseEstimation.py:254-267's pose chain then runs on rank 0).  Returns the concatenated
+    array on rank 0, None elsewhere.  Works without torch.distributed initialised (1 rank)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return poses
+    world, rank = dist.get_world_size(), dist.get_rank()
+    t = torch.from_numpy(np.ascontiguousarray(poses, np.float32)).to(device)
+    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([t.shape[0]], dtype=torch.int64, device=device))
+    sizes = [int(c.item()) for c in counts]
+    pad = torch.zeros((max(sizes), 16), dtype=torch.float32, device=device)
+    pad[: t.shape[0]] = t
+    bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, bufs, dst=0)
+    if rank != 0:
+        return None
+    return np.concatenate([b[:s].cpu().numpy() for b, s in zip(bufs, sizes)], 0)
+
+
+def chain_poses(rel: np.ndarray, Tr: Optional[np.ndarray] = None):
+    """The sequential pose chain of PoseEstimation.py:254-267 on rank 0: rel [P,16] rows ->
+    absolute poses [P+1,12] (KITTI format).  Tr is the 3x4 velodyne->camera calibration row;
+    identity if None."""
+    if Tr is None:
+        Tr = np.c_[np.eye(3), np.zeros(3)]
+    R_Tr, T_Tr = Tr[:, :3].astype(np.float64), Tr[:, 3:4].astype(np.float64)
+    R_Tr_inv = np.linalg.inv(R_Tr)
+    T_Tr_inv = -R_Tr_inv @ T_Tr
+    poses = np.zeros((rel.shape[0] + 1, 12))
+    R_acc, T_acc = np.eye(3), np.zeros((3, 1))
+    poses[0] = np.c_[R_acc, T_acc].reshape(-1)
+    for i in range(rel.shape[0]):
+        R = rel[i, :9].reshape(3, 3).astype(np.float64)
+        T = rel[i, 9:12].reshape(3, 1).astype(np.float64)
+        R_d = R_Tr @ R @ R_Tr_inv
+        T_d = R_Tr @ (R @ T_Tr_inv + T) + T_Tr
+        T_acc = R_acc @ T_d + T_acc
+        R_acc = R_acc @ R_d
+        poses[i + 1] = np.c_[R_acc, T_acc].reshape(-1)
+    return poses

@@ -52,6 +52,12 @@ int caelo_num_sms(const caelo_ctx *ctx);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 int64_t caelo_launch_count(const caelo_ctx *ctx);
 
+/* Per-launch device timing: while enabled every kernel launch is bracketed by CUDA events on
+ * its stream.  caelo_profile_fetch synchronises, writes one "name count total_ms" line per
+ * kernel into buf and clears the records (bench.py's roofline numbers come from here). */
+int caelo_profile_enable(caelo_ctx *ctx, int on);
+int caelo_profile_fetch(caelo_ctx *ctx, char *buf, int buflen);
+
 /* Weights of SphericalRingPCRespondLayer.h5 (HOST pointers, Keras layouts):
  * w1 (3,3,3,32) HWIO, b1 (32), w2 (1,1,32,8), b2 (8).  Replaces keras load_model at
  * Match.py:324, BatchPreprocess.py:168.  Synchronous. */

@@ -148,53 +148,58 @@ def get_patches_list(Pts, AllVoxels0, AllVoxels1, AllVoxels2, return_truncated: 
 
     The reference asks sklearn for the 496 nearest occupied voxels of each key voxel and
     keeps those inside the [-8,8)^3 cube; the scatter uses negative indices, so offset o is
-    stored at index o mod 16.  Set formulation: a cube voxel survives iff its rank among
-    all occupied voxels ordered by (d^2, x, y, z) is < 496 (the tie order at the k-th
-    neighbour is implementation-defined in sklearn — oracle rule, parity unpinned there).
+    stored at index o mod 16.  Here a k-d tree (scipy) returns the same 496 neighbours; when
+    the 496th lies beyond the cube's farthest corner (d^2 > 192) the cut cannot bite and the
+    result is order-independent.  Otherwise ("truncated") the set is decided by the oracle's
+    canonical rule: a voxel survives iff its rank among all occupied voxels ordered by
+    (d^2, x, y, z) is < 496 — the tie order at the k-th neighbour is implementation-defined
+    in sklearn, parity unpinned there.
     """
+    from scipy.spatial import cKDTree
+
     Pts = np.asarray(Pts)
     K = Pts.shape[0]
     Pts_ = Pts + [VisibleLength, VisibleWidth, VisibleHeight]  # float64, as the reference
     patches = []
     truncated = []
-    cube = np.stack(np.meshgrid(*(np.arange(-PatchRadius, PatchRadius),) * 3, indexing="ij"),
-                    -1).reshape(-1, 3)
     ball = _ball_offsets()
+    R2 = 3 * PatchRadius * PatchRadius
     for s, vox in enumerate((AllVoxels0, AllVoxels1, AllVoxels2)):
         vox = np.asarray(vox)
         if vox.shape[0] < N_NEIGHBORS:
             raise ValueError("Expected n_neighbors <= n_samples_fit")  # sklearn's own error
         KeyVoxels = np.array(Pts_ / VoxelSizes[s], dtype=np.int32)
-        keys = np.unique(_pack(vox))
         out = np.zeros((K, PatchSize, PatchSize, PatchSize, 1), np.float32)
         trunc = np.zeros(K, bool)
-
-        def member(q):
-            pos = np.searchsorted(keys, q)
-            pos[pos >= keys.size] = keys.size - 1
-            return keys[pos] == q
-
-        for k0 in range(0, K, 128):
-            kv = KeyVoxels[k0:k0 + 128].astype(np.int64)
-            c = kv[:, None, :] + cube[None]
-            valid = (c >= 0).all(-1)
-            hit = member(_pack(np.where(valid[..., None], c, 0))) & valid
-            b = kv[:, None, :] + ball[None]
-            bvalid = (b >= 0).all(-1)
-            bhit = member(_pack(np.where(bvalid[..., None], b, 0))) & bvalid
-            nball = bhit.sum(1)
-            for i in range(kv.shape[0]):
-                offs = cube[hit[i]]
-                if nball[i] > N_NEIGHBORS:
-                    trunc[k0 + i] = True
-                    bo = ball[bhit[i]]
-                    bc = kv[i] + bo
-                    d2 = (bo * bo).sum(1)
-                    order = np.lexsort((bc[:, 2], bc[:, 1], bc[:, 0], d2))
-                    keep = bo[order[:N_NEIGHBORS]]
-                    incube = ((keep >= -PatchRadius) & (keep < PatchRadius)).all(1)
-                    offs = keep[incube]
-                out[k0 + i, offs[:, 0] % 16, offs[:, 1] % 16, offs[:, 2] % 16, 0] = 1.0
+        if K == 0:
+            patches.append(out)
+            truncated.append(trunc)
+            continue
+        vox64 = vox.astype(np.int64)
+        tree = cKDTree(vox64.astype(np.float64))
+        _, nbr = tree.query(KeyVoxels.astype(np.float64), k=N_NEIGHBORS)
+        off = vox64[nbr] - KeyVoxels[:, None, :].astype(np.int64)       # (K,496,3)
+        d2 = (off * off).sum(-1)
+        trunc = d2.max(1) <= R2                                          # the cut can bite
+        incube = ((off >= -PatchRadius) & (off < PatchRadius)).all(-1)
+        kk, nn = np.nonzero(incube & ~trunc[:, None])
+        o = off[kk, nn]
+        out[kk, o[:, 0] % 16, o[:, 1] % 16, o[:, 2] % 16, 0] = 1.0
+        if trunc.any():
+            keys = np.unique(_pack(vox))
+            for i in np.flatnonzero(trunc):
+                kv = KeyVoxels[i].astype(np.int64)
+                b = kv + ball
+                bvalid = (b >= 0).all(-1)
+                q = _pack(np.where(bvalid[:, None], b, 0))
+                pos = np.minimum(np.searchsorted(keys, q), keys.size - 1)
+                hit = (keys[pos] == q) & bvalid
+                bo = ball[hit]
+                bc = kv + bo
+                order = np.lexsort((bc[:, 2], bc[:, 1], bc[:, 0], (bo * bo).sum(1)))
+                keep = bo[order[:N_NEIGHBORS]]
+                keep = keep[((keep >= -PatchRadius) & (keep < PatchRadius)).all(1)]
+                out[i, keep[:, 0] % 16, keep[:, 1] % 16, keep[:, 2] % 16, 0] = 1.0
         patches.append(out)
         truncated.append(trunc)
     if return_truncated:

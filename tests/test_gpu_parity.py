@@ -73,7 +73,7 @@ def test_keypoints_few_candidates_and_ties(api, oracle_mod):
     H, W = 64, 1792
     ring = np.zeros((H, W, 3), np.float32)
     cnt = np.zeros((69, 1800), np.int32)
-    rr, cc = np.meshgrid(np.arange(10, 50), np.arange(100, 160), indexing="ij")
+    rr, cc = np.meshgrid(np.arange(10, 32), np.arange(100, 140), indexing="ij")
     ring[rr, cc] = (rng.standard_normal(rr.shape + (3,)) * 3 + [20, 5, -1]).astype(np.float32)
     cnt[rr, cc] = 1
     resp = (rng.integers(0, 4, (H, W, 8))).astype(np.float32)  # few distinct values -> many exact ties
