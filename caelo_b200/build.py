@@ -19,6 +19,7 @@ SOURCES = {
     "encoder.cu": [],
     "match.cu": [],
     "pose.cu": ["-fmad=false"],
+    "umma_debug.cu": [],
 }
 
 

@@ -146,6 +146,13 @@ int caelo_kabsch(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int
                  const int64_t *pair_idx, const uint8_t *mask, int P, float *Rt, int32_t *credible,
                  void *stream);
 
+/* Test hook (tests/test_gpu_umma.py): one tcgen05 GEMM D = A*B^T (f16 in, f32 accumulate in
+ * TMEM) with operands staged under caller-chosen SBO/LBO byte strides; dumps the raw 128-lane x
+ * 64-column accumulator.  Pins the descriptor and TMEM-layout facts the encoder relies on. */
+int caelo_debug_umma(caelo_ctx *ctx, const void *A_f16, const void *B_f16, int M, int N, int K,
+                     int sbo_a, int lbo_a, int sbo_b, int lbo_b, int d_lane_off, float *dump,
+                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif
