@@ -105,6 +105,13 @@ extern "C" int caelo_profile_fetch(caelo_ctx *ctx, char *buf, int buflen)
     return CAELO_OK;
 }
 
+extern "C" int caelo_debug_set_timeline(caelo_ctx *ctx, long long *buf)
+{
+    if (!ctx) return CAELO_ERR_ARG;
+    ctx->dbg_timeline = buf;
+    return CAELO_OK;
+}
+
 extern "C" int caelo_num_sms(const caelo_ctx *ctx) { return ctx ? ctx->num_sms : 0; }
 extern "C" int64_t caelo_launch_count(const caelo_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

@@ -35,6 +35,7 @@ struct ProfRec {
 
 struct caelo_ctx {
     bool prof_on = false;
+    long long *dbg_timeline = nullptr;  // caelo_debug_set_timeline
     std::vector<ProfRec> prof;          // one record per launch while profiling is enabled
     std::vector<cudaEvent_t> prof_pool; // recycled events
     int device = 0;

@@ -146,6 +146,10 @@ int caelo_kabsch(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int
                  const int64_t *pair_idx, const uint8_t *mask, int P, float *Rt, int32_t *credible,
                  void *stream);
 
+/* Debug: device buffer [grid][64][8] int64 receiving clock64 stamps of the encoder's per-patch
+ * phases (NULL disables).  Used by tools/encoder_timeline.py. */
+int caelo_debug_set_timeline(caelo_ctx *ctx, long long *buf);
+
 /* Test hook (tests/test_gpu_umma.py): one tcgen05 GEMM D = A*B^T (f16 in, f32 accumulate in
  * TMEM) with operands staged under caller-chosen SBO/LBO byte strides; dumps the raw 128-lane x
  * 64-column accumulator.  Pins the descriptor and TMEM-layout facts the encoder relies on. */

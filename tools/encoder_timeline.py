@@ -1,0 +1,34 @@
+"""Dump per-patch phase timings (SM cycles) of the encoder's conv12 kernel: python tools/encoder_timeline.py"""
+import ctypes, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from caelo_b200 import api, synth
+
+ctx = api.default_context()
+d = synth.make_frames(2, seed=1)
+ring, cnt = api._dev(d["ring3"]), api._dev(d["counter"])
+kpts, _, n = ctx.select_keypoints(ring, cnt, None)
+packed, _, _ = ctx.gather_patches(kpts, api._dev(d["vox"]), d["vox_offsets"], n)
+packed = packed.repeat(8, 1, 1, 1).contiguous()          # 49k patches
+grid = 2 * ctx.lib.caelo_num_sms(ctx.h)
+tl = torch.zeros((grid, 64, 8), dtype=torch.int64, device="cuda")
+ctx.encode_frames(packed)
+ctx.check(ctx.lib.caelo_debug_set_timeline(ctx.h, ctypes.c_void_p(tl.data_ptr())))
+ctx.encode_frames(packed)
+torch.cuda.synchronize()
+ctx.lib.caelo_debug_set_timeline(ctx.h, None)
+t = tl.cpu().numpy()[:, 4:60, :].astype(np.float64)
+def stat(x): return "mean %8.0f  p50 %8.0f  p90 %8.0f" % (x.mean(), np.median(x), np.percentile(x, 90))
+print("conv1            1-0 :", stat(t[..., 1] - t[..., 0]))
+
+print("mma issue        6-5 :", stat(t[..., 6] - t[..., 5]))
+print("mbar wait        3-1 :", stat(t[..., 3] - t[..., 1]))
+print("epilogue         4-3 :", stat(t[..., 4] - t[..., 3]))
+
+print("iteration  next0-0 :", stat(t[:, 1:, 0] - t[:, :-1, 0]))
+raw = tl.cpu().numpy()
+for cta in (0, 150):
+    print("CTA", cta, "(cycles relative to iteration-10 start; columns = stamps 0..7)")
+    base = raw[cta, 10, 0]
+    for i in range(10, 15):
+        print("  it %2d:" % i, " ".join("%8d" % (raw[cta, i, s] - base) for s in range(8)))
