@@ -6,6 +6,7 @@
 #include "common.cuh"
 
 int caelo_encoder_init(caelo_ctx *ctx);
+int caelo_encoder_prepare(caelo_ctx *ctx);
 int caelo_match_init(caelo_ctx *ctx);
 int caelo_select_init(caelo_ctx *ctx);
 
@@ -63,6 +64,7 @@ extern "C" int caelo_destroy(caelo_ctx *ctx)
     for (Scratch *s : all)
         if (s->ptr) cudaFree(s->ptr);
     if (ctx->enc_blob) cudaFree(ctx->enc_blob);
+    if (ctx->enc_w1t_hi) cudaFree(ctx->enc_w1t_hi);
     delete ctx;
     return CAELO_OK;
 }
@@ -145,6 +147,8 @@ extern "C" int caelo_set_encoder_weights(caelo_ctx *ctx, const float *k1, const 
     ctx->enc.k1 = b + off[0]; ctx->enc.b1 = b + off[1]; ctx->enc.k2 = b + off[2]; ctx->enc.b2 = b + off[3];
     ctx->enc.k3 = b + off[4]; ctx->enc.b3 = b + off[5]; ctx->enc.d1 = b + off[6]; ctx->enc.bd1 = b + off[7];
     ctx->enc.d2 = b + off[8]; ctx->enc.bd2 = b + off[9];
+    int rc = caelo_encoder_prepare(ctx);
+    if (rc) return rc;
     ctx->have_encoder = true;
     return CAELO_OK;
 }

@@ -1,5 +1,6 @@
 // common.cuh — ctx layout, scratch management and launch helpers shared by the kernels.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -46,6 +47,7 @@ struct caelo_ctx {
     RespondWeights respond_host;
     EncoderWeightsDev enc;
     float *enc_blob = nullptr;
+    __half *enc_w1t_hi = nullptr, *enc_w1t_lo = nullptr;  // dense1 weights, transposed split fp16 [208][2048]
     // scratch regions (grown on demand, never shrunk)
     Scratch cand;      // select: candidate keys + counters
     Scratch bricks;    // patches: hash tables

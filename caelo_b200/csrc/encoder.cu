@@ -25,6 +25,15 @@
 
 namespace {
 
+// tanh(x) = sign(x) (1 - 2/(exp(2|x|)+1)) on the SFU (ex2.approx + rcp): |err| < 3e-7 absolute
+__device__ __forceinline__ float fast_tanh(float x)
+{
+    float ax = fabsf(x);
+    float e = __expf(2.0f * ax);
+    float t = 1.0f - __fdividef(2.0f, e + 1.0f);
+    return copysignf(t, x);
+}
+
 // ---- conv1 (CUDA cores) + conv2 (tcgen05) --------------------------------------------------
 constexpr int TC_WORKERS = 256;                       // 8 warps: produce operands (conv1), drain accumulators
 constexpr int TC_THREADS = TC_WORKERS + 32;           // + 1 warp whose elected lane issues the MMAs (it
@@ -117,8 +126,8 @@ __device__ __forceinline__ void conv1_to_smem(const unsigned *pk, const float *k
 #pragma unroll
             for (int s = 1; s < 8; ++s) { m0 = fmaxf(m0, acc[s][2 * c]); m1 = fmaxf(m1, acc[s][2 * c + 1]); }
             __half h0, l0, h1, l1;
-            umma::split_f16(tanhf(m0), h0, l0);
-            umma::split_f16(tanhf(m1), h1, l1);
+            umma::split_f16(fast_tanh(m0), h0, l0);
+            umma::split_f16(fast_tanh(m1), h1, l1);
             hi[c] = __halves2half2(h0, h1);
             lo[c] = __halves2half2(l0, l1);
         }
@@ -259,7 +268,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
                 for (int c = 0; c < 8; ++c)
                     if (c == j) { o0 = m[2 * c]; o1 = m[2 * c + 1]; }
                 const int pos = (pair * 4 + q) * 4 + ((lane & 7) >> 1);
-                *reinterpret_cast<float2 *>(out + pos * 16 + 2 * j) = make_float2(tanhf(o0), tanhf(o1));
+                *reinterpret_cast<float2 *>(out + pos * 16 + 2 * j) = make_float2(fast_tanh(o0), fast_tanh(o1));
             }
             umma::fence_before_thread_sync();
             umma::mbar_arrive(&tempty[b]);
@@ -272,160 +281,334 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
     if (warp == 8) umma::tmem_dealloc(tbase, 256);
 }
 
-// ---- conv3 (fp32 CUDA cores) ------------------------------------------------------------------
-constexpr int C3_THREADS = 256;
-constexpr int A2P = 6 * 6 * 6;  // padded 4^3 volume
-constexpr int C3_SMEM = (27 * 16 * 32 + A2P * 16 + 32) * 4;
+// ---- conv3 (tcgen05) ---------------------------------------------------------------------------
+// Per patch an IMPLICIT GEMM  D[64 positions, 32 ch] = sum over 27 taps of A_tap[64,16] W_tap[16,32]:
+// the 4^3 x 16ch input is stored as 9 (dy,dz)-shifted COMPACT copies of a [6(x halo)][4][4] volume per
+// channel half, so that for every tap the 64 output rows are one contiguous run of 16-byte rows
+// (canonical K-major layout, SBO = 128 B) starting dx*256 B into copy (dy,dz); the two channel halves
+// are the two K chunks (LBO = 9*1536 B).  Split fp16: A_hi x [W_hi|W_lo] (N=64) + A_lo x W_hi (N=32),
+// fp32 accumulators in TMEM (2 slots x 64 columns), epilogue adds the halves, bias, tanh, and writes
+// act3 as split fp16 (the dense1 operands).  8 worker warps + 1 MMA-issuer warp, mbarrier pipeline.
+constexpr int C3_WORKERS = 256;
+constexpr int C3_THREADS = C3_WORKERS + 32;
+constexpr int C3_COPY = 6 * 16 * 16;                 // 1536 B: [xi 6][y 4][z 4] x 16 B
+constexpr int C3_HALF = 9 * C3_COPY;                 // 13824 B: 9 (dy,dz) copies of one channel half
+constexpr int C3_PART = 2 * C3_HALF;                 // 27648 B: both halves
+constexpr int C3_BUF = 2 * C3_PART;                  // 55296 B: hi + lo
+constexpr int SM3_C = 0;
+constexpr int SM3_W = 2 * C3_BUF;                    // 110592: W3 [kc 54][n 64][16 B]
+constexpr int SM3_B3 = SM3_W + 54 * 1024;            // 165888
+constexpr int SM3_BAR = SM3_B3 + 128;
+constexpr int C3_SMEM = SM3_BAR + 64;
 
 struct Conv3Args {
     const float *act2;     // [P,64,16]
     const float *k3, *b3;  // (27,16,32), (32)
-    float *act3;           // [P,2048]
+    __half *act3_hi, *act3_lo;  // [P,2048] split fp16 (dense1 operands)
     int P;
 };
 
-__global__ void __launch_bounds__(C3_THREADS, 2) conv3_kernel(const Conv3Args a)
+__global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const Conv3Args a)
 {
-    extern __shared__ __align__(16) float sm3[];
-    float *k3s = sm3, *a2 = sm3 + 27 * 16 * 32, *b3s = a2 + A2P * 16;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < 27 * 16 * 32; i += C3_THREADS) k3s[i] = a.k3[i];
-    for (int i = tid; i < A2P * 16; i += C3_THREADS) a2[i] = 0.0f;
+    extern __shared__ __align__(128) unsigned char sm[];
+    float *b3s = reinterpret_cast<float *>(sm + SM3_B3);
+    uint64_t *full = reinterpret_cast<uint64_t *>(sm + SM3_BAR), *tfull = full + 2, *tempty = full + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SM3_BAR + 48);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+    for (int i = tid; i < SM3_W / 16; i += C3_THREADS) reinterpret_cast<uint4 *>(sm)[i] = make_uint4(0, 0, 0, 0);
+    // B operand: row n (0..31 = W_hi, 32..63 = W_lo of out-channel n%32), chunk kc = tap*2 + ci/8
+    for (int e = tid; e < 27 * 16 * 32; e += C3_THREADS) {
+        int t = e / 512, ci = (e / 32) % 16, co = e % 32;
+        __half h, l;
+        umma::split_f16(a.k3[e], h, l);
+        unsigned char *w = sm + SM3_W + (t * 2 + ci / 8) * 1024 + (ci % 8) * 2;
+        *reinterpret_cast<__half *>(w + (co / 8) * 128 + (co % 8) * 16) = h;
+        *reinterpret_cast<__half *>(w + ((32 + co) / 8) * 128 + (co % 8) * 16) = l;
+    }
     if (tid < 32) b3s[tid] = a.b3[tid];
-    __syncthreads();
-    for (int p = blockIdx.x; p < a.P; p += gridDim.x) {
-        {   // 64 positions x 16 ch = 256 float4
-            int pos = tid >> 2, c4 = tid & 3;
-            int x = pos >> 4, y = (pos >> 2) & 3, z = pos & 3;
-            float4 v = *reinterpret_cast<const float4 *>(a.act2 + (size_t)p * 1024 + pos * 16 + c4 * 4);
-            *reinterpret_cast<float4 *>(a2 + (((x + 1) * 6 + (y + 1)) * 6 + (z + 1)) * 16 + c4 * 4) = v;
+    if (warp == 8) umma::tmem_alloc(tmem_slot, 128);
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            umma::mbar_init(&full[b], C3_WORKERS);
+            umma::mbar_init(&tfull[b], 1);
+            umma::mbar_init(&tempty[b], C3_WORKERS);
         }
-        __syncthreads();
-        {
-            const int g = tid & 7, qq = tid >> 3;  // channels 4g..4g+3, positions qq and qq+32
-            float acc[2][4];
-            int base[2];
+        umma::fence_mbar_init();
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t sC = umma::smem_u32(sm + SM3_C), sW = umma::smem_u32(sm + SM3_W);
+    const int n_my = (a.P - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto patch_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
+
+    if (warp == 8) {
+        const uint32_t idesc64 = umma::idesc_f16_f32(64, 64), idesc32 = umma::idesc_f16_f32(64, 32);
+        for (int j = 0; j < n_my; ++j) {
+            const int b = j & 1, k = j >> 1;
+            umma::mbar_wait(&full[b], (uint32_t)(k & 1));
+            if (k >= 1) umma::mbar_wait(&tempty[b], (uint32_t)((k - 1) & 1));
+            umma::fence_after_thread_sync();
+            if (umma::elect_one()) {
+                const uint32_t d = tbase + b * 64;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                int q = qq + 32 * j;
-                int x = q >> 4, y = (q >> 2) & 3, z = q & 3;
-                base[j] = (x * 6 + y) * 6 + z;
+                for (int part = 0; part < 2; ++part) {
+                    const uint32_t cb = sC + b * C3_BUF + part * C3_PART;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[j][c] = b3s[g * 4 + c];
-            }
-            for (int t = 0; t < 27; ++t) {
-                const int toff = ((t / 9) * 6 + (t / 3) % 3) * 6 + t % 3;
-                const float4 *i0 = reinterpret_cast<const float4 *>(a2 + (base[0] + toff) * 16);
-                const float4 *i1 = reinterpret_cast<const float4 *>(a2 + (base[1] + toff) * 16);
-                const float *wt = k3s + t * 512 + g * 4;
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    float4 u0 = i0[c4], u1 = i1[c4];
-                    float x0[4] = {u0.x, u0.y, u0.z, u0.w}, x1[4] = {u1.x, u1.y, u1.z, u1.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float4 w = *reinterpret_cast<const float4 *>(wt + (c4 * 4 + k) * 32);
-                        acc[0][0] = fmaf(x0[k], w.x, acc[0][0]); acc[0][1] = fmaf(x0[k], w.y, acc[0][1]);
-                        acc[0][2] = fmaf(x0[k], w.z, acc[0][2]); acc[0][3] = fmaf(x0[k], w.w, acc[0][3]);
-                        acc[1][0] = fmaf(x1[k], w.x, acc[1][0]); acc[1][1] = fmaf(x1[k], w.y, acc[1][1]);
-                        acc[1][2] = fmaf(x1[k], w.z, acc[1][2]); acc[1][3] = fmaf(x1[k], w.w, acc[1][3]);
+                    for (int t = 0; t < 27; ++t) {
+                        const int dx = t / 9, dy = (t / 3) % 3, dz = t % 3;
+                        uint64_t da = umma::smem_desc(cb + (dy * 3 + dz) * C3_COPY + dx * 256, C3_HALF, 128);
+                        uint64_t db = umma::smem_desc(sW + t * 2048, 1024, 128);
+                        umma::mma_f16(d, da, db, part ? idesc32 : idesc64, (part | t) ? 1u : 0u);
                     }
                 }
+                umma::commit(&tfull[b]);
             }
-            float *o = a.act3 + (size_t)p * 2048;
+            __syncwarp();
+        }
+    } else {
+        // scatter one patch's activations (split fp16) into the 9 shifted copies of buffer b
+        auto produce = [&](int i) {
+            const int b = i & 1;
+            const int part = tid & 1, idx = tid >> 1, pos = idx >> 1, half = idx & 1;
+            const float4 *src = reinterpret_cast<const float4 *>(a.act2 + (size_t)patch_of(i) * 1024 + pos * 16 + half * 8);
+            float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+            float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            __half hv[8];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                int q = qq + 32 * j;  // flatten index ((x*4+y)*4+z)*32 + c
-                *reinterpret_cast<float4 *>(o + q * 32 + g * 4) =
-                    make_float4(tanhf(acc[j][0]), tanhf(acc[j][1]), tanhf(acc[j][2]), tanhf(acc[j][3]));
+            for (int c = 0; c < 8; ++c) {
+                __half h, l;
+                umma::split_f16(f[c], h, l);
+                hv[c] = part ? l : h;
+            }
+            const uint4 val = *reinterpret_cast<uint4 *>(hv);
+            const int x = pos >> 4, y = (pos >> 2) & 3, z = pos & 3;
+            unsigned char *base = sm + SM3_C + b * C3_BUF + part * C3_PART + half * C3_HALF;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dz = 0; dz < 3; ++dz) {
+                    const int ys = y + 1 - dy, zs = z + 1 - dz;
+                    if ((unsigned)ys < 4u && (unsigned)zs < 4u)
+                        *reinterpret_cast<uint4 *>(base + (dy * 3 + dz) * C3_COPY + (((x + 1) * 4 + ys) * 4 + zs) * 16) = val;
+                }
+            umma::fence_proxy_async();
+            umma::mbar_arrive(&full[b]);
+        };
+        if (n_my > 0) produce(0);
+        for (int i = 0; i < n_my; ++i) {
+            const int b = i & 1;
+            if (i + 1 < n_my) produce(i + 1);  // MMA(i-1) finished reading buffer b^1 (tfull waited last iteration)
+            umma::mbar_wait(&tfull[b], (uint32_t)((i >> 1) & 1));
+            umma::fence_after_thread_sync();
+            const int q = warp & 3, hc = warp >> 2;  // lane quarter, channel half (16 channels)
+            uint32_t v0[16], v1[16];
+            const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16) + b * 64 + hc * 16;
+            umma::tmem_ld_x16(trow, v0);
+            umma::tmem_ld_x16(trow + 32, v1);
+            umma::tmem_ld_wait();
+            umma::fence_before_thread_sync();
+            umma::mbar_arrive(&tempty[b]);
+            if (lane < 16) {  // M=64 accumulator: rows 16q..16q+15 live in lanes 0..15 of quarter q
+                const int pos = 16 * q + lane;
+                __half hh[16], ll[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    float o = fast_tanh((__uint_as_float(v0[c]) + __uint_as_float(v1[c])) + b3s[hc * 16 + c]);
+                    umma::split_f16(o, hh[c], ll[c]);
+                }
+                const size_t o = (size_t)patch_of(i) * 2048 + pos * 32 + hc * 16;
+                uint4 *dh = reinterpret_cast<uint4 *>(a.act3_hi + o), *dl = reinterpret_cast<uint4 *>(a.act3_lo + o);
+                dh[0] = reinterpret_cast<uint4 *>(hh)[0]; dh[1] = reinterpret_cast<uint4 *>(hh)[1];
+                dl[0] = reinterpret_cast<uint4 *>(ll)[0]; dl[1] = reinterpret_cast<uint4 *>(ll)[1];
             }
         }
-        __syncthreads();
     }
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    if (warp == 8) umma::tmem_dealloc(tbase, 128);
 }
 
-// ---- dense1 + tanh + dense2 + tanh ---------------------------------------------------------
-constexpr int DT_ROWS = 64, DT_K = 16, DT_COLS = 208;  // 200 padded to 16*13
-constexpr int DT_SMEM = (DT_K * (DT_ROWS + 4) + DT_K * DT_COLS + DT_ROWS * 201) * 4;
+// ---- dense1 (tcgen05) + tanh + dense2 + tanh ---------------------------------------------------
+// One CTA = 128 patches (M) x 208 outputs (N = 200 padded) x K = 2048, split-fp16 operands:
+//   D0 += A_hi W_hi^T + A_lo W_hi^T,  D1 += A_hi W_lo^T   (fp32 in TMEM), h = tanh(D0 + D1 + b).
+// Operands stream L2 -> smem with cp.async into the canonical K-major layout (two 64-wide K stages),
+// four loader/epilogue warps + one MMA-issuer warp, mbarrier full/empty pipeline.
+constexpr int DN = 208;                       // dense1 outputs padded to a multiple of 16
+constexpr int DK_STAGE = 64;                  // K elements per stage (8 chunks of 16 B)
+constexpr int D_A_BYTES = 128 * DK_STAGE * 2; // 16384
+constexpr int D_W_BYTES = DN * DK_STAGE * 2;  // 26624
+constexpr int D_STAGE = 2 * D_A_BYTES + 2 * D_W_BYTES;  // 86016
+constexpr int D_SM_BAR = 2 * D_STAGE;
+constexpr int D_SMEM = D_SM_BAR + 64;
+constexpr int D_THREADS = 160;
+
 struct DenseArgs {
-    const float *act3;  // [P,2048]
-    const float *d1, *bd1, *d2, *bd2;
+    const __half *a_hi, *a_lo;    // [Ppad,2048]
+    const __half *w_hi, *w_lo;    // [208,2048] (dense1 weights transposed, split)
+    const float *bd1, *d2, *bd2;  // (200), (200,20), (20)
     float *feat;
     int P, feat_stride, feat_col0;
     // frame mode: packed order is [F,3,K]; row p -> feat[(f*K+k)*60 + s*20]
     int frame_mode, K;
 };
 
-__global__ void __launch_bounds__(256) dense_kernel(const DenseArgs a)
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g)
 {
-    extern __shared__ __align__(16) float dsm[];
-    float (*As)[DT_ROWS + 4] = reinterpret_cast<float (*)[DT_ROWS + 4]>(dsm);
-    float (*Bs)[DT_COLS] = reinterpret_cast<float (*)[DT_COLS]>(dsm + DT_K * (DT_ROWS + 4));
-    float (*Hs)[201] = reinterpret_cast<float (*)[201]>(dsm + DT_K * (DT_ROWS + 4) + DT_K * DT_COLS);
-    const int tid = threadIdx.x;
-    const int tr = tid >> 4, tc = tid & 15;  // 16 x 16 thread grid: 4 rows x 13 cols each
-    const int row0 = blockIdx.x * DT_ROWS;
-    float acc[4][13];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 13; ++j) acc[i][j] = 0.0f;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
 
-    for (int k0 = 0; k0 < 2048; k0 += DT_K) {
-        // A tile: 64 rows x 16 k  (one float4 per thread)
-        {
-            int r = tid >> 2, kk = (tid & 3) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row0 + r < a.P) v = *reinterpret_cast<const float4 *>(a.act3 + (size_t)(row0 + r) * 2048 + k0 + kk);
-            As[kk + 0][r] = v.x; As[kk + 1][r] = v.y; As[kk + 2][r] = v.z; As[kk + 3][r] = v.w;
-        }
-        // B tile: 16 k x 200 cols
-        for (int i = tid; i < DT_K * 50; i += 256) {
-            int kk = i / 50, c4 = i % 50;
-            float4 v = *reinterpret_cast<const float4 *>(a.d1 + (size_t)(k0 + kk) * 200 + c4 * 4);
-            *reinterpret_cast<float4 *>(&Bs[kk][c4 * 4]) = v;
-        }
-        if (tid < DT_K * 2) {
-            int kk = tid >> 1, c4 = 50 + (tid & 1);
-            *reinterpret_cast<float4 *>(&Bs[kk][c4 * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < DT_K; ++kk) {
-            float av[4], bv[13];
-            float4 a4 = *reinterpret_cast<const float4 *>(&As[kk][tr * 4]);
-            av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
-#pragma unroll
-            for (int j = 0; j < 13; ++j) bv[j] = Bs[kk][tc + 16 * j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 13; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-        }
-        __syncthreads();
+// rows x 8 chunks of one operand tile: smem [r/8][kc][r%8][16 B]; a warp instruction covers 8 rows x 4 chunks
+__device__ __forceinline__ void load_tile(uint32_t sbase, const __half *g, int rows, int ltid)
+{
+    const int r_l = ltid & 7, kc_l = (ltid >> 3) & 3, wq = ltid >> 5;  // 4 loader warps
+    for (int it = wq; it < (rows / 8) * 2; it += 4) {
+        const int grp = it >> 1, kc = (it & 1) * 4 + kc_l;
+        cp_async16(sbase + grp * 1024 + kc * 128 + r_l * 16, g + (size_t)(grp * 8 + r_l) * 2048 + kc * 8);
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 13; ++j) {
-            int c = tc + 16 * j;
-            if (c < 200) Hs[tr * 4 + i][c] = tanhf(acc[i][j] + a.bd1[c]);
+}
+
+__global__ void __launch_bounds__(D_THREADS, 1) dense_tc_kernel(const DenseArgs a)
+{
+    extern __shared__ __align__(128) unsigned char dsm[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(dsm + D_SM_BAR), *empty = full + 2, *accum = full + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(dsm + D_SM_BAR + 48);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int row0 = blockIdx.x * 128;
+    if (warp == 4) umma::tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            umma::mbar_init(&full[s], 128);
+            umma::mbar_init(&empty[s], 1);
         }
+        umma::mbar_init(accum, 1);
+        umma::fence_mbar_init();
+    }
+    umma::fence_before_thread_sync();
     __syncthreads();
-    // dense2: 64 rows x 20 outputs = 1280 = 5 per thread
-    for (int o = tid; o < DT_ROWS * 20; o += 256) {
-        int r = o / 20, c = o % 20;
-        int p = row0 + r;
-        if (p >= a.P) continue;
-        float s = a.bd2[c];
-        for (int k = 0; k < 200; ++k) s = fmaf(Hs[r][k], __ldg(a.d2 + k * 20 + c), s);
-        float v = tanhf(s);
-        if (a.frame_mode) {
-            int k = p % a.K, sc = (p / a.K) % 3, f = p / (3 * a.K);
-            a.feat[((size_t)f * a.K + k) * 60 + sc * 20 + c] = v;
-        } else {
-            a.feat[(size_t)p * a.feat_stride + a.feat_col0 + c] = v;
+    umma::fence_after_thread_sync();
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t sbase = umma::smem_u32(dsm);
+    constexpr int NKT = 2048 / DK_STAGE;
+
+    if (warp == 4) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = umma::idesc_f16_f32(128, DN);
+        for (int kt = 0; kt < NKT; ++kt) {
+            const int s = kt & 1;
+            umma::mbar_wait(&full[s], (uint32_t)((kt >> 1) & 1));
+            umma::fence_after_thread_sync();
+            if (umma::elect_one()) {
+                const uint32_t st = sbase + s * D_STAGE;
+#pragma unroll
+                for (int j = 0; j < DK_STAGE / 16; ++j) {
+                    uint64_t ah = umma::smem_desc(st + j * 256, 128, 1024);
+                    uint64_t al = umma::smem_desc(st + D_A_BYTES + j * 256, 128, 1024);
+                    uint64_t wh = umma::smem_desc(st + 2 * D_A_BYTES + j * 256, 128, 1024);
+                    uint64_t wl = umma::smem_desc(st + 2 * D_A_BYTES + D_W_BYTES + j * 256, 128, 1024);
+                    const uint32_t acc = (kt | j) ? 1u : 0u;
+                    umma::mma_f16(tbase, ah, wh, idesc, acc);
+                    umma::mma_f16(tbase, al, wh, idesc, 1u);
+                    umma::mma_f16(tbase + 256, ah, wl, idesc, acc);
+                }
+                umma::commit(&empty[s]);
+                if (kt == NKT - 1) umma::commit(accum);
+            }
+            __syncwarp();
         }
+    } else {
+        // ===== loaders (then epilogue) =====
+        const __half *ah = a.a_hi + (size_t)row0 * 2048, *al = a.a_lo + (size_t)row0 * 2048;
+        for (int kt = 0; kt < NKT; ++kt) {
+            const int s = kt & 1;
+            if (kt >= 2) umma::mbar_wait(&empty[s], (uint32_t)(((kt >> 1) - 1) & 1));
+            const uint32_t st = sbase + s * D_STAGE;
+            const int k0 = kt * DK_STAGE;
+            load_tile(st, ah + k0, 128, tid);
+            load_tile(st + D_A_BYTES, al + k0, 128, tid);
+            load_tile(st + 2 * D_A_BYTES, a.w_hi + k0, DN, tid);
+            load_tile(st + 2 * D_A_BYTES + D_W_BYTES, a.w_lo + k0, DN, tid);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (kt >= 1) {
+                asm volatile("cp.async.wait_group 1;" ::: "memory");  // stage kt-1 has landed
+                umma::fence_proxy_async();
+                umma::mbar_arrive(&full[(kt - 1) & 1]);
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        umma::fence_proxy_async();
+        umma::mbar_arrive(&full[(NKT - 1) & 1]);
+
+        // ===== epilogue: h = tanh(D0 + D1 + b) -> smem (aliases the operand stages), dense2 + tanh =====
+        umma::mbar_wait(accum, 0);
+        umma::fence_after_thread_sync();
+        float *Hs = reinterpret_cast<float *>(dsm);              // [128][201]
+        float *W2s = Hs + 128 * 201;                             // [200][20] + bd2[20]
+        for (int i = tid; i < 200 * 20; i += 128) W2s[i] = a.d2[i];
+        if (tid < 20) W2s[4000 + tid] = a.bd2[tid];
+        const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < DN; c0 += 16) {
+            uint32_t v0[16], v1[16];
+            umma::tmem_ld_x16(trow + c0, v0);
+            umma::tmem_ld_x16(trow + 256 + c0, v1);
+            umma::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                int c = c0 + j;
+                if (c < 200) Hs[tid * 201 + c] = tanhf((__uint_as_float(v0[j]) + __uint_as_float(v1[j])) + __ldg(a.bd1 + c));
+            }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int p = row0 + tid;
+        if (p < a.P) {
+            float acc[20];
+#pragma unroll
+            for (int j = 0; j < 20; ++j) acc[j] = W2s[4000 + j];
+            for (int k = 0; k < 200; ++k) {
+                const float h = Hs[tid * 201 + k];
+                const float4 *w = reinterpret_cast<const float4 *>(W2s + k * 20);
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    float4 wv = w[q];
+                    acc[4 * q + 0] = fmaf(h, wv.x, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(h, wv.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(h, wv.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(h, wv.w, acc[4 * q + 3]);
+                }
+            }
+            float *o;
+            if (a.frame_mode) {
+                int k = p % a.K, sc = (p / a.K) % 3, f = p / (3 * a.K);
+                o = a.feat + ((size_t)f * a.K + k) * 60 + sc * 20;
+            } else {
+                o = a.feat + (size_t)p * a.feat_stride + a.feat_col0;
+            }
+#pragma unroll
+            for (int j = 0; j < 20; ++j) o[j] = tanhf(acc[j]);
+        }
+        umma::fence_before_thread_sync();
+    }
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    if (warp == 4) umma::tmem_dealloc(tbase, 512);
+}
+
+// dense1 weights (2048,200) f32 -> transposed split fp16 [208][2048] (rows 200..207 zero)
+__global__ void prep_dense_weights_kernel(const float *d1, __half *w_hi, __half *w_lo)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < DN * 2048; i += gridDim.x * blockDim.x) {
+        int n = i / 2048, k = i % 2048;
+        __half h = __float2half_rn(0.f), l = h;
+        if (n < 200) umma::split_f16(d1[(size_t)k * 200 + n], h, l);
+        w_hi[i] = h;
+        w_lo[i] = l;
     }
 }
 
@@ -452,10 +635,12 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
 {
     if (!ctx->have_encoder) return CAELO_ERR_NO_WEIGHTS;
     if (P <= 0) return CAELO_OK;
-    int rc = caelo_reserve(ctx, ctx->enc_ws, (size_t)P * (2048 + 1024) * 4);
+    const size_t Ppad = ((size_t)P + 127) / 128 * 128;
+    int rc = caelo_reserve(ctx, ctx->enc_ws, Ppad * 2048 * 2 * 2 + (size_t)P * 1024 * 4);
     if (rc) return rc;
-    float *act3 = reinterpret_cast<float *>(ctx->enc_ws.ptr);
-    float *act2 = act3 + (size_t)P * 2048;
+    __half *act3_hi = reinterpret_cast<__half *>(ctx->enc_ws.ptr);
+    __half *act3_lo = act3_hi + Ppad * 2048;
+    float *act2 = reinterpret_cast<float *>(act3_lo + Ppad * 2048);
     Conv12Args c;
     c.packed = packed; c.k1 = ctx->enc.k1; c.b1 = ctx->enc.b1; c.k2 = ctx->enc.k2; c.b2 = ctx->enc.b2;
     c.act2 = act2; c.P = P; c.timeline = ctx->dbg_timeline;
@@ -463,14 +648,16 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
     { ProfScope ps_(ctx, "conv12_tc_kernel", st); conv12_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(c); }
     CAELO_LAUNCH_CHECK(ctx);
     Conv3Args c3;
-    c3.act2 = act2; c3.k3 = ctx->enc.k3; c3.b3 = ctx->enc.b3; c3.act3 = act3; c3.P = P;
-    { ProfScope ps_(ctx, "conv3_kernel", st); conv3_kernel<<<grid, C3_THREADS, C3_SMEM, st>>>(c3); }
+    c3.act2 = act2; c3.k3 = ctx->enc.k3; c3.b3 = ctx->enc.b3; c3.act3_hi = act3_hi; c3.act3_lo = act3_lo; c3.P = P;
+    int grid3 = ctx->num_sms < P ? ctx->num_sms : P;
+    { ProfScope ps_(ctx, "conv3_tc_kernel", st); conv3_tc_kernel<<<grid3, C3_THREADS, C3_SMEM, st>>>(c3); }
     CAELO_LAUNCH_CHECK(ctx);
     DenseArgs d;
-    d.act3 = act3; d.d1 = ctx->enc.d1; d.bd1 = ctx->enc.bd1; d.d2 = ctx->enc.d2; d.bd2 = ctx->enc.bd2;
+    d.a_hi = act3_hi; d.a_lo = act3_lo; d.w_hi = ctx->enc_w1t_hi; d.w_lo = ctx->enc_w1t_lo;
+    d.bd1 = ctx->enc.bd1; d.d2 = ctx->enc.d2; d.bd2 = ctx->enc.bd2;
     d.feat = feat; d.P = P; d.feat_stride = feat_stride; d.feat_col0 = feat_col0;
     d.frame_mode = frame_mode; d.K = K;
-    { ProfScope ps_(ctx, "dense_kernel", st); dense_kernel<<<(P + DT_ROWS - 1) / DT_ROWS, 256, DT_SMEM, st>>>(d); }
+    { ProfScope ps_(ctx, "dense_tc_kernel", st); dense_tc_kernel<<<(unsigned)(Ppad / 128), D_THREADS, D_SMEM, st>>>(d); }
     CAELO_LAUNCH_CHECK(ctx);
     return CAELO_OK;
 }
@@ -480,8 +667,21 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
 int caelo_encoder_init(caelo_ctx *ctx)
 {
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv12_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM));
-    CAELO_CUDA(ctx, cudaFuncSetAttribute(dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
+    return CAELO_OK;
+}
+
+// called from caelo_set_encoder_weights: derived operand forms of the weights
+int caelo_encoder_prepare(caelo_ctx *ctx)
+{
+    if (!ctx->enc_w1t_hi) {
+        CAELO_CUDA(ctx, cudaMalloc(&ctx->enc_w1t_hi, (size_t)DN * 2048 * 2 * 2));
+        ctx->enc_w1t_lo = ctx->enc_w1t_hi + (size_t)DN * 2048;
+    }
+    prep_dense_weights_kernel<<<256, 256>>>(ctx->enc.d1, ctx->enc_w1t_hi, ctx->enc_w1t_lo);
+    CAELO_LAUNCH_CHECK(ctx);
+    CAELO_CUDA(ctx, cudaDeviceSynchronize());
     return CAELO_OK;
 }
 
