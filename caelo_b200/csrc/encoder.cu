@@ -46,7 +46,10 @@ constexpr int SM_W2 = SM_A + 4 * A_VOL_BYTES;         // 64000
 constexpr int SM_K1 = SM_W2 + W2_BYTES;               // floats: k1[216] b1[8] b2[16]
 constexpr int SM_BG = SM_K1 + (216 + 8 + 16) * 4;     // tanh(b1) as fp16 hi (16 B) + lo (16 B)
 constexpr int SM_PK = SM_BG + 32;                     // packed patch [2][128] words
-constexpr int SM_BAR = SM_PK + 2 * 512;               // 6 mbarriers + tmem base
+constexpr int SM_LWIN = SM_PK + 2 * 512;              // non-empty cell list: windows [512] u64
+constexpr int SM_LCELL = SM_LWIN + 512 * 8;           //                      padded cell index [512] u16
+constexpr int SM_LCNT = SM_LCELL + 512 * 2;           //                      count [2] (double-buffered)
+constexpr int SM_BAR = SM_LCNT + 16;                  // 6 mbarriers + tmem base
 constexpr int TC_SMEM = SM_BAR + 64;
 
 struct Conv12Args {
@@ -63,71 +66,102 @@ __device__ __forceinline__ constexpr int tap_off(int t)  // byte offset of tap t
     return (((t / 9) * 10 + (t / 3) % 3) * 10 + t % 3) * 16;
 }
 
-// conv1 + maxpool + tanh for one patch -> A_hi / A_lo interior.  Thread = one (px,py) column and two
-// pz cells: the 16 occupancy rows around the column are read once; a cell whose 4x4x4 window is
-// empty gets the precomputed tanh(b1); otherwise the set bits are visited in ascending order and
-// each adds its weight to the sub-positions it touches (same summation order as tap-ascending).
+// conv1 + maxpool + tanh for one patch -> A_hi / A_lo interior, in two passes so that the work is
+// balanced over the 256 worker threads however the occupied voxels cluster:
+//   pass 1  thread = one (px,py) column, two pz cells: the 16 occupancy rows around the column are read
+//           once; a cell whose 4x4x4 window is empty gets the precomputed tanh(b1), the others are
+//           appended (cell, window) to a list in shared memory;
+//   pass 2  listed cells are dealt round-robin: for each of the 8 pooled sub-positions the 27
+//           neighbourhood bits are gathered from the window and the selected weights summed in
+//           ascending tap order, max over sub-positions, tanh, split to fp16 hi/lo.
 __device__ __forceinline__ void conv1_to_smem(const unsigned *pk, const float *k1s, const float *b1s,
-                                              const uint4 *bg, unsigned char *a_hi, unsigned char *a_lo, int tid)
+                                              const uint4 *bg, unsigned char *a_hi, unsigned char *a_lo,
+                                              unsigned long long *lwin, unsigned short *lcell, int *lcount, int tid)
 {
     const unsigned short *rows = reinterpret_cast<const unsigned short *>(pk);  // row (x,y): 16 z-bits
-    const int col = tid >> 2, zq = tid & 3;
-    const int px = col >> 3, py = col & 7;
-    unsigned r[16];
-    unsigned any = 0;
+    const int lane = tid & 31;
+    {
+        const int col = tid >> 2, zq = tid & 3;
+        const int px = col >> 3, py = col & 7;
+        unsigned r[16];
+        unsigned any = 0;
 #pragma unroll
-    for (int ix = 0; ix < 4; ++ix)
+        for (int ix = 0; ix < 4; ++ix)
 #pragma unroll
-        for (int iy = 0; iy < 4; ++iy) {
-            int x = 2 * px - 1 + ix, y = 2 * py - 1 + iy;
-            unsigned v = 0;
-            if (x >= 0 && x < 16 && y >= 0 && y < 16) v = rows[x * 16 + y];
-            r[ix * 4 + iy] = v << 1;  // bit z+1 <-> voxel z
-            any |= v;
-        }
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        const int pz = 2 * zq + half;
-        const int pi = ((px + 1) * 10 + (py + 1)) * 10 + (pz + 1);
-        unsigned long long win = 0ull;
-        if (any) {
+            for (int iy = 0; iy < 4; ++iy) {
+                int x = 2 * px - 1 + ix, y = 2 * py - 1 + iy;
+                unsigned v = 0;
+                if (x >= 0 && x < 16 && y >= 0 && y < 16) v = rows[x * 16 + y];
+                r[ix * 4 + iy] = v << 1;  // bit z+1 <-> voxel z
+                any |= v;
+            }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) win |= (unsigned long long)((r[i] >> (2 * pz)) & 0xFu) << (i * 4);
-        }
-        if (win == 0ull) {
-            *reinterpret_cast<uint4 *>(a_hi + pi * 16) = bg[0];
-            *reinterpret_cast<uint4 *>(a_lo + pi * 16) = bg[1];
-            continue;
-        }
-        float acc[8][8];
+        for (int half = 0; half < 2; ++half) {
+            const int pz = 2 * zq + half;
+            const int pi = ((px + 1) * 10 + (py + 1)) * 10 + (pz + 1);
+            unsigned long long win = 0ull;
+            if (any) {
 #pragma unroll
-        for (int s = 0; s < 8; ++s)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[s][c] = b1s[c];
-        while (win) {
-            const int bit = __ffsll((long long)win) - 1;
-            win &= win - 1;
-            const int ix = bit >> 4, iy = (bit >> 2) & 3, iz = bit & 3;
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                const int dx = ix - (s >> 2), dy = iy - ((s >> 1) & 1), dz = iz - (s & 1);
-                if ((unsigned)dx < 3u && (unsigned)dy < 3u && (unsigned)dz < 3u) {
-                    const float4 *w = reinterpret_cast<const float4 *>(k1s + ((dx * 3 + dy) * 3 + dz) * 8);
-                    float4 w0 = w[0], w1 = w[1];
-                    acc[s][0] += w0.x; acc[s][1] += w0.y; acc[s][2] += w0.z; acc[s][3] += w0.w;
-                    acc[s][4] += w1.x; acc[s][5] += w1.y; acc[s][6] += w1.z; acc[s][7] += w1.w;
+                for (int i = 0; i < 16; ++i) win |= (unsigned long long)((r[i] >> (2 * pz)) & 0xFu) << (i * 4);
+            }
+            const bool nz = win != 0ull;
+            if (!nz) {
+                *reinterpret_cast<uint4 *>(a_hi + pi * 16) = bg[0];
+                *reinterpret_cast<uint4 *>(a_lo + pi * 16) = bg[1];
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, nz);
+            if (m) {
+                int base = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) base = atomicAdd(lcount, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (nz) {
+                    const int k = base + __popc(m & ((1u << lane) - 1u));
+                    lwin[k] = win;
+                    lcell[k] = (unsigned short)pi;
                 }
+            }
+        }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int n = *lcount;
+    for (int k = tid; k < n; k += TC_WORKERS) {
+        const unsigned long long win = lwin[k];
+        const int pi = lcell[k];
+        float best[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) best[c] = -3.0e38f;
+#pragma unroll
+        for (int sxy = 0; sxy < 4; ++sxy) {
+            const int sx = sxy >> 1, sy = sxy & 1;
+            // 3x3 nibbles (dx,dy) of the window around (sx,sy): nibble j = dx*3+dy at bits 4j..4j+3
+            unsigned long long g = 0ull;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) g |= ((win >> (16 * (sx + dx) + 4 * sy)) & 0xFFFull) << (12 * dx);
+#pragma unroll
+            for (int sz = 0; sz < 2; ++sz) {
+                unsigned long long m = (g >> sz) & 0x777777777ull;  // dz = 0..2 of every nibble
+                float acc[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[c] = b1s[c];
+                while (m) {
+                    const int b = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const float4 *w = reinterpret_cast<const float4 *>(k1s + ((b >> 2) * 3 + (b & 3)) * 8);
+                    const float4 w0 = w[0], w1 = w[1];
+                    acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
+                    acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) best[c] = fmaxf(best[c], acc[c]);
             }
         }
         __half2 hi[4], lo[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            float m0 = acc[0][2 * c], m1 = acc[0][2 * c + 1];
-#pragma unroll
-            for (int s = 1; s < 8; ++s) { m0 = fmaxf(m0, acc[s][2 * c]); m1 = fmaxf(m1, acc[s][2 * c + 1]); }
             __half h0, l0, h1, l1;
-            umma::split_f16(fast_tanh(m0), h0, l0);
-            umma::split_f16(fast_tanh(m1), h1, l1);
+            umma::split_f16(fast_tanh(best[2 * c]), h0, l0);
+            umma::split_f16(fast_tanh(best[2 * c + 1]), h1, l1);
             hi[c] = __halves2half2(h0, h1);
             lo[c] = __halves2half2(l0, l1);
         }
@@ -225,12 +259,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
         }
     } else {
         // ===== workers: conv1 of patch i+1 while MMA(i) runs, then drain patch i =====
+        unsigned long long *lwin = reinterpret_cast<unsigned long long *>(sm + SM_LWIN);
+        unsigned short *lcell = reinterpret_cast<unsigned short *>(sm + SM_LCELL);
+        int *lcnt = reinterpret_cast<int *>(sm + SM_LCNT);
         auto produce = [&](int i) {
             const int b = i & 1;
             if (tid < 128) pk[b * 128 + tid] = a.packed[(size_t)patch_of(i) * 128 + tid];
+            if (tid == 128) lcnt[b] = 0;  // the other counter was read before the previous patch's second barrier
             asm volatile("bar.sync 1, 256;" ::: "memory");
             conv1_to_smem(pk + b * 128, k1s, b1s, bg, sm + SM_A + (2 * b) * A_VOL_BYTES,
-                          sm + SM_A + (2 * b + 1) * A_VOL_BYTES, tid);
+                          sm + SM_A + (2 * b + 1) * A_VOL_BYTES, lwin, lcell, lcnt + b, tid);
             umma::fence_proxy_async();
             umma::mbar_arrive(&full[b]);
         };

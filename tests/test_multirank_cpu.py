@@ -1,0 +1,104 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the multi-GPU path — contiguous pair sharding
+with a one-frame halo, the gather of per-pair pose rows to rank 0 (NCCL on the GPU box, gloo here) and
+the sequential pose chain of PoseEstimation.py:254-267 on rank 0."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from caelo_b200 import pipeline
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _fake_pose_rows(pair_ids):
+    rows = np.zeros((len(pair_ids), 16), np.float32)
+    for i, p in enumerate(pair_ids):
+        a = 0.01 * (p + 1)
+        rows[i, :9] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], np.float32).ravel()
+        rows[i, 9:12] = [0.7 + 0.001 * p, 0.01 * p, 0]
+        rows[i, 12:] = [1, 300 + p, 0.4, 100]
+    return rows
+
+
+def _worker(rank, world, port, n_pairs, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = pipeline.shard_pairs(n_pairs, rank, world)
+    rows = _fake_pose_rows(list(range(lo, hi)))
+    got = pipeline.gather_poses(rows, torch.device("cpu"))
+    if rank == 0:
+        np.save(out, got)
+    else:
+        assert got is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_pairs", [7, 32])
+def test_shard_gather_chain_world2(tmp_path, n_pairs):
+    out = str(tmp_path / "gathered.npy")
+    mp.spawn(_worker, args=(2, _free_port(), n_pairs, out), nprocs=2, join=True)
+    got = np.load(out)
+    want = _fake_pose_rows(list(range(n_pairs)))
+    assert np.array_equal(got, want)                      # rank order == pair order
+    # pose chain on rank 0 == the reference recurrence with identity calibration
+    poses = pipeline.chain_poses(got)
+    R, T = np.eye(3), np.zeros((3, 1))
+    for i in range(n_pairs):
+        Rr = want[i, :9].reshape(3, 3).astype(np.float64)
+        Tr = want[i, 9:12].reshape(3, 1).astype(np.float64)
+        T = R @ Tr + T
+        R = R @ Rr
+    assert np.allclose(poses[-1].reshape(3, 4), np.c_[R, T], atol=1e-12)
+    assert poses.shape == (n_pairs + 1, 12)
+
+
+def test_shard_pairs_cover_everything():
+    for n in (1, 5, 32, 4540):
+        for world in (1, 2, 3, 8):
+            spans = [pipeline.shard_pairs(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_chain_poses_with_calibration():
+    """R_poseDiff = R_Tr R R_Tr^-1, T_poseDiff = R_Tr (R T_Tr_inv + T) + T_Tr (PoseEstimation.py:259-262)."""
+    Tr = np.array([[0, -1, 0, 0.1], [0, 0, -1, -0.2], [1, 0, 0, 0.3]], np.float64)
+    rel = _fake_pose_rows([0, 1, 2])
+    poses = pipeline.chain_poses(rel, Tr)
+    R_Tr, T_Tr = Tr[:, :3], Tr[:, 3:4]
+    R0, T0 = np.eye(3), np.zeros((3, 1))
+    for i in range(3):
+        R = rel[i, :9].reshape(3, 3).astype(np.float64)
+        T = rel[i, 9:12].reshape(3, 1).astype(np.float64)
+        Rd = R_Tr @ R @ np.linalg.inv(R_Tr)
+        Td = R_Tr @ (R @ (-np.linalg.inv(R_Tr) @ T_Tr) + T) + T_Tr
+        T0 = R0 @ Td + T0
+        R0 = R0 @ Rd
+    assert np.allclose(poses[3].reshape(3, 4), np.c_[R0, T0])
+
+
+def test_draw_samples_matches_global_stream():
+    """pipeline.draw_samples(pair_id) == what RANSAC4RT draws after np.random.seed(pair_id) (Match.py:182-184)."""
+    s = pipeline.draw_samples([3, 11], 1024)
+    for row, pid in zip(s, (3, 11)):
+        np.random.seed(pid)
+        for t in range(5):
+            idx = np.array(np.random.random((4,)) * 1024, dtype=np.int32)
+            assert np.array_equal(row[t], idx)
+    np.random.seed(11)
+    np.random.random((500 * 4,))
+    second = pipeline.draw_samples([11], 1024, rounds_done=1)[0]
+    assert np.array_equal(second[0], np.array(np.random.random((4,)) * 1024, dtype=np.int32))
