@@ -63,6 +63,10 @@ extern "C" int caelo_destroy(caelo_ctx *ctx)
     Scratch *all[] = {&ctx->cand, &ctx->bricks, &ctx->enc_ws, &ctx->pose_ws, &ctx->misc};
     for (Scratch *s : all)
         if (s->ptr) cudaFree(s->ptr);
+    for (int i = 0; i < caelo_ctx::kStageSlots; ++i) {
+        if (ctx->stage_ptr[i]) cudaFreeHost(ctx->stage_ptr[i]);
+        if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+    }
     if (ctx->enc_blob) cudaFree(ctx->enc_blob);
     if (ctx->enc_w1t_hi) cudaFree(ctx->enc_w1t_hi);
     delete ctx;

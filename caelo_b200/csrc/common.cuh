@@ -48,6 +48,12 @@ struct caelo_ctx {
     EncoderWeightsDev enc;
     float *enc_blob = nullptr;
     __half *enc_w1t_hi = nullptr, *enc_w1t_lo = nullptr;  // dense1 weights, transposed split fp16 [208][2048]
+    // ring of pinned host staging slots for small async H2D copies (caelo_stage_acquire)
+    static constexpr int kStageSlots = 8;
+    void *stage_ptr[kStageSlots] = {};
+    size_t stage_bytes[kStageSlots] = {};
+    cudaEvent_t stage_ev[kStageSlots] = {};
+    int stage_next = 0;
     // scratch regions (grown on demand, never shrunk)
     Scratch cand;      // select: candidate keys + counters
     Scratch bricks;    // patches: hash tables
@@ -91,6 +97,26 @@ static inline int caelo_reserve(caelo_ctx *ctx, Scratch &s, size_t bytes)
         }                                             \
     } while (0)
 
+
+// A pinned host slot that is safe to overwrite (its previous copy has completed); the caller fills it,
+// enqueues cudaMemcpyAsync from it and records *ev on the same stream.
+static inline int caelo_stage_acquire(caelo_ctx *ctx, size_t bytes, void **host, cudaEvent_t *ev)
+{
+    const int i = ctx->stage_next;
+    ctx->stage_next = (i + 1) % caelo_ctx::kStageSlots;
+    if (!ctx->stage_ev[i]) CAELO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+    else CAELO_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[i]));
+    if (ctx->stage_bytes[i] < bytes) {
+        if (ctx->stage_ptr[i]) CAELO_CUDA(ctx, cudaFreeHost(ctx->stage_ptr[i]));
+        ctx->stage_ptr[i] = nullptr;
+        size_t want = bytes < 4096 ? 4096 : bytes * 2;
+        CAELO_CUDA(ctx, cudaMallocHost(&ctx->stage_ptr[i], want));
+        ctx->stage_bytes[i] = want;
+    }
+    *host = ctx->stage_ptr[i];
+    *ev = ctx->stage_ev[i];
+    return CAELO_OK;
+}
 
 // Per-launch device timing (caelo_profile_enable): events on the launch stream around one kernel.
 struct ProfScope {

@@ -259,8 +259,13 @@ extern "C" int caelo_gather_patches(caelo_ctx *ctx, const void *kpts, int kpts_f
     long long *d_off = reinterpret_cast<long long *>(base + (size_t)nl * sizeof(Table));
     unsigned long long *d_keys = reinterpret_cast<unsigned long long *>(base + head);
     unsigned long long *d_masks = d_keys + total_slots;
-    // host staging (small): tables + offsets
-    Table *h_tables = new Table[nl];
+    // tables + offsets go through a ring of pinned staging slots: no stream synchronisation
+    const size_t stage_bytes = (size_t)nl * sizeof(Table) + (size_t)(nl + 1) * 8;
+    void *h_stage = nullptr;
+    cudaEvent_t ev;
+    rc = caelo_stage_acquire(ctx, stage_bytes, &h_stage, &ev);
+    if (rc) return rc;
+    Table *h_tables = reinterpret_cast<Table *>(h_stage);
     size_t cur = 0;
     for (int l = 0; l < nl; ++l) {
         long long len = vox_offsets[l + 1] - vox_offsets[l];
@@ -271,12 +276,9 @@ extern "C" int caelo_gather_patches(caelo_ctx *ctx, const void *kpts, int kpts_f
         h_tables[l].cap_mask = (unsigned)(cap - 1);
         cur += cap;
     }
-    cudaError_t e = cudaMemcpyAsync(d_tables, h_tables, (size_t)nl * sizeof(Table), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(d_off, vox_offsets, (size_t)(nl + 1) * 8, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // h_tables is pageable and freed below
-    delete[] h_tables;
-    CAELO_CUDA(ctx, e);
+    memcpy(reinterpret_cast<char *>(h_stage) + (size_t)nl * sizeof(Table), vox_offsets, (size_t)(nl + 1) * 8);
+    CAELO_CUDA(ctx, cudaMemcpyAsync(d_tables, h_stage, stage_bytes, cudaMemcpyHostToDevice, st));
+    CAELO_CUDA(ctx, cudaEventRecord(ev, st));
     CAELO_CUDA(ctx, cudaMemsetAsync(d_keys, 0xFF, total_slots * 8, st));
     CAELO_CUDA(ctx, cudaMemsetAsync(d_masks, 0, total_slots * 8, st));
 

@@ -65,17 +65,16 @@ class OdometryPipeline:
         return result, rt, mask, pair_idx
 
     # ---- whole batch ------------------------------------------------------------------------
-    def run_device(self, ring, counter, vox, vox_offsets, samples, pair_ids):
-        """Inputs already in HBM.  Returns poses [P,16] float32 (host): refit R(9) T(3), isSuccess,
-        nInliers, residualThreshold, trials — rows follow ``pair_ids``."""
-        P = ring.shape[0] - 1
-        kpts, feat, n = self.frames_to_descriptors(ring, counter, vox, vox_offsets)
+    def _finish(self, kpts, feat, n, samples, pair_ids):
+        """Pairs stage + one D2H of the per-pair results; returns poses [P,16] float32 (host): refit
+        R(9) T(3), isSuccess, nInliers, residualThreshold, trials — rows follow ``pair_ids``."""
+        P = kpts.shape[0] - 1
         thr = torch.full((P,), 0.4, dtype=torch.float32, device=self.dev)
         result, rt, mask, pair_idx = self.pairs_to_poses(kpts, feat, samples, thr)
-        res = result.cpu().numpy()                      # sync point: tiny D2H of the per-pair results
-        rt_h = rt.cpu().numpy()
-        n_h = n.cpu().numpy()
-        if (n_h != self.K).any():
+        packed = torch.cat([result, rt, n.to(torch.float32)[:-1, None], n.to(torch.float32)[1:, None]], 1)
+        host = packed.cpu().numpy()                     # the one sync point of the batch
+        res, rt_h = host[:, :16], host[:, 16:28]
+        if (host[:, 28] != self.K).any() or (host[:, 29] != self.K).any():
             raise api._lib.CaeloError("a frame yielded fewer than %d keypoints; use the per-pair API" % self.K)
         poses = np.zeros((P, 16), np.float32)
         poses[:, :12] = rt_h
@@ -87,6 +86,46 @@ class OdometryPipeline:
         if failed.size:
             self._ladder(failed, kpts, pair_idx, pair_ids, poses)
         return poses
+
+    def run_device(self, ring, counter, vox, vox_offsets, samples, pair_ids):
+        """Inputs already in HBM."""
+        kpts, feat, n = self.frames_to_descriptors(ring, counter, vox, vox_offsets)
+        return self._finish(kpts, feat, n, samples, pair_ids)
+
+    def run_host(self, ring_h: torch.Tensor, counter_h: torch.Tensor, vox_h: torch.Tensor,
+                 vox_offsets: np.ndarray, pair_ids: Sequence[int], chunks: int = 4):
+        """End-to-end call with HOST (pinned) buffers.  Frames are uploaded in ``chunks`` groups on a copy
+        stream while the compute stream already works on the groups that have landed; the RANSAC sample
+        indices are drawn on the host while the GPU is busy with the frame stages."""
+        F = ring_h.shape[0]
+        voff = np.asarray(vox_offsets, np.int64)
+        cur = torch.cuda.current_stream(self.dev)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(self.dev)
+        cs = self._copy_stream
+        cs.wait_stream(cur)
+        bounds = np.linspace(0, F, min(chunks, F) + 1).astype(int)
+        parts, events = [], []
+        for c0, c1 in zip(bounds[:-1], bounds[1:]):
+            with torch.cuda.stream(cs):
+                r = ring_h[c0:c1].to(self.dev, non_blocking=True)
+                c = counter_h[c0:c1].to(self.dev, non_blocking=True)
+                v = vox_h[voff[3 * c0]:voff[3 * c1]].to(self.dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            parts.append((r, c, v, voff[3 * c0:3 * c1 + 1] - voff[3 * c0]))
+            events.append(ev)
+        outs = []
+        for (r, c, v, o), ev in zip(parts, events):
+            cur.wait_event(ev)
+            for t in (r, c, v):
+                t.record_stream(cur)
+            outs.append(self.frames_to_descriptors(r, c, v, o))
+        smp = torch.from_numpy(draw_samples(pair_ids, self.K)).pin_memory().to(self.dev, non_blocking=True)
+        kpts = torch.cat([o[0] for o in outs], 0)
+        feat = torch.cat([o[1] for o in outs], 0)
+        n = torch.cat([o[2] for o in outs], 0)
+        return self._finish(kpts, feat, n, smp, pair_ids)
 
     def _ladder(self, failed, kpts, pair_idx, pair_ids, poses):
         """Threshold ladder 0.8, 1.6 for the pairs whose first round found no model (Match.py:207-214)."""
@@ -117,16 +156,6 @@ class OdometryPipeline:
                 else:
                     still.append(p)
             failed = np.asarray(still, np.int64)
-
-    def run_host(self, ring_h: torch.Tensor, counter_h: torch.Tensor, vox_h: torch.Tensor,
-                 vox_offsets: np.ndarray, pair_ids: Sequence[int]):
-        """End-to-end call with HOST (pinned) buffers: H2D of the inputs, RANSAC sample drawing,
-        all kernels, D2H of the poses."""
-        ring = ring_h.to(self.dev, non_blocking=True)
-        counter = counter_h.to(self.dev, non_blocking=True)
-        vox = vox_h.to(self.dev, non_blocking=True)
-        smp = torch.from_numpy(draw_samples(pair_ids, self.K)).to(self.dev, non_blocking=True)
-        return self.run_device(ring, counter, vox, vox_offsets, smp, pair_ids)
 
 
 def gather_poses(poses: np.ndarray, device: torch.device):
