@@ -240,7 +240,7 @@ def run_ours(args, rank, local_rank, world):
                 vox=torch.from_numpy(data["vox"]).pin_memory())
     voff = data["vox_offsets"]
     d_ring, d_counter, d_vox = (host[k].to(dev) for k in ("ring", "counter", "vox"))
-    samples_h = pipeline.draw_samples(pair_ids, K_PTS)
+    samples_h = pipeline.draw_samples(pair_ids, K_PTS, rounds=3)   # all three ladder rounds, pre-drawn
     d_samples = torch.from_numpy(samples_h).to(dev)
     flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)
 

@@ -41,11 +41,11 @@ SIGNATURES = {
     "caelo_encode_frames": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "caelo_nn_match": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "caelo_ransac_round": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
-                                   c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "caelo_debug_set_timeline": (c_int, [c_void_p, c_void_p]),
     "caelo_debug_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_void_p, c_void_p]),
-    "caelo_kabsch": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+    "caelo_kabsch": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                              c_void_p, c_void_p, c_void_p]),
 }
 

@@ -198,26 +198,28 @@ class Context:
                    "caelo_nn_match")
         return idx
 
-    def ransac_round(self, pc0, pc1, pair_idx, sample_idx, thr, best_n_in=None, want_counts=False):
+    def ransac_round(self, pc0, pc1, pair_idx, sample_idx, thr, best_n_in=None, want_counts=False, skip_if_ok=None,
+                     out_result=None):
         P, N0, _ = pc0.shape
         N = pc1.shape[1]
         T = sample_idx.shape[1]
-        result = torch.empty((P, 16), dtype=torch.float32, device=self.device)
+        assert sample_idx.is_contiguous() and sample_idx.dtype == torch.int32
+        result = out_result if out_result is not None else torch.empty((P, 16), dtype=torch.float32, device=self.device)
         mask = torch.empty((P, N), dtype=torch.uint8, device=self.device)
         counts = torch.empty((P, T), dtype=torch.int32, device=self.device) if want_counts else None
         rc = self.lib.caelo_ransac_round(self.h, _ptr(pc0), N0, _ptr(pc1), N, _ptr(pair_idx), _ptr(sample_idx),
-                                         T, _ptr(thr), _ptr(best_n_in), P, _ptr(result), _ptr(mask),
+                                         T, _ptr(thr), _ptr(best_n_in), _ptr(skip_if_ok), P, _ptr(result), _ptr(mask),
                                          _ptr(counts), _stream())
         self.check(rc, "caelo_ransac_round")
         return result, mask, counts
 
-    def kabsch(self, pc0, pc1, pair_idx=None, mask=None):
+    def kabsch(self, pc0, pc1, pair_idx=None, mask=None, skip_if_ok=None, out_rt=None):
         P, N0, _ = pc0.shape
         N = pc1.shape[1]
-        rt = torch.empty((P, 12), dtype=torch.float32, device=self.device)
+        rt = out_rt if out_rt is not None else torch.empty((P, 12), dtype=torch.float32, device=self.device)
         cred = torch.empty((P,), dtype=torch.int32, device=self.device)
-        self.check(self.lib.caelo_kabsch(self.h, _ptr(pc0), N0, _ptr(pc1), N, _ptr(pair_idx), _ptr(mask), P,
-                                         _ptr(rt), _ptr(cred), _stream()), "caelo_kabsch")
+        self.check(self.lib.caelo_kabsch(self.h, _ptr(pc0), N0, _ptr(pc1), N, _ptr(pair_idx), _ptr(mask),
+                                         _ptr(skip_if_ok), P, _ptr(rt), _ptr(cred), _stream()), "caelo_kabsch")
         return rt, cred
 
 

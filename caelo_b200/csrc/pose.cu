@@ -189,6 +189,7 @@ struct PoseArgs {
     const int *sample_idx;        // [P,T,4]
     const float *thr;             // [P]
     const int *best_n_in;         // [P] or null
+    const float *skip_if_ok;      // [P,16] or null: pairs with [12] != 0 there are skipped
     int N0, N, T, P;
     int *counts;                  // [P,T]
     float *rt_hyp;                // [P,T,12]
@@ -213,6 +214,7 @@ __global__ void __launch_bounds__(HS_WARPS * 32) hyp_score_kernel(const PoseArgs
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * HS_WARPS + warp;
     if (t >= a.T) return;
+    if (a.skip_if_ok && a.skip_if_ok[(size_t)pair * 16 + 12] != 0.0f) return;
     // Kabsch of the 4 samples: sample i sits in lane i of the K1 reduction
     double s0[3] = {0, 0, 0}, s1[3] = {0, 0, 0};
     float q0[3] = {0, 0, 0}, q1[3] = {0, 0, 0};
@@ -256,6 +258,7 @@ __global__ void __launch_bounds__(256) replay_mask_kernel(const PoseArgs a)
     __shared__ int s_bt, s_bn, s_ok, s_it;
     __shared__ float s_rt[12];
     const int pair = blockIdx.x;
+    if (a.skip_if_ok && a.skip_if_ok[(size_t)pair * 16 + 12] != 0.0f) return;
     if (threadIdx.x == 0) {
         // RANSAC4RT's loop (Match.py:181-206) over the pre-scored trials
         const int N = a.N;
@@ -305,6 +308,7 @@ struct KabschArgs {
     const float *pc0, *pc1;
     const long long *pair_idx;
     const unsigned char *mask;
+    const float *skip_if_ok;  // [P,16] or null
     int N0, N, P;
     float *rt;      // [P,12]
     int *credible;  // [P]
@@ -315,6 +319,7 @@ __global__ void __launch_bounds__(128) kabsch_kernel(const KabschArgs a)
     const int lane = threadIdx.x & 31;
     const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (pair >= a.P) return;
+    if (a.skip_if_ok && a.skip_if_ok[(size_t)pair * 16 + 12] != 0.0f) return;
     double s[6] = {0, 0, 0, 0, 0, 0};
     int cnt = 0;
     auto fetch = [&](int i, float p0[3], float p1[3]) {
@@ -366,8 +371,8 @@ __global__ void __launch_bounds__(128) kabsch_kernel(const KabschArgs a)
 
 extern "C" int caelo_ransac_round(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int N,
                                   const int64_t *pair_idx, const int32_t *sample_idx, int T,
-                                  const float *thr, const int32_t *best_n_in, int P, float *result,
-                                  uint8_t *inlier_mask, int32_t *counts, void *stream)
+                                  const float *thr, const int32_t *best_n_in, const float *skip_if_ok, int P,
+                                  float *result, uint8_t *inlier_mask, int32_t *counts, void *stream)
 {
     if (!ctx || !pc0 || !pc1 || !sample_idx || !thr || !result || !inlier_mask) return CAELO_ERR_ARG;
     if (P <= 0 || N <= 0 || N0 <= 0 || T <= 0 || T > CAELO_MAX_TRIALS) return CAELO_ERR_ARG;
@@ -378,7 +383,7 @@ extern "C" int caelo_ransac_round(caelo_ctx *ctx, const float *pc0, int N0, cons
     if (rc) return rc;
     PoseArgs a;
     a.pc0 = pc0; a.pc1 = pc1; a.pair_idx = reinterpret_cast<const long long *>(pair_idx);
-    a.sample_idx = sample_idx; a.thr = thr; a.best_n_in = best_n_in;
+    a.sample_idx = sample_idx; a.thr = thr; a.best_n_in = best_n_in; a.skip_if_ok = skip_if_ok;
     a.N0 = N0; a.N = N; a.T = T; a.P = P;
     a.rt_hyp = reinterpret_cast<float *>(ctx->pose_ws.ptr);
     a.counts = counts ? counts : reinterpret_cast<int *>(a.rt_hyp + (size_t)P * T * 12);
@@ -392,14 +397,14 @@ extern "C" int caelo_ransac_round(caelo_ctx *ctx, const float *pc0, int N0, cons
 }
 
 extern "C" int caelo_kabsch(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int N,
-                            const int64_t *pair_idx, const uint8_t *mask, int P, float *Rt,
-                            int32_t *credible, void *stream)
+                            const int64_t *pair_idx, const uint8_t *mask, const float *skip_if_ok, int P,
+                            float *Rt, int32_t *credible, void *stream)
 {
     if (!ctx || !pc0 || !pc1 || !Rt || !credible || P <= 0 || N <= 0 || N0 <= 0) return CAELO_ERR_ARG;
     if (!pair_idx && N0 != N) return CAELO_ERR_ARG;
     KabschArgs a;
     a.pc0 = pc0; a.pc1 = pc1; a.pair_idx = reinterpret_cast<const long long *>(pair_idx);
-    a.mask = mask; a.N0 = N0; a.N = N; a.P = P; a.rt = Rt; a.credible = credible;
+    a.mask = mask; a.skip_if_ok = skip_if_ok; a.N0 = N0; a.N = N; a.P = P; a.rt = Rt; a.credible = credible;
     int blocks = (P * 32 + 127) / 128;
     { ProfScope ps_(ctx, "kabsch_kernel", (cudaStream_t)stream); kabsch_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a); }
     CAELO_LAUNCH_CHECK(ctx);

@@ -27,16 +27,21 @@ def shard_pairs(n_pairs: int, rank: int, world: int):
     return lo, hi
 
 
-def draw_samples(pair_ids: Sequence[int], n_points: int, rounds_done: int = 0) -> np.ndarray:
-    """Round ``rounds_done`` sample indices [P,500,4] int32, drawn exactly as RANSAC4RT does
-    after ``np.random.seed(pair_id)`` (Match.py:182-184: 4 doubles per trial, int32(u*N))."""
-    out = np.empty((len(pair_ids), MAX_TRIALS, 4), np.int32)
+LADDER = (0.4, 0.8, 1.6)   # residualThreshold of the three RANSAC4RT rounds (Match.py:170,209-211)
+
+
+def draw_samples(pair_ids: Sequence[int], n_points: int, rounds_done: int = 0, rounds: int = 1) -> np.ndarray:
+    """Sample indices of RANSAC round ``rounds_done`` ([P,500,4] int32), or of ``rounds`` consecutive
+    rounds ([rounds,P,500,4]), drawn exactly as RANSAC4RT does after ``np.random.seed(pair_id)``
+    (Match.py:182-184: 4 doubles per trial, int32(u*N); a failed round consumes all 500 trials)."""
+    out = np.empty((rounds, len(pair_ids), MAX_TRIALS, 4), np.int32)
     for i, pid in enumerate(pair_ids):
         rs = np.random.RandomState(int(pid))
         if rounds_done:
             rs.random_sample((rounds_done * MAX_TRIALS * 4,))
-        out[i] = np.array(rs.random_sample((MAX_TRIALS, 4)) * n_points, dtype=np.int32)
-    return out
+        u = rs.random_sample((rounds, MAX_TRIALS, 4))
+        out[:, i] = np.array(u * n_points, dtype=np.int32)
+    return out[0] if rounds == 1 else out
 
 
 class OdometryPipeline:
@@ -55,36 +60,47 @@ class OdometryPipeline:
         feat = self.ctx.encode_frames(packed)
         return kpts, feat, n
 
-    def pairs_to_poses(self, kpts: torch.Tensor, feat: torch.Tensor, samples: torch.Tensor,
-                       thr: torch.Tensor):
-        """Consecutive pairs (f, f+1): returns result [P,16], refit Rt [P,12], mask, pair_idx."""
-        pc0, pc1 = kpts[:-1], kpts[1:]
-        pair_idx = self.ctx.nn_match(feat[:-1], feat[1:])
-        result, mask, _ = self.ctx.ransac_round(pc0, pc1, pair_idx, samples, thr)
-        rt, _cred = self.ctx.kabsch(pc0, pc1, pair_idx, mask)
-        return result, rt, mask, pair_idx
-
     # ---- whole batch ------------------------------------------------------------------------
     def _finish(self, kpts, feat, n, samples, pair_ids):
         """Pairs stage + one D2H of the per-pair results; returns poses [P,16] float32 (host): refit
-        R(9) T(3), isSuccess, nInliers, residualThreshold, trials — rows follow ``pair_ids``."""
+        R(9) T(3), isSuccess, nInliers, residualThreshold, trials — rows follow ``pair_ids``.
+        ``samples`` is [P,500,4] (first round; failures go through a host-driven ladder) or
+        [3,P,500,4]: then the 0.8 and 1.6 rounds are queued on the device right away and skip every
+        pair that already has a model (no host round trip)."""
         P = kpts.shape[0] - 1
-        thr = torch.full((P,), 0.4, dtype=torch.float32, device=self.dev)
-        result, rt, mask, pair_idx = self.pairs_to_poses(kpts, feat, samples, thr)
-        packed = torch.cat([result, rt, n.to(torch.float32)[:-1, None], n.to(torch.float32)[1:, None]], 1)
+        pc0, pc1 = kpts[:-1], kpts[1:]
+        pair_idx = self.ctx.nn_match(feat[:-1], feat[1:])
+        rounds = samples if samples.dim() == 4 else samples[None]
+        state = rt = None
+        thr_used = torch.full((P,), LADDER[-1], dtype=torch.float32, device=self.dev)
+        for r in range(rounds.shape[0]):
+            thr = torch.full((P,), LADDER[r], dtype=torch.float32, device=self.dev)
+            prev = state
+            res, mask, _ = self.ctx.ransac_round(pc0, pc1, pair_idx, rounds[r], thr, skip_if_ok=prev,
+                                                 out_result=None if prev is None else prev.clone())
+            rt_r, _ = self.ctx.kabsch(pc0, pc1, pair_idx, mask, skip_if_ok=prev,
+                                      out_rt=None if rt is None else rt.clone())
+            newly = (res[:, 12] != 0) if prev is None else ((res[:, 12] != 0) & (prev[:, 12] == 0))
+            thr_used = torch.where(newly, thr, thr_used)
+            state, rt = res, rt_r
+        nf = n.to(torch.float32)
+        packed = torch.cat([state, rt, thr_used[:, None], nf[:-1, None], nf[1:, None]], 1)
         host = packed.cpu().numpy()                     # the one sync point of the batch
         res, rt_h = host[:, :16], host[:, 16:28]
-        if (host[:, 28] != self.K).any() or (host[:, 29] != self.K).any():
+        if (host[:, 29] != self.K).any() or (host[:, 30] != self.K).any():
             raise api._lib.CaeloError("a frame yielded fewer than %d keypoints; use the per-pair API" % self.K)
         poses = np.zeros((P, 16), np.float32)
         poses[:, :12] = rt_h
         poses[:, 12] = res[:, 12]
         poses[:, 13] = res[:, 14]
-        poses[:, 14] = 0.4
+        poses[:, 14] = host[:, 28]
         poses[:, 15] = res[:, 13]
         failed = np.flatnonzero(res[:, 12] == 0)
-        if failed.size:
-            self._ladder(failed, kpts, pair_idx, pair_ids, poses)
+        if failed.size and rounds.shape[0] < len(LADDER):
+            self._ladder(failed, kpts, pair_idx, pair_ids, poses, rounds.shape[0])
+        elif failed.size:                               # total failure: R=I, T=0 (Match.py:277-278)
+            poses[failed, :12] = [1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]
+            poses[failed, 13] = 0
         return poses
 
     def run_device(self, ring, counter, vox, vox_offsets, samples, pair_ids):
@@ -121,16 +137,16 @@ class OdometryPipeline:
             for t in (r, c, v):
                 t.record_stream(cur)
             outs.append(self.frames_to_descriptors(r, c, v, o))
-        smp = torch.from_numpy(draw_samples(pair_ids, self.K)).pin_memory().to(self.dev, non_blocking=True)
+        smp = torch.from_numpy(draw_samples(pair_ids, self.K, rounds=3)).pin_memory().to(self.dev, non_blocking=True)
         kpts = torch.cat([o[0] for o in outs], 0)
         feat = torch.cat([o[1] for o in outs], 0)
         n = torch.cat([o[2] for o in outs], 0)
         return self._finish(kpts, feat, n, smp, pair_ids)
 
-    def _ladder(self, failed, kpts, pair_idx, pair_ids, poses):
-        """Threshold ladder 0.8, 1.6 for the pairs whose first round found no model (Match.py:207-214)."""
-        thr_val = 0.4
-        rounds = 0
+    def _ladder(self, failed, kpts, pair_idx, pair_ids, poses, rounds_done=1):
+        """Host-driven threshold ladder for the pairs that still have no model (Match.py:207-214)."""
+        thr_val = LADDER[rounds_done - 1]
+        rounds = rounds_done - 1
         while failed.size:
             thr_val *= 2
             rounds += 1

@@ -130,21 +130,24 @@ int caelo_nn_match(caelo_ctx *ctx, const float *codes0, const float *codes1, int
  * pc0 dev [P,N0,3], pc1 dev [P,N,3], pair_idx dev [P,N] int64 (Pairs0 = pc0[pair_idx]) or
  * NULL (then N0 == N and Pairs0 = pc0); sample_idx dev [P,T,4] int32 drawn by the caller
  * from np.random exactly as Match.py:182-184 does; thr dev [P] f32; best_n_in dev [P]
- * int32 (curNumInliers carried across ladder rounds) or NULL (= 0).
+ * int32 (curNumInliers carried across ladder rounds) or NULL (= 0); skip_if_ok dev [P,16] f32 or
+ * NULL: pairs whose row there has isSuccess != 0 are skipped and their outputs left untouched (lets
+ * the 0.8 / 1.6 ladder rounds be queued without a host round trip).
  * Outputs (dev): result [P,16] f32 = R(9) T(3) isSuccess trials nInliers bestTrial — R,T of
  * the accepted hypothesis (identity/0 if none); inlier_mask [P,N] uint8 of that hypothesis;
  * counts [P,T] int32 per-hypothesis inlier counts or NULL. */
 int caelo_ransac_round(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int N,
                        const int64_t *pair_idx, const int32_t *sample_idx, int T, const float *thr,
-                       const int32_t *best_n_in, int P, float *result, uint8_t *inlier_mask,
-                       int32_t *counts, void *stream);
+                       const int32_t *best_n_in, const float *skip_if_ok, int P, float *result,
+                       uint8_t *inlier_mask, int32_t *counts, void *stream);
 
 /* a5 — SolveRT (Match.py:138-158) for P independent problems: p0 = pc0[pair_idx] (or pc0),
  * p1 = pc1, restricted to mask != 0 (mask dev [P,N] or NULL = all).  Rt dev [P,12] (R row-major
- * then T), credible dev [P] int32 (+1, -1 = reflection quirk applied, 0 = no points). */
+ * then T), credible dev [P] int32 (+1, -1 = reflection quirk applied, 0 = no points).
+ * skip_if_ok as in caelo_ransac_round. */
 int caelo_kabsch(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int N,
-                 const int64_t *pair_idx, const uint8_t *mask, int P, float *Rt, int32_t *credible,
-                 void *stream);
+                 const int64_t *pair_idx, const uint8_t *mask, const float *skip_if_ok, int P,
+                 float *Rt, int32_t *credible, void *stream);
 
 /* Debug: device buffer [grid][64][8] int64 receiving clock64 stamps of the encoder's per-patch
  * phases (NULL disables).  Used by tools/encoder_timeline.py. */

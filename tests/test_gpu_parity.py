@@ -314,7 +314,7 @@ def test_pipeline_batch_matches_oracle(api, oracle_mod):
     cnt_h = torch.from_numpy(d["counter"]).pin_memory()
     vox_h = torch.from_numpy(d["vox"]).pin_memory()
     poses_host = pipe.run_host(ring_h, cnt_h, vox_h, d["vox_offsets"], pair_ids, chunks=3)
-    smp = torch.from_numpy(pipeline.draw_samples(pair_ids, 1024)).cuda()
+    smp = torch.from_numpy(pipeline.draw_samples(pair_ids, 1024, rounds=3)).cuda()
     poses_dev = pipe.run_device(ring_h.cuda(), cnt_h.cuda(), vox_h.cuda(), d["vox_offsets"], smp, pair_ids)
     assert np.array_equal(poses_host, poses_dev)
     # oracle
