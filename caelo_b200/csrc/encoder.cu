@@ -20,6 +20,8 @@
 //                      One warp issues MMAs; eight warps produce operands / drain accumulators.
 //   conv3_kernel       fp32 CUDA cores (weights in smem) -> act3 [P,2048]
 //   dense_kernel       64-patch tiles: dense1 (register-tiled SGEMM) + tanh + dense2 + tanh
+#include <cuda.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -475,54 +477,53 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const Conv3Args
 // ---- dense1 (tcgen05) + tanh + dense2 + tanh ---------------------------------------------------
 // One CTA = 128 patches (M) x 208 outputs (N = 200 padded) x K = 2048, split-fp16 operands:
 //   D0 += A_hi W_hi^T + A_lo W_hi^T,  D1 += A_hi W_lo^T   (fp32 in TMEM), h = tanh(D0 + D1 + b).
-// Operands stream L2 -> smem with cp.async into the canonical K-major layout (two 64-wide K stages),
-// four loader/epilogue warps + one MMA-issuer warp, mbarrier full/empty pipeline.
+// Operands stream L2 -> smem by TMA (cp.async.bulk.tensor.3d): each row-major [rows][2048] fp16 matrix is
+// described as a 3-D tensor (8 elements, rows, 256 16-byte chunks) so that a box {8, R, 4} lands in shared
+// memory as [chunk][row][16 B] — exactly the canonical K-major no-swizzle UMMA layout (SBO = 128 B,
+// LBO = R*16 B).  Four-stage mbarrier pipeline: 1 TMA-producer thread, 1 MMA-issuer thread, 4 epilogue warps.
 constexpr int DN = 208;                       // dense1 outputs padded to a multiple of 16
-constexpr int DK_STAGE = 64;                  // K elements per stage (8 chunks of 16 B)
-constexpr int D_A_BYTES = 128 * DK_STAGE * 2; // 16384
-constexpr int D_W_BYTES = DN * DK_STAGE * 2;  // 26624
-constexpr int D_STAGE = 2 * D_A_BYTES + 2 * D_W_BYTES;  // 86016
-constexpr int D_SM_BAR = 2 * D_STAGE;
-constexpr int D_SMEM = D_SM_BAR + 64;
-constexpr int D_THREADS = 160;
+constexpr int DK_STAGE = 32;                  // K elements per stage (4 chunks of 16 B)
+constexpr int D_STAGES = 4;
+constexpr int D_A_BYTES = 128 * DK_STAGE * 2; // 8192
+constexpr int D_W_BYTES = DN * DK_STAGE * 2;  // 13312
+constexpr int D_STAGE = 2 * D_A_BYTES + 2 * D_W_BYTES;  // 43008
+constexpr int D_SM_BAR = D_STAGES * D_STAGE;  // 172032
+constexpr int D_SMEM = D_SM_BAR + 128;
+constexpr int D_THREADS = 192;
 
 struct DenseArgs {
-    const __half *a_hi, *a_lo;    // [Ppad,2048]
-    const __half *w_hi, *w_lo;    // [208,2048] (dense1 weights transposed, split)
     const float *bd1, *d2, *bd2;  // (200), (200,20), (20)
     float *feat;
     int P, feat_stride, feat_col0;
     // frame mode: packed order is [F,3,K]; row p -> feat[(f*K+k)*60 + s*20]
     int frame_mode, K;
+    long long *timeline;  // debug: [grid][8] clock64 stamps or null
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g)
+__device__ __forceinline__ void tma_load_3d(uint32_t sdst, const CUtensorMap *map, uint32_t mbar, int c0, int c1, int c2)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(sdst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
 }
 
-// rows x 8 chunks of one operand tile: smem [r/8][kc][r%8][16 B]; a warp instruction covers 8 rows x 4 chunks
-__device__ __forceinline__ void load_tile(uint32_t sbase, const __half *g, int rows, int ltid)
-{
-    const int r_l = ltid & 7, kc_l = (ltid >> 3) & 3, wq = ltid >> 5;  // 4 loader warps
-    for (int it = wq; it < (rows / 8) * 2; it += 4) {
-        const int grp = it >> 1, kc = (it & 1) * 4 + kc_l;
-        cp_async16(sbase + grp * 1024 + kc * 128 + r_l * 16, g + (size_t)(grp * 8 + r_l) * 2048 + kc * 8);
-    }
-}
-
-__global__ void __launch_bounds__(D_THREADS, 1) dense_tc_kernel(const DenseArgs a)
+__global__ void __launch_bounds__(D_THREADS, 1)
+dense_tc_kernel(const DenseArgs a, const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl)
 {
     extern __shared__ __align__(128) unsigned char dsm[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(dsm + D_SM_BAR), *empty = full + 2, *accum = full + 4;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(dsm + D_SM_BAR + 48);
-    const int tid = threadIdx.x, lane = tid & 31;
+    uint64_t *full = reinterpret_cast<uint64_t *>(dsm + D_SM_BAR), *empty = full + D_STAGES, *accum = full + 2 * D_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(dsm + D_SM_BAR + 96);
+    const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int row0 = blockIdx.x * 128;
+    auto stamp = [&](int slot) { if (a.timeline) a.timeline[(size_t)blockIdx.x * 8 + slot] = clock64(); };
+    if (tid == 0) stamp(0);
     if (warp == 4) umma::tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
-            umma::mbar_init(&full[s], 128);
+        for (int s = 0; s < D_STAGES; ++s) {
+            umma::mbar_init(&full[s], 1);
             umma::mbar_init(&empty[s], 1);
         }
         umma::mbar_init(accum, 1);
@@ -535,21 +536,37 @@ __global__ void __launch_bounds__(D_THREADS, 1) dense_tc_kernel(const DenseArgs 
     const uint32_t sbase = umma::smem_u32(dsm);
     constexpr int NKT = 2048 / DK_STAGE;
 
-    if (warp == 4) {
+    if (warp == 5) {
+        // ===== TMA producer =====
+        if (umma::elect_one()) {
+            for (int kt = 0; kt < NKT; ++kt) {
+                const int s = kt % D_STAGES;
+                if (kt >= D_STAGES) umma::mbar_wait(&empty[s], (uint32_t)(((kt / D_STAGES) - 1) & 1));
+                const uint32_t st = sbase + s * D_STAGE, mb = umma::smem_u32(&full[s]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(D_STAGE) : "memory");
+                const int kc = kt * (DK_STAGE / 8);
+                tma_load_3d(st, &map_ah, mb, 0, row0, kc);
+                tma_load_3d(st + D_A_BYTES, &map_al, mb, 0, row0, kc);
+                tma_load_3d(st + 2 * D_A_BYTES, &map_wh, mb, 0, 0, kc);
+                tma_load_3d(st + 2 * D_A_BYTES + D_W_BYTES, &map_wl, mb, 0, 0, kc);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 4) {
         // ===== MMA issuer =====
         const uint32_t idesc = umma::idesc_f16_f32(128, DN);
         for (int kt = 0; kt < NKT; ++kt) {
-            const int s = kt & 1;
-            umma::mbar_wait(&full[s], (uint32_t)((kt >> 1) & 1));
+            const int s = kt % D_STAGES;
+            umma::mbar_wait(&full[s], (uint32_t)((kt / D_STAGES) & 1));
             umma::fence_after_thread_sync();
             if (umma::elect_one()) {
                 const uint32_t st = sbase + s * D_STAGE;
 #pragma unroll
-                for (int j = 0; j < DK_STAGE / 16; ++j) {
-                    uint64_t ah = umma::smem_desc(st + j * 256, 128, 1024);
-                    uint64_t al = umma::smem_desc(st + D_A_BYTES + j * 256, 128, 1024);
-                    uint64_t wh = umma::smem_desc(st + 2 * D_A_BYTES + j * 256, 128, 1024);
-                    uint64_t wl = umma::smem_desc(st + 2 * D_A_BYTES + D_W_BYTES + j * 256, 128, 1024);
+                for (int j = 0; j < DK_STAGE / 16; ++j) {  // chunk stride = rows * 16 B
+                    uint64_t ah = umma::smem_desc(st + j * 2 * 2048, 2048, 128);
+                    uint64_t al = umma::smem_desc(st + D_A_BYTES + j * 2 * 2048, 2048, 128);
+                    uint64_t wh = umma::smem_desc(st + 2 * D_A_BYTES + j * 2 * (DN * 16), DN * 16, 128);
+                    uint64_t wl = umma::smem_desc(st + 2 * D_A_BYTES + D_W_BYTES + j * 2 * (DN * 16), DN * 16, 128);
                     const uint32_t acc = (kt | j) ? 1u : 0u;
                     umma::mma_f16(tbase, ah, wh, idesc, acc);
                     umma::mma_f16(tbase, al, wh, idesc, 1u);
@@ -561,35 +578,17 @@ __global__ void __launch_bounds__(D_THREADS, 1) dense_tc_kernel(const DenseArgs 
             __syncwarp();
         }
     } else {
-        // ===== loaders (then epilogue) =====
-        const __half *ah = a.a_hi + (size_t)row0 * 2048, *al = a.a_lo + (size_t)row0 * 2048;
-        for (int kt = 0; kt < NKT; ++kt) {
-            const int s = kt & 1;
-            if (kt >= 2) umma::mbar_wait(&empty[s], (uint32_t)(((kt >> 1) - 1) & 1));
-            const uint32_t st = sbase + s * D_STAGE;
-            const int k0 = kt * DK_STAGE;
-            load_tile(st, ah + k0, 128, tid);
-            load_tile(st + D_A_BYTES, al + k0, 128, tid);
-            load_tile(st + 2 * D_A_BYTES, a.w_hi + k0, DN, tid);
-            load_tile(st + 2 * D_A_BYTES + D_W_BYTES, a.w_lo + k0, DN, tid);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            if (kt >= 1) {
-                asm volatile("cp.async.wait_group 1;" ::: "memory");  // stage kt-1 has landed
-                umma::fence_proxy_async();
-                umma::mbar_arrive(&full[(kt - 1) & 1]);
-            }
-        }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        umma::fence_proxy_async();
-        umma::mbar_arrive(&full[(NKT - 1) & 1]);
-
         // ===== epilogue: h = tanh(D0 + D1 + b) -> smem (aliases the operand stages), dense2 + tanh =====
-        umma::mbar_wait(accum, 0);
-        umma::fence_after_thread_sync();
         float *Hs = reinterpret_cast<float *>(dsm);              // [128][201]
-        float *W2s = Hs + 128 * 201;                             // [200][20] + bd2[20]
+        float *W2s = Hs + 128 * 201;                             // [200][20] + bd2[20] + bd1[200]
+        if (tid == 0) stamp(2);
+        umma::mbar_wait(accum, 0);                               // all MMAs done: the stages are free
+        umma::fence_after_thread_sync();
+        if (tid == 0) stamp(3);
         for (int i = tid; i < 200 * 20; i += 128) W2s[i] = a.d2[i];
         if (tid < 20) W2s[4000 + tid] = a.bd2[tid];
+        for (int i = tid; i < 200; i += 128) W2s[4032 + i] = a.bd1[i];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
         for (int c0 = 0; c0 < DN; c0 += 16) {
@@ -600,15 +599,16 @@ __global__ void __launch_bounds__(D_THREADS, 1) dense_tc_kernel(const DenseArgs 
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 int c = c0 + j;
-                if (c < 200) Hs[tid * 201 + c] = tanhf((__uint_as_float(v0[j]) + __uint_as_float(v1[j])) + __ldg(a.bd1 + c));
+                if (c < 200) Hs[tid * 201 + c] = fast_tanh((__uint_as_float(v0[j]) + __uint_as_float(v1[j])) + W2s[4032 + c]);
             }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 0) stamp(4);
         const int p = row0 + tid;
         if (p < a.P) {
             float acc[20];
 #pragma unroll
             for (int j = 0; j < 20; ++j) acc[j] = W2s[4000 + j];
+#pragma unroll 4
             for (int k = 0; k < 200; ++k) {
                 const float h = Hs[tid * 201 + k];
                 const float4 *w = reinterpret_cast<const float4 *>(W2s + k * 20);
@@ -631,11 +631,40 @@ __global__ void __launch_bounds__(D_THREADS, 1) dense_tc_kernel(const DenseArgs 
 #pragma unroll
             for (int j = 0; j < 20; ++j) o[j] = tanhf(acc[j]);
         }
+        if (tid == 0) stamp(5);
         umma::fence_before_thread_sync();
     }
     __syncthreads();
     umma::fence_after_thread_sync();
     if (warp == 4) umma::tmem_dealloc(tbase, 512);
+}
+
+// [rows][2048] fp16 row-major matrix as the 3-D tensor (8 elems, rows, 256 chunks of 16 B); box {8, box_rows, 4}
+int make_kmajor_map(caelo_ctx *ctx, CUtensorMap *map, const __half *base, uint64_t rows, uint32_t box_rows)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CAELO_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return CAELO_ERR_UNSUPPORTED;
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t dims[3] = {8, rows, 256};
+    const cuuint64_t strides[2] = {4096, 16};  // bytes: rows, chunks
+    const cuuint32_t box[3] = {8, box_rows, DK_STAGE / 8};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half *>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ctx->last_err = cudaErrorInvalidValue;
+        return CAELO_ERR_CUDA;
+    }
+    return CAELO_OK;
 }
 
 // dense1 weights (2048,200) f32 -> transposed split fp16 [208][2048] (rows 200..207 zero)
@@ -690,12 +719,16 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
     int grid3 = ctx->num_sms < P ? ctx->num_sms : P;
     { ProfScope ps_(ctx, "conv3_tc_kernel", st); conv3_tc_kernel<<<grid3, C3_THREADS, C3_SMEM, st>>>(c3); }
     CAELO_LAUNCH_CHECK(ctx);
+    CUtensorMap m_ah, m_al, m_wh, m_wl;
+    if ((rc = make_kmajor_map(ctx, &m_ah, act3_hi, Ppad, 128))) return rc;
+    if ((rc = make_kmajor_map(ctx, &m_al, act3_lo, Ppad, 128))) return rc;
+    if ((rc = make_kmajor_map(ctx, &m_wh, ctx->enc_w1t_hi, DN, DN))) return rc;
+    if ((rc = make_kmajor_map(ctx, &m_wl, ctx->enc_w1t_lo, DN, DN))) return rc;
     DenseArgs d;
-    d.a_hi = act3_hi; d.a_lo = act3_lo; d.w_hi = ctx->enc_w1t_hi; d.w_lo = ctx->enc_w1t_lo;
     d.bd1 = ctx->enc.bd1; d.d2 = ctx->enc.d2; d.bd2 = ctx->enc.bd2;
     d.feat = feat; d.P = P; d.feat_stride = feat_stride; d.feat_col0 = feat_col0;
-    d.frame_mode = frame_mode; d.K = K;
-    { ProfScope ps_(ctx, "dense_tc_kernel", st); dense_tc_kernel<<<(unsigned)(Ppad / 128), D_THREADS, D_SMEM, st>>>(d); }
+    d.frame_mode = frame_mode; d.K = K; d.timeline = ctx->dbg_timeline ? ctx->dbg_timeline + (size_t)2 * ctx->num_sms * 64 * 8 : nullptr;
+    { ProfScope ps_(ctx, "dense_tc_kernel", st); dense_tc_kernel<<<(unsigned)(Ppad / 128), D_THREADS, D_SMEM, st>>>(d, m_ah, m_al, m_wh, m_wl); }
     CAELO_LAUNCH_CHECK(ctx);
     return CAELO_OK;
 }

@@ -15,6 +15,7 @@
  *   kabsch/ransac  -> the imported reference SolveRT / SolveRelativePose on seeded demo pairs
  *                     (R,t within 1e-4; the reference's own float32 LAPACK noise is the limit)
  */
+#define _GNU_SOURCE
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -447,4 +448,132 @@ void oracle_inlier_mask(const float *p0, const float *p1, int N, const float *Rt
                         uint8_t *mask)
 {
     for (int i = 0; i < N; ++i) mask[i] = (uint8_t)inlier_d1(Rt, Rt + 9, p0 + 3 * i, p1 + 3 * i, thr);
+}
+
+/* ------------------------------------------------------------------------------------
+ * f1  ProjectPC2SphericalRing  (SphericalRing.py:72-94)
+ * Contract P1: r = sqrtf((x*x + y*y) + z*z) in float32 without contraction (numpy's LA.norm
+ *     on a float32 (N,3) slice: elementwise square, add.reduce over 3 in order, sqrt); points
+ *     with r == 0 are dropped (:77-80); col = (int)((pi - atan2((double)y,(double)x)) / az_res)
+ *     and row = ImgH - (int)(asin((double)(z / r)) / v_res + v_off) with z / r a FLOAT32
+ *     quotient (both are np.float32 scalars), everything else double, C truncation (:86-88);
+ *     rows outside [0,ImgH) are skipped (:89-90); columns are NOT bounds-checked by the
+ *     reference (col == ImgW only for atan2 == -pi, where numpy raises IndexError): such
+ *     points are counted in the return value and skipped.  The LAST point in file order owns
+ *     the pixel (:91-92); the counter counts every hit (:93).
+ * ring [ImgH,ImgW,5] f32 and counter [ImgH,ImgW] i32 must be zeroed by the caller.
+ * ------------------------------------------------------------------------------------ */
+int oracle_project_ring(const float *pc, int64_t N, int ImgH, int ImgW, double az_res, double v_res,
+                        double v_off, float *ring, int32_t *counter)
+{
+    int bad_cols = 0;
+    for (int64_t i = 0; i < N; ++i) {
+        const float x = pc[4 * i], y = pc[4 * i + 1], z = pc[4 * i + 2];
+        const float xx = x * x, yy = y * y, zz = z * z;
+        const float s = (xx + yy) + zz;
+        const float r = sqrtf(s);
+        if (!(r > 0.0f)) continue;
+        const int col = (int)((M_PI - atan2((double)y, (double)x)) / az_res);
+        const float q = z / r;
+        const double beta = asin((double)q);
+        const int row = ImgH - (int)(beta / v_res + v_off);
+        if (row < 0 || row >= ImgH) continue;
+        if (col < 0 || col >= ImgW) { ++bad_cols; continue; }
+        float *px = ring + ((size_t)row * ImgW + col) * 5;
+        px[0] = x; px[1] = y; px[2] = z; px[3] = pc[4 * i + 3]; px[4] = r;
+        counter[(size_t)row * ImgW + col] += 1;
+    }
+    return bad_cols;
+}
+
+/* ------------------------------------------------------------------------------------
+ * f2  Voxelization  (Voxel.py:89-173), the parts BatchVoxelization.py:61 writes out.
+ * Contract V1 (float64 on float32 inputs, as numpy 1.18 promotes np.float32 + python float):
+ *     drop |x| > VisL or |y| > VisW or |z| > VisH (:89-97); x_ = (double)x + VisL ...;
+ *     iBlock = (int)(x_ / 1.28); scale-0 voxel = (int)((x_ - iBlock*1.28) / 0.02) + iBlock*64
+ *     (the BLOCK route, :120-139 — not (int)(x_/0.02)); scale-1/2 voxel = (int)(x_ / 0.16),
+ *     (int)(x_ / 0.64) (:143-148).  A point whose scale-0 voxel was seen before is skipped
+ *     entirely (:134-135).  Order: AllVoxels1/2 in first-seen order; AllVoxels0 (and the
+ *     in-block AllVoxels) grouped by block in block-first-seen order, first-seen inside (:161-165).
+ * Outputs: vox0/vox1/vox2 int16 rows (capacity N each), local0 int16 rows (AllVoxels),
+ *     blocks int16 rows (avlBlocksList), cnt int32 [nblocks+1] (cntVoxelsLength);
+ *     counts[4] = {V0, V1, V2, nblocks}.  Returns 0, or -1 if a point indexes outside the
+ *     156x156x23 block grid / 64^3 block (the reference raises IndexError there).
+ * ------------------------------------------------------------------------------------ */
+typedef struct { uint64_t key; int32_t val; } vslot;
+
+static uint32_t vhash(uint64_t k)
+{
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return (uint32_t)k;
+}
+
+/* returns the slot of key, inserting it with val if new (*isnew = 1) */
+static vslot *vfind(vslot *t, uint32_t mask, uint64_t key, int32_t val, int *isnew)
+{
+    uint32_t s = vhash(key) & mask;
+    for (;;) {
+        if (t[s].key == key) { *isnew = 0; return t + s; }
+        if (t[s].key == ~0ull) { t[s].key = key; t[s].val = val; *isnew = 1; return t + s; }
+        s = (s + 1) & mask;
+    }
+}
+
+int oracle_voxelize(const float *pc, int64_t N, int stride, int16_t *vox0, int16_t *vox1, int16_t *vox2,
+                    int16_t *local0, int16_t *blocks, int32_t *cnt, int32_t *counts)
+{
+    const double BRS = 1.28, VS = 0.02;
+    const int nBL = (int)(2 * 100 / BRS), nBW = (int)(2 * 100 / BRS), nBH = (int)(2 * 15 / BRS);
+    const double VisL = nBL / 2.0 * BRS, VisW = nBW / 2.0 * BRS, VisH = nBH / 2.0 * BRS;
+    const double VS1 = VS * 8, VS2 = VS * 32;
+    uint32_t cap = 1024;
+    while (cap < 2 * (uint64_t)N + 2) cap <<= 1;
+    vslot *t0 = malloc(sizeof(vslot) * cap), *t1 = malloc(sizeof(vslot) * cap), *t2 = malloc(sizeof(vslot) * cap),
+          *tb = malloc(sizeof(vslot) * cap);
+    int32_t *blk_of = malloc(sizeof(int32_t) * (N + 1));   /* block rank of the i-th scale-0 voxel (first-seen order) */
+    int16_t *tmp0 = malloc(sizeof(int16_t) * 3 * (N + 1));
+    for (uint32_t i = 0; i < cap; ++i) t0[i].key = t1[i].key = t2[i].key = tb[i].key = ~0ull;
+    int n0 = 0, n1 = 0, n2 = 0, nb = 0, rc = 0;
+    for (int64_t i = 0; i < N; ++i) {
+        const float fx = pc[stride * i], fy = pc[stride * i + 1], fz = pc[stride * i + 2];
+        if (fabs((double)fx) > VisL || fabs((double)fy) > VisW || fabs((double)fz) > VisH) continue;
+        const double x_ = (double)fx + VisL, y_ = (double)fy + VisW, z_ = (double)fz + VisH;
+        const int bx = (int)(x_ / BRS), by = (int)(y_ / BRS), bz = (int)(z_ / BRS);
+        if (bx < 0 || bx >= nBL || by < 0 || by >= nBW || bz < 0 || bz >= nBH) { rc = -1; continue; }
+        const int vx = (int)((x_ - bx * BRS) / VS), vy = (int)((y_ - by * BRS) / VS), vz = (int)((z_ - bz * BRS) / VS);
+        if (vx < 0 || vx >= 64 || vy < 0 || vy >= 64 || vz < 0 || vz >= 64) { rc = -1; continue; }
+        int isnew;
+        const uint64_t kb = (uint64_t)bx | ((uint64_t)by << 16) | ((uint64_t)bz << 32);
+        vslot *sb = vfind(tb, cap - 1, kb, nb, &isnew);
+        if (isnew) { blocks[3 * nb] = (int16_t)bx; blocks[3 * nb + 1] = (int16_t)by; blocks[3 * nb + 2] = (int16_t)bz; ++nb; }
+        const int gx = vx + bx * 64, gy = vy + by * 64, gz = vz + bz * 64;
+        const uint64_t k0 = (uint64_t)gx | ((uint64_t)gy << 16) | ((uint64_t)gz << 32);
+        vfind(t0, cap - 1, k0, n0, &isnew);
+        if (!isnew) continue;
+        tmp0[3 * n0] = (int16_t)gx; tmp0[3 * n0 + 1] = (int16_t)gy; tmp0[3 * n0 + 2] = (int16_t)gz;
+        blk_of[n0] = sb->val;
+        ++n0;
+        const int x1 = (int)(x_ / VS1), y1 = (int)(y_ / VS1), z1 = (int)(z_ / VS1);
+        const int x2 = (int)(x_ / VS2), y2 = (int)(y_ / VS2), z2 = (int)(z_ / VS2);
+        vfind(t1, cap - 1, (uint64_t)x1 | ((uint64_t)y1 << 16) | ((uint64_t)z1 << 32), n1, &isnew);
+        if (isnew) { vox1[3 * n1] = (int16_t)x1; vox1[3 * n1 + 1] = (int16_t)y1; vox1[3 * n1 + 2] = (int16_t)z1; ++n1; }
+        vfind(t2, cap - 1, (uint64_t)x2 | ((uint64_t)y2 << 16) | ((uint64_t)z2 << 32), n2, &isnew);
+        if (isnew) { vox2[3 * n2] = (int16_t)x2; vox2[3 * n2 + 1] = (int16_t)y2; vox2[3 * n2 + 2] = (int16_t)z2; ++n2; }
+    }
+    /* group scale-0 voxels by block, stable (counting sort on the block rank) */
+    for (int b = 0; b <= nb; ++b) cnt[b] = 0;
+    for (int i = 0; i < n0; ++i) cnt[blk_of[i] + 1]++;
+    for (int b = 0; b < nb; ++b) cnt[b + 1] += cnt[b];
+    int32_t *fill = malloc(sizeof(int32_t) * (nb + 1));
+    for (int b = 0; b < nb; ++b) fill[b] = cnt[b];
+    for (int i = 0; i < n0; ++i) {
+        const int b = blk_of[i], o = fill[b]++;
+        for (int c = 0; c < 3; ++c) {
+            vox0[3 * o + c] = tmp0[3 * i + c];
+            local0[3 * o + c] = (int16_t)(tmp0[3 * i + c] - blocks[3 * b + c] * 64);
+        }
+    }
+    counts[0] = n0; counts[1] = n1; counts[2] = n2; counts[3] = nb;
+    free(fill); free(tmp0); free(blk_of); free(t0); free(t1); free(t2); free(tb);
+    return rc;
 }
