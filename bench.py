@@ -302,6 +302,50 @@ def run_ours(args, rank, local_rank, world):
     e2e_s = float(t.item())
     clocks = sampler.stop() if sampler else None
 
+    # ---- same job started one stage earlier: raw scans -> poses ----
+    from_scans = None
+    if not args.no_from_scans:
+        soff = np.zeros(F + 1, np.int64)
+        soff[1:] = np.cumsum([s.shape[0] for s in data["scans"]])
+        scans_h = torch.from_numpy(np.concatenate(data["scans"], 0)).pin_memory()
+        d_scans = scans_h.to(dev)
+        for _ in range(3):
+            poses_s = pipe.run_device_scans(d_scans, soff, d_samples, pair_ids)
+        same = bool(np.array_equal(poses_s, pipe.run_device(d_ring, d_counter, d_vox, voff, d_samples, pair_ids)))
+        ctx.profile(True)
+        ctx.profile_fetch()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        for a, b in evs:
+            flush.zero_()
+            torch.cuda.synchronize()
+            a.record()
+            pipeline.gather_poses(pipe.run_device_scans(d_scans, soff, d_samples, pair_ids), dev)
+            b.record()
+        barrier()
+        prof_s = ctx.profile_fetch()
+        ctx.profile(False)
+        ms_s = sum(a.elapsed_time(b) for a, b in evs)
+        for _ in range(2):
+            pipe.run_host_scans(scans_h, soff, pair_ids)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pipeline.gather_poses(pipe.run_host_scans(scans_h, soff, pair_ids), dev)
+        barrier()
+        e2e_scans_s = time.perf_counter() - t0
+        t = torch.tensor([ms_s, e2e_scans_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        from_scans = {"what": "same step started from the raw (N,4) scans: ProjectPC2SphericalRing + Voxelization's "
+                              "voxel sets computed on the device (f1, f2+a6 fused) in front of the hot path",
+                      "value": world * P * args.steps / (float(t[0].item()) * 1e-3), "unit": UNIT,
+                      "ms_per_step": float(t[0].item()) / args.steps,
+                      "e2e": {"value": world * P * args.steps / float(t[1].item()), "unit": UNIT,
+                              "h2d_bytes_per_step": int(scans_h.numel() * 4 + samples_h.nbytes), "d2h_bytes_per_step": P * 32 * 4},
+                      "poses_identical_to_ring_path": same,
+                      "time_by_kernel_ms_per_step": {k: v[1] / args.steps for k, v in prof_s.items()}}
+
     if rank == 0:
         peaks = _peaks()
         n_patches = F * 3 * K_PTS
@@ -347,7 +391,7 @@ def run_ours(args, rank, local_rank, world):
                 "e2e": {"value": world * P * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "roofline": roofline,
-                "pairs_with_model": ok_pairs}
+                "pairs_with_model": ok_pairs, "from_scans": from_scans}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(data)
         print(json.dumps(line))
@@ -380,6 +424,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=32, help="frame pairs per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-from-scans", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

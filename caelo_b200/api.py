@@ -7,8 +7,11 @@ torch tensors used only as device buffers.  There is no CPU fallback.
     reference symbol (file:line)                          here
     keras.models.load_model (Match.py:313,324)            load_model -> B200Model
     model.predict (SphericalRing.py:407, Match.py:131)    B200Model.predict
+    ProjectPC2SphericalRing (SphericalRing.py:72)         ProjectPC2SphericalRing
+    Voxelization (Voxel.py:100)                           Voxelization
     GetKeyPtsByAE (SphericalRing.py:113)                  GetKeyPtsByAE
     GetKeyPtsFromRawFileName (SphericalRing.py:389)       GetKeyPtsFromRawFileName
+    ExtendKeyPtsInShpericalRing (SphericalRing.py:294)    ExtendKeyPtsInShpericalRing
     GetPatchesList (Voxel.py:177)                         GetPatchesList
     GetFeaturesFromPatches (Match.py:130)                 GetFeaturesFromPatches
     SolveRT / RANSAC4RT / SolveRelativePose (Match.py)    SolveRT / RANSAC4RT / SolveRelativePose
@@ -153,6 +156,60 @@ class Context:
         self.check(rc, "caelo_select_keypoints")
         return kpts, kpix, n
 
+    def project_ring(self, pts: torch.Tensor, pts_offsets: np.ndarray, want=("ring3", "counter_i8")):
+        """f1: pts [sumN,4] f32, pts_offsets host int64 [F+1] -> dict of the requested outputs
+        (ring5 [F,69,1800,5], counter_i32 [F,69,1800], ring3 [F,64,1792,3], counter_i8) + status [F]."""
+        off = np.ascontiguousarray(pts_offsets, np.int64)
+        F = off.shape[0] - 1
+        assert pts.dtype == torch.float32 and pts.is_contiguous() and pts.shape[1] == 4
+        shapes = {"ring5": ((F, ImgH, ImgW, 5), torch.float32), "counter_i32": ((F, ImgH, ImgW), torch.int32),
+                  "ring3": ((F, nLines, ImgW - CropWidth_SphericalRing, 3), torch.float32),
+                  "counter_i8": ((F, ImgH, ImgW), torch.int8)}
+        out = {k: torch.empty(shapes[k][0], dtype=shapes[k][1], device=self.device) for k in want}
+        out["status"] = torch.empty((F,), dtype=torch.int32, device=self.device)
+        self.check(self.lib.caelo_project_ring(self.h, _ptr(pts), off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), F,
+                                               _ptr(out.get("ring5")), _ptr(out.get("counter_i32")),
+                                               _ptr(out.get("ring3")), _ptr(out.get("counter_i8")),
+                                               _ptr(out["status"]), _stream()), "caelo_project_ring")
+        return out
+
+    def voxelize(self, pts: torch.Tensor, pts_offsets: np.ndarray, cap: Optional[int] = None, want_blocks: bool = False):
+        """f2: -> vox int16 [F,3,cap,3], counts int32 [F,4] (+ local0, blocks, cnt when want_blocks), status [F]."""
+        off = np.ascontiguousarray(pts_offsets, np.int64)
+        F = off.shape[0] - 1
+        assert pts.dtype == torch.float32 and pts.is_contiguous() and pts.shape[1] == 4
+        if cap is None:
+            cap = int(np.diff(off).max())
+        out = {"vox": torch.empty((F, 3, cap, 3), dtype=torch.int16, device=self.device),
+               "counts": torch.empty((F, 4), dtype=torch.int32, device=self.device),
+               "status": torch.empty((F,), dtype=torch.int32, device=self.device)}
+        if want_blocks:
+            out["local0"] = torch.empty((F, cap, 3), dtype=torch.int16, device=self.device)
+            out["blocks"] = torch.empty((F, cap, 3), dtype=torch.int16, device=self.device)
+            out["cnt"] = torch.empty((F, cap + 1), dtype=torch.int32, device=self.device)
+        self.check(self.lib.caelo_voxelize(self.h, _ptr(pts), off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), F, cap,
+                                           _ptr(out["vox"]), _ptr(out["counts"]), _ptr(out.get("local0")),
+                                           _ptr(out.get("blocks")), _ptr(out.get("cnt")), _ptr(out["status"]),
+                                           _stream()), "caelo_voxelize")
+        return out
+
+    def extend_keypoints(self, ring: torch.Tensor, counter: torch.Tensor, kpix: torch.Tensor,
+                         n_kpts: Optional[torch.Tensor] = None, zero_counter: bool = False):
+        """ExtendKeyPtsInShpericalRing for B frames -> ext [B,K*169,3] f32, n_ext [B] int32."""
+        B, rH, rW, rC = ring.shape
+        K = kpix.shape[1]
+        assert ring.dtype == torch.float32 and ring.is_contiguous() and counter.is_contiguous()
+        assert kpix.dtype == torch.int64 and kpix.is_contiguous() and kpix.shape[0] == B
+        kind = {torch.int8: 0, torch.int32: 1}[counter.dtype]
+        cap = K * 169
+        ext = torch.empty((B, cap, 3), dtype=torch.float32, device=self.device)
+        n_ext = torch.empty((B,), dtype=torch.int32, device=self.device)
+        self.check(self.lib.caelo_extend_keypoints(self.h, _ptr(ring), rC, rH, rW, _ptr(counter), kind, counter.shape[1],
+                                                   counter.shape[2], _ptr(kpix), _ptr(n_kpts), B, K, _ptr(ext), cap,
+                                                   _ptr(n_ext), 1 if zero_counter else 0, _stream()),
+                   "caelo_extend_keypoints")
+        return ext, n_ext
+
     def gather_patches(self, kpts: torch.Tensor, vox: torch.Tensor, vox_offsets: np.ndarray,
                        n_kpts: Optional[torch.Tensor] = None, want_f32: bool = False, want_trunc: bool = False):
         """kpts [F,K,3] f32|f64; vox int16 [sumV,3]; vox_offsets host int64 [F*3+1] (rows)."""
@@ -169,6 +226,24 @@ class Context:
                                            _ptr(packed), _ptr(f32), _ptr(trunc), _stream())
         self.check(rc, "caelo_gather_patches")
         return packed, f32, trunc
+
+    def gather_patches_scans(self, kpts: torch.Tensor, pts: torch.Tensor, pts_offsets: np.ndarray,
+                             n_kpts: Optional[torch.Tensor] = None, want_f32: bool = False, want_trunc: bool = False):
+        """f2+a6 fused: kpts [F,K,3]; pts [sumN,4] f32 raw scans; -> packed, f32, trunc, nvox [F,3], status [F]."""
+        F, K, _ = kpts.shape
+        off = np.ascontiguousarray(pts_offsets, np.int64)
+        assert off.shape == (F + 1,) and pts.dtype == torch.float32 and pts.is_contiguous() and kpts.is_contiguous()
+        packed = torch.empty((F, 3, K, 128), dtype=torch.int32, device=self.device)
+        f32 = torch.empty((F, 3, K, 16, 16, 16), dtype=torch.float32, device=self.device) if want_f32 else None
+        trunc = torch.empty((F, 3, K), dtype=torch.uint8, device=self.device) if want_trunc else None
+        nvox = torch.empty((F, 3), dtype=torch.int32, device=self.device)
+        status = torch.empty((F,), dtype=torch.int32, device=self.device)
+        rc = self.lib.caelo_gather_patches_scans(self.h, _ptr(kpts), 1 if kpts.dtype == torch.float64 else 0,
+                                                 _ptr(n_kpts), F, K, _ptr(pts),
+                                                 off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _ptr(packed),
+                                                 _ptr(f32), _ptr(trunc), _ptr(nvox), _ptr(status), _stream())
+        self.check(rc, "caelo_gather_patches_scans")
+        return packed, f32, trunc, nvox, status
 
     def encode_frames(self, packed: torch.Tensor) -> torch.Tensor:
         F, S, K, Wd = packed.shape
@@ -303,6 +378,40 @@ def load_model(path: str, ctx: Optional[Context] = None) -> B200Model:
 
 
 # ------------------------------------------------------------------------------------------
+# per-scan pre-stages (f1, f2)
+# ------------------------------------------------------------------------------------------
+def ProjectPC2SphericalRing(PC):
+    """SphericalRing.py:72 — (Image_float (69,1800,5) f32, GridCounter (69,1800) int32)."""
+    PC = np.asarray(PC)
+    assert PC.shape[0] > 3 and PC.shape[1] == 4
+    ctx = default_context()
+    pts = _dev(PC, np.float32)
+    out = ctx.project_ring(pts, np.array([0, pts.shape[0]], np.int64), want=("ring5", "counter_i32"))
+    if int(out["status"].item()):
+        raise IndexError("index %d is out of bounds for axis 1 with size %d" % (ImgW, ImgW))
+    return out["ring5"][0].cpu().numpy(), out["counter_i32"][0].cpu().numpy()
+
+
+def Voxelization(PC):
+    """Voxel.py:100 — (Blocks, VoxelModel1, VoxelModel2, avlBlocksList, cntVoxelsLength, AllVoxels,
+    AllVoxels0, AllVoxels1, AllVoxels2).  The three dense/nested containers (Blocks: 560k python lists,
+    VoxelModel1: a 286 MB int8 grid) are never read on the odometry path and come back as None; the six
+    arrays BatchVoxelization.py:61 stores are exact, order included."""
+    PC = np.asarray(PC)
+    ctx = default_context()
+    pts = np.zeros((PC.shape[0], 4), np.float32)
+    pts[:, :3] = PC[:, :3]
+    d = ctx.voxelize(_dev(pts), np.array([0, pts.shape[0]], np.int64), want_blocks=True)
+    if int(d["status"].item()):
+        raise IndexError("a point indexes outside the block grid")
+    n0, n1, n2, nb = (int(c) for c in d["counts"][0].cpu().numpy())
+    vox = d["vox"][0]
+    return (None, None, None, d["blocks"][0, :nb].cpu().numpy(), d["cnt"][0, :nb + 1].cpu().numpy(),
+            d["local0"][0, :n0].cpu().numpy(), vox[0, :n0].cpu().numpy(), vox[1, :n1].cpu().numpy(),
+            vox[2, :n2].cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------
 # keypoints
 # ------------------------------------------------------------------------------------------
 def _select(SphericalRing, GridCounter, RespondImg):
@@ -330,6 +439,21 @@ def _select(SphericalRing, GridCounter, RespondImg):
 def GetKeyPtsByAE(SphericalRing, GridCounter, RespondImg):
     """SphericalRing.py:113 — (KeyPts (n,3) f32 ascending by score, KeyPixels (n,2) int64, PlanarPts)."""
     return _select(SphericalRing, GridCounter, RespondImg)
+
+
+def ExtendKeyPtsInShpericalRing(SphericalRing, GridCounter, KeyPixels):
+    """SphericalRing.py:294 — ExtendedKeyPts (n,3) f32; like the reference it zeroes the windows of the
+    caller's GridCounter in place."""
+    ctx = default_context()
+    ring = np.asarray(SphericalRing, dtype=np.float32)
+    px = np.ascontiguousarray(np.asarray(KeyPixels).reshape(-1, 2), np.int64)
+    if px.shape[0] == 0:
+        return np.zeros((0, 3), np.float32)
+    cnt = GridCounter if GridCounter.dtype == np.int8 else GridCounter.astype(np.int32, copy=False)
+    d_cnt = _dev(cnt[None])
+    ext, n = ctx.extend_keypoints(_dev(ring[None]), d_cnt, _dev(px[None]), None, zero_counter=True)
+    GridCounter[...] = d_cnt[0].cpu().numpy()
+    return ext[0, :int(n.item())].cpu().numpy()
 
 
 def GetKeyPtsFromRing(SphericalRing, GridCounter):

@@ -16,6 +16,8 @@ SOURCES = {
     "api.cu": [],
     "respond_select.cu": [],
     "patches.cu": [],
+    "scan.cu": [],
+    "extend.cu": [],
     "encoder.cu": [],
     "match.cu": [],
     "pose.cu": ["-fmad=false"],

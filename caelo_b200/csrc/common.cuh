@@ -60,6 +60,7 @@ struct caelo_ctx {
     Scratch enc_ws;    // encoder activations
     Scratch pose_ws;   // ransac: hypotheses
     Scratch misc;
+    Scratch scan_ws;   // projection / voxelisation: pixel owners, hash tables, compaction lists
 };
 
 #define CAELO_CUDA(ctx, call)                         \

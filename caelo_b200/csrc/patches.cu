@@ -11,6 +11,7 @@
 //      (the kNN cut can bite) it re-runs with the exact rank rule (d^2, then x,y,z).
 // Integer-exact; HBM traffic = voxel lists in + 512 B per patch out.
 #include "common.cuh"
+#include "voxel_math.cuh"
 
 namespace {
 
@@ -69,6 +70,51 @@ __global__ void brick_insert_kernel(const BuildArgs a)
     }
 }
 
+// Fused f2+a6 front end: bricks straight from the raw scans (no voxel lists).  The voxel SET is the one
+// Voxelization (Voxel.py:100-173) produces — same arithmetic (voxel_math.cuh) — and the list ORDER never
+// matters to GetPatchesList.  nvox[f*3+s] counts the distinct voxels (= len(AllVoxels_s)) for the
+// sklearn "n_neighbors <= n_samples_fit" check.
+struct ScanBuildArgs {
+    const float *pts;            // rows of 4
+    const long long *offsets;    // dev [F+1]
+    const Table *tables;         // dev [F*3]
+    int *nvox;                   // dev [F*3]
+    int *status;                 // dev [F] or null
+};
+
+__device__ __forceinline__ void brick_set(const Table &t, int x, int y, int z, int *count)
+{
+    unsigned long long key = brick_key(x >> 2, y >> 2, z >> 2);
+    unsigned long long bit = 1ull << (((x & 3) * 4 + (y & 3)) * 4 + (z & 3));
+    unsigned slot = hash64(key) & t.cap_mask;
+    while (true) {
+        unsigned long long old = atomicCAS(t.keys + slot, EMPTY, key);
+        if (old == EMPTY || old == key) {
+            if (!(atomicOr(t.masks + slot, bit) & bit)) atomicAdd(count, 1);
+            break;
+        }
+        slot = (slot + 1) & t.cap_mask;
+    }
+}
+
+__global__ void __launch_bounds__(256) scan_brick_insert_kernel(const ScanBuildArgs a)
+{
+    const int f = blockIdx.y;
+    const long long beg = a.offsets[f], n = a.offsets[f + 1] - beg;
+    const float4 *p4 = reinterpret_cast<const float4 *>(a.pts) + beg;
+    const Table t0 = a.tables[f * 3], t1 = a.tables[f * 3 + 1], t2 = a.tables[f * 3 + 2];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float4 p = p4[i];
+        VoxelOfPoint v;
+        const int st = voxel_of_point(p.x, p.y, p.z, v);
+        if (st < 0 && a.status) atomicAdd(a.status + f, 1);
+        if (st <= 0) continue;
+        brick_set(t0, v.g0[0], v.g0[1], v.g0[2], a.nvox + f * 3);
+        brick_set(t1, v.g1[0], v.g1[1], v.g1[2], a.nvox + f * 3 + 1);
+        brick_set(t2, v.g2[0], v.g2[1], v.g2[2], a.nvox + f * 3 + 2);
+    }
+}
+
 __device__ __forceinline__ unsigned long long brick_lookup(const Table &t, unsigned long long key)
 {
     unsigned slot = hash64(key) & t.cap_mask;
@@ -86,6 +132,8 @@ struct GatherArgs {
     const Table *tables;         // [F*3]
     unsigned *packed;            // [F,3,K,128]
     unsigned char *trunc;        // [F,3,K] or null
+    const int *nvox;             // [F*3] distinct voxels per list, or null (checked on the host)
+    int *few;                    // [F]: |= 2 where a list has < 496 voxels (sklearn raises), with nvox
     double vis[3];               // VisibleLength/Width/Height (Voxel.py:50-52)
     double vsize[3];             // VoxelSizes (Voxel.py:31)
     int kpts_f64, F, K;
@@ -139,7 +187,11 @@ __global__ void __launch_bounds__(kWarps * 32) gather_kernel(const GatherArgs a)
         const int f = (int)(w / (3LL * a.K));
         for (int i = lane; i < 128; i += 32) patch[i] = 0u;
         __syncwarp();
-        const bool live = a.n_kpts == nullptr || k < a.n_kpts[f];
+        bool live = a.n_kpts == nullptr || k < a.n_kpts[f];
+        if (a.nvox && a.nvox[f * 3 + s] < NNB) {   // n_neighbors <= n_samples_fit (Voxel.py:195)
+            if (lane == 0 && k == 0) atomicOr(a.few + f, 0x40000000);
+            live = false;
+        }
         bool flagged = false;
         if (live) {
             double p[3];
@@ -231,36 +283,23 @@ __global__ void unpack_kernel(const unsigned *__restrict__ packed, float *__rest
 
 }  // namespace
 
-extern "C" int caelo_gather_patches(caelo_ctx *ctx, const void *kpts, int kpts_f64,
-                                    const int32_t *n_kpts, int F, int K, const int16_t *vox,
-                                    const int64_t *vox_offsets, uint32_t *packed, float *patches_f32,
-                                    uint8_t *trunc, void *stream)
+// Hash-table geometry + upload: caps[l] slots (power of two) for list l; `offsets` (n_off int64) is staged next
+// to the Table array.  All tables are cleared on the stream.
+static int setup_tables(caelo_ctx *ctx, int nl, const size_t *caps, const int64_t *offsets, int n_off, Table **d_tables,
+                        long long **d_off, cudaStream_t st)
 {
-    if (!ctx || !kpts || !vox || !vox_offsets || !packed || F <= 0 || K <= 0) return CAELO_ERR_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int nl = F * 3;
-    // table geometry from the (host) list sizes
     size_t total_slots = 0;
-    long long maxlen = 0;
-    for (int l = 0; l < nl; ++l) {
-        long long len = vox_offsets[l + 1] - vox_offsets[l];
-        if (len < NNB) return CAELO_ERR_TOO_FEW_VOXELS;  // sklearn: n_neighbors <= n_samples_fit
-        if (len > maxlen) maxlen = len;
-        size_t cap = 1024;
-        while (cap < (size_t)len * 2) cap <<= 1;
-        total_slots += cap;
-    }
-    size_t head = ((size_t)nl * sizeof(Table) + (size_t)(nl + 1) * 8 + 255) / 256 * 256;
-    size_t need = head + total_slots * 16;
-    int rc = caelo_reserve(ctx, ctx->bricks, need);
+    for (int l = 0; l < nl; ++l) total_slots += caps[l];
+    const size_t head = ((size_t)nl * sizeof(Table) + (size_t)n_off * 8 + 255) / 256 * 256;
+    int rc = caelo_reserve(ctx, ctx->bricks, head + total_slots * 16);
     if (rc) return rc;
     char *base = reinterpret_cast<char *>(ctx->bricks.ptr);
-    Table *d_tables = reinterpret_cast<Table *>(base);
-    long long *d_off = reinterpret_cast<long long *>(base + (size_t)nl * sizeof(Table));
+    *d_tables = reinterpret_cast<Table *>(base);
+    *d_off = reinterpret_cast<long long *>(base + (size_t)nl * sizeof(Table));
     unsigned long long *d_keys = reinterpret_cast<unsigned long long *>(base + head);
     unsigned long long *d_masks = d_keys + total_slots;
     // tables + offsets go through a ring of pinned staging slots: no stream synchronisation
-    const size_t stage_bytes = (size_t)nl * sizeof(Table) + (size_t)(nl + 1) * 8;
+    const size_t stage_bytes = (size_t)nl * sizeof(Table) + (size_t)n_off * 8;
     void *h_stage = nullptr;
     cudaEvent_t ev;
     rc = caelo_stage_acquire(ctx, stage_bytes, &h_stage, &ev);
@@ -268,29 +307,33 @@ extern "C" int caelo_gather_patches(caelo_ctx *ctx, const void *kpts, int kpts_f
     Table *h_tables = reinterpret_cast<Table *>(h_stage);
     size_t cur = 0;
     for (int l = 0; l < nl; ++l) {
-        long long len = vox_offsets[l + 1] - vox_offsets[l];
-        size_t cap = 1024;
-        while (cap < (size_t)len * 2) cap <<= 1;
         h_tables[l].keys = d_keys + cur;
         h_tables[l].masks = d_masks + cur;
-        h_tables[l].cap_mask = (unsigned)(cap - 1);
-        cur += cap;
+        h_tables[l].cap_mask = (unsigned)(caps[l] - 1);
+        cur += caps[l];
     }
-    memcpy(reinterpret_cast<char *>(h_stage) + (size_t)nl * sizeof(Table), vox_offsets, (size_t)(nl + 1) * 8);
-    CAELO_CUDA(ctx, cudaMemcpyAsync(d_tables, h_stage, stage_bytes, cudaMemcpyHostToDevice, st));
+    memcpy(reinterpret_cast<char *>(h_stage) + (size_t)nl * sizeof(Table), offsets, (size_t)n_off * 8);
+    CAELO_CUDA(ctx, cudaMemcpyAsync(*d_tables, h_stage, stage_bytes, cudaMemcpyHostToDevice, st));
     CAELO_CUDA(ctx, cudaEventRecord(ev, st));
     CAELO_CUDA(ctx, cudaMemsetAsync(d_keys, 0xFF, total_slots * 8, st));
     CAELO_CUDA(ctx, cudaMemsetAsync(d_masks, 0, total_slots * 8, st));
+    return CAELO_OK;
+}
 
-    BuildArgs b;
-    b.vox = vox; b.offsets = d_off; b.tables = d_tables; b.nlists = nl;
-    int bx = (int)((maxlen + 255) / 256);
-    if (bx > 64) bx = 64;
-    { ProfScope ps_(ctx, "brick_insert_kernel", st); brick_insert_kernel<<<dim3(bx, nl), 256, 0, st>>>(b); }
-    CAELO_LAUNCH_CHECK(ctx);
+static size_t pow2_above(size_t n)
+{
+    size_t cap = 1024;
+    while (cap < n) cap <<= 1;
+    return cap;
+}
 
+static int launch_gather(caelo_ctx *ctx, const void *kpts, int kpts_f64, const int32_t *n_kpts, int F, int K,
+                         const Table *d_tables, const int *nvox, int *few, uint32_t *packed, float *patches_f32,
+                         uint8_t *trunc, cudaStream_t st)
+{
     GatherArgs g;
     g.kpts = kpts; g.n_kpts = n_kpts; g.tables = d_tables; g.packed = packed; g.trunc = trunc;
+    g.nvox = nvox; g.few = few;
     // Voxel.py:40-52: nBlocksL = int(200/1.28) = 156, nBlocksH = int(30/1.28) = 23; Visible* = n/2*1.28
     const double brs = 1.28;
     g.vis[0] = 156 / 2.0 * brs; g.vis[1] = 156 / 2.0 * brs; g.vis[2] = 23 / 2.0 * brs;
@@ -312,4 +355,70 @@ extern "C" int caelo_gather_patches(caelo_ctx *ctx, const void *kpts, int kpts_f
         CAELO_LAUNCH_CHECK(ctx);
     }
     return CAELO_OK;
+}
+
+extern "C" int caelo_gather_patches(caelo_ctx *ctx, const void *kpts, int kpts_f64,
+                                    const int32_t *n_kpts, int F, int K, const int16_t *vox,
+                                    const int64_t *vox_offsets, uint32_t *packed, float *patches_f32,
+                                    uint8_t *trunc, void *stream)
+{
+    if (!ctx || !kpts || !vox || !vox_offsets || !packed || F <= 0 || K <= 0) return CAELO_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nl = F * 3;
+    std::vector<size_t> caps(nl);
+    long long maxlen = 0;
+    for (int l = 0; l < nl; ++l) {
+        long long len = vox_offsets[l + 1] - vox_offsets[l];
+        if (len < NNB) return CAELO_ERR_TOO_FEW_VOXELS;  // sklearn: n_neighbors <= n_samples_fit
+        if (len > maxlen) maxlen = len;
+        caps[l] = pow2_above((size_t)len * 2);
+    }
+    Table *d_tables;
+    long long *d_off;
+    int rc = setup_tables(ctx, nl, caps.data(), vox_offsets, nl + 1, &d_tables, &d_off, st);
+    if (rc) return rc;
+    BuildArgs b;
+    b.vox = vox; b.offsets = d_off; b.tables = d_tables; b.nlists = nl;
+    int bx = (int)((maxlen + 255) / 256);
+    if (bx > 64) bx = 64;
+    { ProfScope ps_(ctx, "brick_insert_kernel", st); brick_insert_kernel<<<dim3(bx, nl), 256, 0, st>>>(b); }
+    CAELO_LAUNCH_CHECK(ctx);
+    return launch_gather(ctx, kpts, kpts_f64, n_kpts, F, K, d_tables, nullptr, nullptr, packed, patches_f32, trunc, st);
+}
+
+// f2+a6 fused: GetPatchesList(Pts, *Voxelization(scan)) without materialising the voxel lists.
+extern "C" int caelo_gather_patches_scans(caelo_ctx *ctx, const void *kpts, int kpts_f64, const int32_t *n_kpts, int F,
+                                          int K, const float *pts, const int64_t *pts_offsets, uint32_t *packed,
+                                          float *patches_f32, uint8_t *trunc, int32_t *nvox, int32_t *status,
+                                          void *stream)
+{
+    if (!ctx || !kpts || !pts || !pts_offsets || !packed || !nvox || !status || F <= 0 || K <= 0) return CAELO_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nl = F * 3;
+    std::vector<size_t> caps(nl);
+    long long maxn = 0;
+    for (int f = 0; f < F; ++f) {
+        long long n = pts_offsets[f + 1] - pts_offsets[f];
+        if (n < 0) return CAELO_ERR_ARG;
+        if (n > maxn) maxn = n;
+        // a brick holds >= 1 voxel and a voxel >= 1 point: n bounds every table; the 64 cm grid has
+        // 78*78*12 = 73,008 bricks at most
+        caps[f * 3] = pow2_above((size_t)n * 2 + 2);
+        caps[f * 3 + 1] = pow2_above((size_t)n + 2);
+        caps[f * 3 + 2] = pow2_above(((size_t)n < 73008 ? (size_t)n : 73008) * 2 + 2);
+    }
+    Table *d_tables;
+    long long *d_off;
+    int rc = setup_tables(ctx, nl, caps.data(), pts_offsets, F + 1, &d_tables, &d_off, st);
+    if (rc) return rc;
+    CAELO_CUDA(ctx, cudaMemsetAsync(nvox, 0, (size_t)nl * 4, st));
+    CAELO_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)F * 4, st));
+    ScanBuildArgs b;
+    b.pts = pts; b.offsets = d_off; b.tables = d_tables; b.nvox = nvox; b.status = status;
+    int bx = (int)((maxn + 255) / 256);
+    if (bx > 128) bx = 128;
+    if (bx < 1) bx = 1;
+    { ProfScope ps_(ctx, "scan_brick_insert_kernel", st); scan_brick_insert_kernel<<<dim3(bx, F), 256, 0, st>>>(b); }
+    CAELO_LAUNCH_CHECK(ctx);
+    return launch_gather(ctx, kpts, kpts_f64, n_kpts, F, K, d_tables, nvox, status, packed, patches_f32, trunc, st);
 }

@@ -49,6 +49,8 @@ class OdometryPipeline:
         self.ctx = ctx or api.default_context()
         self.K = n_keypoints
         self.dev = self.ctx.device
+        self.keep_details = False      # True: keep the batch's keypoints / descriptors / matches / inlier masks
+        self.last_details = None       # (device tensors) for the Features / InliersIdx files of odometry.py
 
     # ---- device-resident stages ---------------------------------------------------------
     def frames_to_descriptors(self, ring: torch.Tensor, counter: torch.Tensor, vox: torch.Tensor,
@@ -60,8 +62,18 @@ class OdometryPipeline:
         feat = self.ctx.encode_frames(packed)
         return kpts, feat, n
 
+    def scans_to_descriptors(self, pts: torch.Tensor, pts_offsets: np.ndarray):
+        """Raw scans (pts [sumN,4] f32 + host row offsets [F+1]) -> kpts, feat, n_kpts, status [F]:
+        f1 projection -> a1+a2 -> f2+a6 fused (bricks straight from the points) -> a3.  ``status`` is
+        non-zero for a frame the reference would have raised on (IndexError / sklearn ValueError)."""
+        r = self.ctx.project_ring(pts, pts_offsets, want=("ring3", "counter_i8"))
+        kpts, _kpix, n = self.ctx.select_keypoints(r["ring3"], r["counter_i8"], None, max_kpts=self.K)
+        packed, _, _, _nvox, st = self.ctx.gather_patches_scans(kpts, pts, pts_offsets, n)
+        feat = self.ctx.encode_frames(packed)
+        return kpts, feat, n, st | r["status"]
+
     # ---- whole batch ------------------------------------------------------------------------
-    def _finish(self, kpts, feat, n, samples, pair_ids):
+    def _finish(self, kpts, feat, n, samples, pair_ids, status=None):
         """Pairs stage + one D2H of the per-pair results; returns poses [P,16] float32 (host): refit
         R(9) T(3), isSuccess, nInliers, residualThreshold, trials — rows follow ``pair_ids``.
         ``samples`` is [P,500,4] (first round; failures go through a host-driven ladder) or
@@ -71,7 +83,7 @@ class OdometryPipeline:
         pc0, pc1 = kpts[:-1], kpts[1:]
         pair_idx = self.ctx.nn_match(feat[:-1], feat[1:])
         rounds = samples if samples.dim() == 4 else samples[None]
-        state = rt = None
+        state = rt = mask_acc = None
         thr_used = torch.full((P,), LADDER[-1], dtype=torch.float32, device=self.dev)
         for r in range(rounds.shape[0]):
             thr = torch.full((P,), LADDER[r], dtype=torch.float32, device=self.dev)
@@ -82,11 +94,20 @@ class OdometryPipeline:
                                       out_rt=None if rt is None else rt.clone())
             newly = (res[:, 12] != 0) if prev is None else ((res[:, 12] != 0) & (prev[:, 12] == 0))
             thr_used = torch.where(newly, thr, thr_used)
+            if self.keep_details:                       # inlier mask of the round that produced the model
+                mask_acc = mask if mask_acc is None else torch.where(newly[:, None], mask, mask_acc)
             state, rt = res, rt_r
+        if self.keep_details:
+            self.last_details = dict(kpts=kpts, feat=feat, pair_idx=pair_idx, mask=mask_acc, ok=state[:, 12] != 0)
         nf = n.to(torch.float32)
-        packed = torch.cat([state, rt, thr_used[:, None], nf[:-1, None], nf[1:, None]], 1)
+        bad = torch.zeros_like(nf) if status is None else (status != 0).to(torch.float32)
+        packed = torch.cat([state, rt, thr_used[:, None], nf[:-1, None], nf[1:, None],
+                            torch.maximum(bad[:-1], bad[1:])[:, None]], 1)
         host = packed.cpu().numpy()                     # the one sync point of the batch
         res, rt_h = host[:, :16], host[:, 16:28]
+        if host[:, 31].any():
+            raise api._lib.CaeloError("a scan has points outside the voxel grid / ring image or fewer than 496 "
+                                      "occupied voxels at some scale (the reference raises on it too)")
         if (host[:, 29] != self.K).any() or (host[:, 30] != self.K).any():
             raise api._lib.CaeloError("a frame yielded fewer than %d keypoints; use the per-pair API" % self.K)
         poses = np.zeros((P, 16), np.float32)
@@ -107,6 +128,38 @@ class OdometryPipeline:
         """Inputs already in HBM."""
         kpts, feat, n = self.frames_to_descriptors(ring, counter, vox, vox_offsets)
         return self._finish(kpts, feat, n, samples, pair_ids)
+
+    def run_device_scans(self, pts, pts_offsets, samples, pair_ids):
+        """Raw scans already in HBM."""
+        kpts, feat, n, st = self.scans_to_descriptors(pts, pts_offsets)
+        return self._finish(kpts, feat, n, samples, pair_ids, st)
+
+    def run_host_scans(self, pts_h: torch.Tensor, pts_offsets: np.ndarray, pair_ids: Sequence[int], chunks: int = 4):
+        """End-to-end from raw scans in HOST (pinned) memory: [sumN,4] f32 + row offsets [F+1].  Same
+        chunked upload / compute overlap as ``run_host``."""
+        off = np.asarray(pts_offsets, np.int64)
+        F = off.shape[0] - 1
+        cur = torch.cuda.current_stream(self.dev)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(self.dev)
+        cs = self._copy_stream
+        cs.wait_stream(cur)
+        bounds = np.linspace(0, F, min(chunks, F) + 1).astype(int)
+        parts = []
+        for c0, c1 in zip(bounds[:-1], bounds[1:]):
+            with torch.cuda.stream(cs):
+                p = pts_h[off[c0]:off[c1]].to(self.dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            parts.append((p, off[c0:c1 + 1] - off[c0], ev))
+        outs = []
+        for p, o, ev in parts:
+            cur.wait_event(ev)
+            p.record_stream(cur)
+            outs.append(self.scans_to_descriptors(p, o))
+        smp = torch.from_numpy(draw_samples(pair_ids, self.K, rounds=3)).pin_memory().to(self.dev, non_blocking=True)
+        kpts, feat, n, st = (torch.cat([o[i] for o in outs], 0) for i in range(4))
+        return self._finish(kpts, feat, n, smp, pair_ids, st)
 
     def run_host(self, ring_h: torch.Tensor, counter_h: torch.Tensor, vox_h: torch.Tensor,
                  vox_offsets: np.ndarray, pair_ids: Sequence[int], chunks: int = 4):
@@ -196,23 +249,28 @@ def gather_poses(poses: np.ndarray, device: torch.device):
 
 
 def chain_poses(rel: np.ndarray, Tr: Optional[np.ndarray] = None):
-    """The sequential pose chain of PoseEstimation.py:254-267 on rank 0: rel [P,16] rows ->
-    absolute poses [P+1,12] (KITTI format).  Tr is the 3x4 velodyne->camera calibration row;
-    identity if None."""
-    if Tr is None:
-        Tr = np.c_[np.eye(3), np.zeros(3)]
-    R_Tr, T_Tr = Tr[:, :3].astype(np.float64), Tr[:, 3:4].astype(np.float64)
+    """The sequential pose chain of PoseEstimation.py:209-267 on rank 0: rel [P,16] rows (R(9) T(3)
+    isSuccess ...) -> absolute poses [P+1,12] float32 (KITTI format, what np.savetxt writes at :272).
+    Tr is the 3x4 velodyne->camera calibration row (calib_.txt line 5, :209-214); identity if None.
+    Dtypes follow the reference: everything float32 until a pair fails — its R = I, T = 0 are float64
+    (Match.py:277-278) and promote the rest of the chain."""
+    Tr = np.asarray(np.c_[np.eye(3), np.zeros(3)] if Tr is None else Tr, dtype=np.float32).reshape(3, 4)
+    R_Tr = Tr[:, 0:3]
     R_Tr_inv = np.linalg.inv(R_Tr)
-    T_Tr_inv = -R_Tr_inv @ T_Tr
-    poses = np.zeros((rel.shape[0] + 1, 12))
-    R_acc, T_acc = np.eye(3), np.zeros((3, 1))
-    poses[0] = np.c_[R_acc, T_acc].reshape(-1)
+    T_Tr = Tr[:, 3].reshape(3, 1)
+    T_Tr_inv = -np.dot(R_Tr_inv, T_Tr)
+    poses = [np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], dtype=np.float32).reshape(12, 1)]
     for i in range(rel.shape[0]):
-        R = rel[i, :9].reshape(3, 3).astype(np.float64)
-        T = rel[i, 9:12].reshape(3, 1).astype(np.float64)
-        R_d = R_Tr @ R @ R_Tr_inv
-        T_d = R_Tr @ (R @ T_Tr_inv + T) + T_Tr
-        T_acc = R_acc @ T_d + T_acc
-        R_acc = R_acc @ R_d
-        poses[i + 1] = np.c_[R_acc, T_acc].reshape(-1)
-    return poses
+        ok = rel[i, 12] != 0
+        dt = np.float32 if ok else np.float64
+        relativeR = np.asarray(rel[i, :9], dtype=dt).reshape(3, 3)
+        relativeT = np.asarray(rel[i, 9:12], dtype=dt).reshape(3, 1)
+        pose0 = poses[i].reshape(3, 4)
+        R0, T0 = pose0[:, 0:3], pose0[:, 3].reshape(3, 1)
+        R_poseDiff = np.dot(R_Tr, np.dot(relativeR, R_Tr_inv))
+        T_poseDiff = np.dot(R_Tr, np.dot(relativeR, T_Tr_inv) + relativeT) + T_Tr
+        R = np.dot(R0, R_poseDiff)
+        T = np.dot(R0, T_poseDiff) + T0
+        poses.append(np.c_[R, T].reshape((12, 1)))
+    out = np.array(poses, dtype=np.float32)
+    return out.reshape(out.shape[0], 12)

@@ -112,14 +112,20 @@ def project_ring(pc: np.ndarray):
 
 
 def voxelize(pc: np.ndarray):
-    """Three occupied-voxel lists (int16 (V,3)) as Voxelization (Voxel.py:100-173) defines them:
-    float64 (p + Visible)/size truncated; unique; order is irrelevant to the hot path."""
+    """Three occupied-voxel lists (int16 (V,3)) as Voxelization (Voxel.py:100-173) defines them: float64
+    (p + Visible) / size truncated, the 2 cm index through the 1.28 m block as the reference computes it
+    (:120-139); unique, in first-seen order (the reference additionally groups list 0 by block — an order
+    the hot path never sees)."""
     p = pc[:, :3].astype(np.float64)
     ok = (np.abs(p[:, 0]) <= VIS[0]) & (np.abs(p[:, 1]) <= VIS[1]) & (np.abs(p[:, 2]) <= VIS[2])
     p = p[ok] + VIS
     out = []
-    for s in VSIZES:
-        v = (p / s).astype(np.int64)
+    for i, s in enumerate(VSIZES):
+        if i == 0:
+            b = (p / 1.28).astype(np.int64)
+            v = ((p - b * 1.28) / s).astype(np.int64) + b * 64
+        else:
+            v = (p / s).astype(np.int64)
         key = (v[:, 0] << 40) | (v[:, 1] << 20) | v[:, 2]
         _, first = np.unique(key, return_index=True)
         out.append(v[np.sort(first)].astype(np.int16))
@@ -149,4 +155,4 @@ def make_frames(n_frames: int, seed: int = 0, first_frame: int = 0):
             off.append(off[-1] + v.shape[0])
         npts.append(pc.shape[0])
     return dict(ring3=ring3, counter=counter, vox=np.concatenate(vox, 0), vox_offsets=np.asarray(off, np.int64),
-                n_points=npts)
+                n_points=npts, scans=scans)

@@ -149,6 +149,53 @@ int caelo_kabsch(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int
                  const int64_t *pair_idx, const uint8_t *mask, const float *skip_if_ok, int P,
                  float *Rt, int32_t *credible, void *stream);
 
+/* f1 — ProjectPC2SphericalRing (SphericalRing.py:72-94) for F scans at once.  pts: dev float32 rows
+ * (x,y,z,intensity), all scans concatenated; pts_offsets: HOST [F+1] int64 row offsets into pts.
+ * Outputs, each dev or NULL (at least one): ring5 [F,69,1800,5] f32 and counter_i32 [F,69,1800] — the
+ * function's two return values; ring3 [F,64,1792,3] f32 = ring5[:, 0:64, 0:1792, 0:3] and counter_i8
+ * [F,69,1800] — what GetAllRespondImgs (BatchPreprocess.py:97-108) builds from them for the CNN (the
+ * int8 copy wraps like numpy's assignment).  Every element of a requested output is written.
+ * status: dev int32 [F] or NULL — number of points whose column index equals ImgW (a point exactly on
+ * the -x axis with y = -0.0; the reference raises IndexError there, here the point is skipped). */
+int caelo_project_ring(caelo_ctx *ctx, const float *pts, const int64_t *pts_offsets, int F, float *ring5,
+                       int32_t *counter_i32, float *ring3, int8_t *counter_i8, int32_t *status,
+                       void *stream);
+
+/* f2 — Voxelization (Voxel.py:100-173) for F scans at once: the ordered occupied-voxel lists that
+ * BatchVoxelization.py:61 stores.  pts / pts_offsets as above; cap = rows reserved per list (>= the
+ * largest scan).  Outputs (dev): vox int16 [F,3,cap,3] — list s of frame f starts at row (f*3+s)*cap
+ * (AllVoxels0 grouped by 1.28 m block in block-first-seen order, AllVoxels1/2 in first-seen order);
+ * counts int32 [F,4] = len(AllVoxels0), len(AllVoxels1), len(AllVoxels2), len(avlBlocksList);
+ * optional local0 int16 [F,cap,3] (AllVoxels), blocks int16 [F,cap,3] (avlBlocksList), cnt int32
+ * [F,cap+1] (cntVoxelsLength); status int32 [F] or NULL — points that index outside the 156x156x23
+ * block grid (the reference raises IndexError; here they are skipped). */
+int caelo_voxelize(caelo_ctx *ctx, const float *pts, const int64_t *pts_offsets, int F, int cap,
+                   int16_t *vox, int32_t *counts, int16_t *local0, int16_t *blocks, int32_t *cnt,
+                   int32_t *status, void *stream);
+
+/* f2+a6 fused — GetPatchesList(Pts, *Voxelization(scan)[6:9]) (Voxel.py:100-216) for F scans without
+ * materialising the voxel lists: the occupancy bricks are built straight from the points with
+ * Voxelization's arithmetic (the list ORDER never reaches GetPatchesList).  kpts / n_kpts / packed /
+ * patches_f32 / trunc as in caelo_gather_patches; pts / pts_offsets as in caelo_voxelize.
+ * nvox: dev int32 [F,3] — distinct voxels per scale (= len(AllVoxels_s)); status: dev int32 [F] — low 30
+ * bits: points outside the block grid (reference: IndexError), bit 30: a list has < 496 voxels
+ * (reference: sklearn ValueError); patches of such a frame are all-zero. */
+int caelo_gather_patches_scans(caelo_ctx *ctx, const void *kpts, int kpts_f64, const int32_t *n_kpts,
+                               int F, int K, const float *pts, const int64_t *pts_offsets,
+                               uint32_t *packed, float *patches_f32, uint8_t *trunc, int32_t *nvox,
+                               int32_t *status, void *stream);
+
+/* f4 (front end) — ExtendKeyPtsInShpericalRing (SphericalRing.py:294-317) for B frames: all occupied pixels
+ * of each key pixel's 13x13 window, first key pixel wins a pixel, output in key-pixel order then row-major
+ * inside the window.  ring / counter as in caelo_select_keypoints (shared pixel origin); kpix dev
+ * [B,max_kpts,2] int64 (row,col), n_kpts dev [B] or NULL.  ext: dev [B,ext_cap,3] f32 (ext_cap <=
+ * max_kpts*169 always suffices), n_ext dev [B].  zero_counter != 0 reproduces the reference's in-place side
+ * effect (the windows of `counter` are zeroed, :307). */
+int caelo_extend_keypoints(caelo_ctx *ctx, const float *ring, int ring_C, int ring_H, int ring_W,
+                           void *counter, int counter_dtype, int cnt_H, int cnt_W, const int64_t *kpix,
+                           const int32_t *n_kpts, int B, int max_kpts, float *ext, int ext_cap,
+                           int32_t *n_ext, int zero_counter, void *stream);
+
 /* Debug: device buffer [grid][64][8] int64 receiving clock64 stamps of the encoder's per-patch
  * phases (NULL disables).  Used by tools/encoder_timeline.py. */
 int caelo_debug_set_timeline(caelo_ctx *ctx, long long *buf);

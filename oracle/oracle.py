@@ -123,6 +123,61 @@ def select_keypoints(ring: np.ndarray, counter: np.ndarray, resp: np.ndarray, ma
     return kpts[:n].copy(), kpix[:n].copy()
 
 
+
+# ---- f1 / f2: the offline pre-stages --------------------------------------------
+import math as _math
+
+AzimuthResolution = 0.20 * (_math.pi / 180)                       # SphericalRing.py:34,48
+VerticalViewDown = -24.8 * (_math.pi / 180)
+VerticalViewUp = 2.0 * (_math.pi / 180)
+VerticalResolution = (VerticalViewUp - VerticalViewDown) / (nLines - 1)
+VerticalPixelsOffset = -VerticalViewDown / VerticalResolution
+
+
+def project_ring(PC: np.ndarray):
+    """ProjectPC2SphericalRing restated (contract P1, SphericalRing.py:72-94).
+    PC (N,4) f32 -> (ring (69,1800,5) f32, counter (69,1800) i32); raises IndexError where numpy does."""
+    pc = np.ascontiguousarray(PC, np.float32)
+    assert pc.shape[0] > 3 and pc.shape[1] == 4
+    ring = np.zeros((ImgH, ImgW, 5), np.float32)
+    counter = np.zeros((ImgH, ImgW), np.int32)
+    f = lib().oracle_project_ring
+    f.restype = ctypes.c_int
+    bad = f(_p(pc), ctypes.c_int64(pc.shape[0]), ImgH, ImgW, ctypes.c_double(AzimuthResolution),
+            ctypes.c_double(VerticalResolution), ctypes.c_double(VerticalPixelsOffset), _p(ring), _p(counter))
+    if bad:
+        raise IndexError("index %d is out of bounds for axis 1 with size %d" % (ImgW, ImgW))
+    return ring, counter
+
+
+def voxelization(PC: np.ndarray):
+    """Voxelization restated (contract V1, Voxel.py:89-173) -> (avlBlocksList, cntVoxelsLength,
+    AllVoxels, AllVoxels0, AllVoxels1, AllVoxels2) exactly as BatchVoxelization.py:61 stores them."""
+    pc = np.ascontiguousarray(PC, np.float32)
+    N, C = pc.shape
+    v0, v1, v2, loc = (np.zeros((N, 3), np.int16) for _ in range(4))
+    blocks = np.zeros((N, 3), np.int16)
+    cnt = np.zeros((N + 1,), np.int32)
+    counts = np.zeros((4,), np.int32)
+    f = lib().oracle_voxelize
+    f.restype = ctypes.c_int
+    rc = f(_p(pc), ctypes.c_int64(N), C, _p(v0), _p(v1), _p(v2), _p(loc), _p(blocks), _p(cnt), _p(counts))
+    if rc:
+        raise IndexError("a point indexes outside the block grid (the reference raises here too)")
+    n0, n1, n2, nb = (int(c) for c in counts)
+    return (blocks[:nb].copy(), cnt[:nb + 1].copy(), loc[:n0].copy(), v0[:n0].copy(), v1[:n1].copy(), v2[:n2].copy())
+
+
+def extend_keypoints(SphericalRing, GridCounter, KeyPixels):
+    """ExtendKeyPtsInShpericalRing restated (SphericalRing.py:294-317): every still-occupied pixel of each key
+    pixel's 13x13 window, in key-pixel order then row-major; the counter window is zeroed IN PLACE."""
+    out = []
+    for iX, iY in np.asarray(KeyPixels).reshape(-1, 2):
+        oneMask = GridCounter[iX - 6:iX + 7, iY - 6:iY + 7]
+        out.append(SphericalRing[iX - 6:iX + 7, iY - 6:iY + 7, 0:3][oneMask > 0])
+        oneMask[:] = 0
+    return np.concatenate(out, 0).astype(np.float32) if out else np.zeros((0, 3), np.float32)
+
 # ---- a6 -----------------------------------------------------------------------------------
 def _pack(v):
     v = v.astype(np.int64)

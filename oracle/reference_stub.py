@@ -39,12 +39,8 @@ class _Dummy(types.ModuleType):
 _loaded = {}
 
 
-def load():
-    """Return a dict of the imported reference modules (cached)."""
-    if _loaded:
-        return _loaded
-    if not available():
-        raise RuntimeError("reference tree not mounted at %s" % REFERENCE_DIR)
+def prepare():
+    """Register the dependency stubs only (no reference module is imported)."""
     if not hasattr(np, "bool"):
         np.bool = bool  # type: ignore[attr-defined]
     if not hasattr(np, "int"):
@@ -57,6 +53,15 @@ def load():
     cp.bool = bool
     cp.argsort = lambda a, *args, **kw: np.argsort(a, kind="stable")
     sys.modules["cupy"] = cp
+
+
+def load():
+    """Return a dict of the imported reference modules (cached)."""
+    if _loaded:
+        return _loaded
+    if not available():
+        raise RuntimeError("reference tree not mounted at %s" % REFERENCE_DIR)
+    prepare()
     sys.path.insert(0, REFERENCE_DIR)
     try:
         import Voxel  # noqa: F401  (≈6 s: builds 560k nested lists, Voxel.py:57-86)

@@ -16,6 +16,10 @@ What is produced and from what:
   pose_SS.npz           outputs of the UNMODIFIED reference SolveRelativePose on the golden
                         descriptors of each demo pair for np.random.seed(0..2)
   usip_*.npz            DemoData third-party 128-D descriptors (nn-match KAT inputs) + scipy result
+  scan_SS_NNNNNN.npz    (``--scans``) two raw DemoData scans (N,4) f32 with the block list / block
+                        offsets / in-block voxels the UNMODIFIED reference Voxelization returns for
+                        them; together with frame_*.npz (ring, counter, AllVoxels0/1/2 from the same
+                        reference run) they pin the f1/f2 pre-stages
 """
 from __future__ import annotations
 
@@ -55,7 +59,25 @@ def export_weights():
         json.dump(meta, f, indent=1)
 
 
+SCAN_FRAMES = [("00", 0), ("01", 495)]
+
+
+def export_scans():
+    ref = reference_stub.load()
+    VX = ref["Voxel"]
+    z = zipfile.ZipFile(ZIP)
+    for seq, fr in SCAN_FRAMES:
+        pc = np.frombuffer(z.read("KITTI_odometry/velodyne/sequences/%s/velodyne/%06d.bin" % (seq, fr)),
+                           np.float32).reshape(-1, 4)
+        vox = VX.Voxelization(pc.astype(np.float64))
+        np.savez_compressed(os.path.join(HERE, "scan_%s_%06d.npz" % (seq, fr)), pc=pc,
+                            avlBlocksList=vox[3], cntVoxelsLength=vox[4], AllVoxels=vox[5])
+        print("scan", seq, fr, pc.shape, vox[3].shape, vox[5].shape)
+
+
 def main():
+    if "--scans" in sys.argv:
+        return export_scans()
     export_weights()
     ref = reference_stub.load()
     SR, VX, MT = ref["SphericalRing"], ref["Voxel"], ref["Match"]
@@ -94,6 +116,8 @@ def main():
                             patches_packed=packed)
         print(tag, "pts", pc.shape[0], "occ", occ.size, "vox", av0.shape[0], av1.shape[0], av2.shape[0],
               "kp5", kp5.shape, "kp3", kp3.shape)
+
+    export_scans()
 
     for seq, f0, f1 in (("00", 0, 1), ("01", 495, 496)):
         k0, c0 = golden["%s_%06d" % (seq, f0)]

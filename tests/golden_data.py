@@ -51,3 +51,12 @@ def unpack_patches(packed):
         bits = np.unpackbits(packed[s], axis=1).astype(np.float32)
         out.append(bits.reshape(-1, 16, 16, 16, 1))
     return out
+
+
+SCANS = ["00_000000", "01_000495"]
+
+
+def scan(tag):
+    """Raw DemoData scan (N,4) f32 + what the unmodified reference Voxelization returned for it."""
+    z = np.load(os.path.join(GOLDEN, "scan_%s.npz" % tag))
+    return {k: z[k] for k in z.files}

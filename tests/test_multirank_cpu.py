@@ -60,7 +60,8 @@ def test_shard_gather_chain_world2(tmp_path, n_pairs):
         Tr = want[i, 9:12].reshape(3, 1).astype(np.float64)
         T = R @ Tr + T
         R = R @ Rr
-    assert np.allclose(poses[-1].reshape(3, 4), np.c_[R, T], atol=1e-12)
+    assert poses.dtype == np.float32                      # the reference chains in float32 (PoseEstimation.py:254-272)
+    assert np.allclose(poses[-1].reshape(3, 4), np.c_[R, T], rtol=1e-4, atol=1e-4 * np.abs(T).max())
     assert poses.shape == (n_pairs + 1, 12)
 
 
@@ -87,7 +88,7 @@ def test_chain_poses_with_calibration():
         Td = R_Tr @ (R @ (-np.linalg.inv(R_Tr) @ T_Tr) + T) + T_Tr
         T0 = R0 @ Td + T0
         R0 = R0 @ Rd
-    assert np.allclose(poses[3].reshape(3, 4), np.c_[R0, T0])
+    assert np.allclose(poses[3].reshape(3, 4), np.c_[R0, T0], rtol=1e-5, atol=1e-5)
 
 
 def test_draw_samples_matches_global_stream():

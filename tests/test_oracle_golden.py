@@ -109,3 +109,51 @@ def test_ransac_failure_ladder(oracle_mod):
     np.random.set_state(st)
     np.random.random((3 * 500 * 4,))
     assert after == np.random.random()         # three full rounds of 500 trials x 4 draws consumed
+
+
+# ---- f1 / f2: the offline pre-stages ------------------------------------------
+@pytest.mark.parametrize("tag", G.SCANS)
+def test_project_ring_bit_identical_to_reference_run(oracle_mod, tag):
+    s, f = G.scan(tag), G.frame(tag)          # frame_*.npz: ProjectPC2SphericalRing run unmodified
+    ring, counter = oracle_mod.project_ring(s["pc"])
+    assert np.array_equal(ring.view(np.uint32), f["ring5"].view(np.uint32))
+    assert np.array_equal(counter, f["counter"])
+
+
+@pytest.mark.parametrize("tag", G.SCANS)
+def test_voxelization_bit_identical_to_reference_run(oracle_mod, tag):
+    s, f = G.scan(tag), G.frame(tag)          # Voxelization (Voxel.py:100) run unmodified
+    blocks, cnt, loc, v0, v1, v2 = oracle_mod.voxelization(s["pc"])
+    assert np.array_equal(blocks, s["avlBlocksList"]) and np.array_equal(cnt, s["cntVoxelsLength"].ravel())
+    assert np.array_equal(loc, s["AllVoxels"])
+    assert np.array_equal(v0, f["vox0"]) and np.array_equal(v1, f["vox1"]) and np.array_equal(v2, f["vox2"])
+
+
+def test_project_ring_edge_cases(oracle_mod):
+    pc = np.zeros((6, 4), np.float32)
+    pc[0] = [0, 0, 0, 1]                      # r == 0: dropped (SphericalRing.py:77-80)
+    pc[1] = [10, 0, 0.1, 0.5]                 # +x axis: col 900
+    pc[2] = [10, 0, 0.1, 0.7]                 # same pixel: the LAST point wins, counter = 2
+    pc[3] = [0, 0, 5, 0.1]                    # straight up: row < 0 -> skipped
+    pc[4] = [3, -4, -1, 0.2]
+    pc[5] = [-10, 1e-30, 0.0, 0.3]            # just short of the -x axis from above: col 0
+    ring, counter = oracle_mod.project_ring(pc)
+    assert counter.sum() == 4 and counter[:, 900].max() == 2
+    r, c = np.argwhere(counter == 2)[0]
+    assert ring[r, c, 3] == np.float32(0.7) and ring[r, c, 4] == np.float32(np.sqrt(np.float32(100.01)))
+    assert counter[:, 0].sum() == 1
+    pc[5] = [-10, -0.0, 0.0, 0.3]             # atan2 = -pi -> column 1800: numpy raises IndexError
+    with pytest.raises(IndexError):
+        oracle_mod.project_ring(pc)
+
+
+def test_voxelization_filter_and_order(oracle_mod):
+    pc = np.array([[1.0, 1.0, 0.0, 0], [50.0, 0, 0, 0], [1.001, 1.001, 0.001, 0],   # same 2 cm voxel as #0
+                   [100.0, 0, 0, 0],                                                # |x| > 99.84: dropped
+                   [1.03, 1.0, 0.0, 0], [50.3, 0, 0, 0], [0, 0, 14.73, 0]], np.float32)
+    blocks, cnt, loc, v0, v1, v2 = oracle_mod.voxelization(pc)
+    assert blocks.shape[0] == 2 and list(cnt) == [0, 2, 4]
+    # grouped by block in block-first-seen order: points 0,4 then 1,5
+    assert np.array_equal(v0[:, 0], [5042, 5043, 7492, 7506])
+    assert v1.shape[0] == 3 and v2.shape[0] == 2
+    assert np.array_equal(loc, v0 - blocks[[0, 0, 1, 1]] * 64)
