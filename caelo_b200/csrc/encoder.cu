@@ -264,9 +264,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
         unsigned long long *lwin = reinterpret_cast<unsigned long long *>(sm + SM_LWIN);
         unsigned short *lcell = reinterpret_cast<unsigned short *>(sm + SM_LCELL);
         int *lcnt = reinterpret_cast<int *>(sm + SM_LCNT);
+        unsigned pk_next = 0u;  // packed word of the next patch to produce, fetched one iteration ahead
+        auto fetch = [&](int i) {
+            if (tid < 128 && i < n_my) pk_next = __ldg(a.packed + (size_t)patch_of(i) * 128 + tid);
+        };
+        fetch(0);
         auto produce = [&](int i) {
             const int b = i & 1;
-            if (tid < 128) pk[b * 128 + tid] = a.packed[(size_t)patch_of(i) * 128 + tid];
+            if (tid < 128) pk[b * 128 + tid] = pk_next;
+            fetch(i + 1);
             if (tid == 128) lcnt[b] = 0;  // the other counter was read before the previous patch's second barrier
             asm volatile("bar.sync 1, 256;" ::: "memory");
             conv1_to_smem(pk + b * 128, k1s, b1s, bg, sm + SM_A + (2 * b) * A_VOL_BYTES,
@@ -411,12 +417,21 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const Conv3Args
             __syncwarp();
         }
     } else {
-        // scatter one patch's activations (split fp16) into the 9 shifted copies of buffer b
+        // scatter one patch's activations (split fp16) into the 9 shifted copies of buffer b; the global loads
+        // of the NEXT patch are issued right after, so their latency hides behind this patch's epilogue
+        const int part = tid & 1, idx = tid >> 1, pos = idx >> 1, half = idx & 1;
+        float4 nv0 = make_float4(0.f, 0.f, 0.f, 0.f), nv1 = nv0;
+        auto fetch = [&](int i) {
+            if (i >= n_my) return;
+            const float4 *src = reinterpret_cast<const float4 *>(a.act2 + (size_t)patch_of(i) * 1024 + pos * 16 + half * 8);
+            nv0 = __ldg(src);
+            nv1 = __ldg(src + 1);
+        };
+        fetch(0);
         auto produce = [&](int i) {
             const int b = i & 1;
-            const int part = tid & 1, idx = tid >> 1, pos = idx >> 1, half = idx & 1;
-            const float4 *src = reinterpret_cast<const float4 *>(a.act2 + (size_t)patch_of(i) * 1024 + pos * 16 + half * 8);
-            float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+            const float4 v0 = nv0, v1 = nv1;
+            fetch(i + 1);
             float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
             __half hv[8];
 #pragma unroll
@@ -475,19 +490,22 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const Conv3Args
 }
 
 // ---- dense1 (tcgen05) + tanh + dense2 + tanh ---------------------------------------------------
-// One CTA = 128 patches (M) x 208 outputs (N = 200 padded) x K = 2048, split-fp16 operands:
-//   D0 += A_hi W_hi^T + A_lo W_hi^T,  D1 += A_hi W_lo^T   (fp32 in TMEM), h = tanh(D0 + D1 + b).
+// One CTA = 256 patches (two M = 128 tiles) x 208 outputs (N = 200 padded) x K = 2048, split-fp16 operands:
+//   D_t += A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T   (one fp32 accumulator per tile in TMEM, 2 x 208 columns),
+//   h = tanh(D_t + b).  The kernel is bound by the L2 -> smem operand stream (the 1.7 MB of weights are
+//   re-streamed per CTA), hence the tall CTA tile: weights are fetched once per 256 patches.
 // Operands stream L2 -> smem by TMA (cp.async.bulk.tensor.3d): each row-major [rows][2048] fp16 matrix is
 // described as a 3-D tensor (8 elements, rows, 256 16-byte chunks) so that a box {8, R, 4} lands in shared
 // memory as [chunk][row][16 B] — exactly the canonical K-major no-swizzle UMMA layout (SBO = 128 B,
-// LBO = R*16 B).  Four-stage mbarrier pipeline: 1 TMA-producer thread, 1 MMA-issuer thread, 4 epilogue warps.
+// LBO = R*16 B).  Three-stage mbarrier pipeline: 1 TMA-producer thread, 1 MMA-issuer thread, 4 epilogue warps.
 constexpr int DN = 208;                       // dense1 outputs padded to a multiple of 16
+constexpr int DM = 256;                       // patches per CTA
 constexpr int DK_STAGE = 32;                  // K elements per stage (4 chunks of 16 B)
-constexpr int D_STAGES = 4;
-constexpr int D_A_BYTES = 128 * DK_STAGE * 2; // 8192
+constexpr int D_STAGES = 3;
+constexpr int D_A_BYTES = DM * DK_STAGE * 2;  // 16384
 constexpr int D_W_BYTES = DN * DK_STAGE * 2;  // 13312
-constexpr int D_STAGE = 2 * D_A_BYTES + 2 * D_W_BYTES;  // 43008
-constexpr int D_SM_BAR = D_STAGES * D_STAGE;  // 172032
+constexpr int D_STAGE = 2 * D_A_BYTES + 2 * D_W_BYTES;  // 59392
+constexpr int D_SM_BAR = D_STAGES * D_STAGE;  // 178176
 constexpr int D_SMEM = D_SM_BAR + 128;
 constexpr int D_THREADS = 192;
 
@@ -517,7 +535,7 @@ dense_tc_kernel(const DenseArgs a, const __grid_constant__ CUtensorMap map_ah, c
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(dsm + D_SM_BAR + 96);
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int row0 = blockIdx.x * 128;
+    const int row0 = blockIdx.x * DM;
     auto stamp = [&](int slot) { if (a.timeline) a.timeline[(size_t)blockIdx.x * 8 + slot] = clock64(); };
     if (tid == 0) stamp(0);
     if (warp == 4) umma::tmem_alloc(tmem_slot, 512);
@@ -563,14 +581,17 @@ dense_tc_kernel(const DenseArgs a, const __grid_constant__ CUtensorMap map_ah, c
                 const uint32_t st = sbase + s * D_STAGE;
 #pragma unroll
                 for (int j = 0; j < DK_STAGE / 16; ++j) {  // chunk stride = rows * 16 B
-                    uint64_t ah = umma::smem_desc(st + j * 2 * 2048, 2048, 128);
-                    uint64_t al = umma::smem_desc(st + D_A_BYTES + j * 2 * 2048, 2048, 128);
-                    uint64_t wh = umma::smem_desc(st + 2 * D_A_BYTES + j * 2 * (DN * 16), DN * 16, 128);
-                    uint64_t wl = umma::smem_desc(st + 2 * D_A_BYTES + D_W_BYTES + j * 2 * (DN * 16), DN * 16, 128);
+                    const uint64_t wh = umma::smem_desc(st + 2 * D_A_BYTES + j * 2 * (DN * 16), DN * 16, 128);
+                    const uint64_t wl = umma::smem_desc(st + 2 * D_A_BYTES + D_W_BYTES + j * 2 * (DN * 16), DN * 16, 128);
                     const uint32_t acc = (kt | j) ? 1u : 0u;
-                    umma::mma_f16(tbase, ah, wh, idesc, acc);
-                    umma::mma_f16(tbase, al, wh, idesc, 1u);
-                    umma::mma_f16(tbase + 256, ah, wl, idesc, acc);
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {          // the two 128-row tiles of the CTA
+                        const uint64_t ah = umma::smem_desc(st + j * 2 * (DM * 16) + t * 2048, DM * 16, 128);
+                        const uint64_t al = umma::smem_desc(st + D_A_BYTES + j * 2 * (DM * 16) + t * 2048, DM * 16, 128);
+                        umma::mma_f16(tbase + t * 256, ah, wh, idesc, acc);
+                        umma::mma_f16(tbase + t * 256, al, wh, idesc, 1u);
+                        umma::mma_f16(tbase + t * 256, ah, wl, idesc, 1u);
+                    }
                 }
                 umma::commit(&empty[s]);
                 if (kt == NKT - 1) umma::commit(accum);
@@ -578,7 +599,7 @@ dense_tc_kernel(const DenseArgs a, const __grid_constant__ CUtensorMap map_ah, c
             __syncwarp();
         }
     } else {
-        // ===== epilogue: h = tanh(D0 + D1 + b) -> smem (aliases the operand stages), dense2 + tanh =====
+        // ===== epilogue: h = tanh(D + b) -> smem (aliases the operand stages), dense2 + tanh =====
         float *Hs = reinterpret_cast<float *>(dsm);              // [128][201]
         float *W2s = Hs + 128 * 201;                             // [200][20] + bd2[20] + bd1[200]
         if (tid == 0) stamp(2);
@@ -589,47 +610,49 @@ dense_tc_kernel(const DenseArgs a, const __grid_constant__ CUtensorMap map_ah, c
         if (tid < 20) W2s[4000 + tid] = a.bd2[tid];
         for (int i = tid; i < 200; i += 128) W2s[4032 + i] = a.bd1[i];
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < DN; c0 += 16) {
-            uint32_t v0[16], v1[16];
-            umma::tmem_ld_x16(trow + c0, v0);
-            umma::tmem_ld_x16(trow + 256 + c0, v1);
-            umma::tmem_ld_wait();
+        for (int t = 0; t < 2; ++t) {
+            const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16) + t * 256;
+#pragma unroll 1
+            for (int c0 = 0; c0 < DN; c0 += 16) {
+                uint32_t v0[16];
+                umma::tmem_ld_x16(trow + c0, v0);
+                umma::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                int c = c0 + j;
-                if (c < 200) Hs[tid * 201 + c] = fast_tanh((__uint_as_float(v0[j]) + __uint_as_float(v1[j])) + W2s[4032 + c]);
-            }
-        }
-        if (tid == 0) stamp(4);
-        const int p = row0 + tid;
-        if (p < a.P) {
-            float acc[20];
-#pragma unroll
-            for (int j = 0; j < 20; ++j) acc[j] = W2s[4000 + j];
-#pragma unroll 4
-            for (int k = 0; k < 200; ++k) {
-                const float h = Hs[tid * 201 + k];
-                const float4 *w = reinterpret_cast<const float4 *>(W2s + k * 20);
-#pragma unroll
-                for (int q = 0; q < 5; ++q) {
-                    float4 wv = w[q];
-                    acc[4 * q + 0] = fmaf(h, wv.x, acc[4 * q + 0]);
-                    acc[4 * q + 1] = fmaf(h, wv.y, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(h, wv.z, acc[4 * q + 2]);
-                    acc[4 * q + 3] = fmaf(h, wv.w, acc[4 * q + 3]);
+                for (int j = 0; j < 16; ++j) {
+                    int c = c0 + j;
+                    if (c < 200) Hs[tid * 201 + c] = fast_tanh(__uint_as_float(v0[j]) + W2s[4032 + c]);
                 }
             }
-            float *o;
-            if (a.frame_mode) {
-                int k = p % a.K, sc = (p / a.K) % 3, f = p / (3 * a.K);
-                o = a.feat + ((size_t)f * a.K + k) * 60 + sc * 20;
-            } else {
-                o = a.feat + (size_t)p * a.feat_stride + a.feat_col0;
-            }
+            if (tid == 0) stamp(4);
+            const int p = row0 + t * 128 + tid;    // each thread reads back only its own row of Hs
+            if (p < a.P) {
+                float acc[20];
 #pragma unroll
-            for (int j = 0; j < 20; ++j) o[j] = tanhf(acc[j]);
+                for (int j = 0; j < 20; ++j) acc[j] = W2s[4000 + j];
+#pragma unroll 4
+                for (int k = 0; k < 200; ++k) {
+                    const float h = Hs[tid * 201 + k];
+                    const float4 *w = reinterpret_cast<const float4 *>(W2s + k * 20);
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        float4 wv = w[q];
+                        acc[4 * q + 0] = fmaf(h, wv.x, acc[4 * q + 0]);
+                        acc[4 * q + 1] = fmaf(h, wv.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(h, wv.z, acc[4 * q + 2]);
+                        acc[4 * q + 3] = fmaf(h, wv.w, acc[4 * q + 3]);
+                    }
+                }
+                float *o;
+                if (a.frame_mode) {
+                    int k = p % a.K, sc = (p / a.K) % 3, f = p / (3 * a.K);
+                    o = a.feat + ((size_t)f * a.K + k) * 60 + sc * 20;
+                } else {
+                    o = a.feat + (size_t)p * a.feat_stride + a.feat_col0;
+                }
+#pragma unroll
+                for (int j = 0; j < 20; ++j) o[j] = tanhf(acc[j]);
+            }
         }
         if (tid == 0) stamp(5);
         umma::fence_before_thread_sync();
@@ -702,7 +725,7 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
 {
     if (!ctx->have_encoder) return CAELO_ERR_NO_WEIGHTS;
     if (P <= 0) return CAELO_OK;
-    const size_t Ppad = ((size_t)P + 127) / 128 * 128;
+    const size_t Ppad = ((size_t)P + DM - 1) / DM * DM;
     int rc = caelo_reserve(ctx, ctx->enc_ws, Ppad * 2048 * 2 * 2 + (size_t)P * 1024 * 4);
     if (rc) return rc;
     __half *act3_hi = reinterpret_cast<__half *>(ctx->enc_ws.ptr);
@@ -720,15 +743,15 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
     { ProfScope ps_(ctx, "conv3_tc_kernel", st); conv3_tc_kernel<<<grid3, C3_THREADS, C3_SMEM, st>>>(c3); }
     CAELO_LAUNCH_CHECK(ctx);
     CUtensorMap m_ah, m_al, m_wh, m_wl;
-    if ((rc = make_kmajor_map(ctx, &m_ah, act3_hi, Ppad, 128))) return rc;
-    if ((rc = make_kmajor_map(ctx, &m_al, act3_lo, Ppad, 128))) return rc;
+    if ((rc = make_kmajor_map(ctx, &m_ah, act3_hi, Ppad, DM))) return rc;
+    if ((rc = make_kmajor_map(ctx, &m_al, act3_lo, Ppad, DM))) return rc;
     if ((rc = make_kmajor_map(ctx, &m_wh, ctx->enc_w1t_hi, DN, DN))) return rc;
     if ((rc = make_kmajor_map(ctx, &m_wl, ctx->enc_w1t_lo, DN, DN))) return rc;
     DenseArgs d;
     d.bd1 = ctx->enc.bd1; d.d2 = ctx->enc.d2; d.bd2 = ctx->enc.bd2;
     d.feat = feat; d.P = P; d.feat_stride = feat_stride; d.feat_col0 = feat_col0;
     d.frame_mode = frame_mode; d.K = K; d.timeline = ctx->dbg_timeline ? ctx->dbg_timeline + (size_t)2 * ctx->num_sms * 64 * 8 : nullptr;
-    { ProfScope ps_(ctx, "dense_tc_kernel", st); dense_tc_kernel<<<(unsigned)(Ppad / 128), D_THREADS, D_SMEM, st>>>(d, m_ah, m_al, m_wh, m_wl); }
+    { ProfScope ps_(ctx, "dense_tc_kernel", st); dense_tc_kernel<<<(unsigned)(Ppad / DM), D_THREADS, D_SMEM, st>>>(d, m_ah, m_al, m_wh, m_wl); }
     CAELO_LAUNCH_CHECK(ctx);
     return CAELO_OK;
 }

@@ -11,7 +11,7 @@
 
 namespace {
 
-constexpr int RADIUS = 6, WIN = 2 * RADIUS + 1;   // nNeighborRadius (SphericalRing.py:295)
+constexpr int RADIUS = 6;                         // nNeighborRadius (SphericalRing.py:295)
 constexpr int NOOWNER = 0x7F7F7F7F;               // what cudaMemset(0x7F) leaves
 
 struct ExtendArgs {

@@ -82,16 +82,22 @@ struct ScanBuildArgs {
     int *status;                 // dev [F] or null
 };
 
-__device__ __forceinline__ void brick_set(const Table &t, int x, int y, int z, int *count)
+// returns true iff this call set a bit that was clear (a voxel seen for the first time).  Most points of a
+// scan fall into a voxel that is already recorded: plain loads filter those before any atomic is issued.
+__device__ __forceinline__ bool brick_set(const Table &t, int x, int y, int z)
 {
-    unsigned long long key = brick_key(x >> 2, y >> 2, z >> 2);
-    unsigned long long bit = 1ull << (((x & 3) * 4 + (y & 3)) * 4 + (z & 3));
+    const unsigned long long key = brick_key(x >> 2, y >> 2, z >> 2);
+    const unsigned long long bit = 1ull << (((x & 3) * 4 + (y & 3)) * 4 + (z & 3));
     unsigned slot = hash64(key) & t.cap_mask;
     while (true) {
-        unsigned long long old = atomicCAS(t.keys + slot, EMPTY, key);
-        if (old == EMPTY || old == key) {
-            if (!(atomicOr(t.masks + slot, bit) & bit)) atomicAdd(count, 1);
-            break;
+        unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(t.keys + slot);
+        if (k == EMPTY) {
+            k = atomicCAS(t.keys + slot, EMPTY, key);
+            if (k == EMPTY) k = key;
+        }
+        if (k == key) {
+            if (*reinterpret_cast<volatile unsigned long long *>(t.masks + slot) & bit) return false;
+            return !(atomicOr(t.masks + slot, bit) & bit);
         }
         slot = (slot + 1) & t.cap_mask;
     }
@@ -99,20 +105,37 @@ __device__ __forceinline__ void brick_set(const Table &t, int x, int y, int z, i
 
 __global__ void __launch_bounds__(256) scan_brick_insert_kernel(const ScanBuildArgs a)
 {
-    const int f = blockIdx.y;
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
     const long long beg = a.offsets[f], n = a.offsets[f + 1] - beg;
     const float4 *p4 = reinterpret_cast<const float4 *>(a.pts) + beg;
     const Table t0 = a.tables[f * 3], t1 = a.tables[f * 3 + 1], t2 = a.tables[f * 3 + 2];
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float4 p = p4[i];
-        VoxelOfPoint v;
-        const int st = voxel_of_point(p.x, p.y, p.z, v);
-        if (st < 0 && a.status) atomicAdd(a.status + f, 1);
-        if (st <= 0) continue;
-        brick_set(t0, v.g0[0], v.g0[1], v.g0[2], a.nvox + f * 3);
-        brick_set(t1, v.g1[0], v.g1[1], v.g1[2], a.nvox + f * 3 + 1);
-        brick_set(t2, v.g2[0], v.g2[1], v.g2[2], a.nvox + f * 3 + 2);
+    int bad = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // warp-uniform trip count: the ballots below need every lane
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {
+        const long long i = i0 + lane;
+        bool n0 = false, n1 = false, n2 = false;
+        if (i < n) {
+            const float4 p = p4[i];
+            VoxelOfPoint v;
+            const int st = voxel_of_point(p.x, p.y, p.z, v);
+            bad += st < 0;
+            if (st > 0) {
+                n0 = brick_set(t0, v.g0[0], v.g0[1], v.g0[2]);
+                n1 = brick_set(t1, v.g1[0], v.g1[1], v.g1[2]);
+                n2 = brick_set(t2, v.g2[0], v.g2[1], v.g2[2]);
+            }
+        }
+        // warp-aggregated voxel counters (one atomic per warp and scale instead of one per new voxel)
+        const unsigned m0 = __ballot_sync(0xffffffffu, n0), m1 = __ballot_sync(0xffffffffu, n1),
+                       m2 = __ballot_sync(0xffffffffu, n2);
+        if (lane == 0) {
+            if (m0) atomicAdd(a.nvox + f * 3, __popc(m0));
+            if (m1) atomicAdd(a.nvox + f * 3 + 1, __popc(m1));
+            if (m2) atomicAdd(a.nvox + f * 3 + 2, __popc(m2));
+        }
     }
+    if (bad && a.status) atomicAdd(a.status + f, bad);
 }
 
 __device__ __forceinline__ unsigned long long brick_lookup(const Table &t, unsigned long long key)

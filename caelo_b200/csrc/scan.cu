@@ -141,13 +141,19 @@ __device__ __forceinline__ unsigned long long vkey(int x, int y, int z)
     return (unsigned long long)(unsigned)x | ((unsigned long long)(unsigned)y << 16) | ((unsigned long long)(unsigned)z << 32);
 }
 
+// Key -> slot with the smallest point index kept in vals.  Plain loads first: most points of a scan repeat a
+// key that is already present with a smaller index, so neither the CAS nor the atomicMin is issued for them.
 __device__ __forceinline__ unsigned claim(unsigned long long *keys, int *vals, unsigned mask, unsigned long long key, int i)
 {
     unsigned slot = hash64(key) & mask;
     while (true) {
-        unsigned long long old = atomicCAS(keys + slot, EMPTY, key);
-        if (old == EMPTY || old == key) {
-            atomicMin(vals + slot, i);
+        unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(keys + slot);
+        if (k == EMPTY) {
+            k = atomicCAS(keys + slot, EMPTY, key);
+            if (k == EMPTY) k = key;
+        }
+        if (k == key) {
+            if (*reinterpret_cast<volatile int *>(vals + slot) > i) atomicMin(vals + slot, i);
             return slot;
         }
         slot = (slot + 1) & mask;

@@ -111,7 +111,7 @@ def test_fused_scan_gather_equals_list_gather(api, oracle_mod):
     off = np.zeros(len(scans) + 1, np.int64)
     off[1:] = np.cumsum([s.shape[0] for s in scans])
     pts = torch.from_numpy(np.concatenate(scans, 0)).cuda()
-    kp = np.stack([G.frame(t)["golden_KeyPts"][:512].astype(np.float32) for t in tags])
+    kp = np.ascontiguousarray(np.stack([G.frame(t)["golden_KeyPts"][:512] for t in tags]), np.float32)
     kpts = torch.from_numpy(kp).cuda()
     packed, _, trunc, nvox, status = ctx.gather_patches_scans(kpts, pts, off, want_trunc=True)
     assert not status.any().item()
