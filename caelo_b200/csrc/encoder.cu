@@ -60,6 +60,7 @@ struct Conv12Args {
     const float *k2, *b2;    // (27,8,16), (16)
     float *act2;             // [P,64,16] fp32
     int P;
+    int K3;                  // frame mode: 3*K (patch order [F][3][K]) — CTAs then walk the patches scale-interleaved; 0 = as stored
     long long *timeline;     // debug: [gridDim.x][64][8] clock64 stamps, or null
 };
 
@@ -73,9 +74,11 @@ __device__ __forceinline__ constexpr int tap_off(int t)  // byte offset of tap t
 //   pass 1  thread = one (px,py) column, two pz cells: the 16 occupancy rows around the column are read
 //           once; a cell whose 4x4x4 window is empty gets the precomputed tanh(b1), the others are
 //           appended (cell, window) to a list in shared memory;
-//   pass 2  listed cells are dealt round-robin: for each of the 8 pooled sub-positions the 27
-//           neighbourhood bits are gathered from the window and the selected weights summed in
-//           ascending tap order, max over sub-positions, tanh, split to fp16 hi/lo.
+//   pass 2  listed cells are dealt 8 per warp, four lanes per cell (one per (sx,sy), each doing both sz):
+//           the 27 neighbourhood bits of a sub-position are gathered from the window and the selected
+//           weights summed in ascending tap order; max over the sub-positions (two channel-halving
+//           exchanges across the four lanes), tanh, split to fp16 hi/lo — each lane finishes two
+//           channels.  Short per-lane chains matter: this phase is latency-bound, not issue-bound.
 __device__ __forceinline__ void conv1_to_smem(const unsigned *pk, const float *k1s, const float *b1s,
                                               const uint4 *bg, unsigned char *a_hi, unsigned char *a_lo,
                                               unsigned long long *lwin, unsigned short *lcell, int *lcount, int tid)
@@ -102,7 +105,7 @@ __device__ __forceinline__ void conv1_to_smem(const unsigned *pk, const float *k
             const int pz = 2 * zq + half;
             const int pi = ((px + 1) * 10 + (py + 1)) * 10 + (pz + 1);
             unsigned long long win = 0ull;
-            if (any) {
+            if (((any << 1) >> (2 * pz)) & 0xFu) {   // some row has a voxel at z = 2pz-1 .. 2pz+2
 #pragma unroll
                 for (int i = 0; i < 16; ++i) win |= (unsigned long long)((r[i] >> (2 * pz)) & 0xFu) << (i * 4);
             }
@@ -126,49 +129,61 @@ __device__ __forceinline__ void conv1_to_smem(const unsigned *pk, const float *k
         }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    // pass 2: four consecutive lanes share a listed cell, lane q = (sx,sy) computes its two sz sub-positions;
+    // a warp takes 8 cells per round (warp-uniform trip count: the shuffles below need every lane)
     const int n = *lcount;
-    for (int k = tid; k < n; k += TC_WORKERS) {
-        const unsigned long long win = lwin[k];
-        const int pi = lcell[k];
+    const int q = tid & 3, sx = q >> 1, sy = q & 1;
+    for (int k0 = (tid >> 5) * 8; k0 < n; k0 += (TC_WORKERS / 32) * 8) {
+        const int k = k0 + ((tid & 31) >> 2);
+        const bool valid = k < n;
+        const unsigned long long win = valid ? lwin[k] : 0ull;
+        // 3x3 nibbles (dx,dy) of the window around (sx,sy): nibble j = dx*3+dy at bits 4j..4j+3
+        const unsigned long long w2 = win >> (16 * sx + 4 * sy);
+        const unsigned long long g = (w2 & 0xFFFull) | (((w2 >> 16) & 0xFFFull) << 12) | (((w2 >> 32) & 0xFFFull) << 24);
         float best[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) best[c] = -3.0e38f;
 #pragma unroll
-        for (int sxy = 0; sxy < 4; ++sxy) {
-            const int sx = sxy >> 1, sy = sxy & 1;
-            // 3x3 nibbles (dx,dy) of the window around (sx,sy): nibble j = dx*3+dy at bits 4j..4j+3
-            unsigned long long g = 0ull;
+        for (int sz = 0; sz < 2; ++sz) {
+            unsigned long long m = (g >> sz) & 0x777777777ull;  // dz = 0..2 of every nibble
+            float acc[8];
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) g |= ((win >> (16 * (sx + dx) + 4 * sy)) & 0xFFFull) << (12 * dx);
-#pragma unroll
-            for (int sz = 0; sz < 2; ++sz) {
-                unsigned long long m = (g >> sz) & 0x777777777ull;  // dz = 0..2 of every nibble
-                float acc[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) acc[c] = b1s[c];
-                while (m) {
-                    const int b = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    const float4 *w = reinterpret_cast<const float4 *>(k1s + ((b >> 2) * 3 + (b & 3)) * 8);
-                    const float4 w0 = w[0], w1 = w[1];
-                    acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
-                    acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
-                }
-#pragma unroll
-                for (int c = 0; c < 8; ++c) best[c] = fmaxf(best[c], acc[c]);
+            for (int c = 0; c < 8; ++c) acc[c] = b1s[c];
+            while (m) {
+                const int b = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                const float4 *w = reinterpret_cast<const float4 *>(k1s + ((b >> 2) * 3 + (b & 3)) * 8);
+                const float4 w0 = w[0], w1 = w[1];
+                acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
+                acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
             }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) best[c] = fmaxf(best[c], acc[c]);
         }
-        __half2 hi[4], lo[4];
+        // max over the four (sx,sy) lanes, halving the channel set a lane carries at each exchange:
+        // after xor-1 a lane keeps 4 channels, after xor-2 its final 2 (lane q ends with channels 2q, 2q+1)
+        float h4[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            __half h0, l0, h1, l1;
-            umma::split_f16(fast_tanh(best[2 * c]), h0, l0);
-            umma::split_f16(fast_tanh(best[2 * c + 1]), h1, l1);
-            hi[c] = __halves2half2(h0, h1);
-            lo[c] = __halves2half2(l0, l1);
+            const float send = (q & 2) ? best[c] : best[4 + c];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+            h4[c] = fmaxf((q & 2) ? best[4 + c] : best[c], recv);
         }
-        *reinterpret_cast<uint4 *>(a_hi + pi * 16) = *reinterpret_cast<uint4 *>(hi);
-        *reinterpret_cast<uint4 *>(a_lo + pi * 16) = *reinterpret_cast<uint4 *>(lo);
+        float o[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float send = (q & 1) ? h4[c] : h4[2 + c];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            o[c] = fmaxf((q & 1) ? h4[2 + c] : h4[c], recv);
+        }
+        if (valid) {
+            const int pi = lcell[k];
+            __half h0, l0, h1, l1;
+            umma::split_f16(fast_tanh(o[0]), h0, l0);
+            umma::split_f16(fast_tanh(o[1]), h1, l1);
+            *reinterpret_cast<__half2 *>(a_hi + pi * 16 + q * 4) = __halves2half2(h0, h1);
+            *reinterpret_cast<__half2 *>(a_lo + pi * 16 + q * 4) = __halves2half2(l0, l1);
+        }
     }
 }
 
@@ -223,7 +238,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
     const uint32_t sA = umma::smem_u32(sm + SM_A), sW = umma::smem_u32(sm + SM_W2);
 
     const int n_my = (a.P - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // patches of this CTA
-    auto patch_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
+    // Patches of the three scales differ a lot in conv1 work (2 / 46 / 127 voxels on average) but not in
+    // conv2 work: in frame mode consecutive patches of a CTA (and the two CTAs of an SM) cycle through the
+    // scales, so CUDA-core-heavy and tensor-heavy patches overlap instead of arriving in phases.
+    auto patch_of = [&](int i) {
+        const int v = (int)blockIdx.x + i * (int)gridDim.x;
+        if (a.K3 == 0) return v;
+        const int f = v / a.K3, r = v - f * a.K3, K = a.K3 / 3;
+        return f * a.K3 + (r % 3) * K + r / 3;
+    };
     auto stamp = [&](int i, int slot) {
         if (a.timeline && i < 64) a.timeline[((size_t)blockIdx.x * 64 + i) * 8 + slot] = clock64();
     };
@@ -300,19 +323,26 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
                 float m[16];
 #pragma unroll
                 for (int c = 0; c < 16; ++c) m[c] = (__uint_as_float(v[c]) + __uint_as_float(v[16 + c])) + b2s[c];
-                // 2x2x2 max-pool: partners differ in z (lane^1), y (lane^8), x-slice (lane^16)
+                // 2x2x2 max-pool: partners differ in x-slice (lane^16), y (lane^8), z (lane^1).  At each exchange a
+                // lane sends the half of its channels the partner keeps and receives the half it keeps itself:
+                // 16 -> 8 -> 4 -> 2 channels, 14 shuffles instead of 48; the lane with bits (x,y,z) = (lane>>4&1,
+                // lane>>3&1, lane&1) ends with channels 8x + 4y + 2z, +1 of the group's pooled cell.
+                float m8[8], m4[4];
+                const bool bx = lane & 16, by = lane & 8, bz = lane & 1;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    m[c] = fmaxf(m[c], __shfl_xor_sync(0xffffffffu, m[c], 1));
-                    m[c] = fmaxf(m[c], __shfl_xor_sync(0xffffffffu, m[c], 8));
-                    m[c] = fmaxf(m[c], __shfl_xor_sync(0xffffffffu, m[c], 16));
+                for (int c = 0; c < 8; ++c) {
+                    const float recv = __shfl_xor_sync(0xffffffffu, bx ? m[c] : m[8 + c], 16);
+                    m8[c] = fmaxf(bx ? m[8 + c] : m[c], recv);
                 }
-                // the 8 lanes of a pooling group share the result; lane j of the group finishes channels 2j, 2j+1
-                const int j = (lane & 1) | ((lane >> 2) & 2) | ((lane >> 2) & 4);
-                float o0 = 0.f, o1 = 0.f;
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    if (c == j) { o0 = m[2 * c]; o1 = m[2 * c + 1]; }
+                for (int c = 0; c < 4; ++c) {
+                    const float recv = __shfl_xor_sync(0xffffffffu, by ? m8[c] : m8[4 + c], 8);
+                    m4[c] = fmaxf(by ? m8[4 + c] : m8[c], recv);
+                }
+                const float r0 = __shfl_xor_sync(0xffffffffu, bz ? m4[0] : m4[2], 1);
+                const float r1 = __shfl_xor_sync(0xffffffffu, bz ? m4[1] : m4[3], 1);
+                const float o0 = fmaxf(bz ? m4[2] : m4[0], r0), o1 = fmaxf(bz ? m4[3] : m4[1], r1);
+                const int j = (bx ? 4 : 0) + (by ? 2 : 0) + (bz ? 1 : 0);   // channel pair index
                 const int pos = (pair * 4 + q) * 4 + ((lane & 7) >> 1);
                 *reinterpret_cast<float2 *>(out + pos * 16 + 2 * j) = make_float2(fast_tanh(o0), fast_tanh(o1));
             }
@@ -733,7 +763,7 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
     float *act2 = reinterpret_cast<float *>(act3_lo + Ppad * 2048);
     Conv12Args c;
     c.packed = packed; c.k1 = ctx->enc.k1; c.b1 = ctx->enc.b1; c.k2 = ctx->enc.k2; c.b2 = ctx->enc.b2;
-    c.act2 = act2; c.P = P; c.timeline = ctx->dbg_timeline;
+    c.act2 = act2; c.P = P; c.K3 = frame_mode ? 3 * K : 0; c.timeline = ctx->dbg_timeline;
     int grid = 2 * ctx->num_sms < P ? 2 * ctx->num_sms : P;
     { ProfScope ps_(ctx, "conv12_tc_kernel", st); conv12_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(c); }
     CAELO_LAUNCH_CHECK(ctx);

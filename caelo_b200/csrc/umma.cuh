@@ -121,8 +121,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *mbar, uint32_t parity)
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity)
 {
-    while (!mbar_try_wait(mbar, parity)) {
-    }
+    // try_wait already suspends for a hardware-chosen time; back off a little more so that parked
+    // warps do not take issue slots from the warps still producing (15% of all issued instructions
+    // of conv12 were this loop before)
+    while (!mbar_try_wait(mbar, parity)) __nanosleep(40);
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *mbar)
 {
