@@ -240,8 +240,7 @@ def run_ours(args, rank, local_rank, world):
                 vox=torch.from_numpy(data["vox"]).pin_memory())
     voff = data["vox_offsets"]
     d_ring, d_counter, d_vox = (host[k].to(dev) for k in ("ring", "counter", "vox"))
-    samples_h = pipeline.draw_samples(pair_ids, K_PTS, rounds=3)   # all three ladder rounds, pre-drawn
-    d_samples = torch.from_numpy(samples_h).to(dev)
+    d_samples = None      # RANSAC sample indices are generated on the device inside every step (ctx.draw_samples)
     flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)
 
     def barrier():
@@ -288,14 +287,27 @@ def run_ours(args, rank, local_rank, world):
     ms_total = float(t.item())
 
     # ---- end to end: host (pinned) inputs, H2D + sample drawing + kernels + D2H every step ----
-    for _ in range(2):
-        step_host()
+    # (the public sequence call: pipeline.run_host_stream uploads batch i+1 while batch i computes; every step
+    #  still copies its own inputs from pinned host memory and reads its own result back)
+    def host_steps(n):
+        for _ in range(n):
+            yield ("rings", host["ring"], host["counter"], host["vox"], voff, pair_ids)
+
+    for poses in pipe.run_host_stream(host_steps(3)):
+        pipeline.gather_poses(poses, dev)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
+    for poses in pipe.run_host_stream(host_steps(args.steps)):
+        pipeline.gather_poses(poses, dev)
     barrier()
     e2e_s = time.perf_counter() - t0
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        step_host()
+    barrier()
+    e2e_single_s = (time.perf_counter() - t0) / 5
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -326,12 +338,16 @@ def run_ours(args, rank, local_rank, world):
         prof_s = ctx.profile_fetch()
         ctx.profile(False)
         ms_s = sum(a.elapsed_time(b) for a, b in evs)
-        for _ in range(2):
-            pipe.run_host_scans(scans_h, soff, pair_ids)
+        def scan_steps(n):
+            for _ in range(n):
+                yield ("scans", scans_h, soff, pair_ids)
+
+        for poses in pipe.run_host_stream(scan_steps(3)):
+            pipeline.gather_poses(poses, dev)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            pipeline.gather_poses(pipe.run_host_scans(scans_h, soff, pair_ids), dev)
+        for poses in pipe.run_host_stream(scan_steps(args.steps)):
+            pipeline.gather_poses(poses, dev)
         barrier()
         e2e_scans_s = time.perf_counter() - t0
         t = torch.tensor([ms_s, e2e_scans_s], dtype=torch.float64, device=dev)
@@ -342,7 +358,7 @@ def run_ours(args, rank, local_rank, world):
                       "value": world * P * args.steps / (float(t[0].item()) * 1e-3), "unit": UNIT,
                       "ms_per_step": float(t[0].item()) / args.steps,
                       "e2e": {"value": world * P * args.steps / float(t[1].item()), "unit": UNIT,
-                              "h2d_bytes_per_step": int(scans_h.numel() * 4 + samples_h.nbytes), "d2h_bytes_per_step": P * 32 * 4},
+                              "h2d_bytes_per_step": int(scans_h.numel() * 4 + soff.nbytes + 8 * P), "d2h_bytes_per_step": P * 32 * 4},
                       "poses_identical_to_ring_path": same,
                       "time_by_kernel_ms_per_step": {k: v[1] / args.steps for k, v in prof_s.items()}}
 
@@ -366,7 +382,7 @@ def run_ours(args, rank, local_rank, world):
             kern("dense_tc_kernel", FLOP_DENSE_PER_PATCH * n_patches, peaks["tf_sustained"], "TFLOP/s", 1e12),
             kern("respond_score_kernel<fused>", BYTES_RESPOND_SELECT_PER_FRAME * F, peaks["hbm"], "GB/s", 1e9),
             kern("gather_kernel", (n_patches * 512 + F * 3 * 4), peaks["hbm"], "GB/s", 1e9),
-            kern("nn_tile_kernel", 2.0 * P * K_PTS * K_PTS * 60, peaks["tf_sustained"], "TFLOP/s", 1e12),
+            kern("nn_tc_kernel", 2.0 * P * K_PTS * K_PTS * 60, peaks["tf_sustained"], "TFLOP/s", 1e12),
         ) if k]
         top = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
         dom = next((k for k in kernels if k["kernel"] == top), kernels[0] if kernels else None)
@@ -382,14 +398,17 @@ def run_ours(args, rank, local_rank, world):
                         "peak_source": peaks["source"] + (" bf16 sustained" if dom["unit"] == "TFLOP/s" else " copy"),
                         "all_kernels": kernels,
                         "time_by_kernel_ms_per_step": {k: v[1] / args.steps for k, v in prof.items()}}
-        h2d = sum(host[k].numel() * host[k].element_size() for k in host) + samples_h.nbytes + voff.nbytes
-        d2h = P * (16 + 12 + 1) * 4
+        h2d = sum(host[k].numel() * host[k].element_size() for k in host) + voff.nbytes + 8 * P
+        d2h = P * 32 * 4
         line = {"metric": METRIC, "value": world * P * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": _config(args, world), "clocks": clocks,
                 "e2e": {"value": world * P * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h)},
+                        "d2h_bytes_per_step": int(d2h),
+                        "how": "pipeline.run_host_stream over the K steps (pinned host inputs; batch i+1's H2D overlaps "
+                               "batch i's kernels); one isolated run_host call (no overlap between calls) gives "
+                               "%.1f %s" % (world * P / e2e_single_s, UNIT)},
                 "gpu_launches": int(launches), "roofline": roofline,
                 "pairs_with_model": ok_pairs, "from_scans": from_scans}
         if world == 1 and not args.no_cpu_baseline:

@@ -42,6 +42,7 @@ SIGNATURES = {
     "caelo_nn_match": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "caelo_ransac_round": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                    c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "caelo_ransac_draw_samples": (c_int, [c_void_p, POINTER(c_int64), c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "caelo_project_ring": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
     "caelo_voxelize": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int, c_int, c_void_p, c_void_p, c_void_p,

@@ -288,6 +288,17 @@ class Context:
         self.check(rc, "caelo_ransac_round")
         return result, mask, counts
 
+    def draw_samples(self, seeds, n_points: int, rounds: int = 1, rounds_done: int = 0, T: int = MAX_TRIALS):
+        """RANSAC sample indices of ``rounds`` ladder rounds for pairs seeded np.random.seed(seeds[i]), generated
+        on the device (numpy's legacy MT19937 stream, bit for bit) -> int32 [rounds,P,T,4]."""
+        sd = np.ascontiguousarray(seeds, np.int64)
+        P = sd.shape[0]
+        out = torch.empty((rounds, P, T, 4), dtype=torch.int32, device=self.device)
+        self.check(self.lib.caelo_ransac_draw_samples(self.h, sd.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), P,
+                                                      int(n_points), T, rounds, rounds_done, _ptr(out), _stream()),
+                   "caelo_ransac_draw_samples")
+        return out
+
     def kabsch(self, pc0, pc1, pair_idx=None, mask=None, skip_if_ok=None, out_rt=None):
         P, N0, _ = pc0.shape
         N = pc1.shape[1]

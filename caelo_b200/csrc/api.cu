@@ -8,6 +8,7 @@
 int caelo_encoder_init(caelo_ctx *ctx);
 int caelo_encoder_prepare(caelo_ctx *ctx);
 int caelo_match_init(caelo_ctx *ctx);
+int caelo_pose_init(caelo_ctx *ctx);
 int caelo_select_init(caelo_ctx *ctx);
 
 extern "C" int caelo_version(void) { return 100; }
@@ -49,6 +50,7 @@ extern "C" int caelo_create(int device_id, caelo_ctx **out)
     memset(&ctx->enc, 0, sizeof(ctx->enc));
     int rc = caelo_encoder_init(ctx);
     if (!rc) rc = caelo_match_init(ctx);
+    if (!rc) rc = caelo_pose_init(ctx);
     if (!rc) rc = caelo_select_init(ctx);
     if (rc) { delete ctx; return rc; }
     *out = ctx;
@@ -60,7 +62,7 @@ extern "C" int caelo_destroy(caelo_ctx *ctx)
     if (!ctx) return CAELO_ERR_ARG;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    Scratch *all[] = {&ctx->cand, &ctx->bricks, &ctx->enc_ws, &ctx->pose_ws, &ctx->misc, &ctx->scan_ws};
+    Scratch *all[] = {&ctx->cand, &ctx->bricks, &ctx->enc_ws, &ctx->pose_ws, &ctx->misc, &ctx->scan_ws, &ctx->seed_ws};
     for (Scratch *s : all)
         if (s->ptr) cudaFree(s->ptr);
     for (int i = 0; i < caelo_ctx::kStageSlots; ++i) {
@@ -69,6 +71,7 @@ extern "C" int caelo_destroy(caelo_ctx *ctx)
     }
     if (ctx->enc_blob) cudaFree(ctx->enc_blob);
     if (ctx->enc_w1t_hi) cudaFree(ctx->enc_w1t_hi);
+    if (ctx->enc_c12_tables) cudaFree(ctx->enc_c12_tables);
     delete ctx;
     return CAELO_OK;
 }

@@ -48,6 +48,7 @@ struct caelo_ctx {
     EncoderWeightsDev enc;
     float *enc_blob = nullptr;
     __half *enc_w1t_hi = nullptr, *enc_w1t_lo = nullptr;  // dense1 weights, transposed split fp16 [208][2048]
+    float *enc_c12_tables = nullptr;                      // conv12: conv1 partial-sum table [9][8][8] + background table [27][16]
     // ring of pinned host staging slots for small async H2D copies (caelo_stage_acquire)
     static constexpr int kStageSlots = 8;
     void *stage_ptr[kStageSlots] = {};
@@ -61,6 +62,7 @@ struct caelo_ctx {
     Scratch pose_ws;   // ransac: hypotheses
     Scratch misc;
     Scratch scan_ws;   // projection / voxelisation: pixel owners, hash tables, compaction lists
+    Scratch seed_ws;   // ransac: per-pair generator seeds
 };
 
 #define CAELO_CUDA(ctx, call)                         \

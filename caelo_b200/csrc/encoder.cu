@@ -45,23 +45,32 @@ constexpr int W2_BYTES = 28 * 512;                    // 28 tap chunks x 32 rows
 // dynamic smem layout (bytes)
 constexpr int SM_A = 0;                               // [buf 2][hi,lo][A_VOL_BYTES]
 constexpr int SM_W2 = SM_A + 4 * A_VOL_BYTES;         // 64000
-constexpr int SM_K1 = SM_W2 + W2_BYTES;               // floats: k1[216] b1[8] b2[16]
-constexpr int SM_BG = SM_K1 + (216 + 8 + 16) * 4;     // tanh(b1) as fp16 hi (16 B) + lo (16 B)
-constexpr int SM_PK = SM_BG + 32;                     // packed patch [2][128] words
-constexpr int SM_LWIN = SM_PK + 2 * 512;              // non-empty cell list: windows [512] u64
-constexpr int SM_LCELL = SM_LWIN + 512 * 8;           //                      padded cell index [512] u16
-constexpr int SM_LCNT = SM_LCELL + 512 * 2;           //                      count [2] (double-buffered)
-constexpr int SM_BAR = SM_LCNT + 16;                  // 6 mbarriers + tmem base
+constexpr int T1_ROW = 8 * 32 + 16;                   // one nibble's 8 partial-sum rows (+16 B: rows 4-7 shifted, no bank conflicts)
+constexpr int SM_T1 = SM_W2 + W2_BYTES;               // conv1 partial sums [9 (dx,dy)][8 dz-patterns][8 ch] f32
+constexpr int SM_B12 = SM_T1 + 9 * T1_ROW;            // floats: b1[8] b2[16]
+constexpr int SM_BG = SM_B12 + (8 + 16) * 4;          // tanh(b1) as fp16 hi (16 B) + lo (16 B)
+constexpr int PK_PITCH = 20;                          // staged occupancy rows: [18 (x halo)][20 (y halo, padded)] u16
+constexpr int PK_BYTES = 18 * PK_PITCH * 2;           // 720
+constexpr int SM_PK = SM_BG + 32;                     // [2][PK_BYTES]
+constexpr int SM_LWIN = SM_PK + 2 * PK_BYTES;         // non-empty cell list: windows [512] u64
+constexpr int SM_LCELL = SM_LWIN + 512 * 8;           //                      padded cell index [2 buffers][512] u16
+constexpr int SM_LCNT = SM_LCELL + 2 * 512 * 2;       //                      count [2] (double-buffered)
+constexpr int SM_XS = SM_LCNT + 16;                   // per buffer: 8 flags "x-slice holds a non-empty cell"
+constexpr int SM_BGP = SM_XS + 16;                    // conv2+pool+tanh of an all-background neighbourhood [27 classes][16]
+constexpr int SM_BAR = SM_BGP + 27 * 16 * 4;          // 6 mbarriers + tmem base
 constexpr int TC_SMEM = SM_BAR + 64;
+static_assert(SM_T1 % 16 == 0 && SM_LWIN % 8 == 0 && SM_XS % 8 == 0 && SM_BGP % 8 == 0 && SM_BAR % 8 == 0, "smem alignment");
 
 struct Conv12Args {
     const unsigned *packed;  // [P,128]
     const float *k1, *b1;    // (27,8), (8)
     const float *k2, *b2;    // (27,8,16), (16)
+    const float *tables;     // prep_conv12_tables_kernel: T1 [9][8][8] then background [27][16]
     float *act2;             // [P,64,16] fp32
     int P;
     int K3;                  // frame mode: 3*K (patch order [F][3][K]) — CTAs then walk the patches scale-interleaved; 0 = as stored
-    long long *timeline;     // debug: [gridDim.x][64][8] clock64 stamps, or null
+    int skip_bg;             // 1: x-slice pairs whose whole conv2 neighbourhood is background skip their MMAs
+    long long *timeline;     // debug: [gridDim.x][64][16] clock64 stamps, or null
 };
 
 __device__ __forceinline__ constexpr int tap_off(int t)  // byte offset of tap t inside the padded volume
@@ -70,51 +79,55 @@ __device__ __forceinline__ constexpr int tap_off(int t)  // byte offset of tap t
 }
 
 // conv1 + maxpool + tanh for one patch -> A_hi / A_lo interior, in two passes so that the work is
-// balanced over the 256 worker threads however the occupied voxels cluster:
-//   pass 1  thread = one (px,py) column, two pz cells: the 16 occupancy rows around the column are read
-//           once; a cell whose 4x4x4 window is empty gets the precomputed tanh(b1), the others are
-//           appended (cell, window) to a list in shared memory;
-//   pass 2  listed cells are dealt 8 per warp, four lanes per cell (one per (sx,sy), each doing both sz):
-//           the 27 neighbourhood bits of a sub-position are gathered from the window and the selected
-//           weights summed in ascending tap order; max over the sub-positions (two channel-halving
-//           exchanges across the four lanes), tanh, split to fp16 hi/lo — each lane finishes two
-//           channels.  Short per-lane chains matter: this phase is latency-bound, not issue-bound.
-__device__ __forceinline__ void conv1_to_smem(const unsigned *pk, const float *k1s, const float *b1s,
-                                              const uint4 *bg, unsigned char *a_hi, unsigned char *a_lo,
-                                              unsigned long long *lwin, unsigned short *lcell, int *lcount, int tid)
+// balanced over the 256 worker threads however the occupied voxels cluster.  The volumes are kept
+// "clean": every interior cell holds tanh(b1) (conv1 of an empty neighbourhood) unless a patch wrote it,
+// and the cells a patch wrote are restored before the buffer is reused — so empty cells cost nothing.
+//   pass 1  thread = one (px,py) column, two pz cells: the 4x4 occupancy rows around the column are read
+//           from the halo-padded staging copy (8 aligned 32-bit loads); cells with a non-empty 4x4x4
+//           window are appended (cell, window) to a list in shared memory;
+//   pass 2  listed cells are dealt 4 per warp, EIGHT lanes per cell — one per pooled sub-position
+//           (sx,sy,sz).  A sub-position's 27 neighbourhood bits are 9 (dx,dy) groups of 3 dz bits; each
+//           group indexes a table of precomputed partial weight sums (9 x 8 patterns x 8 channels), so the
+//           conv is 9 table rows added up: no data-dependent loop, every load independent.  Max over the
+//           sub-positions by three channel-halving exchanges, tanh, split to fp16 hi/lo — each lane
+//           finishes one channel.
+__device__ __forceinline__ void conv1_to_smem(const unsigned short *rows, const unsigned char *t1, const float *b1s,
+                                              unsigned char *a_hi, unsigned char *a_lo,
+                                              unsigned long long *lwin, unsigned short *lcell, int *lcount,
+                                              unsigned char *xs_any, int tid, int &n_listed, long long *tl)
 {
-    const unsigned short *rows = reinterpret_cast<const unsigned short *>(pk);  // row (x,y): 16 z-bits
     const int lane = tid & 31;
     {
         const int col = tid >> 2, zq = tid & 3;
         const int px = col >> 3, py = col & 7;
         unsigned r[16];
-        unsigned any = 0;
+        unsigned any = 0, cells = 0;
+        // staged row (x,y) lives at [(x+1)*PK_PITCH + (y+1)]; the column needs x = 2px-1.., y = 2py-1.. (4 each)
+        const unsigned *rp = reinterpret_cast<const unsigned *>(rows + (2 * px) * PK_PITCH + 2 * py);
 #pragma unroll
-        for (int ix = 0; ix < 4; ++ix)
-#pragma unroll
-            for (int iy = 0; iy < 4; ++iy) {
-                int x = 2 * px - 1 + ix, y = 2 * py - 1 + iy;
-                unsigned v = 0;
-                if (x >= 0 && x < 16 && y >= 0 && y < 16) v = rows[x * 16 + y];
-                r[ix * 4 + iy] = v << 1;  // bit z+1 <-> voxel z
-                any |= v;
-            }
+        for (int ix = 0; ix < 4; ++ix) {
+            const unsigned v01 = rp[ix * (PK_PITCH / 2)], v23 = rp[ix * (PK_PITCH / 2) + 1];
+            r[ix * 4 + 0] = (v01 & 0xFFFFu) << 1;  // bit z+1 <-> voxel z
+            r[ix * 4 + 1] = (v01 >> 16) << 1;
+            r[ix * 4 + 2] = (v23 & 0xFFFFu) << 1;
+            r[ix * 4 + 3] = (v23 >> 16) << 1;
+            any |= v01 | v23;
+        }
+        any = (any | (any >> 16)) & 0xFFFFu;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int pz = 2 * zq + half;
-            const int pi = ((px + 1) * 10 + (py + 1)) * 10 + (pz + 1);
-            unsigned long long win = 0ull;
+            unsigned wlo = 0u, whi = 0u;
             if (((any << 1) >> (2 * pz)) & 0xFu) {   // some row has a voxel at z = 2pz-1 .. 2pz+2
 #pragma unroll
-                for (int i = 0; i < 16; ++i) win |= (unsigned long long)((r[i] >> (2 * pz)) & 0xFu) << (i * 4);
+                for (int i = 0; i < 8; ++i) {
+                    wlo |= ((r[i] >> (2 * pz)) & 0xFu) << (i * 4);
+                    whi |= ((r[8 + i] >> (2 * pz)) & 0xFu) << (i * 4);
+                }
             }
-            const bool nz = win != 0ull;
-            if (!nz) {
-                *reinterpret_cast<uint4 *>(a_hi + pi * 16) = bg[0];
-                *reinterpret_cast<uint4 *>(a_lo + pi * 16) = bg[1];
-            }
+            const bool nz = (wlo | whi) != 0u;
             const unsigned m = __ballot_sync(0xffffffffu, nz);
+            cells |= m;
             if (m) {
                 int base = 0;
                 const int leader = __ffs(m) - 1;
@@ -122,86 +135,87 @@ __device__ __forceinline__ void conv1_to_smem(const unsigned *pk, const float *k
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (nz) {
                     const int k = base + __popc(m & ((1u << lane) - 1u));
-                    lwin[k] = win;
-                    lcell[k] = (unsigned short)pi;
+                    lwin[k] = ((unsigned long long)whi << 32) | wlo;
+                    lcell[k] = (unsigned short)(((px + 1) * 10 + (py + 1)) * 10 + (pz + 1));
                 }
             }
         }
+        if (lane == 0) xs_any[tid >> 5] = cells != 0u;   // warp w owns the cells of x-slice px = w
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    // pass 2: four consecutive lanes share a listed cell, lane q = (sx,sy) computes its two sz sub-positions;
-    // a warp takes 8 cells per round (warp-uniform trip count: the shuffles below need every lane)
+    if (tl && tid == 0) tl[7] = clock64();
+    // pass 2: eight consecutive lanes share a listed cell, lane s = (sx,sy,sz); a warp takes 4 cells per round
+    // (warp-uniform trip count: the shuffles below need every lane)
     const int n = *lcount;
-    const int q = tid & 3, sx = q >> 1, sy = q & 1;
-    for (int k0 = (tid >> 5) * 8; k0 < n; k0 += (TC_WORKERS / 32) * 8) {
-        const int k = k0 + ((tid & 31) >> 2);
+    n_listed = n;
+    const int sub = tid & 7, sx = sub >> 2, sy = (sub >> 1) & 1, sz = sub & 1;
+    for (int k0 = (tid >> 5) * 4; k0 < n; k0 += (TC_WORKERS / 32) * 4) {
+        const int k = k0 + (lane >> 3);
         const bool valid = k < n;
         const unsigned long long win = valid ? lwin[k] : 0ull;
-        // 3x3 nibbles (dx,dy) of the window around (sx,sy): nibble j = dx*3+dy at bits 4j..4j+3
-        const unsigned long long w2 = win >> (16 * sx + 4 * sy);
-        const unsigned long long g = (w2 & 0xFFFull) | (((w2 >> 16) & 0xFFFull) << 12) | (((w2 >> 32) & 0xFFFull) << 24);
-        float best[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) best[c] = -3.0e38f;
-#pragma unroll
-        for (int sz = 0; sz < 2; ++sz) {
-            unsigned long long m = (g >> sz) & 0x777777777ull;  // dz = 0..2 of every nibble
-            float acc[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[c] = b1s[c];
-            while (m) {
-                const int b = __ffsll((long long)m) - 1;
-                m &= m - 1;
-                const float4 *w = reinterpret_cast<const float4 *>(k1s + ((b >> 2) * 3 + (b & 3)) * 8);
-                const float4 w0 = w[0], w1 = w[1];
-                acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
-                acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
-            }
-#pragma unroll
-            for (int c = 0; c < 8; ++c) best[c] = fmaxf(best[c], acc[c]);
+        // 3x3 nibbles (dx,dy) of the window around (sx,sy): nibble j = dx*3+dy at bits 4j..4j+3; dz = 0..2 above sz
+        const unsigned long long w2 = win >> (16 * sx + 4 * sy + sz);
+        const unsigned g0 = (unsigned)w2 & 0x777u, g1 = (unsigned)(w2 >> 16) & 0x777u, g2 = (unsigned)(w2 >> 32) & 0x777u;
+        float acc[8];
+        {
+            const float4 c0 = *reinterpret_cast<const float4 *>(b1s), c1 = *reinterpret_cast<const float4 *>(b1s + 4);
+            acc[0] = c0.x; acc[1] = c0.y; acc[2] = c0.z; acc[3] = c0.w;
+            acc[4] = c1.x; acc[5] = c1.y; acc[6] = c1.z; acc[7] = c1.w;
         }
-        // max over the four (sx,sy) lanes, halving the channel set a lane carries at each exchange:
-        // after xor-1 a lane keeps 4 channels, after xor-2 its final 2 (lane q ends with channels 2q, 2q+1)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const unsigned gj = (j < 3) ? g0 : ((j < 6) ? g1 : g2);
+            const unsigned pat = (gj >> (4 * (j % 3))) & 7u;
+            const float4 *row = reinterpret_cast<const float4 *>(t1 + j * T1_ROW + pat * 32 + (pat >> 2) * 16);
+            const float4 w0 = row[0], w1 = row[1];
+            acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
+            acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
+        }
+        // max over the eight sub-position lanes, halving the channel set a lane carries at each exchange:
+        // lane `sub` ends with channel 4*sx + 2*sy + sz
         float h4[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const float send = (q & 2) ? best[c] : best[4 + c];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
-            h4[c] = fmaxf((q & 2) ? best[4 + c] : best[c], recv);
+            const float recv = __shfl_xor_sync(0xffffffffu, sx ? acc[c] : acc[4 + c], 4);
+            h4[c] = fmaxf(sx ? acc[4 + c] : acc[c], recv);
         }
-        float o[2];
+        float h2[2];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            const float send = (q & 1) ? h4[c] : h4[2 + c];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-            o[c] = fmaxf((q & 1) ? h4[2 + c] : h4[c], recv);
+            const float recv = __shfl_xor_sync(0xffffffffu, sy ? h4[c] : h4[2 + c], 2);
+            h2[c] = fmaxf(sy ? h4[2 + c] : h4[c], recv);
         }
+        const float recv = __shfl_xor_sync(0xffffffffu, sz ? h2[0] : h2[1], 1);
+        const float o = fmaxf(sz ? h2[1] : h2[0], recv);
         if (valid) {
             const int pi = lcell[k];
-            __half h0, l0, h1, l1;
-            umma::split_f16(fast_tanh(o[0]), h0, l0);
-            umma::split_f16(fast_tanh(o[1]), h1, l1);
-            *reinterpret_cast<__half2 *>(a_hi + pi * 16 + q * 4) = __halves2half2(h0, h1);
-            *reinterpret_cast<__half2 *>(a_lo + pi * 16 + q * 4) = __halves2half2(l0, l1);
+            __half h, l;
+            umma::split_f16(fast_tanh(o), h, l);
+            *reinterpret_cast<__half *>(a_hi + pi * 16 + sub * 2) = h;
+            *reinterpret_cast<__half *>(a_lo + pi * 16 + sub * 2) = l;
         }
     }
+    if (tl && tid == 0) tl[8] = clock64();
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Args a)
 {
     extern __shared__ __align__(128) unsigned char sm[];
-    float *k1s = reinterpret_cast<float *>(sm + SM_K1);
-    float *b1s = k1s + 216, *b2s = b1s + 8;
+    float *b1s = reinterpret_cast<float *>(sm + SM_B12), *b2s = b1s + 8;
     const uint4 *bg = reinterpret_cast<const uint4 *>(sm + SM_BG);
-    unsigned *pk = reinterpret_cast<unsigned *>(sm + SM_PK);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(sm + SM_BAR);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SM_BAR + 48);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
 
-    // ---- one-time setup: zero the operand volumes (halo stays zero), stage weights ----
-    for (int i = tid; i < (SM_K1) / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(sm)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 216; i += TC_THREADS) k1s[i] = a.k1[i];
+    // ---- one-time setup: zero the operand volumes and the staged rows (halos stay zero), stage weights/tables ----
+    for (int i = tid; i < SM_T1 / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(sm)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 2 * PK_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(sm + SM_PK)[i] = make_uint4(0, 0, 0, 0);
+    for (int e = tid; e < 9 * 8 * 8; e += TC_THREADS) {       // T1 row (j,pat) at j*T1_ROW + pat*32 + (pat>>2)*16
+        const int j = e >> 6, pat = (e >> 3) & 7, c = e & 7;
+        *reinterpret_cast<float *>(sm + SM_T1 + j * T1_ROW + pat * 32 + (pat >> 2) * 16 + c * 4) = a.tables[e];
+    }
+    for (int e = tid; e < 27 * 16; e += TC_THREADS) reinterpret_cast<float *>(sm + SM_BGP)[e] = a.tables[576 + e];
     if (tid < 8) {
         b1s[tid] = a.b1[tid];
         __half h, l;
@@ -211,6 +225,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
     }
     if (tid < 16) b2s[tid] = a.b2[tid];
     __syncthreads();
+    // every interior cell of the four operand volumes starts as the background value tanh(b1)
+    for (int e = tid; e < 4 * 512; e += TC_THREADS) {
+        const int vol = e >> 9, c = e & 511;
+        const int pi = (((c >> 6) + 1) * 10 + ((c >> 3) & 7) + 1) * 10 + (c & 7) + 1;
+        *reinterpret_cast<uint4 *>(sm + SM_A + vol * A_VOL_BYTES + pi * 16) = bg[vol & 1];
+    }
     // B operand: row n (0..15 = W_hi, 16..31 = W_lo of out-channel n%16), k = tap*8 + ci; chunk = tap
     for (int e = tid; e < 27 * 8 * 16; e += TC_THREADS) {
         int t = e / 128, ci = (e / 16) % 8, co = e % 16;
@@ -248,7 +268,21 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
         return f * a.K3 + (r % 3) * K + r / 3;
     };
     auto stamp = [&](int i, int slot) {
-        if (a.timeline && i < 64) a.timeline[((size_t)blockIdx.x * 64 + i) * 8 + slot] = clock64();
+        if (a.timeline && i < 64) a.timeline[((size_t)blockIdx.x * 64 + i) * 16 + slot] = clock64();
+    };
+
+    // x-slice pairs (= one pooled x) of buffer b that need conv2: some cell of slices 2p-1 .. 2p+2 is non-empty
+    auto active_pairs = [&](int b) -> unsigned {
+        if (!a.skip_bg) return 0xFu;
+        const unsigned long long f = *reinterpret_cast<const unsigned long long *>(sm + SM_XS + 8 * b);
+        unsigned m = 0;  // bit xs: slice xs holds a non-empty cell
+#pragma unroll
+        for (int xs = 0; xs < 8; ++xs) m |= (unsigned)((f >> (8 * xs)) & 1ull) << xs;
+        const unsigned near = m | (m << 1) | (m >> 1);  // slice xs has a non-empty cell within +-1
+        unsigned act = 0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) act |= ((near >> (2 * p)) & 3u) ? (1u << p) : 0u;
+        return act;
     };
 
     if (warp == 8) {
@@ -260,9 +294,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
             if (k >= 1) umma::mbar_wait(&tempty[b], (uint32_t)((k - 1) & 1));
             umma::fence_after_thread_sync();
             if (lane == 0) stamp(j, 5);
+            const unsigned act = active_pairs(b);
             if (umma::elect_one()) {
 #pragma unroll 1
                 for (int xs = 0; xs < 8; ++xs) {  // x-slice: M = 64 positions (y,z)
+                    if (!((act >> (xs >> 1)) & 1u)) continue;
                     const uint32_t d = tbase + ((uint32_t)((xs & 1) * 16) << 16) + b * 128 + (xs >> 1) * 32;
 #pragma unroll
                     for (int part = 0; part < 2; ++part) {
@@ -288,35 +324,71 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
         unsigned short *lcell = reinterpret_cast<unsigned short *>(sm + SM_LCELL);
         int *lcnt = reinterpret_cast<int *>(sm + SM_LCNT);
         unsigned pk_next = 0u;  // packed word of the next patch to produce, fetched one iteration ahead
+        int p_next = 0;         // its patch index
+        int n_dirty0 = 0, n_dirty1 = 0;  // cells of each buffer that the patch before wrote (to be restored to the background)
         auto fetch = [&](int i) {
-            if (tid < 128 && i < n_my) pk_next = __ldg(a.packed + (size_t)patch_of(i) * 128 + tid);
+            if (i < n_my) {
+                p_next = patch_of(i);
+                if (tid < 128) pk_next = __ldg(a.packed + (size_t)p_next * 128 + tid);
+            }
         };
         fetch(0);
         auto produce = [&](int i) {
             const int b = i & 1;
-            if (tid < 128) pk[b * 128 + tid] = pk_next;
+            unsigned char *a_hi = sm + SM_A + (2 * b) * A_VOL_BYTES, *a_lo = a_hi + A_VOL_BYTES;
+            unsigned short *rows = reinterpret_cast<unsigned short *>(sm + SM_PK + b * PK_BYTES);
+            unsigned short *lc = lcell + b * 512;
+            // restore the cells the previous patch of this buffer wrote (its MMAs are complete: tfull was waited on)
+            const int nd = b ? n_dirty1 : n_dirty0;
+            for (int k = tid; k < nd; k += TC_WORKERS) {
+                const int pi = lc[k];
+                *reinterpret_cast<uint4 *>(a_hi + pi * 16) = bg[0];
+                *reinterpret_cast<uint4 *>(a_lo + pi * 16) = bg[1];
+            }
+            if (tid < 128) {  // word tid = occupancy rows (x, y) and (x, y+1), x = tid/8, y = 2*(tid%8)
+                unsigned short *dst = rows + ((tid >> 3) + 1) * PK_PITCH + 2 * (tid & 7) + 1;
+                dst[0] = (unsigned short)(pk_next & 0xFFFFu);
+                dst[1] = (unsigned short)(pk_next >> 16);
+            }
             fetch(i + 1);
             if (tid == 128) lcnt[b] = 0;  // the other counter was read before the previous patch's second barrier
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            conv1_to_smem(pk + b * 128, k1s, b1s, bg, sm + SM_A + (2 * b) * A_VOL_BYTES,
-                          sm + SM_A + (2 * b + 1) * A_VOL_BYTES, lwin, lcell, lcnt + b, tid);
+            long long *tl = (a.timeline && i >= 1 && i <= 64) ? a.timeline + ((size_t)blockIdx.x * 64 + (i - 1)) * 16 : nullptr;
+            if (tl && tid == 0) tl[2] = clock64();
+            int n_listed;
+            conv1_to_smem(rows, sm + SM_T1, b1s, a_hi, a_lo, lwin, lc, lcnt + b, sm + SM_XS + 8 * b, tid, n_listed, tl);
+            if (b) n_dirty1 = n_listed; else n_dirty0 = n_listed;
             umma::fence_proxy_async();
             umma::mbar_arrive(&full[b]);
         };
+        int p_cur = p_next;
         if (n_my > 0) produce(0);
         for (int i = 0; i < n_my; ++i) {
             const int b = i & 1;
             if (tid == 0) stamp(i, 0);
+            const int p_this = p_cur;
+            p_cur = p_next;                    // patch i+1 (set by the fetch inside produce(i))
             if (i + 1 < n_my) produce(i + 1);  // MMA(i-1) finished reading A[b^1]: waited on tfull last iteration
             if (tid == 0) stamp(i, 1);
             umma::mbar_wait(&tfull[b], (uint32_t)((i >> 1) & 1));
             umma::fence_after_thread_sync();
             if (tid == 0) stamp(i, 3);
             const int q = warp & 3, h = warp >> 2;
-            float *out = a.act2 + (size_t)patch_of(i) * 1024;
+            float *out = a.act2 + (size_t)p_this * 1024;
+            const unsigned act = active_pairs(b);
 #pragma unroll 1
             for (int pp = 0; pp < 2; ++pp) {
                 const int pair = 2 * h + pp;
+                if (!((act >> pair) & 1u)) {   // background pair: the precomputed constants (warp-uniform branch)
+                    const int z2 = (lane & 7) >> 1;
+                    const int j = ((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + (lane & 1);
+                    const int cls = (pair == 0 ? 0 : (pair == 3 ? 2 : 1)) * 9 + (q == 0 ? 0 : (q == 3 ? 2 : 1)) * 3 +
+                                    (z2 == 0 ? 0 : (z2 == 3 ? 2 : 1));
+                    const int pos = (pair * 4 + q) * 4 + z2;
+                    *reinterpret_cast<float2 *>(out + pos * 16 + 2 * j) =
+                        *reinterpret_cast<const float2 *>(sm + SM_BGP + (cls * 16 + 2 * j) * 4);
+                    continue;
+                }
                 uint32_t v[32];
                 umma::tmem_ld_x32(tbase + ((uint32_t)(32 * q) << 16) + b * 128 + pair * 32, v);
                 umma::tmem_ld_wait();
@@ -720,6 +792,48 @@ int make_kmajor_map(caelo_ctx *ctx, CUtensorMap *map, const __half *base, uint64
     return CAELO_OK;
 }
 
+// conv12 tables, computed once per weight set.
+//   T1 [9 (dx,dy)][8 dz-patterns][8 ch]: partial conv1 sums  sum_{dz in pattern} k1[(dx,dy,dz)][ch]
+//   BG [27 classes][16 ch]: conv2 + max-pool + tanh where the whole neighbourhood is background.  If every
+//   conv1 cell a pooled conv2 output can see is empty, conv1+pool+tanh is tanh(b1) inside the volume and 0 in
+//   the halo, so the pooled output only depends on whether its coordinate touches the low edge (class 0),
+//   the high edge (2) or neither (1) on each axis.
+__global__ void prep_conv12_tables_kernel(const float *k1, const float *b1, const float *k2, const float *b2, float *tables)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < 576) {
+        const int j = e >> 6, pat = (e >> 3) & 7, c = e & 7;
+        float s = 0.f;
+        for (int dz = 0; dz < 3; ++dz)
+            if ((pat >> dz) & 1) s += k1[(j * 3 + dz) * 8 + c];
+        tables[e] = s;
+    } else if (e < 576 + 27 * 16) {
+        const int cls = (e - 576) >> 4, co = (e - 576) & 15;
+        const int pc[3] = {cls / 9, (cls / 3) % 3, cls % 3};
+        float bgv[8];
+        for (int ci = 0; ci < 8; ++ci) bgv[ci] = tanhf(b1[ci]);
+        float best = -3.0e38f;
+        for (int sub = 0; sub < 8; ++sub) {
+            // edge class of the sub-position on each axis: 0 = first cell (tap 0 reads the halo), 2 = last cell
+            int ec[3];
+            for (int ax = 0; ax < 3; ++ax) {
+                const int sb = (sub >> (2 - ax)) & 1;
+                ec[ax] = (pc[ax] == 0 && sb == 0) ? 0 : ((pc[ax] == 2 && sb == 1) ? 2 : 1);
+            }
+            float acc = 0.f;
+            for (int t = 0; t < 27; ++t) {
+                const int d[3] = {t / 9, (t / 3) % 3, t % 3};
+                bool in = true;
+                for (int ax = 0; ax < 3; ++ax) in = in && !(ec[ax] == 0 && d[ax] == 0) && !(ec[ax] == 2 && d[ax] == 2);
+                if (!in) continue;
+                for (int ci = 0; ci < 8; ++ci) acc = fmaf(bgv[ci], k2[(t * 8 + ci) * 16 + co], acc);
+            }
+            best = fmaxf(best, acc);
+        }
+        tables[e] = fast_tanh(best + b2[co]);
+    }
+}
+
 // dense1 weights (2048,200) f32 -> transposed split fp16 [208][2048] (rows 200..207 zero)
 __global__ void prep_dense_weights_kernel(const float *d1, __half *w_hi, __half *w_lo)
 {
@@ -764,6 +878,11 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
     Conv12Args c;
     c.packed = packed; c.k1 = ctx->enc.k1; c.b1 = ctx->enc.b1; c.k2 = ctx->enc.k2; c.b2 = ctx->enc.b2;
     c.act2 = act2; c.P = P; c.K3 = frame_mode ? 3 * K : 0; c.timeline = ctx->dbg_timeline;
+    c.tables = ctx->enc_c12_tables;
+    {
+        const char *e = getenv("CAELO_CONV12_SKIP_BG");   // debug switch for A/B timing; default on
+        c.skip_bg = !(e && e[0] == '0');
+    }
     int grid = 2 * ctx->num_sms < P ? 2 * ctx->num_sms : P;
     { ProfScope ps_(ctx, "conv12_tc_kernel", st); conv12_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(c); }
     CAELO_LAUNCH_CHECK(ctx);
@@ -780,7 +899,7 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
     DenseArgs d;
     d.bd1 = ctx->enc.bd1; d.d2 = ctx->enc.d2; d.bd2 = ctx->enc.bd2;
     d.feat = feat; d.P = P; d.feat_stride = feat_stride; d.feat_col0 = feat_col0;
-    d.frame_mode = frame_mode; d.K = K; d.timeline = ctx->dbg_timeline ? ctx->dbg_timeline + (size_t)2 * ctx->num_sms * 64 * 8 : nullptr;
+    d.frame_mode = frame_mode; d.K = K; d.timeline = ctx->dbg_timeline ? ctx->dbg_timeline + (size_t)2 * ctx->num_sms * 64 * 16 : nullptr;
     { ProfScope ps_(ctx, "dense_tc_kernel", st); dense_tc_kernel<<<(unsigned)(Ppad / DM), D_THREADS, D_SMEM, st>>>(d, m_ah, m_al, m_wh, m_wl); }
     CAELO_LAUNCH_CHECK(ctx);
     return CAELO_OK;
@@ -804,6 +923,9 @@ int caelo_encoder_prepare(caelo_ctx *ctx)
         ctx->enc_w1t_lo = ctx->enc_w1t_hi + (size_t)DN * 2048;
     }
     prep_dense_weights_kernel<<<256, 256>>>(ctx->enc.d1, ctx->enc_w1t_hi, ctx->enc_w1t_lo);
+    CAELO_LAUNCH_CHECK(ctx);
+    if (!ctx->enc_c12_tables) CAELO_CUDA(ctx, cudaMalloc(&ctx->enc_c12_tables, (576 + 27 * 16) * 4));
+    prep_conv12_tables_kernel<<<4, 256>>>(ctx->enc.k1, ctx->enc.b1, ctx->enc.k2, ctx->enc.b2, ctx->enc_c12_tables);
     CAELO_LAUNCH_CHECK(ctx);
     CAELO_CUDA(ctx, cudaDeviceSynchronize());
     return CAELO_OK;

@@ -1,14 +1,23 @@
 // match.cu — a4: descriptor nearest-neighbour match (reference Match.py:257-258:
 // cdist(Codes0, Codes1,'euclidean') in float64, then argmin(axis=0), ties -> lowest row).
 //
-// Index-exact in two steps:
-//   nn_tile_kernel   float32 direct-difference distances on 64x64 tiles held in shared memory;
+// Index-exact in two steps: a fast approximate pass that keeps, per column, the best and second-best d^2 and
+// decides every column whose runner-up is outside the pass's error margin, then an exact re-scan of the rest.
+//   nn_tc_kernel     (D <= 128) tcgen05: d^2 = |a|^2 + |b|^2 - 2 a.b with the cross term as a split-fp16
+//                    GEMM (a = hi + lo: hi.hi + lo.hi + hi.lo, fp32 accumulators in TMEM); 128 frame-1
+//                    descriptors per CTA are the MMA rows (= TMEM lanes = threads), frame-0 descriptors
+//                    stream through as 128-column tiles, so each thread scans its own row for the running
+//                    (min, second min, argmin) with no cross-thread traffic.  Margin: |error| is assumed
+//                    <= 2^-13 |a|max |b| (about 1000x the analytic split-fp16 bound 3*2^-22 |a||b|).
+//   nn_tile_kernel   (any D) float32 direct-difference distances on 64x64 tiles held in shared memory;
 //                    per column the best and second-best approximate d^2 (+ best row).  The
 //                    float32 sum of D non-negative terms is within (D+4)*2^-24 relative of the
 //                    true value, so a column whose runner-up is outside that margin is decided.
-//   nn_exact_kernel  one warp per column; undecided columns are re-scanned with the reference's
-//                    own arithmetic (contract M1: float64 sequential sum, sqrt, lowest row wins).
+//   nn_exact_kernel  one warp per column; undecided columns are re-scanned: a float32 pass keeps the rows
+//                    inside the margin, those are evaluated with the reference's own arithmetic
+//                    (contract M1: float64 sequential sum, sqrt, lowest row wins).
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace {
 
@@ -22,6 +31,8 @@ struct NNArgs {
     float *second_d;       // [P,M]
     int *best_i;           // [P,M]
     long long *out;        // [P,M]
+    const float *n1;       // [P,M] |c1 row|^2 and
+    const float *nmax0;    // [P] max |c0 row|^2: absolute margins of the tensor-core pass (null: relative float32 margin)
 };
 
 __global__ void __launch_bounds__(MT_THREADS) nn_tile_kernel(const NNArgs a)
@@ -113,6 +124,159 @@ __global__ void __launch_bounds__(MT_THREADS) nn_tile_kernel(const NNArgs a)
     }
 }
 
+
+// ---- tensor-core pass ---------------------------------------------------------------------------
+constexpr int NT_B = 128;                 // rows (frame-1) per CTA and columns (frame-0) per tile
+constexpr int NT_WORKERS = 128;
+constexpr int NT_THREADS = NT_WORKERS + 32;
+
+struct NNTcArgs {
+    const float *c0, *c1;   // [P,N,D], [P,M,D]
+    const float *n0, *n1;   // [P,N], [P,M] squared norms (float64 sums rounded once)
+    int N, M, D, Kp;        // Kp = D rounded up to 16
+    float *best_d, *second_d;
+    int *best_i;
+};
+
+__global__ void __launch_bounds__(256) desc_norm_kernel(const float *c, int rows_per_pair, int D, long long rows,
+                                                        float *norm, float *pair_max)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float *p = c + r * D;
+    double acc = 0.0;
+    for (int k = 0; k < D; ++k) acc += (double)p[k] * (double)p[k];
+    const float v = (float)acc;
+    norm[r] = v;
+    if (pair_max) atomicMax(reinterpret_cast<int *>(pair_max) + r / rows_per_pair, __float_as_int(v));  // v >= 0: int order = float order
+}
+
+// stage `NT_B` rows x Kp of an f32 row-major matrix as split fp16 in the canonical K-major no-swizzle layout
+// [chunk of 8 k][row][16 B] (SBO = 128 B, LBO = NT_B*16 B); rows >= nrows and k >= D are zero
+__device__ __forceinline__ void stage_rows(const float *src, int row0, int nrows, int D, int Kp, unsigned char *hi,
+                                           unsigned char *lo, int tid)
+{
+    for (int e = tid; e < NT_B * (Kp / 8); e += NT_WORKERS) {
+        const int r = e % NT_B, c = e / NT_B;
+        __half h[8], l[8];
+        const bool in = row0 + r < nrows;
+        const float *p = src + (size_t)(row0 + r) * D + c * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float v = (in && c * 8 + k < D) ? __ldg(p + k) : 0.0f;
+            umma::split_f16(v, h[k], l[k]);
+        }
+        *reinterpret_cast<uint4 *>(hi + c * (NT_B * 16) + r * 16) = *reinterpret_cast<uint4 *>(h);
+        *reinterpret_cast<uint4 *>(lo + c * (NT_B * 16) + r * 16) = *reinterpret_cast<uint4 *>(l);
+    }
+}
+
+__global__ void __launch_bounds__(NT_THREADS) nn_tc_kernel(const NNTcArgs a)
+{
+    extern __shared__ __align__(128) unsigned char nsm[];
+    const int opb = a.Kp * NT_B * 2;                 // bytes of one operand half (hi or lo)
+    unsigned char *A_hi = nsm, *A_lo = nsm + opb;
+    unsigned char *B_base = nsm + 2 * opb;           // [buf 2][hi, lo][opb]
+    float *n0s = reinterpret_cast<float *>(nsm + 6 * opb);   // [2][NT_B]
+    uint64_t *full = reinterpret_cast<uint64_t *>(n0s + 2 * NT_B), *tfull = full + 2, *tempty = full + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(full + 6);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int pair = blockIdx.y, j0 = blockIdx.x * NT_B;
+    const float *c0 = a.c0 + (size_t)pair * a.N * a.D;
+    const float *c1 = a.c1 + (size_t)pair * a.M * a.D;
+    const float INF = __int_as_float(0x7f800000);
+
+    if (warp == 4) umma::tmem_alloc(tmem_slot, 2 * NT_B);
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            umma::mbar_init(&full[b], NT_WORKERS);
+            umma::mbar_init(&tfull[b], 1);
+            umma::mbar_init(&tempty[b], NT_WORKERS);
+        }
+        umma::fence_mbar_init();
+    }
+    if (warp < 4) stage_rows(c1, j0, a.M, a.D, a.Kp, A_hi, A_lo, tid);
+    umma::fence_proxy_async();
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tbase = *tmem_slot;
+    const int ntiles = (a.N + NT_B - 1) / NT_B;
+
+    if (warp == 4) {
+        const uint32_t idesc = umma::idesc_f16_f32(NT_B, NT_B);
+        const uint32_t sA_hi = umma::smem_u32(A_hi), sA_lo = umma::smem_u32(A_lo), sB = umma::smem_u32(B_base);
+        for (int t = 0; t < ntiles; ++t) {
+            const int b = t & 1, k = t >> 1;
+            umma::mbar_wait(&full[b], (uint32_t)(k & 1));
+            if (k >= 1) umma::mbar_wait(&tempty[b], (uint32_t)((k - 1) & 1));
+            umma::fence_after_thread_sync();
+            if (umma::elect_one()) {
+                const uint32_t d = tbase + b * NT_B;
+                const uint32_t bh = sB + b * 2 * opb, bl = bh + opb;
+                for (int j = 0; j < a.Kp / 16; ++j) {
+                    const uint32_t off = j * 2 * (NT_B * 16);
+                    const uint64_t ah = umma::smem_desc(sA_hi + off, NT_B * 16, 128), al = umma::smem_desc(sA_lo + off, NT_B * 16, 128);
+                    const uint64_t wh = umma::smem_desc(bh + off, NT_B * 16, 128), wl = umma::smem_desc(bl + off, NT_B * 16, 128);
+                    umma::mma_f16(d, ah, wh, idesc, j ? 1u : 0u);
+                    umma::mma_f16(d, al, wh, idesc, 1u);
+                    umma::mma_f16(d, ah, wl, idesc, 1u);
+                }
+                umma::commit(&tfull[b]);
+            }
+            __syncwarp();
+        }
+    } else {
+        const float *n0 = a.n0 + (size_t)pair * a.N;
+        auto stage = [&](int t) {
+            const int b = t & 1;
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // every worker is done reading n0s[b] (tile t-2)
+            stage_rows(c0, t * NT_B, a.N, a.D, a.Kp, B_base + b * 2 * opb, B_base + b * 2 * opb + opb, tid);
+            n0s[b * NT_B + tid] = (t * NT_B + tid < a.N) ? n0[t * NT_B + tid] : INF;
+            umma::fence_proxy_async();
+            umma::mbar_arrive(&full[b]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // n0s[b] complete before anyone's epilogue reads it
+        };
+        float best = INF, second = INF;
+        int bi = 0x7fffffff;
+        stage(0);
+        for (int t = 0; t < ntiles; ++t) {
+            const int b = t & 1;
+            if (t + 1 < ntiles) stage(t + 1);   // MMA(t-1) has finished reading that buffer: tfull was waited on last iteration
+            umma::mbar_wait(&tfull[b], (uint32_t)((t >> 1) & 1));
+            umma::fence_after_thread_sync();
+#pragma unroll 1
+            for (int cc = 0; cc < NT_B; cc += 32) {
+                uint32_t v[32];
+                umma::tmem_ld_x32(tbase + ((uint32_t)(32 * warp) << 16) + b * NT_B + cc, v);
+                umma::tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const float key = fmaf(-2.0f, __uint_as_float(v[k]), n0s[b * NT_B + cc + k]);  // |a_i|^2 - 2 a_i.b_j
+                    second = fminf(second, fmaxf(key, best));
+                    if (key < best) bi = t * NT_B + cc + k;   // ascending i: the first minimum keeps its index
+                    best = fminf(best, key);
+                }
+            }
+            umma::fence_before_thread_sync();
+            umma::mbar_arrive(&tempty[b]);
+        }
+        const int j = j0 + tid;
+        if (j < a.M) {
+            const size_t o = (size_t)pair * a.M + j;
+            const float n1 = a.n1[o];
+            a.best_d[o] = fmaxf(best + n1, 0.0f);
+            a.second_d[o] = fmaxf(second + n1, 0.0f);
+            a.best_i[o] = bi;
+        }
+    }
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    if (warp == 4) umma::tmem_dealloc(tbase, 2 * NT_B);
+}
+
 __global__ void __launch_bounds__(256) nn_exact_kernel(const NNArgs a, int P)
 {
     const int lane = threadIdx.x & 31;
@@ -120,9 +284,11 @@ __global__ void __launch_bounds__(256) nn_exact_kernel(const NNArgs a, int P)
     if (w >= (long long)P * a.M) return;
     const int pair = (int)(w / a.M), j = (int)(w % a.M);
     const float b = a.best_d[w], s = a.second_d[w];
-    // relative error of each float32 d^2 <= (D+4)*2^-24; undecided if the intervals can overlap
+    // relative error of each float32 d^2 <= (D+4)*2^-24; undecided if the intervals can overlap.  After the
+    // tensor-core pass the error is absolute: E = 2^-13 |a|max |b_j| per value (see the header).
     const float eps = (float)(a.D + 4) * 5.9604645e-8f;
-    const bool decided = s > b * (1.0f + 4.0f * eps) + 1e-30f;
+    const float E = a.nmax0 ? 1.2207031e-4f * sqrtf(a.nmax0[pair] * a.n1[w]) + 1e-30f : 0.0f;
+    const bool decided = s > (b + 2.0f * E) * (1.0f + 4.0f * eps) + 1e-30f;
     if (decided) {
         if (lane == 0) a.out[w] = a.best_i[w];
         return;
@@ -131,8 +297,30 @@ __global__ void __launch_bounds__(256) nn_exact_kernel(const NNArgs a, int P)
     const float *q = a.c1 + ((size_t)pair * a.M + j) * a.D;
     double bd = __longlong_as_double(0x7ff0000000000000ll);
     int bi = 0x7fffffff;
+    // only rows whose float32 d^2 is inside the same error margin can be the float64 minimum; the others are
+    // skipped after a cheap float32 pass (any summation order is within (D+4)*2^-24 of the true value)
+    const float bound = (b + E) * (1.0f + 4.0f * eps) + 1e-30f;
+    const bool vec = (a.D & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.c0) | reinterpret_cast<uintptr_t>(a.c1)) & 15) == 0;  // rows 16-byte aligned
     for (int i = lane; i < a.N; i += 32) {
         const float *p = c0 + (size_t)i * a.D;
+        float acc32;
+        if (vec) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four independent chains: the margin holds for any order
+            for (int k = 0; k < a.D; k += 4) {
+                const float4 pv = __ldg(reinterpret_cast<const float4 *>(p + k));
+                const float4 qv = __ldg(reinterpret_cast<const float4 *>(q + k));
+                const float d0 = pv.x - qv.x, d1 = pv.y - qv.y, d2 = pv.z - qv.z, d3 = pv.w - qv.w;
+                s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+            }
+            acc32 = (s0 + s1) + (s2 + s3);
+        } else {
+            acc32 = 0.0f;
+            for (int k = 0; k < a.D; ++k) {
+                const float d = p[k] - q[k];
+                acc32 = fmaf(d, d, acc32);
+            }
+        }
+        if (acc32 > bound) continue;
         double acc = 0.0;
         for (int k = 0; k < a.D; ++k) {
             double d = __dsub_rn((double)p[k], (double)q[k]);
@@ -152,10 +340,13 @@ __global__ void __launch_bounds__(256) nn_exact_kernel(const NNArgs a, int P)
 
 }  // namespace
 
+static int nt_smem(int Kp) { return 6 * Kp * NT_B * 2 + 2 * NT_B * 4 + 64; }
+
 int caelo_match_init(caelo_ctx *ctx)
 {
     CAELO_CUDA(ctx, cudaFuncSetAttribute(nn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          2 * 256 * TILE * 4));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nt_smem(128)));
     return CAELO_OK;
 }
 
@@ -165,8 +356,8 @@ extern "C" int caelo_nn_match(caelo_ctx *ctx, const float *codes0, const float *
     if (!ctx || !codes0 || !codes1 || !pair_idx || P <= 0 || N <= 0 || M <= 0 || D <= 0 || D > 256)
         return CAELO_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    size_t cols = (size_t)P * M;
-    int rc = caelo_reserve(ctx, ctx->misc, cols * 12 + 256);
+    size_t cols = (size_t)P * M, rows0 = (size_t)P * N;
+    int rc = caelo_reserve(ctx, ctx->misc, cols * 16 + rows0 * 4 + (size_t)P * 4 + 256);
     if (rc) return rc;
     NNArgs a;
     a.c0 = codes0; a.c1 = codes1; a.N = N; a.M = M; a.D = D; a.Dp = (D + 3) & ~3;
@@ -174,10 +365,29 @@ extern "C" int caelo_nn_match(caelo_ctx *ctx, const float *codes0, const float *
     a.second_d = a.best_d + cols;
     a.best_i = reinterpret_cast<int *>(a.second_d + cols);
     a.out = reinterpret_cast<long long *>(pair_idx);
-    dim3 grid((M + TILE - 1) / TILE, P);
-    size_t smem = (size_t)2 * a.Dp * TILE * 4;
-    { ProfScope ps_(ctx, "nn_tile_kernel", st); nn_tile_kernel<<<grid, MT_THREADS, smem, st>>>(a); }
-    CAELO_LAUNCH_CHECK(ctx);
+    a.n1 = nullptr; a.nmax0 = nullptr;
+    const char *force = getenv("CAELO_NN_F32");   // debug switch: float32 CUDA-core pass for every D
+    if (D <= 128 && !(force && force[0] == '1')) {
+        float *n1 = reinterpret_cast<float *>(a.best_i + cols), *n0 = n1 + cols, *nmax = n0 + rows0;
+        CAELO_CUDA(ctx, cudaMemsetAsync(nmax, 0, (size_t)P * 4, st));
+        { ProfScope ps_(ctx, "desc_norm_kernel", st);
+          desc_norm_kernel<<<(unsigned)((rows0 + 255) / 256), 256, 0, st>>>(codes0, N, D, (long long)rows0, n0, nmax);
+          desc_norm_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(codes1, M, D, (long long)cols, n1, nullptr); }
+        CAELO_LAUNCH_CHECK(ctx);
+        ctx->launches++;
+        NNTcArgs t;
+        t.c0 = codes0; t.c1 = codes1; t.n0 = n0; t.n1 = n1; t.N = N; t.M = M; t.D = D; t.Kp = (D + 15) & ~15;
+        t.best_d = a.best_d; t.second_d = a.second_d; t.best_i = a.best_i;
+        { ProfScope ps_(ctx, "nn_tc_kernel", st);
+          nn_tc_kernel<<<dim3((M + NT_B - 1) / NT_B, P), NT_THREADS, nt_smem(t.Kp), st>>>(t); }
+        CAELO_LAUNCH_CHECK(ctx);
+        a.n1 = n1; a.nmax0 = nmax;
+    } else {
+        dim3 grid((M + TILE - 1) / TILE, P);
+        size_t smem = (size_t)2 * a.Dp * TILE * 4;
+        { ProfScope ps_(ctx, "nn_tile_kernel", st); nn_tile_kernel<<<grid, MT_THREADS, smem, st>>>(a); }
+        CAELO_LAUNCH_CHECK(ctx);
+    }
     long long threads = (long long)cols * 32;
     { ProfScope ps_(ctx, "nn_exact_kernel", st); nn_exact_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a, P); }
     CAELO_LAUNCH_CHECK(ctx);

@@ -5,10 +5,14 @@
 // 1.0 into a 16^3 patch using NEGATIVE indices (offset o lands at index o mod 16).  Here:
 //   1. brick_insert_kernel: every occupied voxel sets one bit of a 4x4x4 "brick" (64-bit mask)
 //      kept in an open-addressing hash table keyed by the brick coordinate (per frame, scale);
-//   2. gather_kernel: one warp per (frame, scale, keypoint) probes the <=8^3 bricks that meet
-//      the ball d^2 <= 192 around the key voxel, counts the ball and sets the cube bits of a
-//      512-byte bit-packed patch in shared memory; only if the ball holds more than 496 voxels
-//      (the kNN cut can bite) it re-runs with the exact rank rule (d^2, then x,y,z).
+//      and the thread that claims a brick slot also sets the brick's bit in a second table keyed by
+//      the 4x4x4-brick "super brick" (16^3 voxels);
+//   2. gather_kernel: one warp per (frame, scale, keypoint) looks up the <=27 super bricks that meet
+//      the ball d^2 <= 192 around the key voxel, lists their non-empty bricks (most of the <=8^3
+//      bricks around a key voxel are empty: one probe per super brick instead of one per brick),
+//      probes those, counts the ball and sets the cube bits of a 512-byte bit-packed patch in
+//      shared memory; only if the ball holds more than 496 voxels (the kNN cut can bite) it
+//      re-runs with the exact rank rule (d^2, then x,y,z).
 // Integer-exact; HBM traffic = voxel lists in + 512 B per patch out.
 #include "common.cuh"
 #include "voxel_math.cuh"
@@ -41,10 +45,30 @@ __device__ __forceinline__ unsigned long long brick_key(int bx, int by, int bz)
            ((unsigned long long)(bz + 8192) << 28);
 }
 
+// the brick (bx,by,bz) exists: set its bit in the super-brick table (called once per brick, by the claimer of its slot)
+__device__ __forceinline__ void super_set(const Table &t, int bx, int by, int bz)
+{
+    const unsigned long long key = brick_key(bx >> 2, by >> 2, bz >> 2);
+    const unsigned long long bit = 1ull << (((bx & 3) * 4 + (by & 3)) * 4 + (bz & 3));
+    unsigned slot = hash64(key) & t.cap_mask;
+    while (true) {
+        unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(t.keys + slot);
+        if (k == EMPTY) {
+            k = atomicCAS(t.keys + slot, EMPTY, key);
+            if (k == EMPTY) k = key;
+        }
+        if (k == key) {
+            atomicOr(t.masks + slot, bit);
+            return;
+        }
+        slot = (slot + 1) & t.cap_mask;
+    }
+}
+
 struct BuildArgs {
     const int16_t *vox;          // all lists concatenated, rows of 3
     const long long *offsets;    // dev [F*3+1]
-    const Table *tables;         // dev [F*3]
+    const Table *tables;         // dev [2*F*3]: brick tables, then super-brick tables
     int nlists;
 };
 
@@ -63,6 +87,7 @@ __global__ void brick_insert_kernel(const BuildArgs a)
             unsigned long long old = atomicCAS(t.keys + slot, EMPTY, key);
             if (old == EMPTY || old == key) {
                 atomicOr(t.masks + slot, bit);
+                if (old == EMPTY) super_set(a.tables[a.nlists + list], x >> 2, y >> 2, z >> 2);
                 break;
             }
             slot = (slot + 1) & t.cap_mask;
@@ -77,14 +102,15 @@ __global__ void brick_insert_kernel(const BuildArgs a)
 struct ScanBuildArgs {
     const float *pts;            // rows of 4
     const long long *offsets;    // dev [F+1]
-    const Table *tables;         // dev [F*3]
+    const Table *tables;         // dev [2*F*3]: brick tables, then super-brick tables
+    int nlists;                  // F*3
     int *nvox;                   // dev [F*3]
     int *status;                 // dev [F] or null
 };
 
 // returns true iff this call set a bit that was clear (a voxel seen for the first time).  Most points of a
 // scan fall into a voxel that is already recorded: plain loads filter those before any atomic is issued.
-__device__ __forceinline__ bool brick_set(const Table &t, int x, int y, int z)
+__device__ __forceinline__ bool brick_set(const Table &t, const Table &ts, int x, int y, int z)
 {
     const unsigned long long key = brick_key(x >> 2, y >> 2, z >> 2);
     const unsigned long long bit = 1ull << (((x & 3) * 4 + (y & 3)) * 4 + (z & 3));
@@ -93,7 +119,10 @@ __device__ __forceinline__ bool brick_set(const Table &t, int x, int y, int z)
         unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(t.keys + slot);
         if (k == EMPTY) {
             k = atomicCAS(t.keys + slot, EMPTY, key);
-            if (k == EMPTY) k = key;
+            if (k == EMPTY) {
+                k = key;
+                super_set(ts, x >> 2, y >> 2, z >> 2);
+            }
         }
         if (k == key) {
             if (*reinterpret_cast<volatile unsigned long long *>(t.masks + slot) & bit) return false;
@@ -109,6 +138,7 @@ __global__ void __launch_bounds__(256) scan_brick_insert_kernel(const ScanBuildA
     const long long beg = a.offsets[f], n = a.offsets[f + 1] - beg;
     const float4 *p4 = reinterpret_cast<const float4 *>(a.pts) + beg;
     const Table t0 = a.tables[f * 3], t1 = a.tables[f * 3 + 1], t2 = a.tables[f * 3 + 2];
+    const Table s0 = a.tables[a.nlists + f * 3], s1 = a.tables[a.nlists + f * 3 + 1], s2 = a.tables[a.nlists + f * 3 + 2];
     int bad = 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     // warp-uniform trip count: the ballots below need every lane
@@ -121,9 +151,9 @@ __global__ void __launch_bounds__(256) scan_brick_insert_kernel(const ScanBuildA
             const int st = voxel_of_point(p.x, p.y, p.z, v);
             bad += st < 0;
             if (st > 0) {
-                n0 = brick_set(t0, v.g0[0], v.g0[1], v.g0[2]);
-                n1 = brick_set(t1, v.g1[0], v.g1[1], v.g1[2]);
-                n2 = brick_set(t2, v.g2[0], v.g2[1], v.g2[2]);
+                n0 = brick_set(t0, s0, v.g0[0], v.g0[1], v.g0[2]);
+                n1 = brick_set(t1, s1, v.g1[0], v.g1[1], v.g1[2]);
+                n2 = brick_set(t2, s2, v.g2[0], v.g2[1], v.g2[2]);
             }
         }
         // warp-aggregated voxel counters (one atomic per warp and scale instead of one per new voxel)
@@ -152,7 +182,7 @@ __device__ __forceinline__ unsigned long long brick_lookup(const Table &t, unsig
 struct GatherArgs {
     const void *kpts;            // [F,K,3] f32 or f64
     const int *n_kpts;           // [F] or null
-    const Table *tables;         // [F*3]
+    const Table *tables;         // [2*F*3]: brick tables, then super-brick tables
     unsigned *packed;            // [F,3,K,128]
     unsigned char *trunc;        // [F,3,K] or null
     const int *nvox;             // [F*3] distinct voxels per list, or null (checked on the host)
@@ -162,17 +192,63 @@ struct GatherArgs {
     int kpts_f64, F, K;
 };
 
-// visit every occupied voxel of the bricks meeting [-13,13]^3 around kv; f(dx,dy,dz)
-template <class Fn>
-__device__ __forceinline__ void for_ball_voxels(const Table &t, int kx, int ky, int kz, int lane, Fn f)
+// List the non-empty bricks that meet [-13,13]^3 around the key voxel: lanes 0..26 look up the <=3^3 super
+// bricks, restrict their child masks to the brick range of the box and write the brick coordinates (relative to
+// the box corner, 3 bits per axis) into `list` at warp-scanned offsets.  Returns the count (<= 512).
+__device__ __forceinline__ int list_ball_bricks(const Table &ts, int kx, int ky, int kz, int lane, unsigned short *list,
+                                                int &bx0, int &by0, int &bz0)
 {
-    const int bx0 = (kx - 13) >> 2, by0 = (ky - 13) >> 2, bz0 = (kz - 13) >> 2;
-    const int nx = ((kx + 13) >> 2) - bx0 + 1, ny = ((ky + 13) >> 2) - by0 + 1,
-              nz = ((kz + 13) >> 2) - bz0 + 1;
-    const int nb = nx * ny * nz;
-    for (int i = lane; i < nb; i += 32) {
-        int bz = bz0 + i % nz, by = by0 + (i / nz) % ny, bx = bx0 + i / (nz * ny);
-        if (bx < -8192 || by < -8192 || bz < -8192) continue;
+    bx0 = (kx - 13) >> 2; by0 = (ky - 13) >> 2; bz0 = (kz - 13) >> 2;
+    const int bx1 = (kx + 13) >> 2, by1 = (ky + 13) >> 2, bz1 = (kz + 13) >> 2;
+    const int sx0 = bx0 >> 2, sy0 = by0 >> 2, sz0 = bz0 >> 2;
+    const int nsy = (by1 >> 2) - sy0 + 1, nsz = (bz1 >> 2) - sz0 + 1;
+    const int ns = ((bx1 >> 2) - sx0 + 1) * nsy * nsz;
+    unsigned long long m = 0ull;
+    int sbx = 0, sby = 0, sbz = 0;
+    if (lane < ns) {
+        sbz = sz0 + lane % nsz; sby = sy0 + (lane / nsz) % nsy; sbx = sx0 + lane / (nsz * nsy);
+        if (sbx >= -8192 && sby >= -8192 && sbz >= -8192) m = brick_lookup(ts, brick_key(sbx, sby, sbz));
+        if (m) {
+            // children inside the box: c in [max(b0 - 4 sb, 0), min(b1 - 4 sb, 3)] on each axis
+            auto range = [](int lo, int hi) { lo = lo < 0 ? 0 : lo; hi = hi > 3 ? 3 : hi; return (0xFu >> (3 - hi)) & (0xFu << lo); };
+            const unsigned zr = range(bz0 - 4 * sbz, bz1 - 4 * sbz), yr = range(by0 - 4 * sby, by1 - 4 * sby),
+                           xr = range(bx0 - 4 * sbx, bx1 - 4 * sbx);
+            unsigned yz = 0;  // 16 bits: (cy,cz)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) yz |= ((yr >> c) & 1u) ? (zr << (4 * c)) : 0u;
+            unsigned long long box = 0ull;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) box |= ((xr >> c) & 1u) ? ((unsigned long long)yz << (16 * c)) : 0ull;
+            m &= box;
+        }
+    }
+    const int cnt = __popcll(m);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int pos = incl - cnt;
+    while (m) {
+        const int bit = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const int bx = 4 * sbx + (bit >> 4), by = 4 * sby + ((bit >> 2) & 3), bz = 4 * sbz + (bit & 3);
+        list[pos++] = (unsigned short)(((bx - bx0) << 6) | ((by - by0) << 3) | (bz - bz0));
+    }
+    __syncwarp();
+    return total;
+}
+
+// visit every occupied voxel of the listed bricks; f(dx,dy,dz) relative to the key voxel
+template <class Fn>
+__device__ __forceinline__ void for_ball_voxels(const Table &t, const unsigned short *list, int nlist, int bx0, int by0,
+                                                int bz0, int kx, int ky, int kz, int lane, Fn f)
+{
+    for (int i = lane; i < nlist; i += 32) {
+        const unsigned e = list[i];
+        const int bx = bx0 + (int)(e >> 6), by = by0 + (int)((e >> 3) & 7), bz = bz0 + (int)(e & 7);
         unsigned long long m = brick_lookup(t, brick_key(bx, by, bz));
         while (m) {
             int bit = __ffsll((long long)m) - 1;
@@ -200,6 +276,7 @@ __global__ void __launch_bounds__(kWarps * 32) gather_kernel(const GatherArgs a)
     __shared__ unsigned s_patch[kWarps][128];
     __shared__ int s_hist[kWarps][196];
     __shared__ unsigned s_list[kWarps][256];
+    __shared__ unsigned short s_bricks[kWarps][512];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long total = (long long)a.F * 3 * a.K;
     unsigned *patch = s_patch[warp];
@@ -218,16 +295,21 @@ __global__ void __launch_bounds__(kWarps * 32) gather_kernel(const GatherArgs a)
         bool flagged = false;
         if (live) {
             double p[3];
+#pragma unroll
             for (int c = 0; c < 3; ++c)
                 p[c] = a.kpts_f64 ? reinterpret_cast<const double *>(a.kpts)[((size_t)f * a.K + k) * 3 + c]
                                   : (double)reinterpret_cast<const float *>(a.kpts)[((size_t)f * a.K + k) * 3 + c];
             // KeyVoxels = int32((Pts + Visible) / VoxelSizes[s])  — float64, truncation (Voxel.py:185,193)
-            const int kx = (int)__ddiv_rn(__dadd_rn(p[0], a.vis[0]), a.vsize[s]);
-            const int ky = (int)__ddiv_rn(__dadd_rn(p[1], a.vis[1]), a.vsize[s]);
-            const int kz = (int)__ddiv_rn(__dadd_rn(p[2], a.vis[2]), a.vsize[s]);
+            const double vsz = s == 0 ? a.vsize[0] : (s == 1 ? a.vsize[1] : a.vsize[2]);  // no dynamic param indexing
+            const int kx = (int)__ddiv_rn(__dadd_rn(p[0], a.vis[0]), vsz);
+            const int ky = (int)__ddiv_rn(__dadd_rn(p[1], a.vis[1]), vsz);
+            const int kz = (int)__ddiv_rn(__dadd_rn(p[2], a.vis[2]), vsz);
             const Table t = a.tables[f * 3 + s];
+            int bx0, by0, bz0;
+            const unsigned short *bricks = s_bricks[warp];
+            const int nb = list_ball_bricks(a.tables[a.F * 3 + f * 3 + s], kx, ky, kz, lane, s_bricks[warp], bx0, by0, bz0);
             int ball = 0;
-            for_ball_voxels(t, kx, ky, kz, lane, [&](int dx, int dy, int dz) {
+            for_ball_voxels(t, bricks, nb, bx0, by0, bz0, kx, ky, kz, lane, [&](int dx, int dy, int dz) {
                 int d2 = dx * dx + dy * dy + dz * dz;
                 if (d2 <= 192) {
                     ++ball;
@@ -245,7 +327,7 @@ __global__ void __launch_bounds__(kWarps * 32) gather_kernel(const GatherArgs a)
                 for (int i = lane; i < 196; i += 32) hist[i] = 0;
                 for (int i = lane; i < 128; i += 32) patch[i] = 0u;
                 __syncwarp();
-                for_ball_voxels(t, kx, ky, kz, lane, [&](int dx, int dy, int dz) {
+                for_ball_voxels(t, bricks, nb, bx0, by0, bz0, kx, ky, kz, lane, [&](int dx, int dy, int dz) {
                     int d2 = dx * dx + dy * dy + dz * dz;
                     if (d2 <= 192) atomicAdd(hist + d2, 1);
                 });
@@ -259,7 +341,7 @@ __global__ void __launch_bounds__(kWarps * 32) gather_kernel(const GatherArgs a)
                 const int room = NNB - before;  // how many voxels at d2 == q survive
                 if (lane == 0) hist[193] = 0;
                 __syncwarp();
-                for_ball_voxels(t, kx, ky, kz, lane, [&](int dx, int dy, int dz) {
+                for_ball_voxels(t, bricks, nb, bx0, by0, bz0, kx, ky, kz, lane, [&](int dx, int dy, int dz) {
                     int d2 = dx * dx + dy * dy + dz * dz;
                     if (d2 < q) {
                         if (in_cube(dx, dy, dz)) set_patch_bit(patch, dx, dy, dz);
@@ -388,17 +470,18 @@ extern "C" int caelo_gather_patches(caelo_ctx *ctx, const void *kpts, int kpts_f
     if (!ctx || !kpts || !vox || !vox_offsets || !packed || F <= 0 || K <= 0) return CAELO_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int nl = F * 3;
-    std::vector<size_t> caps(nl);
+    std::vector<size_t> caps(2 * nl);
     long long maxlen = 0;
     for (int l = 0; l < nl; ++l) {
         long long len = vox_offsets[l + 1] - vox_offsets[l];
         if (len < NNB) return CAELO_ERR_TOO_FEW_VOXELS;  // sklearn: n_neighbors <= n_samples_fit
         if (len > maxlen) maxlen = len;
         caps[l] = pow2_above((size_t)len * 2);
+        caps[nl + l] = pow2_above((size_t)len + 2);      // super bricks <= bricks <= voxels
     }
     Table *d_tables;
     long long *d_off;
-    int rc = setup_tables(ctx, nl, caps.data(), vox_offsets, nl + 1, &d_tables, &d_off, st);
+    int rc = setup_tables(ctx, 2 * nl, caps.data(), vox_offsets, nl + 1, &d_tables, &d_off, st);
     if (rc) return rc;
     BuildArgs b;
     b.vox = vox; b.offsets = d_off; b.tables = d_tables; b.nlists = nl;
@@ -418,7 +501,7 @@ extern "C" int caelo_gather_patches_scans(caelo_ctx *ctx, const void *kpts, int 
     if (!ctx || !kpts || !pts || !pts_offsets || !packed || !nvox || !status || F <= 0 || K <= 0) return CAELO_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int nl = F * 3;
-    std::vector<size_t> caps(nl);
+    std::vector<size_t> caps(2 * nl);
     long long maxn = 0;
     for (int f = 0; f < F; ++f) {
         long long n = pts_offsets[f + 1] - pts_offsets[f];
@@ -429,15 +512,19 @@ extern "C" int caelo_gather_patches_scans(caelo_ctx *ctx, const void *kpts, int 
         caps[f * 3] = pow2_above((size_t)n * 2 + 2);
         caps[f * 3 + 1] = pow2_above((size_t)n + 2);
         caps[f * 3 + 2] = pow2_above(((size_t)n < 73008 ? (size_t)n : 73008) * 2 + 2);
+        // super bricks (4^3 bricks): never more than bricks; the 64 cm grid has 20*20*3 = 1,200 of them
+        caps[nl + f * 3] = pow2_above((size_t)n + 2);
+        caps[nl + f * 3 + 1] = pow2_above((size_t)n + 2);
+        caps[nl + f * 3 + 2] = pow2_above(((size_t)n < 1200 ? (size_t)n : 1200) * 2 + 2);
     }
     Table *d_tables;
     long long *d_off;
-    int rc = setup_tables(ctx, nl, caps.data(), pts_offsets, F + 1, &d_tables, &d_off, st);
+    int rc = setup_tables(ctx, 2 * nl, caps.data(), pts_offsets, F + 1, &d_tables, &d_off, st);
     if (rc) return rc;
     CAELO_CUDA(ctx, cudaMemsetAsync(nvox, 0, (size_t)nl * 4, st));
     CAELO_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)F * 4, st));
     ScanBuildArgs b;
-    b.pts = pts; b.offsets = d_off; b.tables = d_tables; b.nvox = nvox; b.status = status;
+    b.pts = pts; b.offsets = d_off; b.tables = d_tables; b.nlists = nl; b.nvox = nvox; b.status = status;
     int bx = (int)((maxn + 255) / 256);
     if (bx > 128) bx = 128;
     if (bx < 1) bx = 1;

@@ -191,6 +191,10 @@ struct PoseArgs {
     const int *best_n_in;         // [P] or null
     const float *skip_if_ok;      // [P,16] or null: pairs with [12] != 0 there are skipped
     int N0, N, T, P;
+    int t0, t1;                   // hyp_score: trials [t0,t1) of every pair; replay: trials [0,t1) are scored
+    int *more;                    // [P] speculation flag (see caelo_ransac_round): 1 = the pair needs trials >= t1
+    int more_mode;                // hyp_score: 1 = only pairs with more[pair]; replay: 1 = first phase (may set more[pair] and
+                                  // leave the outputs alone), 2 = second phase (only pairs with more[pair])
     int *counts;                  // [P,T]
     float *rt_hyp;                // [P,T,12]
     float *result;                // [P,16]
@@ -206,59 +210,100 @@ __device__ __forceinline__ void load_pair(const PoseArgs &a, int pair, int i, fl
     p1[0] = q1[0]; p1[1] = q1[1]; p1[2] = q1[2];
 }
 
-constexpr int HS_WARPS = 8;
+// One CTA = one pair x HS_HYP consecutive trials.  The pair's matched points are staged once in shared memory
+// (SoA), warp 0 solves the HS_HYP four-point Kabsch problems ONE PER LANE (float64 contract K1: with four
+// samples the 32-lane butterfly of the refit reduces to (v0 + v2) + (v1 + v3), lanes 4..31 contributing +0.0),
+// then the eight warps score the hypotheses, one warp per hypothesis at a time.
+constexpr int HS_HYP = 32;
+constexpr int HS_THREADS = 256;
 
-__global__ void __launch_bounds__(HS_WARPS * 32) hyp_score_kernel(const PoseArgs a)
+__device__ __forceinline__ double tree4(double v0, double v1, double v2, double v3) { return (v0 + v2) + (v1 + v3); }
+
+template <bool kStaged>
+__global__ void __launch_bounds__(HS_THREADS) hyp_score_kernel(const PoseArgs a)
 {
+    extern __shared__ float hs_pts[];        // kStaged: [6][N] = x0 y0 z0 x1 y1 z1
+    __shared__ float s_rt[HS_HYP][12];
     const int pair = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * HS_WARPS + warp;
-    if (t >= a.T) return;
+    const int t_base = a.t0 + blockIdx.x * HS_HYP;
     if (a.skip_if_ok && a.skip_if_ok[(size_t)pair * 16 + 12] != 0.0f) return;
-    // Kabsch of the 4 samples: sample i sits in lane i of the K1 reduction
-    double s0[3] = {0, 0, 0}, s1[3] = {0, 0, 0};
-    float q0[3] = {0, 0, 0}, q1[3] = {0, 0, 0};
-    if (lane < 4) {
-        int si = a.sample_idx[((size_t)pair * a.T + t) * 4 + lane];
-        load_pair(a, pair, si, q0, q1);
-        for (int c = 0; c < 3; ++c) { s0[c] = 0.0 + (double)q0[c]; s1[c] = 0.0 + (double)q1[c]; }
+    if (a.more_mode == 1 && !a.more[pair]) return;
+    const int N = a.N;
+    if (kStaged) {
+        for (int i = threadIdx.x; i < N; i += HS_THREADS) {
+            float p0[3], p1[3];
+            load_pair(a, pair, i, p0, p1);
+            hs_pts[i] = p0[0]; hs_pts[N + i] = p0[1]; hs_pts[2 * N + i] = p0[2];
+            hs_pts[3 * N + i] = p1[0]; hs_pts[4 * N + i] = p1[1]; hs_pts[5 * N + i] = p1[2];
+        }
+        __syncthreads();
     }
-    double m0[3], m1[3];
-    for (int c = 0; c < 3; ++c) {
-        m0[c] = warp_tree(s0[c]) / 4.0;
-        m1[c] = warp_tree(s1[c]) / 4.0;
-    }
-    double H[3][3];
-    {
-        double a1[3], a0[3];
-        for (int c = 0; c < 3; ++c) { a1[c] = (double)q1[c] - m1[c]; a0[c] = (double)q0[c] - m0[c]; }
+    auto point = [&](int i, float p0[3], float p1[3]) {
+        if (kStaged) {
+            p0[0] = hs_pts[i]; p0[1] = hs_pts[N + i]; p0[2] = hs_pts[2 * N + i];
+            p1[0] = hs_pts[3 * N + i]; p1[1] = hs_pts[4 * N + i]; p1[2] = hs_pts[5 * N + i];
+        } else {
+            load_pair(a, pair, i, p0, p1);
+        }
+    };
+    if (warp == 0 && t_base + lane < a.t1) {
+        const int t = t_base + lane;
+        const int4 si = *reinterpret_cast<const int4 *>(a.sample_idx + ((size_t)pair * a.T + t) * 4);
+        float q0[4][3], q1[4][3];
+        point(si.x, q0[0], q1[0]); point(si.y, q0[1], q1[1]); point(si.z, q0[2], q1[2]); point(si.w, q0[3], q1[3]);
+        double m0[3], m1[3];
+        for (int c = 0; c < 3; ++c) {
+            m0[c] = tree4(0.0 + (double)q0[0][c], 0.0 + (double)q0[1][c], 0.0 + (double)q0[2][c], 0.0 + (double)q0[3][c]) / 4.0;
+            m1[c] = tree4(0.0 + (double)q1[0][c], 0.0 + (double)q1[1][c], 0.0 + (double)q1[2][c], 0.0 + (double)q1[3][c]) / 4.0;
+        }
+        double a0[4][3], a1[4][3];
+        for (int k = 0; k < 4; ++k)
+            for (int c = 0; c < 3; ++c) { a1[k][c] = (double)q1[k][c] - m1[c]; a0[k][c] = (double)q0[k][c] - m0[c]; }
+        double H[3][3];
         for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < 3; ++c) {
-                double h = lane < 4 ? 0.0 + a1[r] * a0[c] : 0.0;
-                H[r][c] = warp_tree(h);
-            }
-    }
-    float R[9], T[3];
-    kabsch_from_H(H, m0, m1, R, T);
-    const float thr = a.thr[pair];
-    int cnt = 0;
-    for (int i = lane; i < a.N; i += 32) {
-        float p0[3], p1[3];
-        load_pair(a, pair, i, p0, p1);
-        cnt += inlier_d1(R, T, p0, p1, thr) ? 1 : 0;
-    }
+            for (int c = 0; c < 3; ++c)
+                H[r][c] = tree4(0.0 + a1[0][r] * a0[0][c], 0.0 + a1[1][r] * a0[1][c], 0.0 + a1[2][r] * a0[2][c],
+                                0.0 + a1[3][r] * a0[3][c]);
+        float R[9], T[3];
+        kabsch_from_H(H, m0, m1, R, T);
+        float *o = a.rt_hyp + ((size_t)pair * a.T + t) * 12;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) a.counts[(size_t)pair * a.T + t] = cnt;
-    if (lane < 12) a.rt_hyp[((size_t)pair * a.T + t) * 12 + lane] = lane < 9 ? R[lane] : T[lane - 9];
+        for (int k = 0; k < 12; ++k) {
+            const float v = k < 9 ? R[k] : T[k - 9];
+            s_rt[lane][k] = v;
+            o[k] = v;
+        }
+    }
+    __syncthreads();
+    const float thr = a.thr[pair];
+    for (int h = warp; h < HS_HYP && t_base + h < a.t1; h += HS_THREADS / 32) {
+        float R[9], T[3];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = s_rt[h][k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) T[k] = s_rt[h][9 + k];
+        int cnt = 0;
+        for (int i = lane; i < N; i += 32) {
+            float p0[3], p1[3];
+            point(i, p0, p1);
+            cnt += inlier_d1(R, T, p0, p1, thr) ? 1 : 0;
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) a.counts[(size_t)pair * a.T + t_base + h] = cnt;
+    }
 }
 
 __global__ void __launch_bounds__(256) replay_mask_kernel(const PoseArgs a)
 {
-    __shared__ int s_bt, s_bn, s_ok, s_it;
+    __shared__ int s_bt, s_bn, s_ok, s_it, s_more;
     __shared__ float s_rt[12];
     const int pair = blockIdx.x;
-    if (a.skip_if_ok && a.skip_if_ok[(size_t)pair * 16 + 12] != 0.0f) return;
+    if (a.skip_if_ok && a.skip_if_ok[(size_t)pair * 16 + 12] != 0.0f) {
+        if (a.more_mode == 1 && threadIdx.x == 0) a.more[pair] = 0;
+        return;
+    }
+    if (a.more_mode == 2 && !a.more[pair]) return;
     if (threadIdx.x == 0) {
         // RANSAC4RT's loop (Match.py:181-206) over the pre-scored trials
         const int N = a.N;
@@ -267,16 +312,23 @@ __global__ void __launch_bounds__(256) replay_mask_kernel(const PoseArgs a)
         const double succ = 0.25 * (double)N;
         int it = 0, bn = a.best_n_in ? a.best_n_in[pair] : 0, bt = -1, ok = 0;
         const int *cnt = a.counts + (size_t)pair * a.T;
-        while (it < a.T && ((it < 100) || (it < 500 && (double)bn < succ))) {
+        while (it < a.t1 && ((it < 100) || (it < 500 && (double)bn < succ))) {
             int n = cnt[it];
             ++it;
             if (n < least) continue;
             if (n > bn) { bn = n; bt = it - 1; }
             ok = 1;
         }
-        s_bt = bt; s_bn = bn; s_ok = ok; s_it = it;
+        // first phase: the loop ran out of scored trials while the reference would go on -> the second phase decides
+        int more = 0;
+        if (a.more_mode == 1) {
+            more = (it == a.t1 && it < a.T && ((it < 100) || (it < 500 && (double)bn < succ))) ? 1 : 0;
+            a.more[pair] = more;
+        }
+        s_bt = bt; s_bn = bn; s_ok = ok; s_it = it; s_more = more;
     }
     __syncthreads();
+    if (s_more) return;
     const int bt = s_bt;
     if (threadIdx.x < 12) {
         float v = (threadIdx.x == 0 || threadIdx.x == 4 || threadIdx.x == 8) ? 1.0f : 0.0f;  // R_star = I, T_star = 0
@@ -367,7 +419,86 @@ __global__ void __launch_bounds__(128) kabsch_kernel(const KabschArgs a)
     if (lane == 0) a.credible[pair] = cred;
 }
 
+// ---- RANSAC sample indices on the device ------------------------------------------------------
+// RANSAC4RT draws `np.random.random((4,))` per trial and uses int32(u*N) (Match.py:182-184).  The batched
+// pipeline seeds numpy's legacy generator per pair (np.random.seed(pair_id), the harness convention), so the
+// whole index stream of a pair is a pure function of the seed: MT19937 init_genrand(seed), then per double
+// a = next()>>5, b = next()>>6, u = (a*2^26 + b) / 2^53 (numpy's legacy random_sample).  One CTA per pair:
+// thread 0 runs the sequential seeding recurrence, the 624-word twist is done in three data-parallel phases
+// (words [0,227) need only old words, [227,454) and [454,624) need new words 227 places back), tempering and
+// the conversion are element-wise.
+constexpr int MT_N = 624, MT_M = 397;
+
+struct DrawArgs {
+    const long long *seeds;   // dev [P]
+    int *samples;             // dev [rounds,P,T*4]
+    int P, per_round;         // doubles per round = T*4
+    int first, count;         // doubles [first, first+count) of every pair's stream are emitted
+    int n_points;
+};
+
+__device__ __forceinline__ unsigned mt_mix(unsigned hi_word, unsigned lo_word, unsigned far_word)
+{
+    const unsigned y = (hi_word & 0x80000000u) | (lo_word & 0x7fffffffu);
+    return far_word ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+__global__ void __launch_bounds__(256) draw_samples_kernel(const DrawArgs a)
+{
+    __shared__ unsigned key[2][MT_N];
+    const int p = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        unsigned s = (unsigned)a.seeds[p];
+        for (int i = 0; i < MT_N; ++i) {
+            key[0][i] = s;
+            s = 1812433253u * (s ^ (s >> 30)) + (unsigned)(i + 1);
+        }
+    }
+    __syncthreads();
+    const int last = a.first + a.count;          // doubles
+    const int twists = (2 * last + MT_N - 1) / MT_N;
+    int cur = 0;
+    for (int t = 0; t < twists; ++t) {
+        const unsigned *o = key[cur];
+        unsigned *n = key[cur ^ 1];
+        for (int i = tid; i < MT_N - MT_M; i += 256) n[i] = mt_mix(o[i], o[i + 1], o[i + MT_M]);
+        __syncthreads();
+        for (int i = MT_N - MT_M + tid; i < 2 * (MT_N - MT_M); i += 256) n[i] = mt_mix(o[i], o[i + 1], n[i - (MT_N - MT_M)]);
+        __syncthreads();
+        for (int i = 2 * (MT_N - MT_M) + tid; i < MT_N - 1; i += 256) n[i] = mt_mix(o[i], o[i + 1], n[i - (MT_N - MT_M)]);
+        if (tid == 0) n[MT_N - 1] = mt_mix(o[MT_N - 1], n[0], n[MT_M - 1]);
+        __syncthreads();
+        // words [624 t, 624 t + 624) -> doubles [312 t, 312 t + 312)
+        for (int j = tid; j < MT_N / 2; j += 256) {
+            const int k = t * (MT_N / 2) + j;
+            if (k < a.first || k >= last) continue;
+            unsigned w[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                unsigned y = n[2 * j + h];
+                y ^= y >> 11;
+                y ^= (y << 7) & 0x9d2c5680u;
+                y ^= (y << 15) & 0xefc60000u;
+                y ^= y >> 18;
+                w[h] = y;
+            }
+            const double u = __ddiv_rn(__dadd_rn(__dmul_rn((double)(w[0] >> 5), 67108864.0), (double)(w[1] >> 6)),
+                                       9007199254740992.0);
+            const int e = k - a.first, r = e / a.per_round, rem = e - r * a.per_round;
+            a.samples[((size_t)r * a.P + p) * a.per_round + rem] = (int)__dmul_rn(u, (double)a.n_points);
+        }
+        cur ^= 1;
+        // the next twist overwrites key[cur ^ 1] = this twist's `o`: every thread is past its reads of `o` (barriers above)
+    }
+}
+
 }  // namespace
+
+int caelo_pose_init(caelo_ctx *ctx)
+{
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(hyp_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    return CAELO_OK;
+}
 
 extern "C" int caelo_ransac_round(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int N,
                                   const int64_t *pair_idx, const int32_t *sample_idx, int T,
@@ -378,7 +509,7 @@ extern "C" int caelo_ransac_round(caelo_ctx *ctx, const float *pc0, int N0, cons
     if (P <= 0 || N <= 0 || N0 <= 0 || T <= 0 || T > CAELO_MAX_TRIALS) return CAELO_ERR_ARG;
     if (!pair_idx && N0 != N) return CAELO_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    size_t need = (size_t)P * T * 12 * 4 + (size_t)P * T * 4;
+    size_t need = (size_t)P * T * 12 * 4 + (size_t)P * T * 4 + (size_t)P * 4;
     int rc = caelo_reserve(ctx, ctx->pose_ws, need);
     if (rc) return rc;
     PoseArgs a;
@@ -388,11 +519,33 @@ extern "C" int caelo_ransac_round(caelo_ctx *ctx, const float *pc0, int N0, cons
     a.rt_hyp = reinterpret_cast<float *>(ctx->pose_ws.ptr);
     a.counts = counts ? counts : reinterpret_cast<int *>(a.rt_hyp + (size_t)P * T * 12);
     a.result = result; a.mask = inlier_mask;
-    dim3 grid((T + HS_WARPS - 1) / HS_WARPS, P);
-    { ProfScope ps_(ctx, "hyp_score_kernel", st); hyp_score_kernel<<<grid, HS_WARPS * 32, 0, st>>>(a); }
+    a.more = reinterpret_cast<int *>(a.rt_hyp + (size_t)P * T * 12) + (size_t)P * T;
+    // The reference stops after 100 trials once a model with >= 25 % inliers exists (Match.py:181): score the
+    // first 100 trials, replay the accept/stop rule, and only the pairs whose loop would go on get trials
+    // 100..T scored and the rule replayed over all of them (same result as scoring everything up front).
+    const int T1 = (T > 100 && !counts) ? 100 : T;   // a caller asking for every count gets every trial scored
+    a.t0 = 0; a.t1 = T1; a.more_mode = 0;
+    const size_t hs_smem = (size_t)N * 24;
+    const bool staged = hs_smem <= 160 * 1024;
+    auto score = [&](int n_trials) {
+        const dim3 grid((n_trials + HS_HYP - 1) / HS_HYP, P);
+        ProfScope ps_(ctx, "hyp_score_kernel", st);
+        if (staged) hyp_score_kernel<true><<<grid, HS_THREADS, hs_smem, st>>>(a);
+        else hyp_score_kernel<false><<<grid, HS_THREADS, 0, st>>>(a);
+    };
+    score(T1);
     CAELO_LAUNCH_CHECK(ctx);
+    a.more_mode = T1 < T ? 1 : 0;
     { ProfScope ps_(ctx, "replay_mask_kernel", st); replay_mask_kernel<<<P, 256, 0, st>>>(a); }
     CAELO_LAUNCH_CHECK(ctx);
+    if (T1 < T) {
+        a.t0 = T1; a.t1 = T; a.more_mode = 1;
+        score(T - T1);
+        CAELO_LAUNCH_CHECK(ctx);
+        a.more_mode = 2;
+        { ProfScope ps_(ctx, "replay_mask_kernel", st); replay_mask_kernel<<<P, 256, 0, st>>>(a); }
+        CAELO_LAUNCH_CHECK(ctx);
+    }
     return CAELO_OK;
 }
 
@@ -407,6 +560,31 @@ extern "C" int caelo_kabsch(caelo_ctx *ctx, const float *pc0, int N0, const floa
     a.mask = mask; a.skip_if_ok = skip_if_ok; a.N0 = N0; a.N = N; a.P = P; a.rt = Rt; a.credible = credible;
     int blocks = (P * 32 + 127) / 128;
     { ProfScope ps_(ctx, "kabsch_kernel", (cudaStream_t)stream); kabsch_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a); }
+    CAELO_LAUNCH_CHECK(ctx);
+    return CAELO_OK;
+}
+
+extern "C" int caelo_ransac_draw_samples(caelo_ctx *ctx, const int64_t *seeds, int P, int n_points, int T, int rounds,
+                                         int rounds_done, int32_t *samples, void *stream)
+{
+    if (!ctx || !seeds || !samples || P <= 0 || n_points <= 0 || T <= 0 || T > CAELO_MAX_TRIALS || rounds <= 0 ||
+        rounds_done < 0)
+        return CAELO_ERR_ARG;
+    for (int i = 0; i < P; ++i)
+        if (seeds[i] < 0 || seeds[i] > 0xffffffffll) return CAELO_ERR_ARG;  // numpy: "Seed must be between 0 and 2**32 - 1"
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = caelo_reserve(ctx, ctx->seed_ws, (size_t)P * 8);
+    if (rc) return rc;
+    void *h_stage = nullptr;
+    cudaEvent_t ev;
+    if ((rc = caelo_stage_acquire(ctx, (size_t)P * 8, &h_stage, &ev))) return rc;
+    memcpy(h_stage, seeds, (size_t)P * 8);
+    CAELO_CUDA(ctx, cudaMemcpyAsync(ctx->seed_ws.ptr, h_stage, (size_t)P * 8, cudaMemcpyHostToDevice, st));
+    CAELO_CUDA(ctx, cudaEventRecord(ev, st));
+    DrawArgs a;
+    a.seeds = reinterpret_cast<const long long *>(ctx->seed_ws.ptr); a.samples = samples; a.P = P;
+    a.per_round = T * 4; a.first = rounds_done * T * 4; a.count = rounds * T * 4; a.n_points = n_points;
+    { ProfScope ps_(ctx, "draw_samples_kernel", st); draw_samples_kernel<<<P, 256, 0, st>>>(a); }
     CAELO_LAUNCH_CHECK(ctx);
     return CAELO_OK;
 }

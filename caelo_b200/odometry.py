@@ -142,12 +142,17 @@ def estimate_sequence(raw_dir: str, Tr: Optional[np.ndarray] = None, poses_path:
         if d:
             os.makedirs(d, exist_ok=True)
     rows = []
-    for b0 in range(lo, hi, batch_pairs):
-        b1 = min(b0 + batch_pairs, hi)
+    ranges = [(b0, min(b0 + batch_pairs, hi)) for b0 in range(lo, hi, batch_pairs)]
+
+    def batches():                                                          # read one batch ahead of the device
+        for b0, b1 in ranges:
+            chunk = [scans[i] if scans is not None else read_scan(files[i]) for i in range(b0, b1 + 1)]
+            host, off = _stack_scans(chunk)
+            yield ("scans", host.pin_memory(), off, list(range(b0, b1)))
+
+    for (b0, b1), poses_b in zip(ranges, pipe.run_host_stream(batches())):
         ids = list(range(b0, b1 + 1))                                   # frames b0..b1 -> pairs b0..b1-1
-        chunk = [scans[i] if scans is not None else read_scan(files[i]) for i in ids]
-        host, off = _stack_scans(chunk)
-        rows.append(pipe.run_host_scans(host.pin_memory(), off, list(range(b0, b1))))
+        rows.append(poses_b)
         if want_files:
             d = pipe.last_details
             kp, ft = d["kpts"].cpu().numpy(), d["feat"].cpu().numpy()

@@ -35,8 +35,9 @@ def draw_samples(pair_ids: Sequence[int], n_points: int, rounds_done: int = 0, r
     rounds ([rounds,P,500,4]), drawn exactly as RANSAC4RT does after ``np.random.seed(pair_id)``
     (Match.py:182-184: 4 doubles per trial, int32(u*N); a failed round consumes all 500 trials)."""
     out = np.empty((rounds, len(pair_ids), MAX_TRIALS, 4), np.int32)
+    rs = np.random.RandomState(0)                      # one object, re-seeded per pair (constructing one costs ~0.3 ms)
     for i, pid in enumerate(pair_ids):
-        rs = np.random.RandomState(int(pid))
+        rs.seed(int(pid))
         if rounds_done:
             rs.random_sample((rounds_done * MAX_TRIALS * 4,))
         u = rs.random_sample((rounds, MAX_TRIALS, 4))
@@ -73,12 +74,11 @@ class OdometryPipeline:
         return kpts, feat, n, st | r["status"]
 
     # ---- whole batch ------------------------------------------------------------------------
-    def _finish(self, kpts, feat, n, samples, pair_ids, status=None):
-        """Pairs stage + one D2H of the per-pair results; returns poses [P,16] float32 (host): refit
-        R(9) T(3), isSuccess, nInliers, residualThreshold, trials — rows follow ``pair_ids``.
-        ``samples`` is [P,500,4] (first round; failures go through a host-driven ladder) or
-        [3,P,500,4]: then the 0.8 and 1.6 rounds are queued on the device right away and skip every
-        pair that already has a model (no host round trip)."""
+    def _enqueue_pairs(self, kpts, feat, n, samples, pair_ids, status=None):
+        """Queues the pairs stage (a4 + a5 + refit) and the one D2H copy of the per-pair results on the current
+        stream; nothing here waits for the device.  ``samples`` is [P,500,4] (first round; failures go through a
+        host-driven ladder in ``_collect``) or [3,P,500,4]: then the 0.8 and 1.6 rounds are queued on the device
+        right away and skip every pair that already has a model (no host round trip)."""
         P = kpts.shape[0] - 1
         pc0, pc1 = kpts[:-1], kpts[1:]
         pair_idx = self.ctx.nn_match(feat[:-1], feat[1:])
@@ -97,13 +97,28 @@ class OdometryPipeline:
             if self.keep_details:                       # inlier mask of the round that produced the model
                 mask_acc = mask if mask_acc is None else torch.where(newly[:, None], mask, mask_acc)
             state, rt = res, rt_r
+        details = None
         if self.keep_details:
-            self.last_details = dict(kpts=kpts, feat=feat, pair_idx=pair_idx, mask=mask_acc, ok=state[:, 12] != 0)
+            details = dict(kpts=kpts, feat=feat, pair_idx=pair_idx, mask=mask_acc, ok=state[:, 12] != 0)
         nf = n.to(torch.float32)
         bad = torch.zeros_like(nf) if status is None else (status != 0).to(torch.float32)
         packed = torch.cat([state, rt, thr_used[:, None], nf[:-1, None], nf[1:, None],
                             torch.maximum(bad[:-1], bad[1:])[:, None]], 1)
-        host = packed.cpu().numpy()                     # the one sync point of the batch
+        host = torch.empty(packed.shape, dtype=torch.float32, pin_memory=True)
+        host.copy_(packed, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        return dict(host=host, done=done, kpts=kpts, pair_idx=pair_idx, pair_ids=list(pair_ids),
+                    rounds=rounds.shape[0], details=details)
+
+    def _collect(self, h):
+        """Waits for one queued batch (the one sync point of the batch); returns poses [P,16] float32 (host):
+        refit R(9) T(3), isSuccess, nInliers, residualThreshold, trials — rows follow ``pair_ids``."""
+        h["done"].synchronize()
+        if self.keep_details:
+            self.last_details = h["details"]
+        host = h["host"].numpy()
+        P = host.shape[0]
         res, rt_h = host[:, :16], host[:, 16:28]
         if host[:, 31].any():
             raise api._lib.CaeloError("a scan has points outside the voxel grid / ring image or fewer than 496 "
@@ -117,84 +132,124 @@ class OdometryPipeline:
         poses[:, 14] = host[:, 28]
         poses[:, 15] = res[:, 13]
         failed = np.flatnonzero(res[:, 12] == 0)
-        if failed.size and rounds.shape[0] < len(LADDER):
-            self._ladder(failed, kpts, pair_idx, pair_ids, poses, rounds.shape[0])
+        if failed.size and h["rounds"] < len(LADDER):
+            self._ladder(failed, h["kpts"], h["pair_idx"], h["pair_ids"], poses, h["rounds"])
         elif failed.size:                               # total failure: R=I, T=0 (Match.py:277-278)
             poses[failed, :12] = [1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]
             poses[failed, 13] = 0
         return poses
 
+    def _finish(self, kpts, feat, n, samples, pair_ids, status=None):
+        return self._collect(self._enqueue_pairs(kpts, feat, n, samples, pair_ids, status))
+
     def run_device(self, ring, counter, vox, vox_offsets, samples, pair_ids):
-        """Inputs already in HBM."""
+        """Inputs already in HBM.  ``samples`` None: the RANSAC indices of all three ladder rounds are generated
+        on the device from the pair ids (np.random.seed(pair_id) streams)."""
         kpts, feat, n = self.frames_to_descriptors(ring, counter, vox, vox_offsets)
+        if samples is None:
+            samples = self.ctx.draw_samples(pair_ids, self.K, rounds=3)
         return self._finish(kpts, feat, n, samples, pair_ids)
 
     def run_device_scans(self, pts, pts_offsets, samples, pair_ids):
         """Raw scans already in HBM."""
         kpts, feat, n, st = self.scans_to_descriptors(pts, pts_offsets)
+        if samples is None:
+            samples = self.ctx.draw_samples(pair_ids, self.K, rounds=3)
         return self._finish(kpts, feat, n, samples, pair_ids, st)
+
+    # ---- host (pinned) inputs -----------------------------------------------------------------
+    def _copy_stream_(self):
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(self.dev)
+        return self._copy_stream
+
+    def _upload(self, batch, chunks: int = 4):
+        """Queues the H2D copies of one batch on the copy stream in ``chunks`` frame groups; returns the device
+        parts with the event each becomes valid at.  ``batch`` is ("rings", ring_h, counter_h, vox_h, vox_offsets,
+        pair_ids) or ("scans", pts_h, pts_offsets, pair_ids), host tensors pinned."""
+        cs = self._copy_stream_()
+        parts = []
+        if batch[0] == "rings":
+            _, ring_h, counter_h, vox_h, vox_offsets, pair_ids = batch
+            F = ring_h.shape[0]
+            voff = np.asarray(vox_offsets, np.int64)
+            bounds = np.linspace(0, F, min(chunks, F) + 1).astype(int)
+            for c0, c1 in zip(bounds[:-1], bounds[1:]):
+                with torch.cuda.stream(cs):
+                    r = ring_h[c0:c1].to(self.dev, non_blocking=True)
+                    c = counter_h[c0:c1].to(self.dev, non_blocking=True)
+                    v = vox_h[voff[3 * c0]:voff[3 * c1]].to(self.dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                parts.append(((r, c, v), voff[3 * c0:3 * c1 + 1] - voff[3 * c0], ev))
+        else:
+            _, pts_h, pts_offsets, pair_ids = batch
+            off = np.asarray(pts_offsets, np.int64)
+            F = off.shape[0] - 1
+            bounds = np.linspace(0, F, min(chunks, F) + 1).astype(int)
+            for c0, c1 in zip(bounds[:-1], bounds[1:]):
+                with torch.cuda.stream(cs):
+                    p = pts_h[off[c0]:off[c1]].to(self.dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                parts.append(((p,), off[c0:c1 + 1] - off[c0], ev))
+        return dict(kind=batch[0], parts=parts, pair_ids=list(pair_ids))
+
+    def _enqueue(self, up):
+        """Queues every kernel of an uploaded batch on the current stream (each frame group as soon as its copy
+        event has fired); the RANSAC sample indices are generated on the device (ctx.draw_samples)."""
+        cur = torch.cuda.current_stream(self.dev)
+        outs = []
+        for tensors, o, ev in up["parts"]:
+            cur.wait_event(ev)
+            for t in tensors:
+                t.record_stream(cur)
+            if up["kind"] == "rings":
+                kp, ft, n = self.frames_to_descriptors(*tensors, o)
+                outs.append((kp, ft, n, None))
+            else:
+                outs.append(self.scans_to_descriptors(tensors[0], o))
+        smp = self.ctx.draw_samples(up["pair_ids"], self.K, rounds=3)     # all three ladder rounds, on the device
+        kpts, feat, n = (torch.cat([o[i] for o in outs], 0) for i in range(3))
+        st = None if up["kind"] == "rings" else torch.cat([o[3] for o in outs], 0)
+        return self._enqueue_pairs(kpts, feat, n, smp, up["pair_ids"], st)
+
+    def run_host_stream(self, batches, chunks: int = 4):
+        """Generator over an iterable of host batches (see ``_upload``) -> poses [P,16] per batch, in order.
+        Software-pipelined two deep: the H2D copies of batch i+1 run on the copy stream and its kernels are
+        queued while batch i computes; the host only waits for batch i-1's results.  Every batch still pays
+        its own H2D copies and D2H read — they just overlap the neighbouring batches' kernels (this is how
+        ``odometry.estimate_sequence`` walks a sequence)."""
+        it = iter(batches)
+        try:
+            up = self._upload(next(it), chunks)
+        except StopIteration:
+            return
+        pending = None
+        while up is not None:
+            try:
+                nxt = self._upload(next(it), chunks)
+            except StopIteration:
+                nxt = None
+            h = self._enqueue(up)
+            if pending is not None:
+                yield self._collect(pending)
+            pending, up = h, nxt
+        yield self._collect(pending)
 
     def run_host_scans(self, pts_h: torch.Tensor, pts_offsets: np.ndarray, pair_ids: Sequence[int], chunks: int = 4):
         """End-to-end from raw scans in HOST (pinned) memory: [sumN,4] f32 + row offsets [F+1].  Same
         chunked upload / compute overlap as ``run_host``."""
-        off = np.asarray(pts_offsets, np.int64)
-        F = off.shape[0] - 1
-        cur = torch.cuda.current_stream(self.dev)
-        if not hasattr(self, "_copy_stream"):
-            self._copy_stream = torch.cuda.Stream(self.dev)
-        cs = self._copy_stream
-        cs.wait_stream(cur)
-        bounds = np.linspace(0, F, min(chunks, F) + 1).astype(int)
-        parts = []
-        for c0, c1 in zip(bounds[:-1], bounds[1:]):
-            with torch.cuda.stream(cs):
-                p = pts_h[off[c0]:off[c1]].to(self.dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(cs)
-            parts.append((p, off[c0:c1 + 1] - off[c0], ev))
-        outs = []
-        for p, o, ev in parts:
-            cur.wait_event(ev)
-            p.record_stream(cur)
-            outs.append(self.scans_to_descriptors(p, o))
-        smp = torch.from_numpy(draw_samples(pair_ids, self.K, rounds=3)).pin_memory().to(self.dev, non_blocking=True)
-        kpts, feat, n, st = (torch.cat([o[i] for o in outs], 0) for i in range(4))
-        return self._finish(kpts, feat, n, smp, pair_ids, st)
+        self._copy_stream_().wait_stream(torch.cuda.current_stream(self.dev))
+        return self._collect(self._enqueue(self._upload(("scans", pts_h, pts_offsets, pair_ids), chunks)))
 
     def run_host(self, ring_h: torch.Tensor, counter_h: torch.Tensor, vox_h: torch.Tensor,
                  vox_offsets: np.ndarray, pair_ids: Sequence[int], chunks: int = 4):
         """End-to-end call with HOST (pinned) buffers.  Frames are uploaded in ``chunks`` groups on a copy
         stream while the compute stream already works on the groups that have landed; the RANSAC sample
         indices are drawn on the host while the GPU is busy with the frame stages."""
-        F = ring_h.shape[0]
-        voff = np.asarray(vox_offsets, np.int64)
-        cur = torch.cuda.current_stream(self.dev)
-        if not hasattr(self, "_copy_stream"):
-            self._copy_stream = torch.cuda.Stream(self.dev)
-        cs = self._copy_stream
-        cs.wait_stream(cur)
-        bounds = np.linspace(0, F, min(chunks, F) + 1).astype(int)
-        parts, events = [], []
-        for c0, c1 in zip(bounds[:-1], bounds[1:]):
-            with torch.cuda.stream(cs):
-                r = ring_h[c0:c1].to(self.dev, non_blocking=True)
-                c = counter_h[c0:c1].to(self.dev, non_blocking=True)
-                v = vox_h[voff[3 * c0]:voff[3 * c1]].to(self.dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(cs)
-            parts.append((r, c, v, voff[3 * c0:3 * c1 + 1] - voff[3 * c0]))
-            events.append(ev)
-        outs = []
-        for (r, c, v, o), ev in zip(parts, events):
-            cur.wait_event(ev)
-            for t in (r, c, v):
-                t.record_stream(cur)
-            outs.append(self.frames_to_descriptors(r, c, v, o))
-        smp = torch.from_numpy(draw_samples(pair_ids, self.K, rounds=3)).pin_memory().to(self.dev, non_blocking=True)
-        kpts = torch.cat([o[0] for o in outs], 0)
-        feat = torch.cat([o[1] for o in outs], 0)
-        n = torch.cat([o[2] for o in outs], 0)
-        return self._finish(kpts, feat, n, smp, pair_ids)
+        self._copy_stream_().wait_stream(torch.cuda.current_stream(self.dev))
+        return self._collect(self._enqueue(self._upload(("rings", ring_h, counter_h, vox_h, vox_offsets, pair_ids), chunks)))
 
     def _ladder(self, failed, kpts, pair_idx, pair_ids, poses, rounds_done=1):
         """Host-driven threshold ladder for the pairs that still have no model (Match.py:207-214)."""

@@ -149,6 +149,15 @@ int caelo_kabsch(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int
                  const int64_t *pair_idx, const uint8_t *mask, const float *skip_if_ok, int P,
                  float *Rt, int32_t *credible, void *stream);
 
+/* a5 (sample indices) — the index stream RANSAC4RT draws after np.random.seed(seed) (Match.py:182-184:
+ * np.random.random((4,)) per trial, int32(u*N)), generated on the device: numpy's legacy MT19937 seeding and
+ * random_sample arithmetic, bit for bit.  seeds: HOST int64 [P], each in [0, 2^32) (numpy raises otherwise);
+ * rounds_done: threshold-ladder rounds whose T*4 doubles are skipped first (a failed round consumes all T
+ * trials); samples: dev int32 [rounds,P,T,4].  Used by the batched pipeline, where pair i of a sequence is
+ * seeded with i; the per-pair API (SolveRelativePose) keeps drawing from the caller's global numpy stream. */
+int caelo_ransac_draw_samples(caelo_ctx *ctx, const int64_t *seeds, int P, int n_points, int T, int rounds,
+                              int rounds_done, int32_t *samples, void *stream);
+
 /* f1 — ProjectPC2SphericalRing (SphericalRing.py:72-94) for F scans at once.  pts: dev float32 rows
  * (x,y,z,intensity), all scans concatenated; pts_offsets: HOST [F+1] int64 row offsets into pts.
  * Outputs, each dev or NULL (at least one): ring5 [F,69,1800,5] f32 and counter_i32 [F,69,1800] — the
@@ -196,7 +205,7 @@ int caelo_extend_keypoints(caelo_ctx *ctx, const float *ring, int ring_C, int ri
                            const int32_t *n_kpts, int B, int max_kpts, float *ext, int ext_cap,
                            int32_t *n_ext, int zero_counter, void *stream);
 
-/* Debug: device buffer [grid][64][8] int64 receiving clock64 stamps of the encoder's per-patch
+/* Debug: device buffer [grid][64][16] int64 (+ [1024][8] for dense) receiving clock64 stamps of the encoder's per-patch
  * phases (NULL disables).  Used by tools/encoder_timeline.py. */
 int caelo_debug_set_timeline(caelo_ctx *ctx, long long *buf);
 

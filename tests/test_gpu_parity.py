@@ -340,3 +340,54 @@ def test_pipeline_batch_matches_oracle(api, oracle_mod):
             assert np.abs(poses_dev[i, 9:12] - T.ravel()).max() <= 1e-4 * max(1.0, np.abs(T).max())
         else:
             assert abs(int(poses_dev[i, 13]) - len(i0)) <= 3
+
+
+def test_device_sample_stream_is_numpys(api):
+    """caelo_ransac_draw_samples == int32(np.random.random(4) * N) after np.random.seed(seed) (Match.py:182-184),
+    for small and 32-bit seeds, all ladder rounds, and a stream entered after failed rounds."""
+    from caelo_b200 import pipeline
+    ctx = api.default_context()
+    seeds = [0, 1, 7, 4540, 123456789, 2 ** 31, 2 ** 32 - 1]
+    for n_points in (1024, 833, 50):
+        got = ctx.draw_samples(seeds, n_points, rounds=3).cpu().numpy()
+        want = pipeline.draw_samples(seeds, n_points, rounds=3)
+        assert got.shape == want.shape == (3, len(seeds), 500, 4)
+        assert np.array_equal(got, want)
+    late = ctx.draw_samples(seeds, 1024, rounds=1, rounds_done=2).cpu().numpy()
+    assert np.array_equal(late[0], pipeline.draw_samples(seeds, 1024, rounds_done=2))
+    # the reference's own draw, from the global stream
+    np.random.seed(4540)
+    first = np.array([np.int32(np.random.random((4,)) * 1024) for _ in range(3)])
+    assert np.array_equal(got_rows := ctx.draw_samples([4540], 1024).cpu().numpy()[0, 0, :3], first), got_rows
+    with pytest.raises(Exception):
+        ctx.draw_samples([-1], 1024)
+    with pytest.raises(Exception):
+        ctx.draw_samples([2 ** 32], 1024)
+
+
+def test_host_stream_equals_single_calls(api):
+    """pipeline.run_host_stream (uploads of batch i+1 overlapping batch i, results collected one batch late) returns
+    exactly what isolated run_host / run_host_scans calls return, batch by batch."""
+    import torch
+    from caelo_b200 import pipeline, synth
+    pipe = pipeline.OdometryPipeline(api.default_context())
+    d = synth.make_frames(5, seed=11)
+    off = d["vox_offsets"]
+    ring_h, cnt_h, vox_h = (torch.from_numpy(d[k]).pin_memory() for k in ("ring3", "counter", "vox"))
+    batches, singles = [], []
+    for f0, ids in ((0, [100, 101]), (2, [102, 103]), (1, [7, 8, 9])):
+        f1 = f0 + len(ids) + 1
+        vo = off[3 * f0:3 * f1 + 1] - off[3 * f0]
+        args = (ring_h[f0:f1], cnt_h[f0:f1], vox_h[off[3 * f0]:off[3 * f1]], vo, ids)
+        batches.append(("rings",) + args)
+        singles.append(pipe.run_host(*args))
+    soff = np.zeros(6, np.int64)
+    soff[1:] = np.cumsum([s.shape[0] for s in d["scans"]])
+    scans_h = torch.from_numpy(np.concatenate(d["scans"], 0)).pin_memory()
+    batches.append(("scans", scans_h[soff[1]:soff[4]], soff[1:5] - soff[1], [7, 8]))
+    singles.append(pipe.run_host_scans(scans_h[soff[1]:soff[4]], soff[1:5] - soff[1], [7, 8]))
+    got = list(pipe.run_host_stream(iter(batches)))
+    assert len(got) == len(singles)
+    for g, w in zip(got, singles):
+        assert np.array_equal(g, w)
+    assert list(pipe.run_host_stream(iter([]))) == []

@@ -11,20 +11,23 @@ kpts, _, n = ctx.select_keypoints(ring, cnt, None)
 packed, _, _ = ctx.gather_patches(kpts, api._dev(d["vox"]), d["vox_offsets"], n)
 packed = packed.repeat(8, 1, 1, 1).contiguous()          # 49k patches
 grid = 2 * ctx.lib.caelo_num_sms(ctx.h)
-tl = torch.zeros((grid, 64, 8), dtype=torch.int64, device="cuda")
-tl_all = torch.zeros((grid * 64 * 8 + 1024 * 8,), dtype=torch.int64, device="cuda")
+tl_all = torch.zeros((grid * 64 * 16 + 1024 * 8,), dtype=torch.int64, device="cuda")
 ctx.encode_frames(packed)
 ctx.check(ctx.lib.caelo_debug_set_timeline(ctx.h, ctypes.c_void_p(tl_all.data_ptr())))
 ctx.encode_frames(packed)
 torch.cuda.synchronize()
 ctx.lib.caelo_debug_set_timeline(ctx.h, None)
-tl = tl_all[:grid * 64 * 8].view(grid, 64, 8)
-dn = tl_all[grid * 64 * 8:].view(-1, 8).cpu().numpy().astype(np.float64)
+tl = tl_all[:grid * 64 * 16].view(grid, 64, 16)
+dn = tl_all[grid * 64 * 16:].view(-1, 8).cpu().numpy().astype(np.float64)
 dn = dn[dn[:, 0] > 0]
 print("dense_tc per-CTA cycles: start->accum-done %.0f  W2 fill+Hs fill %.0f  dense2 %.0f  total %.0f (n=%d)" % ((dn[:,3]-dn[:,0]).mean(), (dn[:,4]-dn[:,3]).mean(), (dn[:,5]-dn[:,4]).mean(), (dn[:,5]-dn[:,0]).mean(), len(dn)))
 t = tl.cpu().numpy()[:, 4:60, :].astype(np.float64)
 def stat(x): return "mean %8.0f  p50 %8.0f  p90 %8.0f" % (x.mean(), np.median(x), np.percentile(x, 90))
 print("conv1            1-0 :", stat(t[..., 1] - t[..., 0]))
+print("  restore+stage  2-0 :", stat(t[..., 2] - t[..., 0]))
+print("  pass 1         7-2 :", stat(t[..., 7] - t[..., 2]))
+print("  pass 2         8-7 :", stat(t[..., 8] - t[..., 7]))
+print("  fence + arrive 1-8 :", stat(t[..., 1] - t[..., 8]))
 
 print("mma issue        6-5 :", stat(t[..., 6] - t[..., 5]))
 print("mbar wait        3-1 :", stat(t[..., 3] - t[..., 1]))
@@ -36,4 +39,4 @@ for cta in (0, 150):
     print("CTA", cta, "(cycles relative to iteration-10 start; columns = stamps 0..7)")
     base = raw[cta, 10, 0]
     for i in range(10, 15):
-        print("  it %2d:" % i, " ".join("%8d" % (raw[cta, i, s] - base) for s in range(8)))
+        print("  it %2d:" % i, " ".join("%8d" % (raw[cta, i, s] - base) for s in range(9)))
