@@ -42,6 +42,8 @@ SIGNATURES = {
     "caelo_nn_match": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "caelo_ransac_round": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                    c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "caelo_ransac_ladder": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                    POINTER(c_float), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "caelo_ransac_draw_samples": (c_int, [c_void_p, POINTER(c_int64), c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "caelo_project_ring": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
@@ -50,6 +52,10 @@ SIGNATURES = {
     "caelo_gather_patches_scans": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
                                            POINTER(c_int64), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p]),
+    "caelo_bricks_build": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int, c_void_p]),
+    "caelo_bricks_build_scans": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int, c_void_p, c_void_p, c_void_p]),
+    "caelo_bricks_gather": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p]),
     "caelo_extend_keypoints": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                                        c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "caelo_debug_set_timeline": (c_int, [c_void_p, c_void_p]),

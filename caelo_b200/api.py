@@ -49,6 +49,14 @@ nFixedKeyPts = 1024
 MAX_TRIALS = 500
 
 
+class _nullctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -245,6 +253,37 @@ class Context:
         self.check(rc, "caelo_gather_patches_scans")
         return packed, f32, trunc, nvox, status
 
+    # a6 in two steps (the index of a batch can be built on a second stream while its key points are selected)
+    def bricks_build(self, vox: torch.Tensor, vox_offsets: np.ndarray, stream=None):
+        off = np.ascontiguousarray(vox_offsets, np.int64)
+        F = (off.shape[0] - 1) // 3
+        assert vox.dtype == torch.int16 and vox.is_contiguous() and off.shape == (F * 3 + 1,)
+        st = ctypes.c_void_p(stream.cuda_stream) if stream is not None else _stream()
+        self.check(self.lib.caelo_bricks_build(self.h, _ptr(vox), off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), F, st),
+                   "caelo_bricks_build")
+        return F
+
+    def bricks_build_scans(self, pts: torch.Tensor, pts_offsets: np.ndarray, stream=None):
+        off = np.ascontiguousarray(pts_offsets, np.int64)
+        F = off.shape[0] - 1
+        assert pts.dtype == torch.float32 and pts.is_contiguous()
+        st = ctypes.c_void_p(stream.cuda_stream) if stream is not None else _stream()
+        with torch.cuda.stream(stream) if stream is not None else _nullctx():
+            nvox = torch.empty((F, 3), dtype=torch.int32, device=self.device)
+            status = torch.empty((F,), dtype=torch.int32, device=self.device)
+        self.check(self.lib.caelo_bricks_build_scans(self.h, _ptr(pts), off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), F,
+                                                     _ptr(nvox), _ptr(status), st), "caelo_bricks_build_scans")
+        return nvox, status
+
+    def bricks_gather(self, kpts: torch.Tensor, n_kpts=None, nvox=None, status=None):
+        F, K, _ = kpts.shape
+        assert kpts.is_contiguous()
+        packed = torch.empty((F, 3, K, 128), dtype=torch.int32, device=self.device)
+        self.check(self.lib.caelo_bricks_gather(self.h, _ptr(kpts), 1 if kpts.dtype == torch.float64 else 0, _ptr(n_kpts), F, K,
+                                                _ptr(packed), None, None, _ptr(nvox), _ptr(status), _stream()),
+                   "caelo_bricks_gather")
+        return packed
+
     def encode_frames(self, packed: torch.Tensor) -> torch.Tensor:
         F, S, K, Wd = packed.shape
         assert S == 3 and Wd == 128 and packed.is_contiguous()
@@ -287,6 +326,24 @@ class Context:
                                          _ptr(counts), _stream())
         self.check(rc, "caelo_ransac_round")
         return result, mask, counts
+
+    def ransac_ladder(self, pc0, pc1, pair_idx, sample_idx, thresholds):
+        """All ladder rounds + the refit for P pairs in one call (no host round trip): sample_idx int32
+        [rounds,P,T,4] -> result [P,16], mask [P,N] uint8, rt [P,12], thr_used [P]."""
+        P, N0, _ = pc0.shape
+        N = pc1.shape[1]
+        rounds, _, T, _ = sample_idx.shape
+        assert sample_idx.is_contiguous() and sample_idx.dtype == torch.int32 and len(thresholds) == rounds
+        result = torch.empty((P, 16), dtype=torch.float32, device=self.device)
+        mask = torch.empty((P, N), dtype=torch.uint8, device=self.device)
+        rt = torch.empty((P, 12), dtype=torch.float32, device=self.device)
+        thr_used = torch.empty((P,), dtype=torch.float32, device=self.device)
+        cred = torch.empty((P,), dtype=torch.int32, device=self.device)
+        thr = (ctypes.c_float * rounds)(*[float(t) for t in thresholds])
+        self.check(self.lib.caelo_ransac_ladder(self.h, _ptr(pc0), N0, _ptr(pc1), N, _ptr(pair_idx), _ptr(sample_idx), T,
+                                                rounds, thr, P, _ptr(result), _ptr(mask), _ptr(rt), _ptr(thr_used),
+                                                _ptr(cred), _stream()), "caelo_ransac_ladder")
+        return result, mask, rt, thr_used
 
     def draw_samples(self, seeds, n_points: int, rounds: int = 1, rounds_done: int = 0, T: int = MAX_TRIALS):
         """RANSAC sample indices of ``rounds`` ladder rounds for pairs seeded np.random.seed(seeds[i]), generated

@@ -58,6 +58,8 @@ struct caelo_ctx {
     // scratch regions (grown on demand, never shrunk)
     Scratch cand;      // select: candidate keys + counters
     Scratch bricks;    // patches: hash tables
+    void *bricks_tables = nullptr;  // Table array of the last caelo_bricks_build* (inside `bricks`)
+    int bricks_frames = 0;
     Scratch enc_ws;    // encoder activations
     Scratch pose_ws;   // ransac: hypotheses
     Scratch misc;

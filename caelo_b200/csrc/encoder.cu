@@ -443,11 +443,13 @@ constexpr int C3_COPY = 6 * 16 * 16;                 // 1536 B: [xi 6][y 4][z 4]
 constexpr int C3_HALF = 9 * C3_COPY;                 // 13824 B: 9 (dy,dz) copies of one channel half
 constexpr int C3_PART = 2 * C3_HALF;                 // 27648 B: both halves
 constexpr int C3_BUF = 2 * C3_PART;                  // 55296 B: hi + lo
+// NBUF operand buffers: 2 = one CTA per SM, produce(i+1) overlaps MMA(i) inside the CTA; 1 = two CTAs per SM
+// (110.8 KB each) that overlap each other — twice the worker warps to hide the producer/epilogue latencies
 constexpr int SM3_C = 0;
-constexpr int SM3_W = 2 * C3_BUF;                    // 110592: W3 [kc 54][n 64][16 B]
-constexpr int SM3_B3 = SM3_W + 54 * 1024;            // 165888
-constexpr int SM3_BAR = SM3_B3 + 128;
-constexpr int C3_SMEM = SM3_BAR + 64;
+__host__ __device__ constexpr int sm3_w(int nbuf) { return nbuf * C3_BUF; }                 // W3 [kc 54][n 64][16 B]
+__host__ __device__ constexpr int sm3_b3(int nbuf) { return sm3_w(nbuf) + 54 * 1024; }
+__host__ __device__ constexpr int sm3_bar(int nbuf) { return sm3_b3(nbuf) + 128; }
+__host__ __device__ constexpr int c3_smem(int nbuf) { return sm3_bar(nbuf) + 64; }
 
 struct Conv3Args {
     const float *act2;     // [P,64,16]
@@ -456,8 +458,10 @@ struct Conv3Args {
     int P;
 };
 
-__global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const Conv3Args a)
+template <int NBUF>
+__global__ void __launch_bounds__(C3_THREADS, 3 - NBUF) conv3_tc_kernel(const Conv3Args a)
 {
+    constexpr int SM3_W = sm3_w(NBUF), SM3_B3 = sm3_b3(NBUF), SM3_BAR = sm3_bar(NBUF);
     extern __shared__ __align__(128) unsigned char sm[];
     float *b3s = reinterpret_cast<float *>(sm + SM3_B3);
     uint64_t *full = reinterpret_cast<uint64_t *>(sm + SM3_BAR), *tfull = full + 2, *tempty = full + 4;
@@ -505,7 +509,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const Conv3Args
                 const uint32_t d = tbase + b * 64;
 #pragma unroll
                 for (int part = 0; part < 2; ++part) {
-                    const uint32_t cb = sC + b * C3_BUF + part * C3_PART;
+                    const uint32_t cb = sC + (NBUF == 2 ? b : 0) * C3_BUF + part * C3_PART;
 #pragma unroll
                     for (int t = 0; t < 27; ++t) {
                         const int dx = t / 9, dy = (t / 3) % 3, dz = t % 3;
@@ -535,16 +539,16 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const Conv3Args
             const float4 v0 = nv0, v1 = nv1;
             fetch(i + 1);
             float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            __half hv[8];
+            __half2 hv[4];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                __half h, l;
-                umma::split_f16(f[c], h, l);
+            for (int c = 0; c < 4; ++c) {
+                __half2 h, l;
+                umma::split_f16x2(f[2 * c], f[2 * c + 1], h, l);
                 hv[c] = part ? l : h;
             }
             const uint4 val = *reinterpret_cast<uint4 *>(hv);
             const int x = pos >> 4, y = (pos >> 2) & 3, z = pos & 3;
-            unsigned char *base = sm + SM3_C + b * C3_BUF + part * C3_PART + half * C3_HALF;
+            unsigned char *base = sm + SM3_C + (NBUF == 2 ? b : 0) * C3_BUF + part * C3_PART + half * C3_HALF;
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
@@ -559,9 +563,10 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const Conv3Args
         if (n_my > 0) produce(0);
         for (int i = 0; i < n_my; ++i) {
             const int b = i & 1;
-            if (i + 1 < n_my) produce(i + 1);  // MMA(i-1) finished reading buffer b^1 (tfull waited last iteration)
+            if (NBUF == 2 && i + 1 < n_my) produce(i + 1);  // MMA(i-1) finished reading buffer b^1 (tfull waited last iteration)
             umma::mbar_wait(&tfull[b], (uint32_t)((i >> 1) & 1));
             umma::fence_after_thread_sync();
+            if (NBUF == 1 && i + 1 < n_my) produce(i + 1);  // MMA(i) finished reading the one buffer; it ran under the other CTA's work
             const int q = warp & 3, hc = warp >> 2;  // lane quarter, channel half (16 channels)
             uint32_t v0[16], v1[16];
             const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16) + b * 64 + hc * 16;
@@ -572,11 +577,12 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const Conv3Args
             umma::mbar_arrive(&tempty[b]);
             if (lane < 16) {  // M=64 accumulator: rows 16q..16q+15 live in lanes 0..15 of quarter q
                 const int pos = 16 * q + lane;
-                __half hh[16], ll[16];
+                __half2 hh[8], ll[8];
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    float o = fast_tanh((__uint_as_float(v0[c]) + __uint_as_float(v1[c])) + b3s[hc * 16 + c]);
-                    umma::split_f16(o, hh[c], ll[c]);
+                for (int c = 0; c < 8; ++c) {
+                    const float o0 = fast_tanh((__uint_as_float(v0[2 * c]) + __uint_as_float(v1[2 * c])) + b3s[hc * 16 + 2 * c]);
+                    const float o1 = fast_tanh((__uint_as_float(v0[2 * c + 1]) + __uint_as_float(v1[2 * c + 1])) + b3s[hc * 16 + 2 * c + 1]);
+                    umma::split_f16x2(o0, o1, hh[c], ll[c]);
                 }
                 const size_t o = (size_t)patch_of(i) * 2048 + pos * 32 + hc * 16;
                 uint4 *dh = reinterpret_cast<uint4 *>(a.act3_hi + o), *dl = reinterpret_cast<uint4 *>(a.act3_lo + o);
@@ -609,7 +615,7 @@ constexpr int D_W_BYTES = DN * DK_STAGE * 2;  // 13312
 constexpr int D_STAGE = 2 * D_A_BYTES + 2 * D_W_BYTES;  // 59392
 constexpr int D_SM_BAR = D_STAGES * D_STAGE;  // 178176
 constexpr int D_SMEM = D_SM_BAR + 128;
-constexpr int D_THREADS = 192;
+constexpr int D_THREADS = 320;                // warps 0-3 and 6-9: epilogue of tile 0 / tile 1; warp 4: MMA issuer; warp 5: TMA producer
 
 struct DenseArgs {
     const float *bd1, *d2, *bd2;  // (200), (200,20), (20)
@@ -701,62 +707,56 @@ dense_tc_kernel(const DenseArgs a, const __grid_constant__ CUtensorMap map_ah, c
             __syncwarp();
         }
     } else {
-        // ===== epilogue: h = tanh(D + b) -> smem (aliases the operand stages), dense2 + tanh =====
-        float *Hs = reinterpret_cast<float *>(dsm);              // [128][201]
-        float *W2s = Hs + 128 * 201;                             // [200][20] + bd2[20] + bd1[200]
-        if (tid == 0) stamp(2);
+        // ===== epilogue: h = tanh(D + b) in registers -> dense2 (200 -> 20) + tanh; one warp group per 128-row tile =====
+        const int et = warp >= 6 ? 1 : 0, q = warp & 3;           // tile, TMEM lane quarter (a warp may touch lanes 32*(warp%4)..)
+        const int row = q * 32 + (tid & 31), eid = et * 128 + row;
+        float *W2s = reinterpret_cast<float *>(dsm);              // [200][20] + bd2[20] (+pad) + bd1[208]; aliases the operand stages
+        if (eid == 0) stamp(2);
         umma::mbar_wait(accum, 0);                               // all MMAs done: the stages are free
         umma::fence_after_thread_sync();
-        if (tid == 0) stamp(3);
-        for (int i = tid; i < 200 * 20; i += 128) W2s[i] = a.d2[i];
-        if (tid < 20) W2s[4000 + tid] = a.bd2[tid];
-        for (int i = tid; i < 200; i += 128) W2s[4032 + i] = a.bd1[i];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (eid == 0) stamp(3);
+        for (int i = eid; i < 200 * 20; i += 256) W2s[i] = a.d2[i];
+        if (eid < 20) W2s[4000 + eid] = a.bd2[eid];
+        if (eid < 208) W2s[4032 + eid] = eid < 200 ? a.bd1[eid] : 0.0f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (eid == 0) stamp(4);
+        float acc[20];
+#pragma unroll
+        for (int j = 0; j < 20; ++j) acc[j] = W2s[4000 + j];
+        const uint32_t trow = tbase + ((uint32_t)(q * 32) << 16) + et * 256;
 #pragma unroll 1
-        for (int t = 0; t < 2; ++t) {
-            const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16) + t * 256;
-#pragma unroll 1
-            for (int c0 = 0; c0 < DN; c0 += 16) {
-                uint32_t v0[16];
-                umma::tmem_ld_x16(trow + c0, v0);
-                umma::tmem_ld_wait();
+        for (int c0 = 0; c0 < DN; c0 += 16) {
+            uint32_t v0[16];
+            umma::tmem_ld_x16(trow + c0, v0);
+            umma::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    int c = c0 + j;
-                    if (c < 200) Hs[tid * 201 + c] = fast_tanh(__uint_as_float(v0[j]) + W2s[4032 + c]);
+            for (int j = 0; j < 16; ++j) {
+                if (c0 + j >= 200) break;                        // columns 200..207 are padding (compile-time per unrolled j once c0 = 192)
+                const float h = fast_tanh(__uint_as_float(v0[j]) + W2s[4032 + c0 + j]);
+                const float4 *w = reinterpret_cast<const float4 *>(W2s + (c0 + j) * 20);
+#pragma unroll
+                for (int u = 0; u < 5; ++u) {
+                    const float4 wv = w[u];
+                    acc[4 * u + 0] = fmaf(h, wv.x, acc[4 * u + 0]);
+                    acc[4 * u + 1] = fmaf(h, wv.y, acc[4 * u + 1]);
+                    acc[4 * u + 2] = fmaf(h, wv.z, acc[4 * u + 2]);
+                    acc[4 * u + 3] = fmaf(h, wv.w, acc[4 * u + 3]);
                 }
-            }
-            if (tid == 0) stamp(4);
-            const int p = row0 + t * 128 + tid;    // each thread reads back only its own row of Hs
-            if (p < a.P) {
-                float acc[20];
-#pragma unroll
-                for (int j = 0; j < 20; ++j) acc[j] = W2s[4000 + j];
-#pragma unroll 4
-                for (int k = 0; k < 200; ++k) {
-                    const float h = Hs[tid * 201 + k];
-                    const float4 *w = reinterpret_cast<const float4 *>(W2s + k * 20);
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) {
-                        float4 wv = w[q];
-                        acc[4 * q + 0] = fmaf(h, wv.x, acc[4 * q + 0]);
-                        acc[4 * q + 1] = fmaf(h, wv.y, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(h, wv.z, acc[4 * q + 2]);
-                        acc[4 * q + 3] = fmaf(h, wv.w, acc[4 * q + 3]);
-                    }
-                }
-                float *o;
-                if (a.frame_mode) {
-                    int k = p % a.K, sc = (p / a.K) % 3, f = p / (3 * a.K);
-                    o = a.feat + ((size_t)f * a.K + k) * 60 + sc * 20;
-                } else {
-                    o = a.feat + (size_t)p * a.feat_stride + a.feat_col0;
-                }
-#pragma unroll
-                for (int j = 0; j < 20; ++j) o[j] = tanhf(acc[j]);
             }
         }
-        if (tid == 0) stamp(5);
+        const int p = row0 + et * 128 + row;
+        if (p < a.P) {
+            float *o;
+            if (a.frame_mode) {
+                int k = p % a.K, sc = (p / a.K) % 3, f = p / (3 * a.K);
+                o = a.feat + ((size_t)f * a.K + k) * 60 + sc * 20;
+            } else {
+                o = a.feat + (size_t)p * a.feat_stride + a.feat_col0;
+            }
+#pragma unroll
+            for (int j = 0; j < 20; ++j) o[j] = tanhf(acc[j]);
+        }
+        if (eid == 0) stamp(5);
         umma::fence_before_thread_sync();
     }
     __syncthreads();
@@ -888,8 +888,15 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
     CAELO_LAUNCH_CHECK(ctx);
     Conv3Args c3;
     c3.act2 = act2; c3.k3 = ctx->enc.k3; c3.b3 = ctx->enc.b3; c3.act3_hi = act3_hi; c3.act3_lo = act3_lo; c3.P = P;
-    int grid3 = ctx->num_sms < P ? ctx->num_sms : P;
-    { ProfScope ps_(ctx, "conv3_tc_kernel", st); conv3_tc_kernel<<<grid3, C3_THREADS, C3_SMEM, st>>>(c3); }
+    {
+        const char *e = getenv("CAELO_CONV3_NBUF");   // debug switch for A/B timing; default: one CTA per SM, two buffers
+        const bool two_buf = !(e && e[0] == '1');     // (measured: 0.89 ms vs 0.95 ms with two single-buffer CTAs per SM)
+        int grid3 = (two_buf ? 1 : 2) * ctx->num_sms;
+        if (grid3 > P) grid3 = P;
+        ProfScope ps_(ctx, "conv3_tc_kernel", st);
+        if (two_buf) conv3_tc_kernel<2><<<grid3, C3_THREADS, c3_smem(2), st>>>(c3);
+        else conv3_tc_kernel<1><<<grid3, C3_THREADS, c3_smem(1), st>>>(c3);
+    }
     CAELO_LAUNCH_CHECK(ctx);
     CUtensorMap m_ah, m_al, m_wh, m_wl;
     if ((rc = make_kmajor_map(ctx, &m_ah, act3_hi, Ppad, DM))) return rc;
@@ -910,7 +917,8 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
 int caelo_encoder_init(caelo_ctx *ctx)
 {
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv12_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem(1)));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem(2)));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
     return CAELO_OK;
 }

@@ -158,14 +158,14 @@ __device__ __forceinline__ void stage_rows(const float *src, int row0, int nrows
 {
     for (int e = tid; e < NT_B * (Kp / 8); e += NT_WORKERS) {
         const int r = e % NT_B, c = e / NT_B;
-        __half h[8], l[8];
+        __half2 h[4], l[4];
         const bool in = row0 + r < nrows;
         const float *p = src + (size_t)(row0 + r) * D + c * 8;
+        float v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float v = (in && c * 8 + k < D) ? __ldg(p + k) : 0.0f;
-            umma::split_f16(v, h[k], l[k]);
-        }
+        for (int k = 0; k < 8; ++k) v[k] = (in && c * 8 + k < D) ? __ldg(p + k) : 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma::split_f16x2(v[2 * k], v[2 * k + 1], h[k], l[k]);
         *reinterpret_cast<uint4 *>(hi + c * (NT_B * 16) + r * 16) = *reinterpret_cast<uint4 *>(h);
         *reinterpret_cast<uint4 *>(lo + c * (NT_B * 16) + r * 16) = *reinterpret_cast<uint4 *>(l);
     }
@@ -277,65 +277,89 @@ __global__ void __launch_bounds__(NT_THREADS) nn_tc_kernel(const NNTcArgs a)
     if (warp == 4) umma::tmem_dealloc(tbase, 2 * NT_B);
 }
 
-__global__ void __launch_bounds__(256) nn_exact_kernel(const NNArgs a, int P)
+// decided columns get their index; the others are appended to a list for the exact re-scan
+__global__ void __launch_bounds__(256) nn_decide_kernel(const NNArgs a, int P, int *list, int *nlist)
 {
-    const int lane = threadIdx.x & 31;
-    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= (long long)P * a.M) return;
-    const int pair = (int)(w / a.M), j = (int)(w % a.M);
+    const int pair = (int)(w / a.M);
     const float b = a.best_d[w], s = a.second_d[w];
     // relative error of each float32 d^2 <= (D+4)*2^-24; undecided if the intervals can overlap.  After the
     // tensor-core pass the error is absolute: E = 2^-13 |a|max |b_j| per value (see the header).
     const float eps = (float)(a.D + 4) * 5.9604645e-8f;
     const float E = a.nmax0 ? 1.2207031e-4f * sqrtf(a.nmax0[pair] * a.n1[w]) + 1e-30f : 0.0f;
     const bool decided = s > (b + 2.0f * E) * (1.0f + 4.0f * eps) + 1e-30f;
-    if (decided) {
-        if (lane == 0) a.out[w] = a.best_i[w];
-        return;
-    }
-    const float *c0 = a.c0 + (size_t)pair * a.N * a.D;
-    const float *q = a.c1 + ((size_t)pair * a.M + j) * a.D;
-    double bd = __longlong_as_double(0x7ff0000000000000ll);
-    int bi = 0x7fffffff;
-    // only rows whose float32 d^2 is inside the same error margin can be the float64 minimum; the others are
-    // skipped after a cheap float32 pass (any summation order is within (D+4)*2^-24 of the true value)
-    const float bound = (b + E) * (1.0f + 4.0f * eps) + 1e-30f;
-    const bool vec = (a.D & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.c0) | reinterpret_cast<uintptr_t>(a.c1)) & 15) == 0;  // rows 16-byte aligned
-    for (int i = lane; i < a.N; i += 32) {
-        const float *p = c0 + (size_t)i * a.D;
-        float acc32;
-        if (vec) {
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four independent chains: the margin holds for any order
-            for (int k = 0; k < a.D; k += 4) {
-                const float4 pv = __ldg(reinterpret_cast<const float4 *>(p + k));
-                const float4 qv = __ldg(reinterpret_cast<const float4 *>(q + k));
-                const float d0 = pv.x - qv.x, d1 = pv.y - qv.y, d2 = pv.z - qv.z, d3 = pv.w - qv.w;
-                s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+    if (decided) a.out[w] = a.best_i[w];
+    else list[atomicAdd(nlist, 1)] = (int)w;
+}
+
+// one CTA per undecided column (grid-stride over the list): every thread takes rows tid, tid+256, ...; a float32
+// pass keeps the rows inside the margin (any summation order is within (D+4)*2^-24 of the true value), those
+// are evaluated with the reference's own arithmetic (contract M1: float64 sequential sum, sqrt), and the CTA
+// reduces to the smallest (distance, row).
+__global__ void __launch_bounds__(256) nn_exact_kernel(const NNArgs a, const int *list, const int *nlist)
+{
+    __shared__ double s_d[8];
+    __shared__ int s_i[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = *nlist;
+    const bool vec = (a.D & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.c0) | reinterpret_cast<uintptr_t>(a.c1)) & 15) == 0;
+    for (int u = blockIdx.x; u < n; u += gridDim.x) {
+        const long long w = list[u];
+        const int pair = (int)(w / a.M), j = (int)(w % a.M);
+        const float b = a.best_d[w];
+        const float eps = (float)(a.D + 4) * 5.9604645e-8f;
+        const float E = a.nmax0 ? 1.2207031e-4f * sqrtf(a.nmax0[pair] * a.n1[w]) + 1e-30f : 0.0f;
+        const float bound = (b + E) * (1.0f + 4.0f * eps) + 1e-30f;
+        const float *c0 = a.c0 + (size_t)pair * a.N * a.D;
+        const float *q = a.c1 + ((size_t)pair * a.M + j) * a.D;
+        double bd = __longlong_as_double(0x7ff0000000000000ll);
+        int bi = 0x7fffffff;
+        for (int i = threadIdx.x; i < a.N; i += 256) {
+            const float *p = c0 + (size_t)i * a.D;
+            float acc32;
+            if (vec) {
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 5
+                for (int k = 0; k < a.D; k += 4) {
+                    const float4 pv = __ldg(reinterpret_cast<const float4 *>(p + k));
+                    const float4 qv = __ldg(reinterpret_cast<const float4 *>(q + k));
+                    const float d0 = pv.x - qv.x, d1 = pv.y - qv.y, d2 = pv.z - qv.z, d3 = pv.w - qv.w;
+                    s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+                }
+                acc32 = (s0 + s1) + (s2 + s3);
+            } else {
+                acc32 = 0.0f;
+                for (int k = 0; k < a.D; ++k) {
+                    const float d = p[k] - q[k];
+                    acc32 = fmaf(d, d, acc32);
+                }
             }
-            acc32 = (s0 + s1) + (s2 + s3);
-        } else {
-            acc32 = 0.0f;
+            if (acc32 > bound) continue;
+            double acc = 0.0;
+#pragma unroll 4
             for (int k = 0; k < a.D; ++k) {
-                const float d = p[k] - q[k];
-                acc32 = fmaf(d, d, acc32);
+                double d = __dsub_rn((double)p[k], (double)q[k]);
+                acc = __dadd_rn(acc, __dmul_rn(d, d));
             }
+            double dist = __dsqrt_rn(acc);
+            if (dist < bd) { bd = dist; bi = i; }  // ascending i within a thread: first minimum kept
         }
-        if (acc32 > bound) continue;
-        double acc = 0.0;
-        for (int k = 0; k < a.D; ++k) {
-            double d = __dsub_rn((double)p[k], (double)q[k]);
-            acc = __dadd_rn(acc, __dmul_rn(d, d));
-        }
-        double dist = __dsqrt_rn(acc);
-        if (dist < bd) { bd = dist; bi = i; }  // ascending i within a lane: first minimum kept
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        double od = __shfl_xor_sync(0xffffffffu, bd, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        for (int o = 16; o > 0; o >>= 1) {
+            double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        if (lane == 0) { s_d[warp] = bd; s_i[warp] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 1; k < 8; ++k)
+                if (s_d[k] < bd || (s_d[k] == bd && s_i[k] < bi)) { bd = s_d[k]; bi = s_i[k]; }
+            a.out[w] = bi;     // ties -> lowest row, as numpy's argmin
+        }
+        __syncthreads();
     }
-    if (lane == 0) a.out[w] = bi;
 }
 
 }  // namespace
@@ -357,7 +381,7 @@ extern "C" int caelo_nn_match(caelo_ctx *ctx, const float *codes0, const float *
         return CAELO_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     size_t cols = (size_t)P * M, rows0 = (size_t)P * N;
-    int rc = caelo_reserve(ctx, ctx->misc, cols * 16 + rows0 * 4 + (size_t)P * 4 + 256);
+    int rc = caelo_reserve(ctx, ctx->misc, cols * 20 + rows0 * 4 + (size_t)P * 4 + 512);
     if (rc) return rc;
     NNArgs a;
     a.c0 = codes0; a.c1 = codes1; a.N = N; a.M = M; a.D = D; a.Dp = (D + 3) & ~3;
@@ -388,8 +412,13 @@ extern "C" int caelo_nn_match(caelo_ctx *ctx, const float *codes0, const float *
         { ProfScope ps_(ctx, "nn_tile_kernel", st); nn_tile_kernel<<<grid, MT_THREADS, smem, st>>>(a); }
         CAELO_LAUNCH_CHECK(ctx);
     }
-    long long threads = (long long)cols * 32;
-    { ProfScope ps_(ctx, "nn_exact_kernel", st); nn_exact_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a, P); }
+    // undecided-column list lives behind every other array of the scratch block
+    int *nlist = reinterpret_cast<int *>(reinterpret_cast<char *>(ctx->misc.ptr) + ((cols * 16 + rows0 * 4 + (size_t)P * 4 + 255) / 256) * 256);
+    int *list = nlist + 16;
+    CAELO_CUDA(ctx, cudaMemsetAsync(nlist, 0, 4, st));
+    { ProfScope ps_(ctx, "nn_decide_kernel", st); nn_decide_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(a, P, list, nlist); }
+    CAELO_LAUNCH_CHECK(ctx);
+    { ProfScope ps_(ctx, "nn_exact_kernel", st); nn_exact_kernel<<<4 * ctx->num_sms, 256, 0, st>>>(a, list, nlist); }
     CAELO_LAUNCH_CHECK(ctx);
     return CAELO_OK;
 }

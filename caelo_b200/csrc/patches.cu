@@ -462,12 +462,11 @@ static int launch_gather(caelo_ctx *ctx, const void *kpts, int kpts_f64, const i
     return CAELO_OK;
 }
 
-extern "C" int caelo_gather_patches(caelo_ctx *ctx, const void *kpts, int kpts_f64,
-                                    const int32_t *n_kpts, int F, int K, const int16_t *vox,
-                                    const int64_t *vox_offsets, uint32_t *packed, float *patches_f32,
-                                    uint8_t *trunc, void *stream)
+// ---- a6 in two steps: the occupancy index of a batch does not depend on its key points, so a caller can build it
+//      on a second stream while the key points are still being selected -----------------------------------------
+extern "C" int caelo_bricks_build(caelo_ctx *ctx, const int16_t *vox, const int64_t *vox_offsets, int F, void *stream)
 {
-    if (!ctx || !kpts || !vox || !vox_offsets || !packed || F <= 0 || K <= 0) return CAELO_ERR_ARG;
+    if (!ctx || !vox || !vox_offsets || F <= 0) return CAELO_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int nl = F * 3;
     std::vector<size_t> caps(2 * nl);
@@ -489,16 +488,15 @@ extern "C" int caelo_gather_patches(caelo_ctx *ctx, const void *kpts, int kpts_f
     if (bx > 64) bx = 64;
     { ProfScope ps_(ctx, "brick_insert_kernel", st); brick_insert_kernel<<<dim3(bx, nl), 256, 0, st>>>(b); }
     CAELO_LAUNCH_CHECK(ctx);
-    return launch_gather(ctx, kpts, kpts_f64, n_kpts, F, K, d_tables, nullptr, nullptr, packed, patches_f32, trunc, st);
+    ctx->bricks_tables = d_tables;
+    ctx->bricks_frames = F;
+    return CAELO_OK;
 }
 
-// f2+a6 fused: GetPatchesList(Pts, *Voxelization(scan)) without materialising the voxel lists.
-extern "C" int caelo_gather_patches_scans(caelo_ctx *ctx, const void *kpts, int kpts_f64, const int32_t *n_kpts, int F,
-                                          int K, const float *pts, const int64_t *pts_offsets, uint32_t *packed,
-                                          float *patches_f32, uint8_t *trunc, int32_t *nvox, int32_t *status,
-                                          void *stream)
+extern "C" int caelo_bricks_build_scans(caelo_ctx *ctx, const float *pts, const int64_t *pts_offsets, int F, int32_t *nvox,
+                                        int32_t *status, void *stream)
 {
-    if (!ctx || !kpts || !pts || !pts_offsets || !packed || !nvox || !status || F <= 0 || K <= 0) return CAELO_ERR_ARG;
+    if (!ctx || !pts || !pts_offsets || !nvox || !status || F <= 0) return CAELO_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int nl = F * 3;
     std::vector<size_t> caps(2 * nl);
@@ -530,5 +528,40 @@ extern "C" int caelo_gather_patches_scans(caelo_ctx *ctx, const void *kpts, int 
     if (bx < 1) bx = 1;
     { ProfScope ps_(ctx, "scan_brick_insert_kernel", st); scan_brick_insert_kernel<<<dim3(bx, F), 256, 0, st>>>(b); }
     CAELO_LAUNCH_CHECK(ctx);
-    return launch_gather(ctx, kpts, kpts_f64, n_kpts, F, K, d_tables, nvox, status, packed, patches_f32, trunc, st);
+    ctx->bricks_tables = d_tables;
+    ctx->bricks_frames = F;
+    return CAELO_OK;
+}
+
+extern "C" int caelo_bricks_gather(caelo_ctx *ctx, const void *kpts, int kpts_f64, const int32_t *n_kpts, int F, int K,
+                                   uint32_t *packed, float *patches_f32, uint8_t *trunc, const int32_t *nvox,
+                                   int32_t *status, void *stream)
+{
+    if (!ctx || !kpts || !packed || F <= 0 || K <= 0 || (nvox && !status)) return CAELO_ERR_ARG;
+    if (!ctx->bricks_tables || ctx->bricks_frames != F) return CAELO_ERR_ARG;   // no index built for this batch
+    return launch_gather(ctx, kpts, kpts_f64, n_kpts, F, K, reinterpret_cast<const Table *>(ctx->bricks_tables), nvox, status,
+                         packed, patches_f32, trunc, (cudaStream_t)stream);
+}
+
+extern "C" int caelo_gather_patches(caelo_ctx *ctx, const void *kpts, int kpts_f64,
+                                    const int32_t *n_kpts, int F, int K, const int16_t *vox,
+                                    const int64_t *vox_offsets, uint32_t *packed, float *patches_f32,
+                                    uint8_t *trunc, void *stream)
+{
+    if (!ctx || !kpts || !vox || !vox_offsets || !packed || F <= 0 || K <= 0) return CAELO_ERR_ARG;
+    int rc = caelo_bricks_build(ctx, vox, vox_offsets, F, stream);
+    if (rc) return rc;
+    return caelo_bricks_gather(ctx, kpts, kpts_f64, n_kpts, F, K, packed, patches_f32, trunc, nullptr, nullptr, stream);
+}
+
+// f2+a6 fused: GetPatchesList(Pts, *Voxelization(scan)) without materialising the voxel lists.
+extern "C" int caelo_gather_patches_scans(caelo_ctx *ctx, const void *kpts, int kpts_f64, const int32_t *n_kpts, int F,
+                                          int K, const float *pts, const int64_t *pts_offsets, uint32_t *packed,
+                                          float *patches_f32, uint8_t *trunc, int32_t *nvox, int32_t *status,
+                                          void *stream)
+{
+    if (!ctx || !kpts || !pts || !pts_offsets || !packed || !nvox || !status || F <= 0 || K <= 0) return CAELO_ERR_ARG;
+    int rc = caelo_bricks_build_scans(ctx, pts, pts_offsets, F, nvox, status, stream);
+    if (rc) return rc;
+    return caelo_bricks_gather(ctx, kpts, kpts_f64, n_kpts, F, K, packed, patches_f32, trunc, nvox, status, stream);
 }

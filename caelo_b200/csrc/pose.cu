@@ -187,7 +187,9 @@ struct PoseArgs {
     const float *pc0, *pc1;       // [P,N0,3], [P,N,3]
     const long long *pair_idx;    // [P,N] or null
     const int *sample_idx;        // [P,T,4]
-    const float *thr;             // [P]
+    const float *thr;             // [P], or null: thr_scalar for every pair
+    float thr_scalar;
+    float *thr_out;               // [P] or null: replay writes the threshold of the last round the pair took part in
     const int *best_n_in;         // [P] or null
     const float *skip_if_ok;      // [P,16] or null: pairs with [12] != 0 there are skipped
     int N0, N, T, P;
@@ -210,20 +212,51 @@ __device__ __forceinline__ void load_pair(const PoseArgs &a, int pair, int i, fl
     p1[0] = q1[0]; p1[1] = q1[1]; p1[2] = q1[2];
 }
 
-// One CTA = one pair x HS_HYP consecutive trials.  The pair's matched points are staged once in shared memory
-// (SoA), warp 0 solves the HS_HYP four-point Kabsch problems ONE PER LANE (float64 contract K1: with four
-// samples the 32-lane butterfly of the refit reduces to (v0 + v2) + (v1 + v3), lanes 4..31 contributing +0.0),
-// then the eight warps score the hypotheses, one warp per hypothesis at a time.
+// Hypotheses: ONE THREAD per (pair, trial) solves the four-point Kabsch problem (float64 contract K1: with four
+// samples the 32-lane butterfly of the refit reduces to (v0 + v2) + (v1 + v3), lanes 4..31 contributing +0.0).
+// The float64 Jacobi is a long dependent chain (divisions, square roots): all P*T of them run side by side.
+__device__ __forceinline__ double tree4(double v0, double v1, double v2, double v3) { return (v0 + v2) + (v1 + v3); }
+
+__global__ void __launch_bounds__(64) hyp_kabsch_kernel(const PoseArgs a)
+{
+    const int pair = blockIdx.y;
+    const int t = blockIdx.x * 64 + threadIdx.x;
+    if (t >= a.T) return;
+    if (a.skip_if_ok && a.skip_if_ok[(size_t)pair * 16 + 12] != 0.0f) return;
+    const int4 si = *reinterpret_cast<const int4 *>(a.sample_idx + ((size_t)pair * a.T + t) * 4);
+    float q0[4][3], q1[4][3];
+    load_pair(a, pair, si.x, q0[0], q1[0]); load_pair(a, pair, si.y, q0[1], q1[1]);
+    load_pair(a, pair, si.z, q0[2], q1[2]); load_pair(a, pair, si.w, q0[3], q1[3]);
+    double m0[3], m1[3];
+    for (int c = 0; c < 3; ++c) {
+        m0[c] = tree4(0.0 + (double)q0[0][c], 0.0 + (double)q0[1][c], 0.0 + (double)q0[2][c], 0.0 + (double)q0[3][c]) / 4.0;
+        m1[c] = tree4(0.0 + (double)q1[0][c], 0.0 + (double)q1[1][c], 0.0 + (double)q1[2][c], 0.0 + (double)q1[3][c]) / 4.0;
+    }
+    double a0[4][3], a1[4][3];
+    for (int k = 0; k < 4; ++k)
+        for (int c = 0; c < 3; ++c) { a1[k][c] = (double)q1[k][c] - m1[c]; a0[k][c] = (double)q0[k][c] - m0[c]; }
+    double H[3][3];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+            H[r][c] = tree4(0.0 + a1[0][r] * a0[0][c], 0.0 + a1[1][r] * a0[1][c], 0.0 + a1[2][r] * a0[2][c],
+                            0.0 + a1[3][r] * a0[3][c]);
+    float R[9], T[3];
+    kabsch_from_H(H, m0, m1, R, T);
+    float4 *o = reinterpret_cast<float4 *>(a.rt_hyp + ((size_t)pair * a.T + t) * 12);
+    o[0] = make_float4(R[0], R[1], R[2], R[3]);
+    o[1] = make_float4(R[4], R[5], R[6], R[7]);
+    o[2] = make_float4(R[8], T[0], T[1], T[2]);
+}
+
+// Scoring: one CTA = one pair x HS_HYP consecutive trials.  The pair's matched points are staged once in shared
+// memory (SoA) and the eight warps count inliers, one warp per hypothesis at a time (contract D1).
 constexpr int HS_HYP = 32;
 constexpr int HS_THREADS = 256;
-
-__device__ __forceinline__ double tree4(double v0, double v1, double v2, double v3) { return (v0 + v2) + (v1 + v3); }
 
 template <bool kStaged>
 __global__ void __launch_bounds__(HS_THREADS) hyp_score_kernel(const PoseArgs a)
 {
     extern __shared__ float hs_pts[];        // kStaged: [6][N] = x0 y0 z0 x1 y1 z1
-    __shared__ float s_rt[HS_HYP][12];
     const int pair = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t_base = a.t0 + blockIdx.x * HS_HYP;
@@ -239,54 +272,24 @@ __global__ void __launch_bounds__(HS_THREADS) hyp_score_kernel(const PoseArgs a)
         }
         __syncthreads();
     }
-    auto point = [&](int i, float p0[3], float p1[3]) {
-        if (kStaged) {
-            p0[0] = hs_pts[i]; p0[1] = hs_pts[N + i]; p0[2] = hs_pts[2 * N + i];
-            p1[0] = hs_pts[3 * N + i]; p1[1] = hs_pts[4 * N + i]; p1[2] = hs_pts[5 * N + i];
-        } else {
-            load_pair(a, pair, i, p0, p1);
-        }
-    };
-    if (warp == 0 && t_base + lane < a.t1) {
-        const int t = t_base + lane;
-        const int4 si = *reinterpret_cast<const int4 *>(a.sample_idx + ((size_t)pair * a.T + t) * 4);
-        float q0[4][3], q1[4][3];
-        point(si.x, q0[0], q1[0]); point(si.y, q0[1], q1[1]); point(si.z, q0[2], q1[2]); point(si.w, q0[3], q1[3]);
-        double m0[3], m1[3];
-        for (int c = 0; c < 3; ++c) {
-            m0[c] = tree4(0.0 + (double)q0[0][c], 0.0 + (double)q0[1][c], 0.0 + (double)q0[2][c], 0.0 + (double)q0[3][c]) / 4.0;
-            m1[c] = tree4(0.0 + (double)q1[0][c], 0.0 + (double)q1[1][c], 0.0 + (double)q1[2][c], 0.0 + (double)q1[3][c]) / 4.0;
-        }
-        double a0[4][3], a1[4][3];
-        for (int k = 0; k < 4; ++k)
-            for (int c = 0; c < 3; ++c) { a1[k][c] = (double)q1[k][c] - m1[c]; a0[k][c] = (double)q0[k][c] - m0[c]; }
-        double H[3][3];
-        for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < 3; ++c)
-                H[r][c] = tree4(0.0 + a1[0][r] * a0[0][c], 0.0 + a1[1][r] * a0[1][c], 0.0 + a1[2][r] * a0[2][c],
-                                0.0 + a1[3][r] * a0[3][c]);
-        float R[9], T[3];
-        kabsch_from_H(H, m0, m1, R, T);
-        float *o = a.rt_hyp + ((size_t)pair * a.T + t) * 12;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) {
-            const float v = k < 9 ? R[k] : T[k - 9];
-            s_rt[lane][k] = v;
-            o[k] = v;
-        }
-    }
-    __syncthreads();
-    const float thr = a.thr[pair];
+    const float thr = a.thr ? a.thr[pair] : a.thr_scalar;
     for (int h = warp; h < HS_HYP && t_base + h < a.t1; h += HS_THREADS / 32) {
         float R[9], T[3];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) R[k] = s_rt[h][k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) T[k] = s_rt[h][9 + k];
+        {
+            const float4 *rt = reinterpret_cast<const float4 *>(a.rt_hyp + ((size_t)pair * a.T + t_base + h) * 12);
+            const float4 r0 = __ldg(rt), r1 = __ldg(rt + 1), r2 = __ldg(rt + 2);
+            R[0] = r0.x; R[1] = r0.y; R[2] = r0.z; R[3] = r0.w; R[4] = r1.x; R[5] = r1.y; R[6] = r1.z; R[7] = r1.w;
+            R[8] = r2.x; T[0] = r2.y; T[1] = r2.z; T[2] = r2.w;
+        }
         int cnt = 0;
         for (int i = lane; i < N; i += 32) {
             float p0[3], p1[3];
-            point(i, p0, p1);
+            if (kStaged) {
+                p0[0] = hs_pts[i]; p0[1] = hs_pts[N + i]; p0[2] = hs_pts[2 * N + i];
+                p1[0] = hs_pts[3 * N + i]; p1[1] = hs_pts[4 * N + i]; p1[2] = hs_pts[5 * N + i];
+            } else {
+                load_pair(a, pair, i, p0, p1);
+            }
             cnt += inlier_d1(R, T, p0, p1, thr) ? 1 : 0;
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -296,7 +299,8 @@ __global__ void __launch_bounds__(HS_THREADS) hyp_score_kernel(const PoseArgs a)
 
 __global__ void __launch_bounds__(256) replay_mask_kernel(const PoseArgs a)
 {
-    __shared__ int s_bt, s_bn, s_ok, s_it, s_more;
+    __shared__ int s_bt, s_bn, s_ok, s_it, s_more, s_first;
+    __shared__ long long s_best;
     __shared__ float s_rt[12];
     const int pair = blockIdx.x;
     if (a.skip_if_ok && a.skip_if_ok[(size_t)pair * 16 + 12] != 0.0f) {
@@ -304,20 +308,50 @@ __global__ void __launch_bounds__(256) replay_mask_kernel(const PoseArgs a)
         return;
     }
     if (a.more_mode == 2 && !a.more[pair]) return;
+    // RANSAC4RT's loop (Match.py:181-206) over the pre-scored trials, evaluated in closed form by the whole CTA:
+    //   eff_j = cnt_j if cnt_j >= leastInliers else "skipped";  bn_i = max(bn0, eff_0..eff_{i-1}) never decreases, so
+    //   the loop `while it < t1 and (it < 100 or (it < 500 and bn < succ))` ends at
+    //   it = min(t1, max(100, j*+1), 500) with j* the first trial whose eff reaches succ (or bn0 >= succ: 100);
+    //   bn / bt are the maximum over the trials before `it` (first index on ties, only if it beats bn0).
+    const int N = a.N;
+    int least = (int)(0.2 * (double)N);
+    if (least > 100) least = 100;
+    const double succ = 0.25 * (double)N;
+    const int bn0 = a.best_n_in ? a.best_n_in[pair] : 0;
+    const int *cnt = a.counts + (size_t)pair * a.T;
+    if (threadIdx.x == 0) { s_first = 0x7fffffff; s_best = -1ll; }
+    __syncthreads();
+    int eff[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int j = threadIdx.x + u * 256;
+        eff[u] = -1;
+        if (j < a.t1) {
+            const int n = cnt[j];
+            if (n >= least) eff[u] = n;
+            if (eff[u] >= 0 && !((double)eff[u] < succ)) atomicMin(&s_first, j);
+        }
+    }
+    __syncthreads();
+    int it = a.t1;
+    {
+        int stop = 500;
+        if (!((double)bn0 < succ)) stop = 100;
+        else if (s_first != 0x7fffffff) stop = s_first + 1 > 100 ? s_first + 1 : 100;
+        if (stop < it) it = stop;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int j = threadIdx.x + u * 256;
+        if (j < it && eff[u] >= 0) atomicMax(&s_best, ((long long)eff[u] << 10) | (long long)(1023 - j));
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        // RANSAC4RT's loop (Match.py:181-206) over the pre-scored trials
-        const int N = a.N;
-        int least = (int)(0.2 * (double)N);
-        if (least > 100) least = 100;
-        const double succ = 0.25 * (double)N;
-        int it = 0, bn = a.best_n_in ? a.best_n_in[pair] : 0, bt = -1, ok = 0;
-        const int *cnt = a.counts + (size_t)pair * a.T;
-        while (it < a.t1 && ((it < 100) || (it < 500 && (double)bn < succ))) {
-            int n = cnt[it];
-            ++it;
-            if (n < least) continue;
-            if (n > bn) { bn = n; bt = it - 1; }
+        int bn = bn0, bt = -1, ok = 0;
+        if (s_best >= 0) {
             ok = 1;
+            const int n = (int)(s_best >> 10);
+            if (n > bn0) { bn = n; bt = 1023 - (int)(s_best & 1023); }
         }
         // first phase: the loop ran out of scored trials while the reference would go on -> the second phase decides
         int more = 0;
@@ -344,7 +378,8 @@ __global__ void __launch_bounds__(256) replay_mask_kernel(const PoseArgs a)
     float R[9], T[3];
     for (int i = 0; i < 9; ++i) R[i] = s_rt[i];
     for (int i = 0; i < 3; ++i) T[i] = s_rt[9 + i];
-    const float thr = a.thr[pair];
+    const float thr = a.thr ? a.thr[pair] : a.thr_scalar;
+    if (threadIdx.x == 0 && a.thr_out) a.thr_out[pair] = thr;   // last round a pair took part in: the one that gave its model, or the final one
     for (int i = threadIdx.x; i < a.N; i += blockDim.x) {
         unsigned char m = 0;
         if (bt >= 0) {
@@ -366,23 +401,56 @@ struct KabschArgs {
     int *credible;  // [P]
 };
 
-__global__ void __launch_bounds__(128) kabsch_kernel(const KabschArgs a)
+// One CTA per problem.  All 256 threads first gather the masked points into shared memory (the gathers through
+// pair_idx are two dependent L2 round trips per point: 4 per thread side by side instead of 32 in a row per lane),
+// then warp 0 runs contract K1 on them: lane l sums points l, l+32, ... sequentially, xor-butterfly across lanes.
+constexpr int KB_THREADS = 256;
+
+template <bool kStaged>
+__global__ void __launch_bounds__(KB_THREADS) kabsch_kernel(const KabschArgs a)
 {
+    extern __shared__ float kb_pts[];   // kStaged: [6][N] x0 y0 z0 x1 y1 z1, then N mask bytes
     const int lane = threadIdx.x & 31;
-    const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (pair >= a.P) return;
+    const int pair = blockIdx.x;
     if (a.skip_if_ok && a.skip_if_ok[(size_t)pair * 16 + 12] != 0.0f) return;
-    double s[6] = {0, 0, 0, 0, 0, 0};
-    int cnt = 0;
-    auto fetch = [&](int i, float p0[3], float p1[3]) {
+    const int N = a.N;
+    unsigned char *kb_mask = reinterpret_cast<unsigned char *>(kb_pts + 6 * (size_t)N);
+    auto fetch_global = [&](int i, float p0[3], float p1[3]) {
         long long j = a.pair_idx ? a.pair_idx[(size_t)pair * a.N + i] : i;
         const float *q0 = a.pc0 + ((size_t)pair * a.N0 + j) * 3;
         const float *q1 = a.pc1 + ((size_t)pair * a.N + i) * 3;
         p0[0] = q0[0]; p0[1] = q0[1]; p0[2] = q0[2];
         p1[0] = q1[0]; p1[1] = q1[1]; p1[2] = q1[2];
     };
-    for (int i = lane; i < a.N; i += 32) {
-        if (a.mask && !a.mask[(size_t)pair * a.N + i]) continue;
+    if (kStaged) {
+        for (int i = threadIdx.x; i < N; i += KB_THREADS) {
+            const unsigned char m = a.mask ? a.mask[(size_t)pair * N + i] : 1;
+            kb_mask[i] = m;
+            if (m) {
+                float p0[3], p1[3];
+                fetch_global(i, p0, p1);
+                kb_pts[i] = p0[0]; kb_pts[N + i] = p0[1]; kb_pts[2 * N + i] = p0[2];
+                kb_pts[3 * N + i] = p1[0]; kb_pts[4 * N + i] = p1[1]; kb_pts[5 * N + i] = p1[2];
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x >= 32) return;
+    auto masked_out = [&](int i) -> bool {
+        return kStaged ? !kb_mask[i] : (a.mask && !a.mask[(size_t)pair * N + i]);
+    };
+    auto fetch = [&](int i, float p0[3], float p1[3]) {
+        if (kStaged) {
+            p0[0] = kb_pts[i]; p0[1] = kb_pts[N + i]; p0[2] = kb_pts[2 * N + i];
+            p1[0] = kb_pts[3 * N + i]; p1[1] = kb_pts[4 * N + i]; p1[2] = kb_pts[5 * N + i];
+        } else {
+            fetch_global(i, p0, p1);
+        }
+    };
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    int cnt = 0;
+    for (int i = lane; i < N; i += 32) {
+        if (masked_out(i)) continue;
         float p0[3], p1[3];
         fetch(i, p0, p1);
         for (int c = 0; c < 3; ++c) { s[c] = s[c] + (double)p0[c]; s[3 + c] = s[3 + c] + (double)p1[c]; }
@@ -401,8 +469,8 @@ __global__ void __launch_bounds__(128) kabsch_kernel(const KabschArgs a)
         m1[c] = warp_tree(s[3 + c]) / (double)cnt;
     }
     double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = lane; i < a.N; i += 32) {
-        if (a.mask && !a.mask[(size_t)pair * a.N + i]) continue;
+    for (int i = lane; i < N; i += 32) {
+        if (masked_out(i)) continue;
         float p0[3], p1[3];
         fetch(i, p0, p1);
         double a1[3], a0[3];
@@ -497,34 +565,24 @@ __global__ void __launch_bounds__(256) draw_samples_kernel(const DrawArgs a)
 int caelo_pose_init(caelo_ctx *ctx)
 {
     CAELO_CUDA(ctx, cudaFuncSetAttribute(hyp_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(kabsch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     return CAELO_OK;
 }
 
-extern "C" int caelo_ransac_round(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int N,
-                                  const int64_t *pair_idx, const int32_t *sample_idx, int T,
-                                  const float *thr, const int32_t *best_n_in, const float *skip_if_ok, int P,
-                                  float *result, uint8_t *inlier_mask, int32_t *counts, void *stream)
+// one threshold round for the pairs of `a` (pc0 .. skip_if_ok, thr, result, mask set by the caller)
+static int run_round(caelo_ctx *ctx, PoseArgs a, int32_t *counts, cudaStream_t st)
 {
-    if (!ctx || !pc0 || !pc1 || !sample_idx || !thr || !result || !inlier_mask) return CAELO_ERR_ARG;
-    if (P <= 0 || N <= 0 || N0 <= 0 || T <= 0 || T > CAELO_MAX_TRIALS) return CAELO_ERR_ARG;
-    if (!pair_idx && N0 != N) return CAELO_ERR_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
+    const int P = a.P, T = a.T, N = a.N;
     size_t need = (size_t)P * T * 12 * 4 + (size_t)P * T * 4 + (size_t)P * 4;
     int rc = caelo_reserve(ctx, ctx->pose_ws, need);
     if (rc) return rc;
-    PoseArgs a;
-    a.pc0 = pc0; a.pc1 = pc1; a.pair_idx = reinterpret_cast<const long long *>(pair_idx);
-    a.sample_idx = sample_idx; a.thr = thr; a.best_n_in = best_n_in; a.skip_if_ok = skip_if_ok;
-    a.N0 = N0; a.N = N; a.T = T; a.P = P;
     a.rt_hyp = reinterpret_cast<float *>(ctx->pose_ws.ptr);
     a.counts = counts ? counts : reinterpret_cast<int *>(a.rt_hyp + (size_t)P * T * 12);
-    a.result = result; a.mask = inlier_mask;
     a.more = reinterpret_cast<int *>(a.rt_hyp + (size_t)P * T * 12) + (size_t)P * T;
     // The reference stops after 100 trials once a model with >= 25 % inliers exists (Match.py:181): score the
     // first 100 trials, replay the accept/stop rule, and only the pairs whose loop would go on get trials
     // 100..T scored and the rule replayed over all of them (same result as scoring everything up front).
     const int T1 = (T > 100 && !counts) ? 100 : T;   // a caller asking for every count gets every trial scored
-    a.t0 = 0; a.t1 = T1; a.more_mode = 0;
     const size_t hs_smem = (size_t)N * 24;
     const bool staged = hs_smem <= 160 * 1024;
     auto score = [&](int n_trials) {
@@ -533,6 +591,9 @@ extern "C" int caelo_ransac_round(caelo_ctx *ctx, const float *pc0, int N0, cons
         if (staged) hyp_score_kernel<true><<<grid, HS_THREADS, hs_smem, st>>>(a);
         else hyp_score_kernel<false><<<grid, HS_THREADS, 0, st>>>(a);
     };
+    a.t0 = 0; a.t1 = T1; a.more_mode = 0;
+    { ProfScope ps_(ctx, "hyp_kabsch_kernel", st); hyp_kabsch_kernel<<<dim3((T + 63) / 64, P), 64, 0, st>>>(a); }
+    CAELO_LAUNCH_CHECK(ctx);
     score(T1);
     CAELO_LAUNCH_CHECK(ctx);
     a.more_mode = T1 < T ? 1 : 0;
@@ -549,6 +610,66 @@ extern "C" int caelo_ransac_round(caelo_ctx *ctx, const float *pc0, int N0, cons
     return CAELO_OK;
 }
 
+extern "C" int caelo_ransac_round(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int N,
+                                  const int64_t *pair_idx, const int32_t *sample_idx, int T,
+                                  const float *thr, const int32_t *best_n_in, const float *skip_if_ok, int P,
+                                  float *result, uint8_t *inlier_mask, int32_t *counts, void *stream)
+{
+    if (!ctx || !pc0 || !pc1 || !sample_idx || !thr || !result || !inlier_mask) return CAELO_ERR_ARG;
+    if (P <= 0 || N <= 0 || N0 <= 0 || T <= 0 || T > CAELO_MAX_TRIALS) return CAELO_ERR_ARG;
+    if (!pair_idx && N0 != N) return CAELO_ERR_ARG;
+    PoseArgs a;
+    a.pc0 = pc0; a.pc1 = pc1; a.pair_idx = reinterpret_cast<const long long *>(pair_idx);
+    a.sample_idx = sample_idx; a.thr = thr; a.thr_scalar = 0.f; a.thr_out = nullptr;
+    a.best_n_in = best_n_in; a.skip_if_ok = skip_if_ok;
+    a.N0 = N0; a.N = N; a.T = T; a.P = P;
+    a.result = result; a.mask = inlier_mask;
+    return run_round(ctx, a, counts, (cudaStream_t)stream);
+}
+
+static int launch_kabsch(caelo_ctx *ctx, const KabschArgs &a, cudaStream_t st)
+{
+    const size_t smem = (size_t)a.N * 25;
+    {
+        ProfScope ps_(ctx, "kabsch_kernel", st);
+        if (smem <= 160 * 1024) kabsch_kernel<true><<<a.P, KB_THREADS, smem, st>>>(a);
+        else kabsch_kernel<false><<<a.P, KB_THREADS, 0, st>>>(a);
+    }
+    CAELO_LAUNCH_CHECK(ctx);
+    return CAELO_OK;
+}
+
+// The whole threshold ladder of RANSAC4RT + the refit of SolveRelativePose for P pairs in one call: round r runs
+// only for the pairs that still have no model (their result row is left untouched by the others), the inlier
+// mask of the round that produced the model stays in place, and one masked Kabsch at the end refits every pair.
+extern "C" int caelo_ransac_ladder(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int N,
+                                   const int64_t *pair_idx, const int32_t *sample_idx, int T, int rounds,
+                                   const float *thr_ladder, int P, float *result, uint8_t *inlier_mask, float *Rt,
+                                   float *thr_used, int32_t *credible, void *stream)
+{
+    if (!ctx || !pc0 || !pc1 || !sample_idx || !thr_ladder || !result || !inlier_mask || !Rt || !thr_used || !credible)
+        return CAELO_ERR_ARG;
+    if (P <= 0 || N <= 0 || N0 <= 0 || T <= 0 || T > CAELO_MAX_TRIALS || rounds <= 0 || rounds > 8) return CAELO_ERR_ARG;
+    if (!pair_idx && N0 != N) return CAELO_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    PoseArgs a;
+    a.pc0 = pc0; a.pc1 = pc1; a.pair_idx = reinterpret_cast<const long long *>(pair_idx);
+    a.thr = nullptr; a.thr_out = thr_used; a.best_n_in = nullptr;
+    a.N0 = N0; a.N = N; a.T = T; a.P = P;
+    a.result = result; a.mask = inlier_mask;
+    for (int r = 0; r < rounds; ++r) {
+        a.sample_idx = sample_idx + (size_t)r * P * T * 4;
+        a.thr_scalar = thr_ladder[r];
+        a.skip_if_ok = r == 0 ? nullptr : result;     // in place: rows with isSuccess != 0 are final
+        int rc = run_round(ctx, a, nullptr, st);
+        if (rc) return rc;
+    }
+    KabschArgs k;
+    k.pc0 = pc0; k.pc1 = pc1; k.pair_idx = a.pair_idx; k.mask = inlier_mask; k.skip_if_ok = nullptr;
+    k.N0 = N0; k.N = N; k.P = P; k.rt = Rt; k.credible = credible;
+    return launch_kabsch(ctx, k, st);
+}
+
 extern "C" int caelo_kabsch(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int N,
                             const int64_t *pair_idx, const uint8_t *mask, const float *skip_if_ok, int P,
                             float *Rt, int32_t *credible, void *stream)
@@ -558,10 +679,7 @@ extern "C" int caelo_kabsch(caelo_ctx *ctx, const float *pc0, int N0, const floa
     KabschArgs a;
     a.pc0 = pc0; a.pc1 = pc1; a.pair_idx = reinterpret_cast<const long long *>(pair_idx);
     a.mask = mask; a.skip_if_ok = skip_if_ok; a.N0 = N0; a.N = N; a.P = P; a.rt = Rt; a.credible = credible;
-    int blocks = (P * 32 + 127) / 128;
-    { ProfScope ps_(ctx, "kabsch_kernel", (cudaStream_t)stream); kabsch_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a); }
-    CAELO_LAUNCH_CHECK(ctx);
-    return CAELO_OK;
+    return launch_kabsch(ctx, a, (cudaStream_t)stream);
 }
 
 extern "C" int caelo_ransac_draw_samples(caelo_ctx *ctx, const int64_t *seeds, int P, int n_points, int T, int rounds,

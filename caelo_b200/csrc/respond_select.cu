@@ -115,56 +115,77 @@ respond_score_kernel(const __grid_constant__ RespondWeights w, const SelectArgs 
         }
         __syncthreads();
     }
-    for (int i = threadIdx.x; i < NPIX; i += kThreads) {
-        int lr = i / RW, lc = i % RW;
-        int rr = r0 + lr, cc = c0 + lc;
-        bool in = rr >= 0 && rr < H && cc >= 0 && cc < W;
-        occ_s[i] = (in && occupied(a, b, rr, cc)) ? 1 : 0;
+    // ---- occupancy of the region + two compact work lists: occupied pixels (the only ones whose response is
+    //      ever read: as a centre or as a valid neighbour) and interior pixels that can be key points ----
+    unsigned short *list_occ = reinterpret_cast<unsigned short *>(in_s + (kFused ? IH * IW * 3 : 0));  // [NPIX]
+    unsigned short *list_ctr = list_occ + NPIX;                                                        // [TH*TW]
+    __shared__ int s_nocc, s_nctr;
+    if (threadIdx.x == 0) { s_nocc = 0; s_nctr = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int i0 = 0; i0 < NPIX; i0 += kThreads) {   // uniform trip count: the ballots need every lane
+        const int i = i0 + threadIdx.x;
+        bool occ = false, ctr = false;
+        if (i < NPIX) {
+            const int lr = i / RW, lc = i % RW;
+            const int rr = r0 + lr, cc = c0 + lc;
+            const bool in = rr >= 0 && rr < H && cc >= 0 && cc < W;
+            occ = in && occupied(a, b, rr, cc);
+            occ_s[i] = occ ? 1 : 0;
+            // rows [8,H-8); cols [8,W-8) from the final filter; quirk 2 removes cols [H-8,H)
+            ctr = occ && lr >= HALO && lr < HALO + TH && lc >= HALO && lc < HALO + TW && rr >= EDGE && rr < H - EDGE &&
+                  cc >= EDGE && cc < W - EDGE && !(cc >= H - EDGE && cc < H);
+        }
+        const unsigned mo = __ballot_sync(0xffffffffu, occ), mc = __ballot_sync(0xffffffffu, ctr);
+        int bo = 0, bc = 0;
+        if (lane == 0) {
+            if (mo) bo = atomicAdd(&s_nocc, __popc(mo));
+            if (mc) bc = atomicAdd(&s_nctr, __popc(mc));
+        }
+        bo = __shfl_sync(0xffffffffu, bo, 0);
+        bc = __shfl_sync(0xffffffffu, bc, 0);
+        if (occ) list_occ[bo + __popc(mo & ((1u << lane) - 1u))] = (unsigned short)i;
+        if (ctr) list_ctr[bc + __popc(mc & ((1u << lane) - 1u))] = (unsigned short)i;
+    }
+    __syncthreads();
+    const int nocc = s_nocc, nctr = s_nctr;
+    // ---- response of the occupied pixels ----
+    for (int n = threadIdx.x; n < nocc; n += kThreads) {
+        const int i = list_occ[n];
+        const int lr = i / RW, lc = i % RW;
         float out[8];
         if (kFused) {
-            if (in) {
-                float x[27];
+            float x[27];
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
+            for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx)
+                for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                        for (int ci = 0; ci < 3; ++ci)
-                            x[(ky * 3 + kx) * 3 + ci] = in_s[((lr + ky) * IW + (lc + kx)) * 3 + ci];
-                respond_pixel(w, x, out);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) out[k] = 0.0f;
-            }
+                    for (int ci = 0; ci < 3; ++ci)
+                        x[(ky * 3 + kx) * 3 + ci] = in_s[((lr + ky) * IW + (lc + kx)) * 3 + ci];
+            respond_pixel(w, x, out);
         } else {
-            if (in) {
-                const float4 *q = reinterpret_cast<const float4 *>(
-                    a.resp + (((size_t)b * H + rr) * W + cc) * 8);
-                float4 v0 = __ldg(q), v1 = __ldg(q + 1);
-                out[0] = v0.x; out[1] = v0.y; out[2] = v0.z; out[3] = v0.w;
-                out[4] = v1.x; out[5] = v1.y; out[6] = v1.z; out[7] = v1.w;
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) out[k] = 0.0f;
-            }
+            const float4 *q = reinterpret_cast<const float4 *>(
+                a.resp + (((size_t)b * H + (r0 + lr)) * W + (c0 + lc)) * 8);
+            float4 v0 = __ldg(q), v1 = __ldg(q + 1);
+            out[0] = v0.x; out[1] = v0.y; out[2] = v0.z; out[3] = v0.w;
+            out[4] = v1.x; out[5] = v1.y; out[6] = v1.z; out[7] = v1.w;
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) resp_s[k * NPIX + i] = out[k];
     }
     __syncthreads();
 
-    // ---- score the TH x TW interior (contract S1) ----
-    const int lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < TH * TW; i += kThreads) {  // TH*TW is a multiple of kThreads
-        int lr = i / TW + HALO, lc = i % TW + HALO;
-        int r = r0 + lr, c = c0 + lc;
-        int li = lr * RW + lc;
+    // ---- score the listed centres (contract S1) ----
+    for (int n0 = 0; n0 < nctr; n0 += kThreads) {   // uniform trip count for the ballot below
+        const int n = n0 + threadIdx.x;
         bool keep = false;
         float best = __int_as_float(0x7f800000);
-        // rows [8,H-8); cols [8,W-8) from the final filter; quirk 2 removes cols [H-8,H)
-        bool self_ok = occ_s[li] && r >= EDGE && r < H - EDGE && c >= EDGE && c < W - EDGE &&
-                       !(c >= H - EDGE && c < H);
-        if (self_ok) {
+        int r = 0, c = 0;
+        if (n < nctr) {
+            const int li = list_ctr[n];
+            const int lr = li / RW, lc = li % RW;
+            r = r0 + lr; c = c0 + lc;
             float ctr[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) ctr[k] = resp_s[k * NPIX + li];
@@ -184,8 +205,8 @@ respond_score_kernel(const __grid_constant__ RespondWeights w, const SelectArgs 
                     }
                     float s = __fadd_rn(__fadd_rn(__fadd_rn(sq[0], sq[1]), __fadd_rn(sq[2], sq[3])),
                                         __fadd_rn(__fadd_rn(sq[4], sq[5]), __fadd_rn(sq[6], sq[7])));
-                    float n = __fsqrt_rn(s);
-                    best = fminf(best, n);
+                    float nrm = __fsqrt_rn(s);
+                    best = fminf(best, nrm);
                     ++count;
                 }
             if (count >= 5 && (double)best > 0.2) {
@@ -252,27 +273,57 @@ __global__ void __launch_bounds__(1024) topk_kernel(const TopkArgs a)
             __syncthreads();
             const unsigned long long prefix = s_prefix;
             const unsigned long long hmask = pass == 0 ? 0ull : (~0ull << (shift + 8));
-            for (int i = tid; i < n; i += blockDim.x) {
-                unsigned long long k = keys[i];
-                if ((k & hmask) == prefix) atomicAdd(&hist[(int)((k >> shift) & 0xff)], 1);
+            // the leading digits of the scores are nearly constant (same exponent): aggregate equal digits inside
+            // a warp so that one shared-memory atomic stands for up to 32 keys (uniform trip count for the match)
+            for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+                const int i = i0 + tid;
+                int digit = -1;
+                if (i < n) {
+                    unsigned long long k = keys[i];
+                    if ((k & hmask) == prefix) digit = (int)((k >> shift) & 0xff);
+                }
+                const unsigned grp = __match_any_sync(0xffffffffu, digit);
+                if (digit >= 0 && (tid & 31) == __ffs(grp) - 1) atomicAdd(&hist[digit], __popc(grp));
             }
             __syncthreads();
-            if (tid == 0) {
-                int krem = s_krem, d = 255, cum = 0;
-                for (; d > 0; --d) {
-                    if (cum + hist[d] >= krem) break;
-                    cum += hist[d];
+            if (tid < 32) {
+                // descending scan for the digit holding the krem-th largest key: lane L owns digits 255-8L .. 248-8L
+                int c[8], tot = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * tid - j]; tot += c[j]; }
+                int incl = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += v;
                 }
-                s_krem = krem - cum;
-                s_prefix = prefix | ((unsigned long long)d << shift);
+                const int krem = s_krem;
+                int cum = incl - tot;
+                if (cum < krem && krem <= incl) {
+                    int d = 255 - 8 * tid;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (cum + c[j] >= krem) break;
+                        cum += c[j];
+                        --d;
+                    }
+                    s_krem = krem - cum;
+                    s_prefix = prefix | ((unsigned long long)d << shift);
+                }
             }
             __syncthreads();
         }
         const unsigned long long kth = s_prefix;
-        for (int i = tid; i < n; i += blockDim.x) {
-            unsigned long long k = keys[i];
-            if (k >= kth) {
-                int pos = atomicAdd(&s_fill, 1);
+        for (int i0 = 0; i0 < n; i0 += blockDim.x) {   // uniform trip count for the ballot
+            const int i = i0 + tid;
+            const unsigned long long k = i < n ? keys[i] : 0ull;
+            const bool take = i < n && k >= kth;
+            const unsigned m = __ballot_sync(0xffffffffu, take);
+            int base = 0;
+            if (m && (tid & 31) == 0) base = atomicAdd(&s_fill, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (take) {
+                const int pos = base + __popc(m & ((1u << (tid & 31)) - 1u));
                 if (pos < S) sk[pos] = k;
             }
         }
@@ -338,7 +389,7 @@ int launch_select(caelo_ctx *ctx, bool fused, const float *resp, int H, int W, c
     a.ring_C = ring_C; a.ring_H = ring_H; a.ring_W = ring_W; a.cnt_kind = counter_dtype;
     a.cnt_H = cnt_H; a.cnt_W = cnt_W; a.H = H; a.W = W; a.B = B;
     dim3 grid((W - 2 * EDGE + TW - 1) / TW, (H - 2 * EDGE + TH - 1) / TH, B);
-    size_t smem = (size_t)8 * NPIX * 4 + ((NPIX + 15) / 16) * 16 + (fused ? (size_t)IH * IW * 3 * 4 : 0);
+    size_t smem = (size_t)8 * NPIX * 4 + ((NPIX + 15) / 16) * 16 + (fused ? (size_t)IH * IW * 3 * 4 : 0) + (NPIX + TH * TW) * 2;
     if (fused) {
         { ProfScope ps_(ctx, "respond_score_kernel<fused>", st); respond_score_kernel<true><<<grid, kThreads, smem, st>>>(ctx->respond_host, a); }
     } else {
@@ -363,8 +414,10 @@ int launch_select(caelo_ctx *ctx, bool fused, const float *resp, int H, int W, c
 
 int caelo_select_init(caelo_ctx *ctx)
 {
-    const int smem = 8 * NPIX * 4 + ((NPIX + 15) / 16) * 16 + IH * IW * 3 * 4;
+    const int smem = 8 * NPIX * 4 + ((NPIX + 15) / 16) * 16 + IH * IW * 3 * 4 + (NPIX + TH * TW) * 2;
     CAELO_CUDA(ctx, cudaFuncSetAttribute(respond_score_kernel<true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(respond_score_kernel<false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return CAELO_OK;
 }

@@ -170,4 +170,13 @@ __device__ __forceinline__ void split_f16(float x, __half &hi, __half &lo)
     lo = __float2half_rn(x - __half2float(hi));
 }
 
+// the same split for two values at once: one packed cvt per half2 instead of one F2F per element (the conversion
+// pipe runs at a quarter of the FMA rate)
+__device__ __forceinline__ void split_f16x2(float x0, float x1, __half2 &hi, __half2 &lo)
+{
+    hi = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(hi);
+    lo = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+}
+
 }  // namespace umma

@@ -58,6 +58,8 @@ class OdometryPipeline:
                               vox_offsets: np.ndarray):
         """ring [F,64,1792,3] (or [F,69,1800,5]), counter [F,69,1800] i8/i32, voxel lists ->
         kpts [F,K,3], feat [F,K,60], n_kpts [F]."""
+        # (building the a6 index on a second stream under the selection was measured: the two compete for the same SMs,
+        #  brick_insert 0.19 -> 0.45 ms, respond_score 0.40 -> 0.60 ms, step 4.69 -> 4.75 ms — so one stream)
         kpts, _kpix, n = self.ctx.select_keypoints(ring, counter, None, max_kpts=self.K)
         packed, _, _ = self.ctx.gather_patches(kpts, vox, vox_offsets, n)
         feat = self.ctx.encode_frames(packed)
@@ -82,21 +84,8 @@ class OdometryPipeline:
         P = kpts.shape[0] - 1
         pc0, pc1 = kpts[:-1], kpts[1:]
         pair_idx = self.ctx.nn_match(feat[:-1], feat[1:])
-        rounds = samples if samples.dim() == 4 else samples[None]
-        state = rt = mask_acc = None
-        thr_used = torch.full((P,), LADDER[-1], dtype=torch.float32, device=self.dev)
-        for r in range(rounds.shape[0]):
-            thr = torch.full((P,), LADDER[r], dtype=torch.float32, device=self.dev)
-            prev = state
-            res, mask, _ = self.ctx.ransac_round(pc0, pc1, pair_idx, rounds[r], thr, skip_if_ok=prev,
-                                                 out_result=None if prev is None else prev.clone())
-            rt_r, _ = self.ctx.kabsch(pc0, pc1, pair_idx, mask, skip_if_ok=prev,
-                                      out_rt=None if rt is None else rt.clone())
-            newly = (res[:, 12] != 0) if prev is None else ((res[:, 12] != 0) & (prev[:, 12] == 0))
-            thr_used = torch.where(newly, thr, thr_used)
-            if self.keep_details:                       # inlier mask of the round that produced the model
-                mask_acc = mask if mask_acc is None else torch.where(newly[:, None], mask, mask_acc)
-            state, rt = res, rt_r
+        rounds = (samples if samples.dim() == 4 else samples[None]).contiguous()
+        state, mask_acc, rt, thr_used = self.ctx.ransac_ladder(pc0, pc1, pair_idx, rounds, LADDER[:rounds.shape[0]])
         details = None
         if self.keep_details:
             details = dict(kpts=kpts, feat=feat, pair_idx=pair_idx, mask=mask_acc, ok=state[:, 12] != 0)
@@ -163,37 +152,63 @@ class OdometryPipeline:
             self._copy_stream = torch.cuda.Stream(self.dev)
         return self._copy_stream
 
+    def _slot_buffer(self, slot: dict, name: str, like: torch.Tensor, rows: int) -> torch.Tensor:
+        """Device staging buffer ``name`` of an upload slot with at least ``rows`` rows shaped/typed like ``like``
+        (grown geometrically, never shrunk): the hot path allocates nothing for its inputs."""
+        buf = slot.get(name)
+        if buf is None or buf.shape[0] < rows or buf.shape[1:] != like.shape[1:] or buf.dtype != like.dtype:
+            if buf is not None:
+                torch.cuda.current_stream(self.dev).synchronize()        # rare: a bigger batch than ever before
+                self._copy_stream_().synchronize()
+            buf = torch.empty((int(rows * 1.25) + 1,) + tuple(like.shape[1:]), dtype=like.dtype, device=self.dev)
+            slot[name] = buf
+        return buf
+
     def _upload(self, batch, chunks: int = 4):
-        """Queues the H2D copies of one batch on the copy stream in ``chunks`` frame groups; returns the device
-        parts with the event each becomes valid at.  ``batch`` is ("rings", ring_h, counter_h, vox_h, vox_offsets,
-        pair_ids) or ("scans", pts_h, pts_offsets, pair_ids), host tensors pinned."""
+        """Queues the H2D copies of one batch on the copy stream in ``chunks`` frame groups, into one of two
+        preallocated device slots (a slot is reused once the kernels of the batch that last used it have been
+        queued AND have run: its `free` event); returns the device parts with the event each becomes valid at.
+        ``batch`` is ("rings", ring_h, counter_h, vox_h, vox_offsets, pair_ids) or ("scans", pts_h, pts_offsets,
+        pair_ids), host tensors pinned."""
         cs = self._copy_stream_()
+        if not hasattr(self, "_slots"):
+            self._slots, self._slot_next = [dict(), dict()], 0
+        slot = self._slots[self._slot_next]
+        self._slot_next ^= 1
+        if "free" in slot:
+            cs.wait_event(slot["free"])
         parts = []
         if batch[0] == "rings":
             _, ring_h, counter_h, vox_h, vox_offsets, pair_ids = batch
             F = ring_h.shape[0]
             voff = np.asarray(vox_offsets, np.int64)
+            d_ring = self._slot_buffer(slot, "ring", ring_h, F)
+            d_cnt = self._slot_buffer(slot, "cnt_" + str(counter_h.dtype), counter_h, F)
+            d_vox = self._slot_buffer(slot, "vox", vox_h, int(voff[-1]))
             bounds = np.linspace(0, F, min(chunks, F) + 1).astype(int)
             for c0, c1 in zip(bounds[:-1], bounds[1:]):
+                v0, v1 = int(voff[3 * c0]), int(voff[3 * c1])
                 with torch.cuda.stream(cs):
-                    r = ring_h[c0:c1].to(self.dev, non_blocking=True)
-                    c = counter_h[c0:c1].to(self.dev, non_blocking=True)
-                    v = vox_h[voff[3 * c0]:voff[3 * c1]].to(self.dev, non_blocking=True)
+                    d_ring[c0:c1].copy_(ring_h[c0:c1], non_blocking=True)
+                    d_cnt[c0:c1].copy_(counter_h[c0:c1], non_blocking=True)
+                    d_vox[v0:v1].copy_(vox_h[v0:v1], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(cs)
-                parts.append(((r, c, v), voff[3 * c0:3 * c1 + 1] - voff[3 * c0], ev))
+                parts.append(((d_ring[c0:c1], d_cnt[c0:c1], d_vox[v0:v1]), voff[3 * c0:3 * c1 + 1] - voff[3 * c0], ev))
         else:
             _, pts_h, pts_offsets, pair_ids = batch
             off = np.asarray(pts_offsets, np.int64)
             F = off.shape[0] - 1
+            d_pts = self._slot_buffer(slot, "pts", pts_h, int(off[-1]))
             bounds = np.linspace(0, F, min(chunks, F) + 1).astype(int)
             for c0, c1 in zip(bounds[:-1], bounds[1:]):
+                p0, p1 = int(off[c0]), int(off[c1])
                 with torch.cuda.stream(cs):
-                    p = pts_h[off[c0]:off[c1]].to(self.dev, non_blocking=True)
+                    d_pts[p0:p1].copy_(pts_h[p0:p1], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(cs)
-                parts.append(((p,), off[c0:c1 + 1] - off[c0], ev))
-        return dict(kind=batch[0], parts=parts, pair_ids=list(pair_ids))
+                parts.append(((d_pts[p0:p1],), off[c0:c1 + 1] - off[c0], ev))
+        return dict(kind=batch[0], parts=parts, pair_ids=list(pair_ids), slot=slot)
 
     def _enqueue(self, up):
         """Queues every kernel of an uploaded batch on the current stream (each frame group as soon as its copy
@@ -202,8 +217,6 @@ class OdometryPipeline:
         outs = []
         for tensors, o, ev in up["parts"]:
             cur.wait_event(ev)
-            for t in tensors:
-                t.record_stream(cur)
             if up["kind"] == "rings":
                 kp, ft, n = self.frames_to_descriptors(*tensors, o)
                 outs.append((kp, ft, n, None))
@@ -212,17 +225,22 @@ class OdometryPipeline:
         smp = self.ctx.draw_samples(up["pair_ids"], self.K, rounds=3)     # all three ladder rounds, on the device
         kpts, feat, n = (torch.cat([o[i] for o in outs], 0) for i in range(3))
         st = None if up["kind"] == "rings" else torch.cat([o[3] for o in outs], 0)
+        free = torch.cuda.Event()                     # every kernel that reads the slot's inputs is queued before this point
+        free.record(cur)
+        up["slot"]["free"] = free
         return self._enqueue_pairs(kpts, feat, n, smp, up["pair_ids"], st)
 
-    def run_host_stream(self, batches, chunks: int = 4):
+    def run_host_stream(self, batches, chunks: int = 1, first_chunks: int = 4):
         """Generator over an iterable of host batches (see ``_upload``) -> poses [P,16] per batch, in order.
         Software-pipelined two deep: the H2D copies of batch i+1 run on the copy stream and its kernels are
         queued while batch i computes; the host only waits for batch i-1's results.  Every batch still pays
         its own H2D copies and D2H read — they just overlap the neighbouring batches' kernels (this is how
-        ``odometry.estimate_sequence`` walks a sequence)."""
+        ``odometry.estimate_sequence`` walks a sequence).  Only the first batch is uploaded in ``first_chunks``
+        frame groups (nothing else is running that could hide its copy); the others go up whole, so that every
+        kernel sees the full batch (per-frame stages such as the top-k are latency-bound per launch)."""
         it = iter(batches)
         try:
-            up = self._upload(next(it), chunks)
+            up = self._upload(next(it), first_chunks)
         except StopIteration:
             return
         pending = None

@@ -141,6 +141,16 @@ int caelo_ransac_round(caelo_ctx *ctx, const float *pc0, int N0, const float *pc
                        const int32_t *best_n_in, const float *skip_if_ok, int P, float *result,
                        uint8_t *inlier_mask, int32_t *counts, void *stream);
 
+/* a5 — the whole RANSAC4RT threshold ladder (Match.py:207-214) + SolveRelativePose's refit (Match.py:273-283) for
+ * P pairs in one call, no host round trip: round r (threshold thr_ladder[r], HOST [rounds]) only runs for the pairs
+ * that have no model yet.  sample_idx dev [rounds,P,T,4] (caelo_ransac_draw_samples).  Outputs (dev): result
+ * [P,16] as in caelo_ransac_round, inlier_mask [P,N] of the accepted hypothesis (all 0 if none), Rt [P,12] refit
+ * over the inliers, thr_used [P] threshold of the round that produced the model (last one if none), credible [P]. */
+int caelo_ransac_ladder(caelo_ctx *ctx, const float *pc0, int N0, const float *pc1, int N,
+                        const int64_t *pair_idx, const int32_t *sample_idx, int T, int rounds,
+                        const float *thr_ladder, int P, float *result, uint8_t *inlier_mask, float *Rt,
+                        float *thr_used, int32_t *credible, void *stream);
+
 /* a5 — SolveRT (Match.py:138-158) for P independent problems: p0 = pc0[pair_idx] (or pc0),
  * p1 = pc1, restricted to mask != 0 (mask dev [P,N] or NULL = all).  Rt dev [P,12] (R row-major
  * then T), credible dev [P] int32 (+1, -1 = reflection quirk applied, 0 = no points).
@@ -193,6 +203,17 @@ int caelo_gather_patches_scans(caelo_ctx *ctx, const void *kpts, int kpts_f64, c
                                int F, int K, const float *pts, const int64_t *pts_offsets,
                                uint32_t *packed, float *patches_f32, uint8_t *trunc, int32_t *nvox,
                                int32_t *status, void *stream);
+
+/* a6 / f2+a6 in two steps.  The occupancy index (bricks) of a batch does not depend on its key points, so it can
+ * be built on a second stream while the key points are still being selected: caelo_bricks_build[_scans] (arguments
+ * as in caelo_gather_patches[_scans]) then caelo_bricks_gather for the same F.  The index lives in the ctx (one at a
+ * time); nvox / status of the scans variant are passed on to the gather (NULL, NULL after caelo_bricks_build). */
+int caelo_bricks_build(caelo_ctx *ctx, const int16_t *vox, const int64_t *vox_offsets, int F, void *stream);
+int caelo_bricks_build_scans(caelo_ctx *ctx, const float *pts, const int64_t *pts_offsets, int F, int32_t *nvox,
+                             int32_t *status, void *stream);
+int caelo_bricks_gather(caelo_ctx *ctx, const void *kpts, int kpts_f64, const int32_t *n_kpts, int F, int K,
+                        uint32_t *packed, float *patches_f32, uint8_t *trunc, const int32_t *nvox,
+                        int32_t *status, void *stream);
 
 /* f4 (front end) — ExtendKeyPtsInShpericalRing (SphericalRing.py:294-317) for B frames: all occupied pixels
  * of each key pixel's 13x13 window, first key pixel wins a pixel, output in key-pixel order then row-major
