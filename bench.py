@@ -250,11 +250,11 @@ def run_ours(args, rank, local_rank, world):
 
     def step_device():
         poses = pipe.run_device(d_ring, d_counter, d_vox, voff, d_samples, pair_ids)
-        return pipeline.gather_poses(poses, dev)
+        return pipeline.gather_poses(poses, dev, cap=P)
 
     def step_host():
         poses = pipe.run_host(host["ring"], host["counter"], host["vox"], voff, pair_ids)
-        return pipeline.gather_poses(poses, dev)
+        return pipeline.gather_poses(poses, dev, cap=P)
 
     # ---- warm-up ----
     for _ in range(max(args.warmup, 3)):
@@ -294,11 +294,11 @@ def run_ours(args, rank, local_rank, world):
             yield ("rings", host["ring"], host["counter"], host["vox"], voff, pair_ids)
 
     for poses in pipe.run_host_stream(host_steps(3)):
-        pipeline.gather_poses(poses, dev)
+        pipeline.gather_poses(poses, dev, cap=P)
     barrier()
     t0 = time.perf_counter()
     for poses in pipe.run_host_stream(host_steps(args.steps)):
-        pipeline.gather_poses(poses, dev)
+        pipeline.gather_poses(poses, dev, cap=P)
     barrier()
     e2e_s = time.perf_counter() - t0
     step_host()
@@ -332,7 +332,7 @@ def run_ours(args, rank, local_rank, world):
             flush.zero_()
             torch.cuda.synchronize()
             a.record()
-            pipeline.gather_poses(pipe.run_device_scans(d_scans, soff, d_samples, pair_ids), dev)
+            pipeline.gather_poses(pipe.run_device_scans(d_scans, soff, d_samples, pair_ids), dev, cap=P)
             b.record()
         barrier()
         prof_s = ctx.profile_fetch()
@@ -343,11 +343,11 @@ def run_ours(args, rank, local_rank, world):
                 yield ("scans", scans_h, soff, pair_ids)
 
         for poses in pipe.run_host_stream(scan_steps(3)):
-            pipeline.gather_poses(poses, dev)
+            pipeline.gather_poses(poses, dev, cap=P)
         barrier()
         t0 = time.perf_counter()
         for poses in pipe.run_host_stream(scan_steps(args.steps)):
-            pipeline.gather_poses(poses, dev)
+            pipeline.gather_poses(poses, dev, cap=P)
         barrier()
         e2e_scans_s = time.perf_counter() - t0
         t = torch.tensor([ms_s, e2e_scans_s], dtype=torch.float64, device=dev)

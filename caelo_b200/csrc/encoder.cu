@@ -45,7 +45,8 @@ constexpr int W2_BYTES = 28 * 512;                    // 28 tap chunks x 32 rows
 // dynamic smem layout (bytes)
 constexpr int SM_A = 0;                               // [buf 2][hi,lo][A_VOL_BYTES]
 constexpr int SM_W2 = SM_A + 4 * A_VOL_BYTES;         // 64000
-constexpr int T1_ROW = 8 * 32 + 16;                   // one nibble's 8 partial-sum rows (+16 B: rows 4-7 shifted, no bank conflicts)
+constexpr int T1_PAT = 48;                            // a partial-sum row (32 B) every 48 B: the 8 rows of a nibble hit 8 distinct 16-B bank groups
+constexpr int T1_ROW = 8 * T1_PAT;                    // one nibble's 8 partial-sum rows
 constexpr int SM_T1 = SM_W2 + W2_BYTES;               // conv1 partial sums [9 (dx,dy)][8 dz-patterns][8 ch] f32
 constexpr int SM_B12 = SM_T1 + 9 * T1_ROW;            // floats: b1[8] b2[16]
 constexpr int SM_BG = SM_B12 + (8 + 16) * 4;          // tanh(b1) as fp16 hi (16 B) + lo (16 B)
@@ -156,21 +157,24 @@ __device__ __forceinline__ void conv1_to_smem(const unsigned short *rows, const 
         // 3x3 nibbles (dx,dy) of the window around (sx,sy): nibble j = dx*3+dy at bits 4j..4j+3; dz = 0..2 above sz
         const unsigned long long w2 = win >> (16 * sx + 4 * sy + sz);
         const unsigned g0 = (unsigned)w2 & 0x777u, g1 = (unsigned)(w2 >> 16) & 0x777u, g2 = (unsigned)(w2 >> 32) & 0x777u;
-        float acc[8];
+        float2 acc2[4];   // channels (0,1) (2,3) (4,5) (6,7): packed f32x2 adds, one instruction per two channels
         {
             const float4 c0 = *reinterpret_cast<const float4 *>(b1s), c1 = *reinterpret_cast<const float4 *>(b1s + 4);
-            acc[0] = c0.x; acc[1] = c0.y; acc[2] = c0.z; acc[3] = c0.w;
-            acc[4] = c1.x; acc[5] = c1.y; acc[6] = c1.z; acc[7] = c1.w;
+            acc2[0] = make_float2(c0.x, c0.y); acc2[1] = make_float2(c0.z, c0.w);
+            acc2[2] = make_float2(c1.x, c1.y); acc2[3] = make_float2(c1.z, c1.w);
         }
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
             const unsigned gj = (j < 3) ? g0 : ((j < 6) ? g1 : g2);
             const unsigned pat = (gj >> (4 * (j % 3))) & 7u;
-            const float4 *row = reinterpret_cast<const float4 *>(t1 + j * T1_ROW + pat * 32 + (pat >> 2) * 16);
+            const float4 *row = reinterpret_cast<const float4 *>(t1 + j * T1_ROW + pat * T1_PAT);
             const float4 w0 = row[0], w1 = row[1];
-            acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
-            acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
+            acc2[0] = __fadd2_rn(acc2[0], make_float2(w0.x, w0.y));
+            acc2[1] = __fadd2_rn(acc2[1], make_float2(w0.z, w0.w));
+            acc2[2] = __fadd2_rn(acc2[2], make_float2(w1.x, w1.y));
+            acc2[3] = __fadd2_rn(acc2[3], make_float2(w1.z, w1.w));
         }
+        const float acc[8] = {acc2[0].x, acc2[0].y, acc2[1].x, acc2[1].y, acc2[2].x, acc2[2].y, acc2[3].x, acc2[3].y};
         // max over the eight sub-position lanes, halving the channel set a lane carries at each exchange:
         // lane `sub` ends with channel 4*sx + 2*sy + sz
         float h4[4];
@@ -211,9 +215,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
     // ---- one-time setup: zero the operand volumes and the staged rows (halos stay zero), stage weights/tables ----
     for (int i = tid; i < SM_T1 / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(sm)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < 2 * PK_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(sm + SM_PK)[i] = make_uint4(0, 0, 0, 0);
-    for (int e = tid; e < 9 * 8 * 8; e += TC_THREADS) {       // T1 row (j,pat) at j*T1_ROW + pat*32 + (pat>>2)*16
+    for (int e = tid; e < 9 * 8 * 8; e += TC_THREADS) {       // T1 row (j,pat) at j*T1_ROW + pat*T1_PAT
         const int j = e >> 6, pat = (e >> 3) & 7, c = e & 7;
-        *reinterpret_cast<float *>(sm + SM_T1 + j * T1_ROW + pat * 32 + (pat >> 2) * 16 + c * 4) = a.tables[e];
+        *reinterpret_cast<float *>(sm + SM_T1 + j * T1_ROW + pat * T1_PAT + c * 4) = a.tables[e];
     }
     for (int e = tid; e < 27 * 16; e += TC_THREADS) reinterpret_cast<float *>(sm + SM_BGP)[e] = a.tables[576 + e];
     if (tid < 8) {
@@ -394,7 +398,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
                 umma::tmem_ld_wait();
                 float m[16];
 #pragma unroll
-                for (int c = 0; c < 16; ++c) m[c] = (__uint_as_float(v[c]) + __uint_as_float(v[16 + c])) + b2s[c];
+                for (int c = 0; c < 16; c += 2) {   // (hi.hi + lo.hi columns) + (hi.lo columns) + bias, two channels per packed add
+                    const float2 s2 = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])),
+                                                            make_float2(__uint_as_float(v[16 + c]), __uint_as_float(v[17 + c]))),
+                                                 *reinterpret_cast<const float2 *>(b2s + c));
+                    m[c] = s2.x; m[c + 1] = s2.y;
+                }
                 // 2x2x2 max-pool: partners differ in x-slice (lane^16), y (lane^8), z (lane^1).  At each exchange a
                 // lane sends the half of its channels the partner keeps and receives the half it keeps itself:
                 // 16 -> 8 -> 4 -> 2 channels, 14 shuffles instead of 48; the lane with bits (x,y,z) = (lane>>4&1,
@@ -720,9 +729,9 @@ dense_tc_kernel(const DenseArgs a, const __grid_constant__ CUtensorMap map_ah, c
         if (eid < 208) W2s[4032 + eid] = eid < 200 ? a.bd1[eid] : 0.0f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (eid == 0) stamp(4);
-        float acc[20];
+        float2 acc2[10];                                         // dense2 accumulators, two outputs per packed FFMA2
 #pragma unroll
-        for (int j = 0; j < 20; ++j) acc[j] = W2s[4000 + j];
+        for (int j = 0; j < 10; ++j) acc2[j] = make_float2(W2s[4000 + 2 * j], W2s[4001 + 2 * j]);
         const uint32_t trow = tbase + ((uint32_t)(q * 32) << 16) + et * 256;
 #pragma unroll 1
         for (int c0 = 0; c0 < DN; c0 += 16) {
@@ -731,19 +740,21 @@ dense_tc_kernel(const DenseArgs a, const __grid_constant__ CUtensorMap map_ah, c
             umma::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                if (c0 + j >= 200) break;                        // columns 200..207 are padding (compile-time per unrolled j once c0 = 192)
+                if (c0 + j >= 200) break;                        // columns 200..207 are padding
                 const float h = fast_tanh(__uint_as_float(v0[j]) + W2s[4032 + c0 + j]);
+                const float2 hh = make_float2(h, h);
                 const float4 *w = reinterpret_cast<const float4 *>(W2s + (c0 + j) * 20);
 #pragma unroll
                 for (int u = 0; u < 5; ++u) {
                     const float4 wv = w[u];
-                    acc[4 * u + 0] = fmaf(h, wv.x, acc[4 * u + 0]);
-                    acc[4 * u + 1] = fmaf(h, wv.y, acc[4 * u + 1]);
-                    acc[4 * u + 2] = fmaf(h, wv.z, acc[4 * u + 2]);
-                    acc[4 * u + 3] = fmaf(h, wv.w, acc[4 * u + 3]);
+                    acc2[2 * u] = __ffma2_rn(hh, make_float2(wv.x, wv.y), acc2[2 * u]);
+                    acc2[2 * u + 1] = __ffma2_rn(hh, make_float2(wv.z, wv.w), acc2[2 * u + 1]);
                 }
             }
         }
+        float acc[20];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) { acc[2 * j] = acc2[j].x; acc[2 * j + 1] = acc2[j].y; }
         const int p = row0 + et * 128 + row;
         if (p < a.P) {
             float *o;

@@ -23,7 +23,9 @@ constexpr int NPIX = RH * RW;
 constexpr int kThreads = 256;
 constexpr int EDGE = 8;  // Size4FilterTopEdge, SphericalRing.py:42
 
-// contract R1 for one pixel; x[27] in (ky,kx,ci) order, out[8]
+// contract R1 for one pixel; x[27] in (ky,kx,ci) order, out[8].  Scalar FFMA with the weight as a constant-bank
+// operand: the packed FFMA2 form was measured 2x SLOWER here (0.40 -> 0.81 ms) — a 64-bit weight pair cannot be
+// an immediate constant operand and has to come through uniform-register loads.
 __device__ __forceinline__ void respond_pixel(const RespondWeights &w, const float (&x)[27],
                                               float (&out)[8])
 {

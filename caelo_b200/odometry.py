@@ -170,7 +170,7 @@ def estimate_sequence(raw_dir: str, Tr: Optional[np.ndarray] = None, poses_path:
                                {"iFrame0": ids[j], "iFrame1": ids[j + 1], "inliersIdx0": pidx[j][m],
                                 "inliersIdx1": np.arange(mask.shape[1])[m]})
     rel_local = np.concatenate(rows, 0) if rows else np.zeros((0, 16), np.float32)
-    rel = pipeline.gather_poses(rel_local, pipe.dev)
+    rel = pipeline.gather_poses(rel_local, pipe.dev, cap=-(-P // world))
     if rel is None:
         return None, rel_local
     poses = pipeline.chain_poses(rel, Tr)

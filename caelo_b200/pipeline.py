@@ -300,25 +300,46 @@ class OdometryPipeline:
             failed = np.asarray(still, np.int64)
 
 
-def gather_poses(poses: np.ndarray, device: torch.device):
+_comm_streams = {}
+
+
+def gather_poses(poses: np.ndarray, device: torch.device, cap: Optional[int] = None):
     """NCCL gather of the per-rank [P_local,16] pose rows to rank 0 (the only collective on the
     path; PoseEstimation.py:254-267's pose chain then runs on rank 0).  Returns the concatenated
-    array on rank 0, None elsewhere.  Works without torch.distributed initialised (1 rank)."""
+    array on rank 0, None elsewhere.  Works without torch.distributed initialised (1 rank).
+    ``cap``: an upper bound of P_local that every rank knows (e.g. ceil(P_total / world)); then ONE gather of
+    [cap+1,16] rows moves everything (row 0 carries the row count) instead of a count exchange first.  The
+    collective runs on its own CUDA stream, so it never waits for kernels queued on the compute stream."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return poses
     world, rank = dist.get_world_size(), dist.get_rank()
-    t = torch.from_numpy(np.ascontiguousarray(poses, np.float32)).to(device)
-    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(counts, torch.tensor([t.shape[0]], dtype=torch.int64, device=device))
-    sizes = [int(c.item()) for c in counts]
-    pad = torch.zeros((max(sizes), 16), dtype=torch.float32, device=device)
-    pad[: t.shape[0]] = t
-    bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
-    dist.gather(pad, bufs, dst=0)
-    if rank != 0:
-        return None
-    return np.concatenate([b[:s].cpu().numpy() for b, s in zip(bufs, sizes)], 0)
+    import contextlib
+    if device.type == "cuda":
+        comm = _comm_streams.get(device)
+        if comm is None:
+            comm = _comm_streams[device] = torch.cuda.Stream(device)
+        on_comm = torch.cuda.stream(comm)
+    else:                                   # gloo (the CPU tests of the sharding logic)
+        on_comm = contextlib.nullcontext()
+    rows = np.ascontiguousarray(poses, np.float32)
+    with on_comm:
+        if cap is None:
+            n_loc = torch.tensor([rows.shape[0]], dtype=torch.int64, device=device)
+            counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+            dist.all_gather(counts, n_loc)
+            cap = max(int(c.item()) for c in counts)
+        assert rows.shape[0] <= cap
+        buf = np.zeros((cap + 1, 16), np.float32)
+        buf[0, 0] = rows.shape[0]
+        buf[1:1 + rows.shape[0]] = rows
+        t = torch.from_numpy(buf).to(device)
+        bufs = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, bufs, dst=0)
+        if rank != 0:
+            return None
+        allr = torch.stack(bufs).cpu().numpy()          # waits for the comm stream only
+    return np.concatenate([allr[r, 1:1 + int(allr[r, 0, 0])] for r in range(world)], 0)
 
 
 def chain_poses(rel: np.ndarray, Tr: Optional[np.ndarray] = None):

@@ -391,3 +391,27 @@ def test_host_stream_equals_single_calls(api):
     for g, w in zip(got, singles):
         assert np.array_equal(g, w)
     assert list(pipe.run_host_stream(iter([]))) == []
+
+
+def test_bricks_two_step_equals_gather(api):
+    """caelo_bricks_build + caelo_bricks_gather (and the scans variant) == caelo_gather_patches[_scans]."""
+    import torch
+    from caelo_b200 import synth
+    ctx = api.default_context()
+    d = synth.make_frames(2, seed=5)
+    kpts, _px, n = ctx.select_keypoints(api._dev(d["ring3"]), api._dev(d["counter"]), None)
+    vox = api._dev(d["vox"])
+    want, _, _ = ctx.gather_patches(kpts, vox, d["vox_offsets"], n)
+    ctx.bricks_build(vox, d["vox_offsets"])
+    got = ctx.bricks_gather(kpts, n)
+    assert torch.equal(got, want)
+    soff = np.zeros(3, np.int64)
+    soff[1:] = np.cumsum([s.shape[0] for s in d["scans"]])
+    pts = api._dev(np.concatenate(d["scans"], 0))
+    want_s, _, _, nvox_w, st_w = ctx.gather_patches_scans(kpts, pts, soff, n)
+    nvox, st = ctx.bricks_build_scans(pts, soff)
+    got_s = ctx.bricks_gather(kpts, n, nvox, st)
+    assert torch.equal(got_s, want_s) and torch.equal(nvox, nvox_w) and torch.equal(st, st_w)
+    assert torch.equal(got_s, want)          # Voxelization's voxel sets = the voxel lists of the synthetic frames
+    with pytest.raises(Exception):           # no index for a batch of another size
+        ctx.bricks_gather(kpts[:1].contiguous(), n[:1].contiguous())

@@ -31,12 +31,12 @@ def _fake_pose_rows(pair_ids):
     return rows
 
 
-def _worker(rank, world, port, n_pairs, out):
+def _worker(rank, world, port, n_pairs, out, use_cap=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, hi = pipeline.shard_pairs(n_pairs, rank, world)
     rows = _fake_pose_rows(list(range(lo, hi)))
-    got = pipeline.gather_poses(rows, torch.device("cpu"))
+    got = pipeline.gather_poses(rows, torch.device("cpu"), cap=-(-n_pairs // world) if use_cap else None)
     if rank == 0:
         np.save(out, got)
     else:
@@ -45,10 +45,10 @@ def _worker(rank, world, port, n_pairs, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_pairs", [7, 32])
-def test_shard_gather_chain_world2(tmp_path, n_pairs):
+@pytest.mark.parametrize("n_pairs,use_cap", [(7, False), (32, False), (7, True), (33, True)])
+def test_shard_gather_chain_world2(tmp_path, n_pairs, use_cap):
     out = str(tmp_path / "gathered.npy")
-    mp.spawn(_worker, args=(2, _free_port(), n_pairs, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), n_pairs, out, use_cap), nprocs=2, join=True)
     got = np.load(out)
     want = _fake_pose_rows(list(range(n_pairs)))
     assert np.array_equal(got, want)                      # rank order == pair order

@@ -1,0 +1,37 @@
+"""Host-side cost of one pipelined step (python + ctypes + torch allocator), measured while the device is busy:
+python tools/host_overhead.py"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from caelo_b200 import api, pipeline, synth
+
+P = 32
+ctx = api.default_context(); pipe = pipeline.OdometryPipeline(ctx)
+d = synth.make_frames(P + 1, seed=1)
+host = {k: torch.from_numpy(d[k]).pin_memory() for k in ("ring3", "counter", "vox")}
+voff = d["vox_offsets"]; ids = list(range(P))
+batch = ("rings", host["ring3"], host["counter"], host["vox"], voff, ids)
+for _ in pipe.run_host_stream([batch] * 3): pass
+acc = {"upload": [], "enqueue": [], "collect": []}
+pending = None
+up = pipe._upload(batch, 1)
+torch.cuda.synchronize()
+t_all = time.perf_counter()
+for it in range(20):
+    t0 = time.perf_counter(); nxt = pipe._upload(batch, 1)
+    t1 = time.perf_counter(); h = pipe._enqueue(up)
+    t2 = time.perf_counter()
+    if pending is not None: pipe._collect(pending)
+    t3 = time.perf_counter()
+    pending, up = h, nxt
+    acc["upload"].append(t1 - t0); acc["enqueue"].append(t2 - t1); acc["collect"].append(t3 - t2)
+pipe._collect(pending)
+torch.cuda.synchronize()
+print("wall per step %.3f ms" % ((time.perf_counter() - t_all) / 20 * 1e3))
+for k, v in acc.items(): print("%-8s host %.3f ms (median)" % (k, 1e3 * float(np.median(v))))
+# finer: the calls inside _enqueue
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable()
+for _ in pipe.run_host_stream([batch] * 10): pass
+pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
