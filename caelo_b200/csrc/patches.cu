@@ -72,22 +72,38 @@ struct BuildArgs {
     int nlists;
 };
 
-__global__ void brick_insert_kernel(const BuildArgs a)
+__global__ void __launch_bounds__(256) brick_insert_kernel(const BuildArgs a)
 {
-    const int list = blockIdx.y;
+    const int list = blockIdx.y, lane = threadIdx.x & 31;
     const long long beg = a.offsets[list], end = a.offsets[list + 1];
     const Table t = a.tables[list];
-    for (long long i = beg + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < end;
-         i += (long long)gridDim.x * blockDim.x) {
-        int x = a.vox[i * 3 + 0], y = a.vox[i * 3 + 1], z = a.vox[i * 3 + 2];
-        unsigned long long key = brick_key(x >> 2, y >> 2, z >> 2);
-        unsigned long long bit = 1ull << (((x & 3) * 4 + (y & 3)) * 4 + (z & 3));
+    // Consecutive voxels of a list are neighbours in space (scan order), so several lanes of a warp usually hit the
+    // same brick — and atomics on one address serialise in L2: lanes with equal keys merge their bits first and
+    // only the group leader touches the table (warp-uniform trip count for the match / reduce).
+    for (long long i0 = beg + (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < end;
+         i0 += (long long)gridDim.x * blockDim.x) {
+        const long long i = i0 + lane;
+        const bool valid = i < end;
+        int x = 0, y = 0, z = 0;
+        if (valid) { x = a.vox[i * 3 + 0]; y = a.vox[i * 3 + 1]; z = a.vox[i * 3 + 2]; }
+        const unsigned long long key = valid ? brick_key(x >> 2, y >> 2, z >> 2) : EMPTY;
+        const unsigned long long bit = valid ? 1ull << (((x & 3) * 4 + (y & 3)) * 4 + (z & 3)) : 0ull;
+        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        const unsigned lo = __reduce_or_sync(grp, (unsigned)bit), hi = __reduce_or_sync(grp, (unsigned)(bit >> 32));
+        if (!valid || lane != __ffs(grp) - 1) continue;
+        const unsigned long long bits = ((unsigned long long)hi << 32) | lo;
         unsigned slot = hash64(key) & t.cap_mask;
         while (true) {
-            unsigned long long old = atomicCAS(t.keys + slot, EMPTY, key);
-            if (old == EMPTY || old == key) {
-                atomicOr(t.masks + slot, bit);
-                if (old == EMPTY) super_set(a.tables[a.nlists + list], x >> 2, y >> 2, z >> 2);
+            // most voxels fall into a brick that is already claimed: a plain load sees it, no CAS needed
+            unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(t.keys + slot);
+            bool claimed = false;
+            if (old == EMPTY) {
+                old = atomicCAS(t.keys + slot, EMPTY, key);
+                claimed = old == EMPTY;
+            }
+            if (claimed || old == key) {
+                atomicOr(t.masks + slot, bits);
+                if (claimed) super_set(a.tables[a.nlists + list], x >> 2, y >> 2, z >> 2);
                 break;
             }
             slot = (slot + 1) & t.cap_mask;

@@ -247,12 +247,14 @@ struct TopkArgs {
     int *n_kpts;        // [B]
 };
 
+constexpr int TOPK_CAND = 3072;   // keys tied with the 16-bit prefix that fit the shared-memory stage
+
 __global__ void __launch_bounds__(1024) topk_kernel(const TopkArgs a)
 {
     extern __shared__ unsigned long long sk[];  // [sort_n]
     __shared__ int hist[256];
     __shared__ unsigned long long s_prefix;
-    __shared__ int s_krem, s_fill;
+    __shared__ int s_krem, s_fill, s_surv, s_ncand;
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int n = a.count[b];
@@ -267,21 +269,49 @@ __global__ void __launch_bounds__(1024) topk_kernel(const TopkArgs a)
     if (n <= want) {
         for (int i = tid; i < n; i += blockDim.x) sk[i] = keys[i];
     } else {
-        // MSB-first radix select of the want-th largest key (keys are unique)
-        if (tid == 0) { s_prefix = 0ull; s_krem = want; }
+        // MSB-first radix select of the want-th largest key (keys are unique).  The first two digits (16 bits of
+        // the score) are counted over all n keys in global memory; then the keys still tied with the prefix —
+        // usually a few dozen — are compacted into shared memory (the ones above it go straight to the output),
+        // and the remaining six digits and the final collection only touch those.
+        unsigned long long *cand = sk + S;   // [TOPK_CAND]
+        if (tid == 0) { s_prefix = 0ull; s_krem = want; s_ncand = 0; }
+        const unsigned long long *src = keys;
+        int nsrc = n;
+        bool compact = false;
         for (int pass = 0; pass < 8; ++pass) {
             const int shift = 56 - 8 * pass;
             if (tid < 256) hist[tid] = 0;
             __syncthreads();
+            if (pass == 2 && s_surv <= TOPK_CAND) {
+                const unsigned long long p16 = s_prefix >> 48;
+                for (int i0 = 0; i0 < n; i0 += blockDim.x) {   // uniform trip count for the ballots
+                    const int i = i0 + tid;
+                    const unsigned long long k = i < n ? keys[i] : 0ull;
+                    const bool above = i < n && (k >> 48) > p16, tied = i < n && (k >> 48) == p16;
+                    const unsigned ma = __ballot_sync(0xffffffffu, above), mt = __ballot_sync(0xffffffffu, tied);
+                    int ba = 0, bt = 0;
+                    if ((tid & 31) == 0) {
+                        if (ma) ba = atomicAdd(&s_fill, __popc(ma));
+                        if (mt) bt = atomicAdd(&s_ncand, __popc(mt));
+                    }
+                    ba = __shfl_sync(0xffffffffu, ba, 0);
+                    bt = __shfl_sync(0xffffffffu, bt, 0);
+                    const unsigned below = (1u << (tid & 31)) - 1u;
+                    if (above) { const int pos = ba + __popc(ma & below); if (pos < S) sk[pos] = k; }
+                    if (tied) cand[bt + __popc(mt & below)] = k;
+                }
+                __syncthreads();
+                src = cand; nsrc = s_ncand; compact = true;
+            }
             const unsigned long long prefix = s_prefix;
             const unsigned long long hmask = pass == 0 ? 0ull : (~0ull << (shift + 8));
             // the leading digits of the scores are nearly constant (same exponent): aggregate equal digits inside
             // a warp so that one shared-memory atomic stands for up to 32 keys (uniform trip count for the match)
-            for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+            for (int i0 = 0; i0 < nsrc; i0 += blockDim.x) {
                 const int i = i0 + tid;
                 int digit = -1;
-                if (i < n) {
-                    unsigned long long k = keys[i];
+                if (i < nsrc) {
+                    unsigned long long k = src[i];
                     if ((k & hmask) == prefix) digit = (int)((k >> shift) & 0xff);
                 }
                 const unsigned grp = __match_any_sync(0xffffffffu, digit);
@@ -302,24 +332,26 @@ __global__ void __launch_bounds__(1024) topk_kernel(const TopkArgs a)
                 const int krem = s_krem;
                 int cum = incl - tot;
                 if (cum < krem && krem <= incl) {
-                    int d = 255 - 8 * tid;
+                    int d = 255 - 8 * tid, surv = c[7];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        if (cum + c[j] >= krem) break;
+                        if (cum + c[j] >= krem) { surv = c[j]; break; }
                         cum += c[j];
                         --d;
                     }
                     s_krem = krem - cum;
                     s_prefix = prefix | ((unsigned long long)d << shift);
+                    s_surv = surv;       // keys that share the digits chosen so far
                 }
             }
             __syncthreads();
         }
         const unsigned long long kth = s_prefix;
-        for (int i0 = 0; i0 < n; i0 += blockDim.x) {   // uniform trip count for the ballot
+        // collect every key >= kth (with the compacted source the keys above the 16-bit prefix are already in)
+        for (int i0 = 0; i0 < nsrc; i0 += blockDim.x) {   // uniform trip count for the ballot
             const int i = i0 + tid;
-            const unsigned long long k = i < n ? keys[i] : 0ull;
-            const bool take = i < n && k >= kth;
+            const unsigned long long k = i < nsrc ? src[i] : 0ull;
+            const bool take = i < nsrc && k >= kth;
             const unsigned m = __ballot_sync(0xffffffffu, take);
             int base = 0;
             if (m && (tid & 31) == 0) base = atomicAdd(&s_fill, __popc(m));
@@ -329,6 +361,7 @@ __global__ void __launch_bounds__(1024) topk_kernel(const TopkArgs a)
                 if (pos < S) sk[pos] = k;
             }
         }
+        (void)compact;
     }
     __syncthreads();
 
@@ -407,7 +440,7 @@ int launch_select(caelo_ctx *ctx, bool fused, const float *resp, int H, int W, c
     while (S < max_kpts + 1) S <<= 1;
     t.sort_n = S;
     t.kpts = kpts; t.kpix = reinterpret_cast<long long *>(kpix); t.n_kpts = n_kpts;
-    { ProfScope ps_(ctx, "topk_kernel", st); topk_kernel<<<B, 1024, (size_t)S * 8, st>>>(t); }
+    { ProfScope ps_(ctx, "topk_kernel", st); topk_kernel<<<B, 1024, (size_t)(S + TOPK_CAND) * 8, st>>>(t); }
     CAELO_LAUNCH_CHECK(ctx);
     return CAELO_OK;
 }
@@ -421,6 +454,7 @@ int caelo_select_init(caelo_ctx *ctx)
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(respond_score_kernel<false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + TOPK_CAND) * 8));
     return CAELO_OK;
 }
 
