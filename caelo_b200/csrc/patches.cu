@@ -23,11 +23,15 @@ constexpr unsigned long long EMPTY = ~0ull;
 constexpr int kWarps = 8;
 constexpr int NNB = 496;  // n_neighbors, Voxel.py:182
 
+// Open-addressing table of 16-byte slots {key, ~mask}: key and occupancy word share one 32-byte sector (a probe is
+// one memory transaction), and the whole table is cleared by ONE memset to 0xFF (empty key = all ones, the mask is
+// stored inverted: a set voxel/brick bit is a CLEARED bit).
 struct Table {
-    unsigned long long *keys;
-    unsigned long long *masks;
-    unsigned cap_mask;  // capacity - 1 (power of two)
+    unsigned long long *slots;   // [2 * capacity]: slots[2i] = key, slots[2i+1] = ~mask
+    unsigned cap_mask;           // capacity - 1 (power of two)
 };
+__device__ __forceinline__ unsigned long long *key_of(const Table &t, unsigned slot) { return t.slots + 2 * (size_t)slot; }
+__device__ __forceinline__ unsigned long long *inv_mask_of(const Table &t, unsigned slot) { return t.slots + 2 * (size_t)slot + 1; }
 
 __device__ __forceinline__ unsigned hash64(unsigned long long k)
 {
@@ -52,13 +56,13 @@ __device__ __forceinline__ void super_set(const Table &t, int bx, int by, int bz
     const unsigned long long bit = 1ull << (((bx & 3) * 4 + (by & 3)) * 4 + (bz & 3));
     unsigned slot = hash64(key) & t.cap_mask;
     while (true) {
-        unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(t.keys + slot);
+        unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(key_of(t, slot));
         if (k == EMPTY) {
-            k = atomicCAS(t.keys + slot, EMPTY, key);
+            k = atomicCAS(key_of(t, slot), EMPTY, key);
             if (k == EMPTY) k = key;
         }
         if (k == key) {
-            atomicOr(t.masks + slot, bit);
+            atomicAnd(inv_mask_of(t, slot), ~bit);
             return;
         }
         slot = (slot + 1) & t.cap_mask;
@@ -95,14 +99,14 @@ __global__ void __launch_bounds__(256) brick_insert_kernel(const BuildArgs a)
         unsigned slot = hash64(key) & t.cap_mask;
         while (true) {
             // most voxels fall into a brick that is already claimed: a plain load sees it, no CAS needed
-            unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(t.keys + slot);
+            unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(key_of(t, slot));
             bool claimed = false;
             if (old == EMPTY) {
-                old = atomicCAS(t.keys + slot, EMPTY, key);
+                old = atomicCAS(key_of(t, slot), EMPTY, key);
                 claimed = old == EMPTY;
             }
             if (claimed || old == key) {
-                atomicOr(t.masks + slot, bits);
+                atomicAnd(inv_mask_of(t, slot), ~bits);
                 if (claimed) super_set(a.tables[a.nlists + list], x >> 2, y >> 2, z >> 2);
                 break;
             }
@@ -132,17 +136,17 @@ __device__ __forceinline__ bool brick_set(const Table &t, const Table &ts, int x
     const unsigned long long bit = 1ull << (((x & 3) * 4 + (y & 3)) * 4 + (z & 3));
     unsigned slot = hash64(key) & t.cap_mask;
     while (true) {
-        unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(t.keys + slot);
+        unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(key_of(t, slot));
         if (k == EMPTY) {
-            k = atomicCAS(t.keys + slot, EMPTY, key);
+            k = atomicCAS(key_of(t, slot), EMPTY, key);
             if (k == EMPTY) {
                 k = key;
                 super_set(ts, x >> 2, y >> 2, z >> 2);
             }
         }
         if (k == key) {
-            if (*reinterpret_cast<volatile unsigned long long *>(t.masks + slot) & bit) return false;
-            return !(atomicOr(t.masks + slot, bit) & bit);
+            if (!(*reinterpret_cast<volatile unsigned long long *>(inv_mask_of(t, slot)) & bit)) return false;   // already set
+            return (atomicAnd(inv_mask_of(t, slot), ~bit) & bit) != 0ull;
         }
         slot = (slot + 1) & t.cap_mask;
     }
@@ -188,9 +192,9 @@ __device__ __forceinline__ unsigned long long brick_lookup(const Table &t, unsig
 {
     unsigned slot = hash64(key) & t.cap_mask;
     while (true) {
-        unsigned long long k = t.keys[slot];
-        if (k == key) return t.masks[slot];
-        if (k == EMPTY) return 0ull;
+        const ulonglong2 kv = *reinterpret_cast<const ulonglong2 *>(key_of(t, slot));   // one 16-byte load: key, ~mask
+        if (kv.x == key) return ~kv.y;
+        if (kv.x == EMPTY) return 0ull;
         slot = (slot + 1) & t.cap_mask;
     }
 }
@@ -417,8 +421,7 @@ static int setup_tables(caelo_ctx *ctx, int nl, const size_t *caps, const int64_
     char *base = reinterpret_cast<char *>(ctx->bricks.ptr);
     *d_tables = reinterpret_cast<Table *>(base);
     *d_off = reinterpret_cast<long long *>(base + (size_t)nl * sizeof(Table));
-    unsigned long long *d_keys = reinterpret_cast<unsigned long long *>(base + head);
-    unsigned long long *d_masks = d_keys + total_slots;
+    unsigned long long *d_slots = reinterpret_cast<unsigned long long *>(base + head);
     // tables + offsets go through a ring of pinned staging slots: no stream synchronisation
     const size_t stage_bytes = (size_t)nl * sizeof(Table) + (size_t)n_off * 8;
     void *h_stage = nullptr;
@@ -428,16 +431,14 @@ static int setup_tables(caelo_ctx *ctx, int nl, const size_t *caps, const int64_
     Table *h_tables = reinterpret_cast<Table *>(h_stage);
     size_t cur = 0;
     for (int l = 0; l < nl; ++l) {
-        h_tables[l].keys = d_keys + cur;
-        h_tables[l].masks = d_masks + cur;
+        h_tables[l].slots = d_slots + 2 * cur;
         h_tables[l].cap_mask = (unsigned)(caps[l] - 1);
         cur += caps[l];
     }
     memcpy(reinterpret_cast<char *>(h_stage) + (size_t)nl * sizeof(Table), offsets, (size_t)n_off * 8);
     CAELO_CUDA(ctx, cudaMemcpyAsync(*d_tables, h_stage, stage_bytes, cudaMemcpyHostToDevice, st));
     CAELO_CUDA(ctx, cudaEventRecord(ev, st));
-    CAELO_CUDA(ctx, cudaMemsetAsync(d_keys, 0xFF, total_slots * 8, st));
-    CAELO_CUDA(ctx, cudaMemsetAsync(d_masks, 0, total_slots * 8, st));
+    CAELO_CUDA(ctx, cudaMemsetAsync(d_slots, 0xFF, total_slots * 16, st));
     return CAELO_OK;
 }
 

@@ -193,6 +193,7 @@ struct PoseArgs {
     const int *best_n_in;         // [P] or null
     const float *skip_if_ok;      // [P,16] or null: pairs with [12] != 0 there are skipped
     int N0, N, T, P;
+    int hyp_per_cta;              // hyp_score: trials per CTA (a multiple of the 8 warps)
     int t0, t1;                   // hyp_score: trials [t0,t1) of every pair; replay: trials [0,t1) are scored
     int *more;                    // [P] speculation flag (see caelo_ransac_round): 1 = the pair needs trials >= t1
     int more_mode;                // hyp_score: 1 = only pairs with more[pair]; replay: 1 = first phase (may set more[pair] and
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(64) hyp_kabsch_kernel(const PoseArgs a)
 
 // Scoring: one CTA = one pair x HS_HYP consecutive trials.  The pair's matched points are staged once in shared
 // memory (SoA) and the eight warps count inliers, one warp per hypothesis at a time (contract D1).
-constexpr int HS_HYP = 32;
+constexpr int HS_HYP = 8;     // default trials per CTA = one per warp: many small CTAs hide the staging latency best
 constexpr int HS_THREADS = 256;
 
 template <bool kStaged>
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(HS_THREADS) hyp_score_kernel(const PoseArgs a)
     extern __shared__ float hs_pts[];        // kStaged: [6][N] = x0 y0 z0 x1 y1 z1
     const int pair = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t_base = a.t0 + blockIdx.x * HS_HYP;
+    const int t_base = a.t0 + blockIdx.x * a.hyp_per_cta;
     if (a.skip_if_ok && a.skip_if_ok[(size_t)pair * 16 + 12] != 0.0f) return;
     if (a.more_mode == 1 && !a.more[pair]) return;
     const int N = a.N;
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(HS_THREADS) hyp_score_kernel(const PoseArgs a)
         __syncthreads();
     }
     const float thr = a.thr ? a.thr[pair] : a.thr_scalar;
-    for (int h = warp; h < HS_HYP && t_base + h < a.t1; h += HS_THREADS / 32) {
+    for (int h = warp; h < a.hyp_per_cta && t_base + h < a.t1; h += HS_THREADS / 32) {
         float R[9], T[3];
         {
             const float4 *rt = reinterpret_cast<const float4 *>(a.rt_hyp + ((size_t)pair * a.T + t_base + h) * 12);
@@ -585,8 +586,13 @@ static int run_round(caelo_ctx *ctx, PoseArgs a, int32_t *counts, cudaStream_t s
     const int T1 = (T > 100 && !counts) ? 100 : T;   // a caller asking for every count gets every trial scored
     const size_t hs_smem = (size_t)N * 24;
     const bool staged = hs_smem <= 160 * 1024;
+    {
+        const char *e = getenv("CAELO_HS_HYP");   // debug switch for A/B timing
+        a.hyp_per_cta = e ? atoi(e) : HS_HYP;
+        if (a.hyp_per_cta < 8) a.hyp_per_cta = 8;
+    }
     auto score = [&](int n_trials) {
-        const dim3 grid((n_trials + HS_HYP - 1) / HS_HYP, P);
+        const dim3 grid((n_trials + a.hyp_per_cta - 1) / a.hyp_per_cta, P);
         ProfScope ps_(ctx, "hyp_score_kernel", st);
         if (staged) hyp_score_kernel<true><<<grid, HS_THREADS, hs_smem, st>>>(a);
         else hyp_score_kernel<false><<<grid, HS_THREADS, 0, st>>>(a);
