@@ -37,9 +37,10 @@ __device__ __forceinline__ float fast_tanh(float x)
 }
 
 // ---- conv1 (CUDA cores) + conv2 (tcgen05) --------------------------------------------------
-constexpr int TC_WORKERS = 256;                       // 8 warps: produce operands (conv1), drain accumulators
-constexpr int TC_THREADS = TC_WORKERS + 32;           // + 1 warp whose elected lane issues the MMAs (it
-                                                      // absorbs the tensor-queue back-pressure)
+constexpr int TC_WORKERS = 256;                       // warps 0-7: produce operands (conv1)
+constexpr int TC_ISSUER = 8;                          // warp 8: its elected lane issues the MMAs (absorbs the tensor-queue back-pressure)
+constexpr int TC_EPI_WARPS = 4;                       // warps 9-12: drain accumulators (one per TMEM lane quarter)
+constexpr int TC_THREADS = TC_WORKERS + 32 + TC_EPI_WARPS * 32;
 constexpr int A_VOL_BYTES = 10 * 10 * 10 * 16;        // padded 8^3 volume, 8 ch fp16 per position
 constexpr int W2_BYTES = 28 * 512;                    // 28 tap chunks x 32 rows x 16 B
 // dynamic smem layout (bytes)
@@ -56,8 +57,8 @@ constexpr int SM_PK = SM_BG + 32;                     // [2][PK_BYTES]
 constexpr int SM_LWIN = SM_PK + 2 * PK_BYTES;         // non-empty cell list: windows [512] u64
 constexpr int SM_LCELL = SM_LWIN + 512 * 8;           //                      padded cell index [2 buffers][512] u16
 constexpr int SM_LCNT = SM_LCELL + 2 * 512 * 2;       //                      count [2] (double-buffered)
-constexpr int SM_XS = SM_LCNT + 16;                   // per buffer: 8 flags "x-slice holds a non-empty cell"
-constexpr int SM_BGP = SM_XS + 16;                    // conv2+pool+tanh of an all-background neighbourhood [27 classes][16]
+constexpr int SM_XS = SM_LCNT + 16;                   // per patch (ring of 4): 8 flags "x-slice holds a non-empty cell"
+constexpr int SM_BGP = SM_XS + 32;                    // conv2+pool+tanh of an all-background neighbourhood [27 classes][16]
 constexpr int SM_BAR = SM_BGP + 27 * 16 * 4;          // 6 mbarriers + tmem base
 constexpr int TC_SMEM = SM_BAR + 64;
 static_assert(SM_T1 % 16 == 0 && SM_LWIN % 8 == 0 && SM_XS % 8 == 0 && SM_BGP % 8 == 0 && SM_BAR % 8 == 0, "smem alignment");
@@ -202,7 +203,7 @@ __device__ __forceinline__ void conv1_to_smem(const unsigned short *rows, const 
     if (tl && tid == 0) tl[8] = clock64();
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Args a)
+__global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Args a)   // 416 threads x 2 CTAs: <= 78 registers
 {
     extern __shared__ __align__(128) unsigned char sm[];
     float *b1s = reinterpret_cast<float *>(sm + SM_B12), *b2s = b1s + 8;
@@ -244,13 +245,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
         *reinterpret_cast<__half *>(w + (co / 8) * 128 + (co % 8) * 16 + ci * 2) = h;
         *reinterpret_cast<__half *>(w + ((16 + co) / 8) * 128 + (co % 8) * 16 + ci * 2) = l;
     }
-    if (warp == 8) umma::tmem_alloc(tmem_slot, 256);
+    if (warp == TC_ISSUER) umma::tmem_alloc(tmem_slot, 256);
     uint64_t *full = mbar, *tfull = mbar + 2, *tempty = mbar + 4;
     if (tid == 0) {
         for (int b = 0; b < 2; ++b) {
             umma::mbar_init(&full[b], TC_WORKERS);    // operands of buffer b written (every worker arrives)
             umma::mbar_init(&tfull[b], 1);            // MMAs into TMEM[b] complete (tcgen05.commit)
-            umma::mbar_init(&tempty[b], TC_WORKERS);  // TMEM[b] drained by the epilogue
+            umma::mbar_init(&tempty[b], TC_EPI_WARPS * 32);  // TMEM[b] drained by the epilogue warps
         }
         umma::fence_mbar_init();
     }
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
     // x-slice pairs (= one pooled x) of buffer b that need conv2: some cell of slices 2p-1 .. 2p+2 is non-empty
     auto active_pairs = [&](int b) -> unsigned {
         if (!a.skip_bg) return 0xFu;
-        const unsigned long long f = *reinterpret_cast<const unsigned long long *>(sm + SM_XS + 8 * b);
+        const unsigned long long f = *reinterpret_cast<const unsigned long long *>(sm + SM_XS + 8 * b);   // b = patch ordinal & 3
         unsigned m = 0;  // bit xs: slice xs holds a non-empty cell
 #pragma unroll
         for (int xs = 0; xs < 8; ++xs) m |= (unsigned)((f >> (8 * xs)) & 1ull) << xs;
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
         return act;
     };
 
-    if (warp == 8) {
+    if (warp == TC_ISSUER) {
         // ===== MMA issuer: waits for operands + a free accumulator, queues 224 MMAs, commits =====
         const uint32_t idesc32 = umma::idesc_f16_f32(64, 32), idesc16 = umma::idesc_f16_f32(64, 16);
         for (int j = 0; j < n_my; ++j) {
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
             if (k >= 1) umma::mbar_wait(&tempty[b], (uint32_t)((k - 1) & 1));
             umma::fence_after_thread_sync();
             if (lane == 0) stamp(j, 5);
-            const unsigned act = active_pairs(b);
+            const unsigned act = active_pairs(j & 3);
             if (umma::elect_one()) {
 #pragma unroll 1
                 for (int xs = 0; xs < 8; ++xs) {  // x-slice: M = 64 positions (y,z)
@@ -322,8 +323,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
             __syncwarp();
             if (lane == 0) stamp(j, 6);
         }
-    } else {
-        // ===== workers: conv1 of patch i+1 while MMA(i) runs, then drain patch i =====
+    } else if (warp < TC_ISSUER) {
+        // ===== producers (8 warps): conv1 of patch i into operand buffer i&1, as soon as MMA(i-2) has released it =====
         unsigned long long *lwin = reinterpret_cast<unsigned long long *>(sm + SM_LWIN);
         unsigned short *lcell = reinterpret_cast<unsigned short *>(sm + SM_LCELL);
         int *lcnt = reinterpret_cast<int *>(sm + SM_LCNT);
@@ -357,32 +358,36 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
             fetch(i + 1);
             if (tid == 128) lcnt[b] = 0;  // the other counter was read before the previous patch's second barrier
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            long long *tl = (a.timeline && i >= 1 && i <= 64) ? a.timeline + ((size_t)blockIdx.x * 64 + (i - 1)) * 16 : nullptr;
+            long long *tl = (a.timeline && i < 64) ? a.timeline + ((size_t)blockIdx.x * 64 + i) * 16 : nullptr;
             if (tl && tid == 0) tl[2] = clock64();
             int n_listed;
-            conv1_to_smem(rows, sm + SM_T1, b1s, a_hi, a_lo, lwin, lc, lcnt + b, sm + SM_XS + 8 * b, tid, n_listed, tl);
+            conv1_to_smem(rows, sm + SM_T1, b1s, a_hi, a_lo, lwin, lc, lcnt + b, sm + SM_XS + 8 * (i & 3), tid, n_listed, tl);
             if (b) n_dirty1 = n_listed; else n_dirty0 = n_listed;
             umma::fence_proxy_async();
             umma::mbar_arrive(&full[b]);
         };
-        int p_cur = p_next;
-        if (n_my > 0) produce(0);
         for (int i = 0; i < n_my; ++i) {
             const int b = i & 1;
             if (tid == 0) stamp(i, 0);
-            const int p_this = p_cur;
-            p_cur = p_next;                    // patch i+1 (set by the fetch inside produce(i))
-            if (i + 1 < n_my) produce(i + 1);  // MMA(i-1) finished reading A[b^1]: waited on tfull last iteration
+            if (i >= 2) {   // MMA(i-2) must have finished reading operand buffer b
+                umma::mbar_wait(&tfull[b], (uint32_t)(((i - 2) >> 1) & 1));
+                umma::fence_after_thread_sync();
+            }
+            produce(i);
             if (tid == 0) stamp(i, 1);
+        }
+    } else {
+        // ===== epilogue (4 warps, one per TMEM lane quarter): drain patch i while conv1(i+1) and MMA(i+1) run =====
+        const int q = warp & 3;
+        for (int i = 0; i < n_my; ++i) {
+            const int b = i & 1;
             umma::mbar_wait(&tfull[b], (uint32_t)((i >> 1) & 1));
             umma::fence_after_thread_sync();
-            if (tid == 0) stamp(i, 3);
-            const int q = warp & 3, h = warp >> 2;
-            float *out = a.act2 + (size_t)p_this * 1024;
-            const unsigned act = active_pairs(b);
+            if (warp == TC_ISSUER + 1 && lane == 0) stamp(i, 3);
+            float *out = a.act2 + (size_t)patch_of(i) * 1024;
+            const unsigned act = active_pairs(i & 3);
 #pragma unroll 1
-            for (int pp = 0; pp < 2; ++pp) {
-                const int pair = 2 * h + pp;
+            for (int pair = 0; pair < 4; ++pair) {
                 if (!((act >> pair) & 1u)) {   // background pair: the precomputed constants (warp-uniform branch)
                     const int z2 = (lane & 7) >> 1;
                     const int j = ((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + (lane & 1);
@@ -429,13 +434,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
             }
             umma::fence_before_thread_sync();
             umma::mbar_arrive(&tempty[b]);
-            if (tid == 0) stamp(i, 4);
+            if (warp == TC_ISSUER + 1 && lane == 0) stamp(i, 4);
         }
     }
     umma::fence_before_thread_sync();
     __syncthreads();
     umma::fence_after_thread_sync();
-    if (warp == 8) umma::tmem_dealloc(tbase, 256);
+    if (warp == TC_ISSUER) umma::tmem_dealloc(tbase, 256);
 }
 
 // ---- conv3 (tcgen05) ---------------------------------------------------------------------------
@@ -446,8 +451,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
 // are the two K chunks (LBO = 9*1536 B).  Split fp16: A_hi x [W_hi|W_lo] (N=64) + A_lo x W_hi (N=32),
 // fp32 accumulators in TMEM (2 slots x 64 columns), epilogue adds the halves, bias, tanh, and writes
 // act3 as split fp16 (the dense1 operands).  8 worker warps + 1 MMA-issuer warp, mbarrier pipeline.
-constexpr int C3_WORKERS = 256;
-constexpr int C3_THREADS = C3_WORKERS + 32;
+constexpr int C3_ISSUER = 12;                        // warps 0-3 produce operands, 4-11 drain accumulators, 12 issues the MMAs
+constexpr int C3_THREADS = (C3_ISSUER + 1) * 32;
 constexpr int C3_COPY = 6 * 16 * 16;                 // 1536 B: [xi 6][y 4][z 4] x 16 B
 constexpr int C3_HALF = 9 * C3_COPY;                 // 13824 B: 9 (dy,dz) copies of one channel half
 constexpr int C3_PART = 2 * C3_HALF;                 // 27648 B: both halves
@@ -489,12 +494,12 @@ __global__ void __launch_bounds__(C3_THREADS, 3 - NBUF) conv3_tc_kernel(const Co
         *reinterpret_cast<__half *>(w + ((32 + co) / 8) * 128 + (co % 8) * 16) = l;
     }
     if (tid < 32) b3s[tid] = a.b3[tid];
-    if (warp == 8) umma::tmem_alloc(tmem_slot, 128);
+    if (warp == C3_ISSUER) umma::tmem_alloc(tmem_slot, 128);
     if (tid == 0) {
         for (int b = 0; b < 2; ++b) {
-            umma::mbar_init(&full[b], C3_WORKERS);
+            umma::mbar_init(&full[b], 128);     // the four producer warps
             umma::mbar_init(&tfull[b], 1);
-            umma::mbar_init(&tempty[b], C3_WORKERS);
+            umma::mbar_init(&tempty[b], 256);   // the eight epilogue warps
         }
         umma::fence_mbar_init();
     }
@@ -507,7 +512,7 @@ __global__ void __launch_bounds__(C3_THREADS, 3 - NBUF) conv3_tc_kernel(const Co
     const int n_my = (a.P - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     auto patch_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
 
-    if (warp == 8) {
+    if (warp == C3_ISSUER) {
         const uint32_t idesc64 = umma::idesc_f16_f32(64, 64), idesc32 = umma::idesc_f16_f32(64, 32);
         for (int j = 0; j < n_my; ++j) {
             const int b = j & 1, k = j >> 1;
@@ -531,10 +536,11 @@ __global__ void __launch_bounds__(C3_THREADS, 3 - NBUF) conv3_tc_kernel(const Co
             }
             __syncwarp();
         }
-    } else {
-        // scatter one patch's activations (split fp16) into the 9 shifted copies of buffer b; the global loads
-        // of the NEXT patch are issued right after, so their latency hides behind this patch's epilogue
-        const int part = tid & 1, idx = tid >> 1, pos = idx >> 1, half = idx & 1;
+    } else if (warp < 4) {
+        // ===== producers (4 warps): scatter one patch's activations (split fp16) into the 9 shifted copies of
+        // buffer b.  Thread = (position, channel half): it writes the hi AND the lo part.  The global loads of the
+        // NEXT patch are issued before this patch's stores, so their latency hides behind the conversion.
+        const int pos = tid >> 1, half = tid & 1;
         float4 nv0 = make_float4(0.f, 0.f, 0.f, 0.f), nv1 = nv0;
         auto fetch = [&](int i) {
             if (i >= n_my) return;
@@ -543,67 +549,73 @@ __global__ void __launch_bounds__(C3_THREADS, 3 - NBUF) conv3_tc_kernel(const Co
             nv1 = __ldg(src + 1);
         };
         fetch(0);
-        auto produce = [&](int i) {
+        const int x = pos >> 4, y = (pos >> 2) & 3, z = pos & 3;
+        for (int i = 0; i < n_my; ++i) {
             const int b = i & 1;
             const float4 v0 = nv0, v1 = nv1;
             fetch(i + 1);
-            float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            __half2 hv[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                __half2 h, l;
-                umma::split_f16x2(f[2 * c], f[2 * c + 1], h, l);
-                hv[c] = part ? l : h;
+            if (i >= 2) {   // MMA(i-2) must have finished reading buffer b
+                umma::mbar_wait(&tfull[b], (uint32_t)(((i - 2) >> 1) & 1));
+                umma::fence_after_thread_sync();
             }
-            const uint4 val = *reinterpret_cast<uint4 *>(hv);
-            const int x = pos >> 4, y = (pos >> 2) & 3, z = pos & 3;
-            unsigned char *base = sm + SM3_C + (NBUF == 2 ? b : 0) * C3_BUF + part * C3_PART + half * C3_HALF;
+            const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            __half2 hv[4], lv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) umma::split_f16x2(f[2 * c], f[2 * c + 1], hv[c], lv[c]);
+            const uint4 vh = *reinterpret_cast<uint4 *>(hv), vl = *reinterpret_cast<uint4 *>(lv);
+            unsigned char *base = sm + SM3_C + (NBUF == 2 ? b : 0) * C3_BUF + half * C3_HALF;
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                 for (int dz = 0; dz < 3; ++dz) {
                     const int ys = y + 1 - dy, zs = z + 1 - dz;
-                    if ((unsigned)ys < 4u && (unsigned)zs < 4u)
-                        *reinterpret_cast<uint4 *>(base + (dy * 3 + dz) * C3_COPY + (((x + 1) * 4 + ys) * 4 + zs) * 16) = val;
+                    if ((unsigned)ys < 4u && (unsigned)zs < 4u) {
+                        unsigned char *p = base + (dy * 3 + dz) * C3_COPY + (((x + 1) * 4 + ys) * 4 + zs) * 16;
+                        *reinterpret_cast<uint4 *>(p) = vh;
+                        *reinterpret_cast<uint4 *>(p + C3_PART) = vl;
+                    }
                 }
             umma::fence_proxy_async();
             umma::mbar_arrive(&full[b]);
-        };
-        if (n_my > 0) produce(0);
+        }
+    } else {
+        // ===== epilogue (8 warps = TMEM lane quarter x channel half): hi/lo halves added, bias, tanh, act3 as split fp16 =====
+        const int q = warp & 3, hc = (warp - 4) >> 2;
         for (int i = 0; i < n_my; ++i) {
             const int b = i & 1;
-            if (NBUF == 2 && i + 1 < n_my) produce(i + 1);  // MMA(i-1) finished reading buffer b^1 (tfull waited last iteration)
             umma::mbar_wait(&tfull[b], (uint32_t)((i >> 1) & 1));
             umma::fence_after_thread_sync();
-            if (NBUF == 1 && i + 1 < n_my) produce(i + 1);  // MMA(i) finished reading the one buffer; it ran under the other CTA's work
-            const int q = warp & 3, hc = warp >> 2;  // lane quarter, channel half (16 channels)
             uint32_t v0[16], v1[16];
             const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16) + b * 64 + hc * 16;
-            umma::tmem_ld_x16(trow, v0);
-            umma::tmem_ld_x16(trow + 32, v1);
+            umma::tmem_ld_x16(trow, v0);        // columns 0..31: W_hi (A_hi + A_lo products)
+            umma::tmem_ld_x16(trow + 32, v1);   // columns 32..63: W_lo
             umma::tmem_ld_wait();
             umma::fence_before_thread_sync();
             umma::mbar_arrive(&tempty[b]);
             if (lane < 16) {  // M=64 accumulator: rows 16q..16q+15 live in lanes 0..15 of quarter q
                 const int pos = 16 * q + lane;
-                __half2 hh[8], ll[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float o0 = fast_tanh((__uint_as_float(v0[2 * c]) + __uint_as_float(v1[2 * c])) + b3s[hc * 16 + 2 * c]);
-                    const float o1 = fast_tanh((__uint_as_float(v0[2 * c + 1]) + __uint_as_float(v1[2 * c + 1])) + b3s[hc * 16 + 2 * c + 1]);
-                    umma::split_f16x2(o0, o1, hh[c], ll[c]);
-                }
                 const size_t o = (size_t)patch_of(i) * 2048 + pos * 32 + hc * 16;
                 uint4 *dh = reinterpret_cast<uint4 *>(a.act3_hi + o), *dl = reinterpret_cast<uint4 *>(a.act3_lo + o);
-                dh[0] = reinterpret_cast<uint4 *>(hh)[0]; dh[1] = reinterpret_cast<uint4 *>(hh)[1];
-                dl[0] = reinterpret_cast<uint4 *>(ll)[0]; dl[1] = reinterpret_cast<uint4 *>(ll)[1];
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {   // 8 channels at a time
+                    __half2 hh[4], ll[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int ch = 8 * g + 2 * c;
+                        const float o0 = fast_tanh((__uint_as_float(v0[ch]) + __uint_as_float(v1[ch])) + b3s[hc * 16 + ch]);
+                        const float o1 = fast_tanh((__uint_as_float(v0[ch + 1]) + __uint_as_float(v1[ch + 1])) + b3s[hc * 16 + ch + 1]);
+                        umma::split_f16x2(o0, o1, hh[c], ll[c]);
+                    }
+                    dh[g] = *reinterpret_cast<uint4 *>(hh);
+                    dl[g] = *reinterpret_cast<uint4 *>(ll);
+                }
             }
         }
     }
     umma::fence_before_thread_sync();
     __syncthreads();
     umma::fence_after_thread_sync();
-    if (warp == 8) umma::tmem_dealloc(tbase, 128);
+    if (warp == C3_ISSUER) umma::tmem_dealloc(tbase, 128);
 }
 
 // ---- dense1 (tcgen05) + tanh + dense2 + tanh ---------------------------------------------------
@@ -900,13 +912,11 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
     Conv3Args c3;
     c3.act2 = act2; c3.k3 = ctx->enc.k3; c3.b3 = ctx->enc.b3; c3.act3_hi = act3_hi; c3.act3_lo = act3_lo; c3.P = P;
     {
-        const char *e = getenv("CAELO_CONV3_NBUF");   // debug switch for A/B timing; default: one CTA per SM, two buffers
-        const bool two_buf = !(e && e[0] == '1');     // (measured: 0.89 ms vs 0.95 ms with two single-buffer CTAs per SM)
-        int grid3 = (two_buf ? 1 : 2) * ctx->num_sms;
+        // one CTA per SM with two operand buffers (two single-buffer CTAs per SM measured slower: 0.95 vs 0.89 ms)
+        int grid3 = ctx->num_sms;
         if (grid3 > P) grid3 = P;
         ProfScope ps_(ctx, "conv3_tc_kernel", st);
-        if (two_buf) conv3_tc_kernel<2><<<grid3, C3_THREADS, c3_smem(2), st>>>(c3);
-        else conv3_tc_kernel<1><<<grid3, C3_THREADS, c3_smem(1), st>>>(c3);
+        conv3_tc_kernel<2><<<grid3, C3_THREADS, c3_smem(2), st>>>(c3);
     }
     CAELO_LAUNCH_CHECK(ctx);
     CUtensorMap m_ah, m_al, m_wh, m_wl;
@@ -928,7 +938,6 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
 int caelo_encoder_init(caelo_ctx *ctx)
 {
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv12_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem(1)));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem(2)));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
     return CAELO_OK;
