@@ -1,0 +1,146 @@
+"""GPU tests of the odometry file plumbing (caelo_b200/odometry.py) and of the BASELINE
+configs that are parity cases rather than bench lines: a whole (short) sequence through
+``estimate_sequence`` — files in the reference's formats, sharded like configs[2] — and the descriptor
+NN-match microbench shape of configs[3] (up to 16k x 16k x 128)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from caelo_b200 import api as a
+    a.default_context()
+    return a
+
+
+@pytest.fixture(scope="module")
+def sequence(tmp_path_factory):
+    """Seven synthetic KITTI-shaped scans written as velodyne/NNNNNN.bin + a calib_.txt with a non-trivial Tr."""
+    from caelo_b200 import synth
+    d = synth.make_frames(7, seed=21)
+    root = tmp_path_factory.mktemp("seq")
+    raw = root / "velodyne"
+    raw.mkdir()
+    for i, pc in enumerate(d["scans"]):
+        np.asarray(pc, np.float32).tofile(str(raw / ("%06d.bin" % i)))
+    calib = np.zeros((5, 12))
+    calib[:4] = np.eye(3, 4).ravel()
+    a = 0.02
+    Tr = np.array([[np.cos(a), -np.sin(a), 0, 0.1], [np.sin(a), np.cos(a), 0, -0.2], [0, 0, 1, 0.3]])
+    calib[4] = Tr.ravel()
+    np.savetxt(str(root / "calib_.txt"), calib)
+    return dict(root=str(root), raw=str(raw), scans=d["scans"], Tr=np.asarray(Tr, np.float32))
+
+
+def test_estimate_sequence_matches_per_pair_api_and_writes_reference_files(api, sequence, tmp_path):
+    """PoseEstimation.py:185-310 for one sequence: rel poses == the per-pair functions (ProjectPC2SphericalRing ->
+    GetKeyPtsByAE -> Voxelization -> GetPatchesList -> encoder -> SolveRelativePose with np.random.seed(pair)),
+    poses_/SS.txt == the reference's chaining recurrence, Features / InliersIdx .mat files as the reference writes."""
+    from scipy import io
+    from caelo_b200 import odometry, pipeline
+    Tr = odometry.read_calib_Tr(os.path.join(sequence["root"], "calib_.txt"))
+    assert np.allclose(Tr, sequence["Tr"])
+    poses_path = str(tmp_path / "poses_" / "00.txt")
+    fdir, idir = str(tmp_path / "Features"), str(tmp_path / "InliersIdx")
+    poses, rel = odometry.estimate_sequence(sequence["raw"], Tr=Tr, poses_path=poses_path, features_dir=fdir,
+                                            inliers_dir=idir, batch_pairs=4)
+    F = len(sequence["scans"])
+    assert poses.shape == (F, 12) and rel.shape == (F - 1, 16)
+    assert np.allclose(np.loadtxt(poses_path), poses)
+    assert np.array_equal(poses, pipeline.chain_poses(rel, Tr))
+    # per-pair API on the same scans
+    enc = api.load_model(os.path.join(api.WEIGHT_DIR, "encoder.npz"))
+    kps, feats = [], []
+    for pc in sequence["scans"]:
+        ring, counter = api.ProjectPC2SphericalRing(pc)
+        kp, _px, _ = api.GetKeyPtsFromRing(np.ascontiguousarray(ring[0:64, 0:1792, 0:3]), counter.astype(np.int8))
+        vox = api.Voxelization(pc)
+        _, pl = api.GetPatchesList(kp, *vox[6:9])
+        kps.append(kp)
+        feats.append(api.GetFeaturesFromPatches(enc, pl))
+    for i in range(F - 1):
+        np.random.seed(i)
+        R, T, ok, i0, i1, thr = api.SolveRelativePose(kps[i], feats[i], None, kps[i + 1], feats[i + 1], None)
+        assert bool(rel[i, 12]) == ok and int(rel[i, 13]) == len(i0) and abs(rel[i, 14] - thr) < 1e-6
+        assert np.array_equal(rel[i, :9].reshape(3, 3), np.asarray(R, np.float32))
+        assert np.array_equal(rel[i, 9:12], np.asarray(T, np.float32).ravel())
+        m = io.loadmat(os.path.join(idir, "%06d-%06d.bin.mat" % (i, i + 1)))
+        assert int(m["iFrame0"].item()) == i and int(m["iFrame1"].item()) == i + 1
+        assert np.array_equal(m["inliersIdx0"].ravel(), i0) and np.array_equal(m["inliersIdx1"].ravel(), i1)
+    for i in range(F):
+        m = io.loadmat(os.path.join(fdir, "%06d.bin.mat" % i))
+        assert np.array_equal(m["KeyPts"], kps[i]) and np.array_equal(m["Features"], feats[i])
+        assert m["Weights"].shape == (1024, 1) and (m["Weights"] == 1).all()
+    # the readers of Match.py:65-72 see what was written
+    k, f, w = odometry.LoadKeyPtsAndFeatures(os.path.join(str(tmp_path), "velodyne", "000003.bin"))
+    assert np.array_equal(k, kps[3]) and np.array_equal(f, feats[3])
+
+
+def test_estimate_sequence_sharded_equals_single_rank(api, sequence):
+    """configs[2] semantics without a process group: the pair ranges of two 'ranks' (one-frame halo recomputed)
+    concatenate to exactly the single-rank result, whatever the batch size."""
+    from caelo_b200 import odometry
+    _, rel_all = odometry.estimate_sequence(sequence["raw"], scans=sequence["scans"], batch_pairs=32)
+    parts = [odometry.estimate_sequence(sequence["raw"], scans=sequence["scans"], batch_pairs=2, rank=r, world=2)[1]
+             for r in range(2)]
+    assert np.array_equal(np.concatenate(parts, 0), rel_all)
+
+
+def test_preprocess_sequence_writes_what_the_loaders_read(api, sequence, oracle_mod):
+    """BatchPreprocess.py:44-67 / BatchVoxelization.py:42-64 outputs for two frames: .mat contents == the oracle's
+    ProjectPC2SphericalRing / Voxelization, and LoadVoxelModelAndKeyPts (Match.py:46-61) reads them back."""
+    from scipy import io
+    from caelo_b200 import odometry
+    n = odometry.preprocess_sequence(sequence["root"], frames=[0, 5], rings=True, voxels=True, keypts=True, batch=2)
+    assert n == 2
+    for i in (0, 5):
+        pc = sequence["scans"][i]
+        name = "%06d.bin.mat" % i
+        m = io.loadmat(os.path.join(sequence["root"], "SphericalRing", name))
+        ring, counter = oracle_mod.project_ring(pc)
+        assert np.array_equal(m["SphericalRing"].view(np.uint32), ring.view(np.uint32))
+        assert np.array_equal(m["GridCounter"], counter)
+        v = io.loadmat(os.path.join(sequence["root"], "VoxelModel", name))
+        want = oracle_mod.voxelization(pc)   # (avlBlocksList, cntVoxelsLength, AllVoxels, AllVoxels0, AllVoxels1, AllVoxels2)
+        for key, w in zip(("avlBlocksList", "AllVoxels", "AllVoxels0", "AllVoxels1", "AllVoxels2"),
+                          (want[0], want[2], want[3], want[4], want[5])):
+            assert np.array_equal(v[key], w), key
+        assert np.array_equal(v["cntVoxelsLength"].ravel(), want[1].ravel())
+        kp, v0, v1, v2 = odometry.LoadVoxelModelAndKeyPts(os.path.join(sequence["raw"], "%06d.bin" % i))
+        assert kp.shape == (1024, 3) and np.array_equal(v0, want[3]) and np.array_equal(v2, want[5])
+        k = io.loadmat(os.path.join(sequence["root"], "KeyPts", name))
+        assert k["ExtendedKeyPts"].shape[1] == 3 and k["ExtendedKeyPts"].shape[0] >= 1024
+
+
+@pytest.mark.parametrize("n,d", [(1024, 128), (4096, 128), (16384, 128), (3000, 60)])
+def test_nn_match_microbench_shapes(api, n, d):
+    """configs[3]: N x N x D argmin.  Descriptors tanh(N(0,1)); frame 1 = frame-0 rows permuted, 40 % with small
+    noise (known answer) and 60 % fresh.  Known answers must be hit, a random subset of columns is checked against
+    float64 cdist+argmin exactly, and every index must be in range."""
+    import torch
+    from scipy.spatial.distance import cdist
+    ctx = api.default_context()
+    rng = np.random.default_rng(n + d)
+    c0 = np.tanh(rng.standard_normal((n, d))).astype(np.float32)
+    perm = rng.permutation(n)
+    c1 = c0[perm].copy()
+    noisy = rng.random(n) < 0.4
+    c1[noisy] += (0.05 * rng.standard_normal((int(noisy.sum()), d))).astype(np.float32)
+    c1[~noisy] = np.tanh(rng.standard_normal((int((~noisy).sum()), d))).astype(np.float32)
+    if n >= 8:                       # exact duplicates: ties -> lowest row
+        c1[3] = c0[5]
+        c0[n - 1] = c0[5]
+    got = ctx.nn_match(torch.from_numpy(c0[None]).cuda(), torch.from_numpy(c1[None]).cuda())[0].cpu().numpy()
+    assert got.dtype == np.int64 and got.min() >= 0 and got.max() < n
+    assert got[3] == 5
+    cols = np.unique(np.r_[rng.integers(0, n, 192), 3, np.flatnonzero(noisy)[:64]])
+    want = cdist(c0.astype(np.float64), c1[cols].astype(np.float64), "euclidean").argmin(axis=0)
+    assert np.array_equal(got[cols], want)
+    assert (got[noisy] == perm[noisy]).mean() > 0.99
