@@ -65,6 +65,7 @@ struct caelo_ctx {
     Scratch misc;
     Scratch scan_ws;   // projection / voxelisation: pixel owners, hash tables, compaction lists
     Scratch seed_ws;   // ransac: per-pair generator seeds
+    Scratch match_ops; // nn match: split-fp16 operand tiles + padded norms
 };
 
 #define CAELO_CUDA(ctx, call)                         \

@@ -3,11 +3,14 @@
 //
 // Index-exact in two steps: a fast approximate pass that keeps, per column, the best and second-best d^2 and
 // decides every column whose runner-up is outside the pass's error margin, then an exact re-scan of the rest.
+//   desc_prep_kernel one pass per descriptor set: squared norms + the split-fp16 operands (a = hi + lo) written
+//                    once, tile by tile, in the layout the tensor core reads;
 //   nn_tc_kernel     (D <= 128) tcgen05: d^2 = |a|^2 + |b|^2 - 2 a.b with the cross term as a split-fp16
-//                    GEMM (a = hi + lo: hi.hi + lo.hi + hi.lo, fp32 accumulators in TMEM); 128 frame-1
-//                    descriptors per CTA are the MMA rows (= TMEM lanes = threads), frame-0 descriptors
-//                    stream through as 128-column tiles, so each thread scans its own row for the running
-//                    (min, second min, argmin) with no cross-thread traffic.  Margin: |error| is assumed
+//                    GEMM (hi.hi + lo.hi + hi.lo, fp32 accumulators in TMEM); 128 frame-1 descriptors per CTA
+//                    are the MMA rows (= TMEM lanes = threads), frame-0 descriptors stream through as
+//                    128-column tiles fetched by bulk copies (cp.async.bulk, mbarrier complete_tx; producer
+//                    thread / MMA issuer / four scan warps), so each thread scans its own accumulator row for
+//                    the running (min, second min, argmin) with no cross-thread traffic.  Margin: |error| is assumed
 //                    <= 2^-13 |a|max |b| (about 1000x the analytic split-fp16 bound 3*2^-22 |a||b|).
 //   nn_tile_kernel   (any D) float32 direct-difference distances on 64x64 tiles held in shared memory;
 //                    per column the best and second-best approximate d^2 (+ best row).  The
@@ -127,86 +130,113 @@ __global__ void __launch_bounds__(MT_THREADS) nn_tile_kernel(const NNArgs a)
 
 // ---- tensor-core pass ---------------------------------------------------------------------------
 constexpr int NT_B = 128;                 // rows (frame-1) per CTA and columns (frame-0) per tile
-constexpr int NT_WORKERS = 128;
-constexpr int NT_THREADS = NT_WORKERS + 32;
+constexpr int NT_THREADS = 192;           // warps 0-3: scan accumulators; warp 4: MMA issuer; warp 5: bulk-copy producer
 
 struct NNTcArgs {
-    const float *c0, *c1;   // [P,N,D], [P,M,D]
-    const float *n0, *n1;   // [P,N], [P,M] squared norms (float64 sums rounded once)
-    int N, M, D, Kp;        // Kp = D rounded up to 16
+    const unsigned char *ops0, *ops1;   // split-fp16 operand tiles of frame 0 / frame 1 (desc_prep_kernel)
+    const float *n0p;                   // [P, tiles0*128] squared norms of frame 0, +inf in the padding rows
+    const float *n1;                    // [P, M]
+    int N, M, Kp, tiles0, tiles1;       // Kp = D rounded up to 16
     float *best_d, *second_d;
     int *best_i;
 };
 
-__global__ void __launch_bounds__(256) desc_norm_kernel(const float *c, int rows_per_pair, int D, long long rows,
-                                                        float *norm, float *pair_max)
+// One pass over a descriptor set: squared norms (float64 sums rounded once; the pair's maximum by atomicMax) and
+// the split-fp16 MMA operands, written once in the layout the tensor core reads: per 128-row tile one contiguous
+// block [hi, lo][chunk of 8 k][row][16 B] (canonical K-major no-swizzle: SBO = 128 B, LBO = 128*16 B), so that a
+// tile reaches shared memory with ONE bulk copy and no further conversion.  Rows beyond the set and k >= D are zero.
+__global__ void __launch_bounds__(128) desc_prep_kernel(const float *c, int rows_per_pair, int D, int Kp, int tiles,
+                                                        unsigned char *ops, float *norm, float *norm_padded, float *pair_max)
 {
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rows) return;
-    const float *p = c + r * D;
+    const int pair = blockIdx.y, tile = blockIdx.x, r = threadIdx.x;
+    const int row = tile * NT_B + r;
+    const bool in = row < rows_per_pair;
+    const float *p = c + ((size_t)pair * rows_per_pair + row) * D;
+    unsigned char *blk = ops + ((size_t)pair * tiles + tile) * ((size_t)Kp * NT_B * 4);
     double acc = 0.0;
-    for (int k = 0; k < D; ++k) acc += (double)p[k] * (double)p[k];
-    const float v = (float)acc;
-    norm[r] = v;
-    if (pair_max) atomicMax(reinterpret_cast<int *>(pair_max) + r / rows_per_pair, __float_as_int(v));  // v >= 0: int order = float order
-}
-
-// stage `NT_B` rows x Kp of an f32 row-major matrix as split fp16 in the canonical K-major no-swizzle layout
-// [chunk of 8 k][row][16 B] (SBO = 128 B, LBO = NT_B*16 B); rows >= nrows and k >= D are zero
-__device__ __forceinline__ void stage_rows(const float *src, int row0, int nrows, int D, int Kp, unsigned char *hi,
-                                           unsigned char *lo, int tid)
-{
-    for (int e = tid; e < NT_B * (Kp / 8); e += NT_WORKERS) {
-        const int r = e % NT_B, c = e / NT_B;
-        __half2 h[4], l[4];
-        const bool in = row0 + r < nrows;
-        const float *p = src + (size_t)(row0 + r) * D + c * 8;
+    for (int ch = 0; ch < Kp / 8; ++ch) {
         float v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = (in && c * 8 + k < D) ? __ldg(p + k) : 0.0f;
+        for (int k = 0; k < 8; ++k) v[k] = (in && ch * 8 + k < D) ? __ldg(p + ch * 8 + k) : 0.0f;
+        __half2 h[4], l[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma::split_f16x2(v[2 * k], v[2 * k + 1], h[k], l[k]);
-        *reinterpret_cast<uint4 *>(hi + c * (NT_B * 16) + r * 16) = *reinterpret_cast<uint4 *>(h);
-        *reinterpret_cast<uint4 *>(lo + c * (NT_B * 16) + r * 16) = *reinterpret_cast<uint4 *>(l);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += (double)v[k] * (double)v[k];
+        *reinterpret_cast<uint4 *>(blk + (size_t)ch * (NT_B * 16) + r * 16) = *reinterpret_cast<uint4 *>(h);
+        *reinterpret_cast<uint4 *>(blk + (size_t)Kp * NT_B * 2 + (size_t)ch * (NT_B * 16) + r * 16) = *reinterpret_cast<uint4 *>(l);
     }
+    const float nv = (float)acc;
+    if (in) {
+        if (norm) norm[(size_t)pair * rows_per_pair + row] = nv;
+        if (pair_max) atomicMax(reinterpret_cast<int *>(pair_max) + pair, __float_as_int(nv));  // nv >= 0: int order = float order
+    }
+    if (norm_padded) norm_padded[((size_t)pair * tiles + tile) * NT_B + r] = in ? nv : __int_as_float(0x7f800000);
+}
+
+__device__ __forceinline__ void bulk_g2s(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     umma::smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(umma::smem_u32(mbar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(mbar)), "r"(bytes) : "memory");
 }
 
 __global__ void __launch_bounds__(NT_THREADS) nn_tc_kernel(const NNTcArgs a)
 {
     extern __shared__ __align__(128) unsigned char nsm[];
-    const int opb = a.Kp * NT_B * 2;                 // bytes of one operand half (hi or lo)
-    unsigned char *A_hi = nsm, *A_lo = nsm + opb;
+    const int opb = a.Kp * NT_B * 2;                 // bytes of one operand half (hi or lo); a tile block is 2*opb
+    unsigned char *A_blk = nsm;                      // [hi, lo][opb]
     unsigned char *B_base = nsm + 2 * opb;           // [buf 2][hi, lo][opb]
     float *n0s = reinterpret_cast<float *>(nsm + 6 * opb);   // [2][NT_B]
-    uint64_t *full = reinterpret_cast<uint64_t *>(n0s + 2 * NT_B), *tfull = full + 2, *tempty = full + 4;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(full + 6);
+    uint64_t *full = reinterpret_cast<uint64_t *>(n0s + 2 * NT_B), *tfull = full + 2, *tempty = full + 4, *afull = full + 6;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(full + 7);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int pair = blockIdx.y, j0 = blockIdx.x * NT_B;
-    const float *c0 = a.c0 + (size_t)pair * a.N * a.D;
-    const float *c1 = a.c1 + (size_t)pair * a.M * a.D;
     const float INF = __int_as_float(0x7f800000);
 
     if (warp == 4) umma::tmem_alloc(tmem_slot, 2 * NT_B);
     if (tid == 0) {
         for (int b = 0; b < 2; ++b) {
-            umma::mbar_init(&full[b], NT_WORKERS);
-            umma::mbar_init(&tfull[b], 1);
-            umma::mbar_init(&tempty[b], NT_WORKERS);
+            umma::mbar_init(&full[b], 1);             // producer's expect_tx arrival + the bytes of the bulk copies
+            umma::mbar_init(&tfull[b], 1);            // MMAs of the tile complete (tcgen05.commit)
+            umma::mbar_init(&tempty[b], 128);         // accumulators + norms of the tile consumed by the four scan warps
         }
+        umma::mbar_init(afull, 1);
         umma::fence_mbar_init();
     }
-    if (warp < 4) stage_rows(c1, j0, a.M, a.D, a.Kp, A_hi, A_lo, tid);
-    umma::fence_proxy_async();
     umma::fence_before_thread_sync();
     __syncthreads();
     umma::fence_after_thread_sync();
     const uint32_t tbase = *tmem_slot;
-    const int ntiles = (a.N + NT_B - 1) / NT_B;
+    const int ntiles = a.tiles0;
 
-    if (warp == 4) {
+    if (warp == 5) {
+        // ===== producer: one elected thread streams the operand tiles with bulk copies =====
+        if (umma::elect_one()) {
+            mbar_expect_tx(afull, 2 * opb);
+            bulk_g2s(A_blk, a.ops1 + ((size_t)pair * a.tiles1 + blockIdx.x) * (size_t)(2 * opb), 2 * opb, afull);
+            for (int t = 0; t < ntiles; ++t) {
+                const int b = t & 1, k = t >> 1;
+                if (k >= 1) {   // MMA(t-2) has read the operand buffer, the scan warps have read its norms
+                    umma::mbar_wait(&tfull[b], (uint32_t)((k - 1) & 1));
+                    umma::mbar_wait(&tempty[b], (uint32_t)((k - 1) & 1));
+                }
+                mbar_expect_tx(&full[b], 2 * opb + NT_B * 4);
+                bulk_g2s(B_base + b * 2 * opb, a.ops0 + ((size_t)pair * a.tiles0 + t) * (size_t)(2 * opb), 2 * opb, &full[b]);
+                bulk_g2s(n0s + b * NT_B, a.n0p + ((size_t)pair * a.tiles0 + t) * NT_B, NT_B * 4, &full[b]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 4) {
         const uint32_t idesc = umma::idesc_f16_f32(NT_B, NT_B);
-        const uint32_t sA_hi = umma::smem_u32(A_hi), sA_lo = umma::smem_u32(A_lo), sB = umma::smem_u32(B_base);
+        const uint32_t sA_hi = umma::smem_u32(A_blk), sA_lo = sA_hi + opb, sB = umma::smem_u32(B_base);
+        umma::mbar_wait(afull, 0);
         for (int t = 0; t < ntiles; ++t) {
             const int b = t & 1, k = t >> 1;
             umma::mbar_wait(&full[b], (uint32_t)(k & 1));
@@ -228,23 +258,13 @@ __global__ void __launch_bounds__(NT_THREADS) nn_tc_kernel(const NNTcArgs a)
             __syncwarp();
         }
     } else {
-        const float *n0 = a.n0 + (size_t)pair * a.N;
-        auto stage = [&](int t) {
-            const int b = t & 1;
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // every worker is done reading n0s[b] (tile t-2)
-            stage_rows(c0, t * NT_B, a.N, a.D, a.Kp, B_base + b * 2 * opb, B_base + b * 2 * opb + opb, tid);
-            n0s[b * NT_B + tid] = (t * NT_B + tid < a.N) ? n0[t * NT_B + tid] : INF;
-            umma::fence_proxy_async();
-            umma::mbar_arrive(&full[b]);
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // n0s[b] complete before anyone's epilogue reads it
-        };
+        // ===== scan warps: thread = one frame-1 descriptor (an accumulator row), running (min, second min, argmin) =====
         float best = INF, second = INF;
         int bi = 0x7fffffff;
-        stage(0);
         for (int t = 0; t < ntiles; ++t) {
             const int b = t & 1;
-            if (t + 1 < ntiles) stage(t + 1);   // MMA(t-1) has finished reading that buffer: tfull was waited on last iteration
-            umma::mbar_wait(&tfull[b], (uint32_t)((t >> 1) & 1));
+            umma::mbar_wait(&full[b], (uint32_t)((t >> 1) & 1));    // the tile's norms have landed (bulk copy observed by this thread)
+            umma::mbar_wait(&tfull[b], (uint32_t)((t >> 1) & 1));   // its MMAs are complete
             umma::fence_after_thread_sync();
 #pragma unroll 1
             for (int cc = 0; cc < NT_B; cc += 32) {
@@ -392,18 +412,24 @@ extern "C" int caelo_nn_match(caelo_ctx *ctx, const float *codes0, const float *
     a.n1 = nullptr; a.nmax0 = nullptr;
     const char *force = getenv("CAELO_NN_F32");   // debug switch: float32 CUDA-core pass for every D
     if (D <= 128 && !(force && force[0] == '1')) {
-        float *n1 = reinterpret_cast<float *>(a.best_i + cols), *n0 = n1 + cols, *nmax = n0 + rows0;
+        const int Kp = (D + 15) & ~15, tiles0 = (N + NT_B - 1) / NT_B, tiles1 = (M + NT_B - 1) / NT_B;
+        const size_t blk = (size_t)Kp * NT_B * 4;                     // one tile: hi + lo
+        rc = caelo_reserve(ctx, ctx->match_ops, (size_t)P * (tiles0 + tiles1) * blk + (size_t)P * tiles0 * NT_B * 4 + 256);
+        if (rc) return rc;
+        unsigned char *ops0 = reinterpret_cast<unsigned char *>(ctx->match_ops.ptr), *ops1 = ops0 + (size_t)P * tiles0 * blk;
+        float *n0p = reinterpret_cast<float *>(ops1 + (size_t)P * tiles1 * blk);
+        float *n1 = reinterpret_cast<float *>(a.best_i + cols), *nmax = n1 + cols + rows0;
         CAELO_CUDA(ctx, cudaMemsetAsync(nmax, 0, (size_t)P * 4, st));
-        { ProfScope ps_(ctx, "desc_norm_kernel", st);
-          desc_norm_kernel<<<(unsigned)((rows0 + 255) / 256), 256, 0, st>>>(codes0, N, D, (long long)rows0, n0, nmax);
-          desc_norm_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(codes1, M, D, (long long)cols, n1, nullptr); }
+        { ProfScope ps_(ctx, "desc_prep_kernel", st);
+          desc_prep_kernel<<<dim3(tiles0, P), NT_B, 0, st>>>(codes0, N, D, Kp, tiles0, ops0, nullptr, n0p, nmax);
+          desc_prep_kernel<<<dim3(tiles1, P), NT_B, 0, st>>>(codes1, M, D, Kp, tiles1, ops1, n1, nullptr, nullptr); }
         CAELO_LAUNCH_CHECK(ctx);
         ctx->launches++;
         NNTcArgs t;
-        t.c0 = codes0; t.c1 = codes1; t.n0 = n0; t.n1 = n1; t.N = N; t.M = M; t.D = D; t.Kp = (D + 15) & ~15;
+        t.ops0 = ops0; t.ops1 = ops1; t.n0p = n0p; t.n1 = n1; t.N = N; t.M = M; t.Kp = Kp; t.tiles0 = tiles0; t.tiles1 = tiles1;
         t.best_d = a.best_d; t.second_d = a.second_d; t.best_i = a.best_i;
         { ProfScope ps_(ctx, "nn_tc_kernel", st);
-          nn_tc_kernel<<<dim3((M + NT_B - 1) / NT_B, P), NT_THREADS, nt_smem(t.Kp), st>>>(t); }
+          nn_tc_kernel<<<dim3(tiles1, P), NT_THREADS, nt_smem(t.Kp), st>>>(t); }
         CAELO_LAUNCH_CHECK(ctx);
         a.n1 = n1; a.nmax0 = nmax;
     } else {
