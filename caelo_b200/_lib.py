@@ -58,6 +58,9 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p]),
     "caelo_extend_keypoints": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                                        c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "caelo_nn3": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, ctypes.c_double, c_void_p, c_void_p,
+                          c_void_p]),
+    "caelo_transform_points": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "caelo_debug_set_timeline": (c_int, [c_void_p, c_void_p]),
     "caelo_debug_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_void_p, c_void_p]),

@@ -356,6 +356,25 @@ class Context:
                    "caelo_ransac_draw_samples")
         return out
 
+    def nn3(self, pc0: torch.Tensor, pc1: torch.Tensor, thr: float = 0.0, want_mask: bool = False):
+        """Exact 3-D 1-NN of every pc1 row among pc0 (f4, MyICP.py:33-34) -> idx int64 [M], dist float64 [M],
+        mask uint8 [M] (dist < thr) and count int32 [1] when ``want_mask``."""
+        N, M = pc0.shape[0], pc1.shape[0]
+        assert pc0.dtype == torch.float32 and pc1.dtype == torch.float32 and pc0.is_contiguous() and pc1.is_contiguous()
+        idx = torch.empty((M,), dtype=torch.int64, device=self.device)
+        dist = torch.empty((M,), dtype=torch.float64, device=self.device)
+        mask = torch.empty((M,), dtype=torch.uint8, device=self.device) if want_mask else None
+        count = torch.empty((1,), dtype=torch.int32, device=self.device) if want_mask else None
+        self.check(self.lib.caelo_nn3(self.h, _ptr(pc0), N, _ptr(pc1), M, _ptr(idx), _ptr(dist), float(thr), _ptr(mask),
+                                      _ptr(count), _stream()), "caelo_nn3")
+        return idx, dist, mask, count
+
+    def transform_points(self, rt: torch.Tensor, pc: torch.Tensor):
+        """pc <- R pc + T in place (contract U1); rt dev [12]."""
+        assert rt.dtype == torch.float32 and rt.numel() == 12 and pc.dtype == torch.float32 and pc.is_contiguous()
+        self.check(self.lib.caelo_transform_points(self.h, _ptr(rt), _ptr(pc), pc.shape[0], _stream()),
+                   "caelo_transform_points")
+
     def kabsch(self, pc0, pc1, pair_idx=None, mask=None, skip_if_ok=None, out_rt=None):
         P, N0, _ = pc0.shape
         N = pc1.shape[1]
@@ -667,3 +686,71 @@ def SolveRelativePose(OriPC0, OriCodes0, Weights0, OriPC1, OriCodes1, Weights1):
     rt, _ = ctx.kabsch(pc0, pc1, pair_idx, mask)
     rt = rt.cpu().numpy()[0]
     return rt[:9].reshape(3, 3).copy(), rt[9:].reshape(3, 1).copy(), ok, inliersIdx0, inliersIdx1, thr
+
+
+# ------------------------------------------------------------------------------------------
+# f4: ICP on the extended key points (MyICP.py)
+# ------------------------------------------------------------------------------------------
+RADIAN2DEGREE = 180.0 / np.pi
+
+
+def RotateMat2EulerAngle_XYZ(R):
+    """Transformations.py:181-186 (degrees)."""
+    import math
+    angles = np.zeros((3,))
+    angles[0] = math.atan2(R[2, 1], R[2, 2]) * RADIAN2DEGREE
+    angles[1] = math.atan2(-R[2, 0], math.sqrt(math.pow(R[2, 1], 2) + math.pow(R[2, 2], 2))) * RADIAN2DEGREE
+    angles[2] = math.atan2(R[1, 0], R[0, 0]) * RADIAN2DEGREE
+    return angles
+
+
+def GetPtsInliners(PC0, PC1, inlierThreshold):
+    """MyICP.py:76-85 — nearest PC0 point of every PC1 point, pairs closer than the threshold."""
+    ctx = default_context()
+    p0, p1 = np.ascontiguousarray(PC0, np.float32), np.ascontiguousarray(PC1, np.float32)
+    idx, _dist, mask, _ = ctx.nn3(_dev(p0), _dev(p1), inlierThreshold, want_mask=True)
+    idx1 = mask.cpu().numpy().astype(bool)
+    idx0 = idx.cpu().numpy()[idx1]
+    return PC0[idx0, :], PC1[idx1, :]
+
+
+def ICP(PC0, PC1, maxIterTimes=50, minIterTimes=20 - 1, inlierThreshold=0.5, smallShiftThreshold=0.05, decay_rate=0.9,
+        ep=0.001, info=None):
+    """MyICP.py:28-73, same arguments and return values (R_star (3,3) f64, T_star (3,1) f64, isSuccess) and the
+    same progress line on stdout.  Per iteration the device does the exact 1-NN search (caelo_nn3), SolveRT on the
+    inlier pairs (caelo_kabsch) and the update of PC1 (caelo_transform_points); ONE small D2H (R, T, inlier count)
+    feeds the reference's own loop control here: fewer than 100 inliers -> failure, Euler-angle / translation
+    convergence test after minIterTimes, threshold decay while the step is small."""
+    ctx = default_context()
+    R_star = np.eye(3, dtype=np.float64)
+    T_star = np.zeros((3, 1), dtype=np.float64)
+    pc0 = _dev(np.ascontiguousarray(PC0, np.float32))
+    pc1 = _dev(np.ascontiguousarray(PC1, np.float32)).clone()
+    n_in = 0
+    iIter = -1
+    for iIter in range(maxIterTimes):
+        idx, _dist, mask, count = ctx.nn3(pc0, pc1, inlierThreshold, want_mask=True)
+        rt, _cred = ctx.kabsch(pc0[None], pc1[None], idx[None], mask[None])
+        host = torch.cat([rt[0], count.to(torch.float32)]).cpu().numpy()          # the iteration's one sync
+        n_in = int(host[12])
+        if n_in < 100:
+            print('ICP iters:', iIter + 1, ',  inliers:', n_in, ',  inlierThreshold:', round(inlierThreshold, 5))
+            if info is not None:
+                info.update(iters=iIter + 1, inliers=n_in, threshold=inlierThreshold)
+            return R_star, T_star, False
+        R, T = host[:9].reshape(3, 3).copy(), host[9:12].reshape(3, 1).copy()
+        ctx.transform_points(rt[0], pc1)
+        R_star = np.dot(R, R_star)
+        T_star = np.dot(R, T_star) + T
+        eulers = RotateMat2EulerAngle_XYZ(R)
+        normEulers = np.linalg.norm(eulers)
+        normT = np.linalg.norm(T)
+        if iIter >= minIterTimes:
+            if normEulers < ep and normT < ep:
+                break
+        if normEulers < smallShiftThreshold and normT < smallShiftThreshold:
+            inlierThreshold *= decay_rate
+    print('ICP iters:', iIter + 1, ',  inliers:', n_in, ',  inlierThreshold:', round(inlierThreshold, 5))
+    if info is not None:
+        info.update(iters=iIter + 1, inliers=n_in, threshold=inlierThreshold)
+    return R_star, T_star, True

@@ -21,6 +21,7 @@ SOURCES = {
     "encoder.cu": [],
     "match.cu": [],
     "pose.cu": ["-fmad=false"],
+    "icp.cu": ["-fmad=false"],
     "umma_debug.cu": [],
 }
 

@@ -402,83 +402,89 @@ struct KabschArgs {
     int *credible;  // [P]
 };
 
-// One CTA per problem.  All 256 threads first gather the masked points into shared memory (the gathers through
-// pair_idx are two dependent L2 round trips per point: 4 per thread side by side instead of 32 in a row per lane),
-// then warp 0 runs contract K1 on them: lane l sums points l, l+32, ... sequentially, xor-butterfly across lanes.
+// One CTA per problem.  The points go through shared memory in chunks of KB_CHUNK: all 256 threads gather a chunk
+// (the gathers through pair_idx are two dependent L2 round trips per point: many side by side instead of one after
+// the other per lane), then warp 0 runs contract K1 on it: lane l sums points l, l+32, ... in ascending order
+// (chunk boundaries are multiples of 32, so the order is the same as over the whole array), xor-butterfly across
+// lanes at the end of each of the two passes (means, then H).
 constexpr int KB_THREADS = 256;
+constexpr int KB_CHUNK = 1024;   // 25 KB of static shared memory (the pipeline's N = 1024 key points fit in one chunk)
 
-template <bool kStaged>
 __global__ void __launch_bounds__(KB_THREADS) kabsch_kernel(const KabschArgs a)
 {
-    extern __shared__ float kb_pts[];   // kStaged: [6][N] x0 y0 z0 x1 y1 z1, then N mask bytes
+    __shared__ float kb_pts[6][KB_CHUNK];   // x0 y0 z0 x1 y1 z1
+    __shared__ unsigned char kb_mask[KB_CHUNK];
+    __shared__ double s_mean[6];
+    __shared__ int s_cnt;
     const int lane = threadIdx.x & 31;
     const int pair = blockIdx.x;
     if (a.skip_if_ok && a.skip_if_ok[(size_t)pair * 16 + 12] != 0.0f) return;
     const int N = a.N;
-    unsigned char *kb_mask = reinterpret_cast<unsigned char *>(kb_pts + 6 * (size_t)N);
-    auto fetch_global = [&](int i, float p0[3], float p1[3]) {
-        long long j = a.pair_idx ? a.pair_idx[(size_t)pair * a.N + i] : i;
-        const float *q0 = a.pc0 + ((size_t)pair * a.N0 + j) * 3;
-        const float *q1 = a.pc1 + ((size_t)pair * a.N + i) * 3;
-        p0[0] = q0[0]; p0[1] = q0[1]; p0[2] = q0[2];
-        p1[0] = q1[0]; p1[1] = q1[1]; p1[2] = q1[2];
-    };
-    if (kStaged) {
-        for (int i = threadIdx.x; i < N; i += KB_THREADS) {
+    auto stage = [&](int c0) {
+        __syncthreads();                      // warp 0 is done with the previous chunk
+        for (int e = threadIdx.x; e < KB_CHUNK && c0 + e < N; e += KB_THREADS) {
+            const int i = c0 + e;
             const unsigned char m = a.mask ? a.mask[(size_t)pair * N + i] : 1;
-            kb_mask[i] = m;
+            kb_mask[e] = m;
             if (m) {
-                float p0[3], p1[3];
-                fetch_global(i, p0, p1);
-                kb_pts[i] = p0[0]; kb_pts[N + i] = p0[1]; kb_pts[2 * N + i] = p0[2];
-                kb_pts[3 * N + i] = p1[0]; kb_pts[4 * N + i] = p1[1]; kb_pts[5 * N + i] = p1[2];
+                const long long j = a.pair_idx ? a.pair_idx[(size_t)pair * N + i] : i;
+                const float *q0 = a.pc0 + ((size_t)pair * a.N0 + j) * 3;
+                const float *q1 = a.pc1 + ((size_t)pair * N + i) * 3;
+                kb_pts[0][e] = q0[0]; kb_pts[1][e] = q0[1]; kb_pts[2][e] = q0[2];
+                kb_pts[3][e] = q1[0]; kb_pts[4][e] = q1[1]; kb_pts[5][e] = q1[2];
             }
         }
         __syncthreads();
-    }
-    if (threadIdx.x >= 32) return;
-    auto masked_out = [&](int i) -> bool {
-        return kStaged ? !kb_mask[i] : (a.mask && !a.mask[(size_t)pair * N + i]);
     };
-    auto fetch = [&](int i, float p0[3], float p1[3]) {
-        if (kStaged) {
-            p0[0] = kb_pts[i]; p0[1] = kb_pts[N + i]; p0[2] = kb_pts[2 * N + i];
-            p1[0] = kb_pts[3 * N + i]; p1[1] = kb_pts[4 * N + i]; p1[2] = kb_pts[5 * N + i];
-        } else {
-            fetch_global(i, p0, p1);
-        }
-    };
+    // ---- pass 1: means ----
     double s[6] = {0, 0, 0, 0, 0, 0};
     int cnt = 0;
-    for (int i = lane; i < N; i += 32) {
-        if (masked_out(i)) continue;
-        float p0[3], p1[3];
-        fetch(i, p0, p1);
-        for (int c = 0; c < 3; ++c) { s[c] = s[c] + (double)p0[c]; s[3 + c] = s[3 + c] + (double)p1[c]; }
-        ++cnt;
+    for (int c0 = 0; c0 < N; c0 += KB_CHUNK) {
+        stage(c0);
+        if (threadIdx.x < 32) {
+            const int n = N - c0 < KB_CHUNK ? N - c0 : KB_CHUNK;
+            for (int e = lane; e < n; e += 32) {
+                if (!kb_mask[e]) continue;
+                for (int c = 0; c < 3; ++c) { s[c] = s[c] + (double)kb_pts[c][e]; s[3 + c] = s[3 + c] + (double)kb_pts[3 + c][e]; }
+                ++cnt;
+            }
+        }
     }
+    if (threadIdx.x < 32) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        double m[6];
+        for (int c = 0; c < 6; ++c) m[c] = warp_tree(s[c]);
+        if (lane == 0) {
+            s_cnt = cnt;
+            for (int c = 0; c < 6; ++c) s_mean[c] = cnt ? m[c] / (double)cnt : 0.0;
+        }
+    }
+    __syncthreads();
+    cnt = s_cnt;
     if (cnt == 0) {
-        if (lane < 12) a.rt[(size_t)pair * 12 + lane] = (lane == 0 || lane == 4 || lane == 8) ? 1.0f : 0.0f;
-        if (lane == 0) a.credible[pair] = 0;
+        if (threadIdx.x < 12) a.rt[(size_t)pair * 12 + threadIdx.x] = (threadIdx.x == 0 || threadIdx.x == 4 || threadIdx.x == 8) ? 1.0f : 0.0f;
+        if (threadIdx.x == 0) a.credible[pair] = 0;
         return;
     }
     double m0[3], m1[3];
-    for (int c = 0; c < 3; ++c) {
-        m0[c] = warp_tree(s[c]) / (double)cnt;
-        m1[c] = warp_tree(s[3 + c]) / (double)cnt;
-    }
+    for (int c = 0; c < 3; ++c) { m0[c] = s_mean[c]; m1[c] = s_mean[3 + c]; }
+    // ---- pass 2: H ----
     double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = lane; i < N; i += 32) {
-        if (masked_out(i)) continue;
-        float p0[3], p1[3];
-        fetch(i, p0, p1);
-        double a1[3], a0[3];
-        for (int c = 0; c < 3; ++c) { a1[c] = (double)p1[c] - m1[c]; a0[c] = (double)p0[c] - m0[c]; }
-        for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < 3; ++c) h[r * 3 + c] = h[r * 3 + c] + a1[r] * a0[c];
+    for (int c0 = 0; c0 < N; c0 += KB_CHUNK) {
+        if (N > KB_CHUNK || c0 > 0) stage(c0);      // a single chunk is still in place from pass 1
+        if (threadIdx.x < 32) {
+            const int n = N - c0 < KB_CHUNK ? N - c0 : KB_CHUNK;
+            for (int e = lane; e < n; e += 32) {
+                if (!kb_mask[e]) continue;
+                double a1[3], a0[3];
+                for (int c = 0; c < 3; ++c) { a1[c] = (double)kb_pts[3 + c][e] - m1[c]; a0[c] = (double)kb_pts[c][e] - m0[c]; }
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) h[r * 3 + c] = h[r * 3 + c] + a1[r] * a0[c];
+            }
+        }
     }
+    if (threadIdx.x >= 32) return;
     double H[3][3];
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) H[r][c] = warp_tree(h[r * 3 + c]);
@@ -566,7 +572,6 @@ __global__ void __launch_bounds__(256) draw_samples_kernel(const DrawArgs a)
 int caelo_pose_init(caelo_ctx *ctx)
 {
     CAELO_CUDA(ctx, cudaFuncSetAttribute(hyp_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CAELO_CUDA(ctx, cudaFuncSetAttribute(kabsch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     return CAELO_OK;
 }
 
@@ -635,12 +640,7 @@ extern "C" int caelo_ransac_round(caelo_ctx *ctx, const float *pc0, int N0, cons
 
 static int launch_kabsch(caelo_ctx *ctx, const KabschArgs &a, cudaStream_t st)
 {
-    const size_t smem = (size_t)a.N * 25;
-    {
-        ProfScope ps_(ctx, "kabsch_kernel", st);
-        if (smem <= 160 * 1024) kabsch_kernel<true><<<a.P, KB_THREADS, smem, st>>>(a);
-        else kabsch_kernel<false><<<a.P, KB_THREADS, 0, st>>>(a);
-    }
+    { ProfScope ps_(ctx, "kabsch_kernel", st); kabsch_kernel<<<a.P, KB_THREADS, 0, st>>>(a); }
     CAELO_LAUNCH_CHECK(ctx);
     return CAELO_OK;
 }

@@ -32,6 +32,7 @@ HOT = {
     "Match": {"GetFeaturesFromPatches": api.GetFeaturesFromPatches, "SolveRT": api.SolveRT, "RANSAC4RT": api.RANSAC4RT,
               "SolveRelativePose": api.SolveRelativePose, "LoadVoxelModelAndKeyPts": odometry.LoadVoxelModelAndKeyPts,
               "LoadKeyPtsAndFeatures": odometry.LoadKeyPtsAndFeatures},
+    "MyICP": {"ICP": api.ICP, "GetPtsInliners": api.GetPtsInliners},      # f4 (RefinePoses.py does `from MyICP import *`)
 }
 
 # module-level constants the drivers read after ``from X import *`` (Voxel.py:15-52, SphericalRing.py:28-62, Dirs.py:29-30)
@@ -45,6 +46,7 @@ CONSTANTS = {
     "Match": dict(nFixedKeyPts=api.nFixedKeyPts,
                   strRespondNetModelPath="./TrainedModels/SphericalRingPCRespondLayer.h5",
                   strVoxelPatchEncoderPath="./TrainedModels/EncoderModel4VoxelPatch.h5"),
+    "MyICP": dict(),
 }
 
 
@@ -74,7 +76,7 @@ def install(reference_dir: Optional[str] = None, keras_shim: bool = True):
     if reference_dir:
         sys.path.insert(0, reference_dir)
     try:
-        for name in ("Voxel", "SphericalRing", "Match"):       # dependency order of the reference
+        for name in ("Voxel", "SphericalRing", "Match", "MyICP"):       # dependency order of the reference
             if reference_dir and os.path.isfile(os.path.join(reference_dir, name + ".py")):
                 mod = _load_original(name, reference_dir)
             else:

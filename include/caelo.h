@@ -226,6 +226,16 @@ int caelo_extend_keypoints(caelo_ctx *ctx, const float *ring, int ring_C, int ri
                            const int32_t *n_kpts, int B, int max_kpts, float *ext, int ext_cap,
                            int32_t *n_ext, int zero_counter, void *stream);
 
+/* f4 — the device side of MyICP.py:28-73 `ICP` (one iteration = caelo_nn3, caelo_kabsch on the inliers,
+ * caelo_transform_points; the loop control stays on the host as in the reference).
+ * caelo_nn3: exact 1-nearest neighbour of every pc1 point (dev [M,3] f32) among pc0 (dev [N,3] f32) — what the
+ * reference asks sklearn for (MyICP.py:33-34, :77-78): idx dev int64 [M], dist dev float64 [M] (float64 Euclidean
+ * distance, ties -> lowest index); mask dev uint8 [M] or NULL = dist < thr; count dev int32 [1] or NULL = number of
+ * inliers.  caelo_transform_points: pc <- R pc + T in place (MyICP.py:51), Rt dev [12] (R row-major, T). */
+int caelo_nn3(caelo_ctx *ctx, const float *pc0, int N, const float *pc1, int M, int64_t *idx, double *dist,
+              double thr, uint8_t *mask, int32_t *count, void *stream);
+int caelo_transform_points(caelo_ctx *ctx, const float *Rt, float *pc, int M, void *stream);
+
 /* Debug: device buffer [grid][64][16] int64 (+ [1024][8] for dense) receiving clock64 stamps of the encoder's per-patch
  * phases (NULL disables).  Used by tools/encoder_timeline.py. */
 int caelo_debug_set_timeline(caelo_ctx *ctx, long long *buf);

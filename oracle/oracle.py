@@ -414,3 +414,83 @@ def solve_relative_pose(PC0, Codes0, W0, PC1, Codes1, W1, info=None):
         return R, T, ok, idx0, idx1, thr
     R, T, _ = solve_rt_masked(Pairs0, PC1, mask)  # == SolveRT(PC0[idx0], PC1[idx1]) (Match.py:280-282)
     return R, T, ok, idx0, idx1, thr
+
+
+# ---- f4: ICP on the extended key points (MyICP.py:28-73, 76-85, 127-201) ------------------------------------
+RADIAN2DEGREE = 180.0 / np.pi   # Transformations.py
+
+
+def rotate_mat_to_euler_xyz(R):
+    """RotateMat2EulerAngle_XYZ (Transformations.py:181-186), degrees, float64."""
+    import math
+    a = np.zeros((3,))
+    a[0] = math.atan2(R[2, 1], R[2, 2]) * RADIAN2DEGREE
+    a[1] = math.atan2(-R[2, 0], math.sqrt(math.pow(R[2, 1], 2) + math.pow(R[2, 2], 2))) * RADIAN2DEGREE
+    a[2] = math.atan2(R[1, 0], R[0, 0]) * RADIAN2DEGREE
+    return a
+
+
+def nn3(PC0: np.ndarray, PC1: np.ndarray):
+    """Exact 1-nearest neighbour of every PC1 point among PC0 (what sklearn's kd-tree returns for
+    NearestNeighbors(n_neighbors=1), MyICP.py:33-34), contract N1: float32 inputs widened to float64,
+    d = sqrt(((dx*dx) + (dy*dy)) + (dz*dz)); ties -> lowest PC0 index.  -> (idx int64 [M], dist float64 [M])."""
+    from scipy.spatial import cKDTree
+    p0 = np.ascontiguousarray(PC0, np.float32).astype(np.float64)
+    p1 = np.ascontiguousarray(PC1, np.float32).astype(np.float64)
+    k = min(4, p0.shape[0])
+    _, cand = cKDTree(p0).query(p1, k=k)                     # candidates; the contract arithmetic decides among them
+    cand = cand.reshape(p1.shape[0], k)
+    d = p0[cand] - p1[:, None, :]
+    dk = np.sqrt(((d[..., 0] * d[..., 0]) + (d[..., 1] * d[..., 1])) + (d[..., 2] * d[..., 2]))
+    best = dk.min(axis=1, keepdims=True)
+    idx = np.where(dk == best, cand, np.iinfo(np.int64).max).min(axis=1)   # exact ties -> lowest index
+    dist = best[:, 0]
+    return idx.astype(np.int64), dist
+
+
+def transform_points(R, T, PC):
+    """PC1 = (R PC1^T + T)^T (MyICP.py:51) under contract U1: float64 products and sums in the order
+    ((r0*x + r1*y) + r2*z) + t, one rounding to float32."""
+    R = np.asarray(R, np.float32).astype(np.float64).reshape(3, 3)
+    T = np.asarray(T, np.float32).astype(np.float64).reshape(3)
+    p = np.ascontiguousarray(PC, np.float32).astype(np.float64)
+    out = np.empty(p.shape, np.float64)
+    for a in range(3):
+        out[:, a] = ((R[a, 0] * p[:, 0] + R[a, 1] * p[:, 1]) + R[a, 2] * p[:, 2]) + T[a]
+    return out.astype(np.float32)
+
+
+def icp(PC0, PC1, maxIterTimes=50, minIterTimes=20 - 1, inlierThreshold=0.5, smallShiftThreshold=0.05,
+        decay_rate=0.9, ep=0.001, min_inliers=100, decay_rate1=None, info=None):
+    """ICP (MyICP.py:28-73) restated: per iteration exact 1-NN (N1), inliers dist < threshold, SolveRT on them
+    (K1, summed in original-index lanes like the device refit), PC1 update (U1), R*/T* accumulation in float64,
+    Euler-angle / translation convergence test and threshold decay exactly as the reference's loop.
+    -> (R_star f64 (3,3), T_star f64 (3,1), isSuccess)."""
+    R_star = np.eye(3, dtype=np.float64)
+    T_star = np.zeros((3, 1), dtype=np.float64)
+    PC0 = np.ascontiguousarray(PC0, np.float32)
+    PC1 = np.ascontiguousarray(PC1, np.float32)
+    n_in, it_done = 0, 0
+    for iIter in range(maxIterTimes):
+        idx, dist = nn3(PC0, PC1)
+        mask = dist < inlierThreshold
+        n_in = int(mask.sum())
+        it_done = iIter + 1
+        if n_in < min_inliers:
+            if info is not None:
+                info.update(iters=it_done, inliers=n_in, threshold=inlierThreshold)
+            return R_star, T_star, False
+        R, T, _ = solve_rt_masked(PC0[idx], PC1, mask)
+        PC1 = transform_points(R, T, PC1)
+        R_star = np.dot(R, R_star)
+        T_star = np.dot(R, T_star) + T
+        normEulers = np.linalg.norm(rotate_mat_to_euler_xyz(R))
+        normT = np.linalg.norm(T)
+        if iIter >= minIterTimes:
+            if normEulers < ep and normT < ep:
+                break
+        if normEulers < smallShiftThreshold and normT < smallShiftThreshold:
+            inlierThreshold *= decay_rate
+    if info is not None:
+        info.update(iters=it_done, inliers=n_in, threshold=inlierThreshold)
+    return R_star, T_star, True

@@ -144,3 +144,49 @@ def test_nn_match_microbench_shapes(api, n, d):
     want = cdist(c0.astype(np.float64), c1[cols].astype(np.float64), "euclidean").argmin(axis=0)
     assert np.array_equal(got[cols], want)
     assert (got[noisy] == perm[noisy]).mean() > 0.99
+
+
+# ---- f4: ICP (MyICP.py:28-73) --------------------------------------------------------------------------------
+def test_nn3_transform_bit_exact(api, oracle_mod):
+    import torch
+    ctx = api.default_context()
+    rng = np.random.default_rng(9)
+    p0 = rng.uniform(-60, 60, (5000, 3)).astype(np.float32)
+    p1 = np.r_[p0[:700] + rng.normal(0, 0.05, (700, 3)).astype(np.float32), rng.uniform(-60, 60, (1300, 3)).astype(np.float32)]
+    p0[4000] = p0[10]                                        # duplicate: ties -> lowest index
+    p1[10] = p0[10]
+    idx, dist, mask, count = ctx.nn3(torch.from_numpy(p0).cuda(), torch.from_numpy(p1).cuda(), 0.1, want_mask=True)
+    wi, wd = oracle_mod.nn3(p0, p1)
+    assert np.array_equal(idx.cpu().numpy(), wi) and idx[10].item() == 10
+    assert np.array_equal(dist.cpu().numpy(), wd)            # float64, bit for bit
+    assert np.array_equal(mask.cpu().numpy().astype(bool), wd < 0.1) and int(count.item()) == int((wd < 0.1).sum())
+    rt = np.array([0.99, -0.1, 0.02, 0.1, 0.99, 0.0, -0.02, 0.0, 1.0, 0.5, -0.25, 0.125], np.float32)
+    d1 = torch.from_numpy(p1).cuda()
+    ctx.transform_points(torch.from_numpy(rt).cuda(), d1)
+    assert np.array_equal(d1.cpu().numpy(), oracle_mod.transform_points(rt[:9].reshape(3, 3), rt[9:], p1))
+    i0, i1 = api.GetPtsInliners(p0, p1, 0.1)
+    assert np.array_equal(i0, p0[wi[wd < 0.1]]) and np.array_equal(i1, p1[wd < 0.1])
+
+
+@pytest.mark.parametrize("seq", ["00", "01"])
+def test_icp_matches_oracle_and_reference_run(api, oracle_mod, seq, capsys):
+    """api.ICP on the extended key points of the demo pairs == oracle.icp (same contracts: bit-identical pose,
+    iteration count, inlier count, final threshold) and, within the oracle's own pinned tolerance, the UNMODIFIED
+    reference run (tests/golden/icp_SS.npz)."""
+    import sys
+    import golden_data as G
+    sys.path.insert(0, G.GOLDEN)
+    import make_icp_golden as M
+    z = np.load(os.path.join(G.GOLDEN, "icp_%s.npz" % seq))
+    k0, k1, k1_ = M.icp_inputs(seq)
+    for pc1, kw, tag in ((k1_, dict(inlierThreshold=0.3, smallShiftThreshold=0.1, ep=0.01), "tight"), (k1_, {}, "aligned"),
+                         (k1, {}, "raw")):
+        gi, oi = {}, {}
+        R, T, ok = api.ICP(k0, pc1, info=gi, **kw)
+        Ro, To, oko = oracle_mod.icp(k0, pc1, info=oi, **kw)
+        assert ok == oko and gi == oi, (tag, gi, oi)
+        assert np.array_equal(R, Ro) and np.array_equal(T, To)
+        assert R.dtype == np.float64 and T.shape == (3, 1)
+        if tag == "tight":
+            assert ok and np.abs(R - z["R_tight"]).max() < 1e-5 and np.abs(T - z["T_tight"]).max() < 2e-4
+    assert "ICP iters:" in capsys.readouterr().out          # the reference's progress line

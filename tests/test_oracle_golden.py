@@ -1,6 +1,8 @@
 """Pin the CPU oracle (oracle/) against (i) the reference's own golden vectors in DemoData
 (Features/*.mat: KeyPts + Features) and (ii) outputs of the UNMODIFIED reference functions run
 in the build container (tests/golden/make_golden.py).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 
@@ -157,3 +159,44 @@ def test_voxelization_filter_and_order(oracle_mod):
     assert np.array_equal(v0[:, 0], [5042, 5043, 7492, 7506])
     assert v1.shape[0] == 3 and v2.shape[0] == 2
     assert np.array_equal(loc, v0 - blocks[[0, 0, 1, 1]] * 64)
+
+
+# ---- f4: ICP on the extended key points (MyICP.py:28-73) ------------------------------------------------------
+def _icp_inputs(seq):
+    import sys
+    sys.path.insert(0, G.GOLDEN)
+    import make_icp_golden as M
+    return M.icp_inputs(seq)
+
+
+@pytest.mark.parametrize("seq", ["00", "01"])
+def test_icp_vs_reference_run(oracle_mod, seq):
+    """oracle.icp vs the UNMODIFIED reference MyICP.ICP (sklearn kd-tree + numpy float32 SolveRT) run in the build
+    container (tests/golden/icp_SS.npz).  The well-conditioned case ("tight": the loop ends by convergence) agrees in
+    iteration count and to 1e-5 / 2e-4 in R / T; in the reference's default setting the threshold decays to ~1 cm
+    until fewer than 100 pairs are left and float32 noise decides the last inlier sets — there only the outcome
+    flag and the accumulated pose (1e-4 / 2e-3) are compared."""
+    z = np.load(os.path.join(G.GOLDEN, "icp_%s.npz" % seq))
+    k0, k1, k1_ = _icp_inputs(seq)
+    info = {}
+    R, T, ok = oracle_mod.icp(k0, k1_, inlierThreshold=0.3, smallShiftThreshold=0.1, ep=0.01, info=info)
+    assert ok and bool(z["ok_tight"]) and ("iters: %d " % info["iters"]) in str(z["log_tight"])
+    assert np.abs(R - z["R_tight"]).max() < 1e-5 and np.abs(T - z["T_tight"]).max() < 2e-4
+    R, T, ok = oracle_mod.icp(k0, k1_)
+    assert ok == bool(z["ok_aligned"])
+    assert np.abs(R - z["R_aligned"]).max() < 1e-4 and np.abs(T - z["T_aligned"]).max() < 2e-3
+
+
+def test_nn3_and_transform_contracts(oracle_mod):
+    rng = np.random.default_rng(5)
+    p0 = rng.uniform(-40, 40, (500, 3)).astype(np.float32)
+    p1 = np.r_[p0[:50] + np.float32(0.01), rng.uniform(-40, 40, (70, 3)).astype(np.float32)]
+    p0[77] = p0[3]                                           # duplicate point: ties -> lowest index
+    idx, dist = oracle_mod.nn3(p0, p1)
+    from scipy.spatial.distance import cdist
+    D = cdist(p0.astype(np.float64), p1.astype(np.float64))
+    assert np.array_equal(idx, D.argmin(0)) and np.allclose(dist, D.min(0), rtol=0, atol=1e-12) and idx[3] == 3
+    R = np.array([[0.99, -0.1, 0.02], [0.1, 0.99, 0.0], [-0.02, 0.0, 1.0]], np.float32)
+    T = np.array([[0.5], [-0.25], [0.125]], np.float32)
+    got = oracle_mod.transform_points(R, T, p1)
+    assert got.dtype == np.float32 and np.abs(got - (p1.astype(np.float64) @ R.astype(np.float64).T + T.T.astype(np.float64))).max() < 4e-6
