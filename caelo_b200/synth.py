@@ -23,6 +23,14 @@ VSIZES = [0.02, 0.02 * 8, 0.02 * 32]
 
 
 class World:
+    """A street scene that repeats every ``PERIOD`` metres along the driving direction, so that every frame of an
+    arbitrarily long drive (rank r of an 8-GPU run starts 0.7 * 32 * r metres down the road) sees the same kind of
+    surroundings: ~50 boxes and ~40 poles per tile on a ground plane, side walls along the road and cross walls
+    with a gap for the road where two tiles meet (the upper beams return too: KITTI seq 00 is urban, ~88k of 115k
+    pixels hit)."""
+    W, F, Hh = 58.0, 76.0, 25.0
+    PERIOD = 58.0 + 76.0
+
     def __init__(self, seed: int, n_boxes: int = 50, n_poles: int = 40):
         rng = np.random.default_rng(seed)
         c = rng.uniform(-70, 70, (n_boxes, 2))
@@ -36,15 +44,27 @@ class World:
         cen = np.concatenate([c, pc])
         hal = np.concatenate([half, ph])
         hei = np.concatenate([h, hh])
-        keep = (np.abs(cen[:, 0]) > 8) | (np.abs(cen[:, 1]) > 4)   # keep the road clear
+        keep = (np.abs(cen[:, 0]) > 8) | (np.abs(cen[:, 1]) > 4)   # keep the start of the road clear
+        keep &= np.abs(cen[:, 1]) - hal[:, 1] > 3.0                # ... and the road itself, all along the tile
         lo = np.c_[cen - hal, np.full(len(cen), -1.73)][keep]
         hi = np.c_[cen + hal, hei - 1.73][keep]
-        # far walls so that the upper beams return too (KITTI seq 00 is urban: ~88k of 115k pixels hit)
-        W, F, Hh = 58.0, 76.0, 25.0
-        walls_lo = [[-W - 1, -W, -1.73], [F, -W, -1.73], [-W, -W - 1, -1.73], [-W, W, -1.73]]
-        walls_hi = [[-W, W, Hh], [F + 1, W, Hh], [F, -W, Hh], [F, W + 1, Hh]]
+        W, F, Hh, G = self.W, self.F, self.Hh, 6.0                 # G: half width of the road gap in the cross walls
+        walls_lo = [[F, -W, -1.73], [F, G, -1.73], [-W, -W - 1, -1.73], [-W, W, -1.73]]
+        walls_hi = [[F + 1, -G, Hh], [F + 1, W, Hh], [F, -W, Hh], [F, W + 1, Hh]]
         self.lo = np.concatenate([lo, walls_lo]).astype(np.float32)
         self.hi = np.concatenate([hi, walls_hi]).astype(np.float32)
+
+    def boxes_near(self, x: float, reach: float = 85.0):
+        """Boxes (lo, hi) of the tiles around position x along the road that can be hit within ``reach`` metres."""
+        k0 = int(np.floor((x + self.W) / self.PERIOD))
+        los, his = [], []
+        for k in (k0 - 1, k0, k0 + 1):
+            off = np.array([k * self.PERIOD, 0.0, 0.0], np.float32)
+            lo, hi = self.lo + off, self.hi + off
+            near = (hi[:, 0] > x - reach) & (lo[:, 0] < x + reach)
+            los.append(lo[near])
+            his.append(hi[near])
+        return np.concatenate(los), np.concatenate(his)
 
 
 def _rays():
@@ -74,9 +94,10 @@ def scan(world: World, frame: int, seed: int, step: float = 0.7, yaw_step_deg: f
     t[down] = (-1.73 - pos[2]) / d[down, 2]
     with np.errstate(divide="ignore", invalid="ignore"):
         inv = (1.0 / d).astype(np.float32)
-        for b0 in range(0, world.lo.shape[0], 16):
-            lo = world.lo[b0:b0 + 16][None]
-            hi = world.hi[b0:b0 + 16][None]
+        wlo, whi = world.boxes_near(float(pos[0]))
+        for b0 in range(0, wlo.shape[0], 16):
+            lo = wlo[b0:b0 + 16][None]
+            hi = whi[b0:b0 + 16][None]
             t1 = (lo - pos) * inv[:, None, :]
             t2 = (hi - pos) * inv[:, None, :]
             tn = np.minimum(t1, t2).max(-1)

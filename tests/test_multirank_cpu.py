@@ -103,3 +103,18 @@ def test_draw_samples_matches_global_stream():
     np.random.random((500 * 4,))
     second = pipeline.draw_samples([11], 1024, rounds_done=1)[0]
     assert np.array_equal(second[0], np.array(np.random.random((4,)) * 1024, dtype=np.int32))
+
+
+def test_synthetic_world_does_not_run_out_down_the_road():
+    """bench.py gives rank r the frames [32 r, 32 r + 32] of one long drive: the scene must look the same 5.6 km
+    down the road as at the start (a world that ended after 76 m made rank 3 of a 4-GPU run fail with fewer than
+    496 coarse voxels)."""
+    from caelo_b200 import synth
+    w = synth.World(3)
+    for frame in (0, 224, 8000):
+        pc = synth.scan(w, frame, 11 + frame)
+        assert pc.shape[0] > 60000
+        v0, v1, v2 = synth.voxelize(pc)
+        assert v0.shape[0] > 50000 and v1.shape[0] > 15000 and v2.shape[0] > 3000
+        ring, counter = synth.project_ring(pc)
+        assert (counter[:64, :1792] > 0).sum() > 60000
