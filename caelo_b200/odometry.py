@@ -178,3 +178,120 @@ def estimate_sequence(raw_dir: str, Tr: Optional[np.ndarray] = None, poses_path:
         os.makedirs(os.path.dirname(os.path.abspath(poses_path)), exist_ok=True)
         np.savetxt(poses_path, poses)
     return poses, rel
+
+
+# ---- f4: pose refinement on the extended key points (RefinePoses.py:120-143, 273-334) -------------------------
+def GetRtFromOnePose(pose):
+    """Transformations.py:164-168."""
+    pose = pose.reshape(3, 4)
+    return pose[:, 0:3], pose[:, 3].reshape(3, 1)
+
+
+def GetRelRtBetween2Poses(pose0, pose1):
+    """Transformations.py:106-113 — from pose1 to pose0."""
+    R0, T0 = GetRtFromOnePose(pose0)
+    R0_inv = np.linalg.inv(R0)
+    T0_inv = -np.dot(R0_inv, T0)
+    R1, T1 = GetRtFromOnePose(pose1)
+    return np.dot(R0_inv, R1), np.dot(R0_inv, T1) + T0_inv
+
+
+def GetLidarRelRtBetween2Poses(pose0, pose1, R_Tr, T_Tr, R_Tr_inv, T_Tr_inv):
+    """Transformations.py:118-125 — the same in the LiDAR frame (Tr = velodyne -> camera)."""
+    R0, T0 = GetRtFromOnePose(pose0)
+    R0_inv = np.linalg.inv(R0)
+    T0_inv = -np.dot(R0_inv, T0)
+    R1, T1 = GetRtFromOnePose(pose1)
+    R = np.dot(R_Tr_inv, np.dot(R0_inv, np.dot(R1, R_Tr)))
+    T = np.dot(R_Tr_inv, np.dot(R0_inv, np.dot(R1, T_Tr) + T1) + T0_inv) + T_Tr_inv
+    return R, T
+
+
+def ForwardUpdatePoses(poses, frameNum, newPose, relRs, relTs):
+    """RefinePoses.py:120-143: replace pose ``frameNum`` and re-chain every later pose with the stored relative
+    motions."""
+    poses_, relRs_, relTs_ = poses.copy(), relRs.copy(), relTs.copy()
+    poses_[frameNum, :] = newPose
+    relR, relT = GetRelRtBetween2Poses(poses_[frameNum - 1, :], newPose)
+    relRs_[frameNum - 1, :, :] = relR
+    relTs_[frameNum - 1, :] = relT.reshape(3,)
+    for iFrame in range(frameNum + 1, poses_.shape[0], 1):
+        R0, T0 = GetRtFromOnePose(poses_[iFrame - 1])
+        relativeR = relRs_[iFrame - 1, :, :]
+        relativeT = relTs_[iFrame - 1, :].reshape(3, 1)
+        R = np.dot(R0, relativeR)
+        T = np.dot(R0, relativeT) + T0
+        poses_[iFrame, :] = np.c_[R, T].reshape((1, 12))
+    return poses_, relRs_, relTs_
+
+
+def extended_key_points(scans: Sequence[np.ndarray], batch: int = 16, ctx: Optional[api.Context] = None):
+    """ExtendedKeyPts of every scan (BatchPreprocess.py:136-141: GetKeyPtsByAE on the 3-channel ring, then
+    ExtendKeyPtsInShpericalRing), batched on the device."""
+    ctx = ctx or api.default_context()
+    out = []
+    for b0 in range(0, len(scans), batch):
+        host, off = _stack_scans(scans[b0:b0 + batch])
+        r = ctx.project_ring(host.to(ctx.device), off, want=("ring5", "counter_i32"))
+        _kp, px, n = ctx.select_keypoints(r["ring5"], r["counter_i32"], None, max_kpts=api.nFixedKeyPts)
+        ext, n_ext = ctx.extend_keypoints(r["ring5"], r["counter_i32"], px, n)
+        ne = n_ext.cpu().numpy()
+        out += [ext[j, :int(ne[j])].cpu().numpy() for j in range(ext.shape[0])]
+    return out
+
+
+def RefinementCore(poses, KeyPts0, KeyPts1, iFrame0, iFrame1, relRs, relTs, Tr, inlierThreshold0=0.5):
+    """RefinePoses.py:273-334 for one frame pair: move frame 1's extended key points by the odometry pose, register
+    them against frame 0's with ICP, reject the result if it moves the pose by more than 10 degrees / 5 m, otherwise
+    replace pose ``iFrame1`` and forward-update the rest.  Returns (code, poses, relRs, relTs) with the reference's
+    codes: -1 = ICP failed, 0 = change too large, 1 = refined.
+    The reference calls ICP_Pt2PtAndPt2Plane here with the frames' planar points, which are always empty in the
+    shipped pipeline (SphericalRing.py:219,285) and make that function raise; this is the point-to-point variant the
+    reference keeps commented out next to it (``R_ICP, T_ICP, isSuccess = ICP(KeyPts0, KeyPts1_)``, :297) with the
+    thresholds of the call it replaces."""
+    Tr = np.asarray(Tr, np.float32).reshape(3, 4)
+    R_Tr, T_Tr = GetRtFromOnePose(Tr)
+    R_Tr_inv = np.linalg.inv(R_Tr)
+    T_Tr_inv = -np.dot(R_Tr_inv, T_Tr)
+    pose0, pose1 = poses[iFrame0, :], poses[iFrame1, :]
+    oriRelR, oriRelT = GetLidarRelRtBetween2Poses(pose0, pose1, R_Tr, T_Tr, R_Tr_inv, T_Tr_inv)
+    KeyPts1_ = np.array(((np.dot(oriRelR, KeyPts1.T) + oriRelT).T), dtype=np.float32)
+    R_ICP, T_ICP, isSuccess = api.ICP(KeyPts0, KeyPts1_, maxIterTimes=50, minIterTimes=20 - 1,
+                                      inlierThreshold=inlierThreshold0, decay_rate=0.9, smallShiftThreshold=0.1, ep=0.001)
+    if not isSuccess:
+        return -1, poses.copy(), relRs, relTs
+    relativeR = np.dot(R_ICP, oriRelR)
+    relativeT = np.dot(R_ICP, oriRelT) + T_ICP
+    diffRelEulers = np.linalg.norm(api.RotateMat2EulerAngle_XYZ(oriRelR) - api.RotateMat2EulerAngle_XYZ(relativeR))
+    diffRelT = np.linalg.norm(oriRelT - relativeT)
+    if diffRelEulers > 10 or diffRelT > 5:
+        return 0, poses.copy(), relRs, relTs
+    R0, T0 = GetRtFromOnePose(pose0)
+    R_poseDiff = np.dot(R_Tr, np.dot(relativeR, R_Tr_inv))
+    T_poseDiff = np.dot(R_Tr, np.dot(relativeR, T_Tr_inv) + relativeT) + T_Tr
+    R = np.dot(R0, R_poseDiff)
+    T = np.dot(R0, T_poseDiff) + T0
+    pose1 = np.c_[R, T].reshape((12,))
+    poses_, relRs, relTs = ForwardUpdatePoses(poses, iFrame1, pose1, relRs, relTs)
+    return 1, poses_, relRs, relTs
+
+
+def refine_sequence(scans: Sequence[np.ndarray], poses: np.ndarray, Tr: Optional[np.ndarray] = None,
+                    inlierThreshold0: float = 0.5):
+    """Frame-to-frame refinement of a whole pose file (the iRefineOdometry stage of RefinePoses.py with key frames =
+    consecutive frames): RefinementCore for every pair (i, i+1) on the device-computed extended key points.
+    Returns (poses [F,12] float64, codes [F-1])."""
+    Tr = np.asarray(np.c_[np.eye(3), np.zeros(3)] if Tr is None else Tr, np.float32).reshape(3, 4)
+    poses = np.asarray(poses, np.float64).copy()
+    F = poses.shape[0]
+    relRs = np.zeros((F - 1, 3, 3), np.float64)
+    relTs = np.zeros((F - 1, 3), np.float64)
+    for i in range(F - 1):
+        R, T = GetRelRtBetween2Poses(poses[i], poses[i + 1])
+        relRs[i], relTs[i] = R, T.reshape(3,)
+    ext = extended_key_points(scans)
+    codes = []
+    for i in range(F - 1):
+        code, poses, relRs, relTs = RefinementCore(poses, ext[i], ext[i + 1], i, i + 1, relRs, relTs, Tr, inlierThreshold0)
+        codes.append(code)
+    return poses, np.asarray(codes)

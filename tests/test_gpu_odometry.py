@@ -190,3 +190,83 @@ def test_icp_matches_oracle_and_reference_run(api, oracle_mod, seq, capsys):
         if tag == "tight":
             assert ok and np.abs(R - z["R_tight"]).max() < 1e-5 and np.abs(T - z["T_tight"]).max() < 2e-4
     assert "ICP iters:" in capsys.readouterr().out          # the reference's progress line
+
+
+# ---- accuracy on a drive with known motion + the f4 refinement flow -------------------------------------------
+def _ground_truth(n_frames, step=0.7, yaw_step_deg=0.3):
+    """Absolute sensor poses of synth.scan (x_world = Rz(yaw_f) x_f + pos_f) as [F,12] rows."""
+    out = []
+    for f in range(n_frames):
+        a = np.radians(yaw_step_deg) * f
+        R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+        T = np.array([[step * f], [0.02 * f], [0.0]])
+        out.append(np.c_[R, T].reshape(12))
+    return np.asarray(out)
+
+
+def _pose_errors(poses, gt):
+    """Per-frame relative rotation error (degrees) and translation error (m) of consecutive-frame motions — the
+    RRE / RTE of EvaluationOnRegistration.py:108-130."""
+    from caelo_b200 import odometry
+    rre, rte = [], []
+    for i in range(poses.shape[0] - 1):
+        R, T = odometry.GetRelRtBetween2Poses(poses[i], poses[i + 1])
+        Rg, Tg = odometry.GetRelRtBetween2Poses(gt[i], gt[i + 1])
+        c = np.clip((np.trace(np.dot(Rg.T, R)) - 1) / 2, -1, 1)
+        rre.append(np.degrees(np.arccos(c)))
+        rte.append(np.linalg.norm(T - Tg))
+    return np.asarray(rre), np.asarray(rte)
+
+
+def test_odometry_and_refinement_accuracy_on_known_motion(api, sequence, capsys):
+    """The whole path on a synthetic drive with known motion (0.7 m forward, 0.3 degrees yaw per frame, 2 cm range
+    noise): every pair registers well inside the reference's success criterion (RRE < 1 degree, RTE < 0.5 m,
+    EvaluationOnRegistration.py:23-24); the ICP refinement on the extended key points (RefinePoses.py:273-334)
+    accepts every pair and does not make the trajectory worse."""
+    from caelo_b200 import odometry
+    scans = sequence["scans"]
+    poses, rel = odometry.estimate_sequence(sequence["raw"], scans=scans, batch_pairs=8)
+    assert (rel[:, 12] == 1).all()
+    gt = _ground_truth(len(scans))
+    rre, rte = _pose_errors(poses.astype(np.float64), gt)
+    assert rre.max() < 0.5 and rte.max() < 0.2, (rre, rte)          # the paper's own figure: 0.18 deg / 0.054 +- 0.063 m
+    ext = odometry.extended_key_points(scans)
+    assert all(e.shape[1] == 3 and e.shape[0] > 1024 for e in ext)
+    refined, codes = odometry.refine_sequence(scans, poses)
+    assert (codes == 1).all() and refined.shape == poses.shape
+    rre2, rte2 = _pose_errors(refined, gt)
+    assert rre2.max() < 0.5 and rte2.max() < 0.2 and rte2.mean() <= rte.mean() + 0.01, (rte, rte2)
+    print('RTE odometry %.3f m -> refined %.3f m; RRE %.3f -> %.3f deg' % (rte.mean(), rte2.mean(), rre.mean(), rre2.mean()))
+    assert np.array_equal(refined[0], poses[0].astype(np.float64))          # the first pose is never touched
+    assert "ICP iters:" in capsys.readouterr().out
+
+
+def test_forward_update_and_relative_pose_helpers():
+    """ForwardUpdatePoses / GetRelRtBetween2Poses / GetLidarRelRtBetween2Poses round trips (pure host math)."""
+    from caelo_b200 import odometry, pipeline
+    rng = np.random.default_rng(2)
+    rel = np.zeros((5, 16), np.float32)
+    for i in range(5):
+        a = 0.01 * (i + 1)
+        rel[i, :9] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], np.float32).ravel()
+        rel[i, 9:12] = rng.normal(0, 0.5, 3)
+        rel[i, 12] = 1
+    Tr = np.array([[0, -1, 0, 0.1], [0, 0, -1, -0.2], [1, 0, 0, 0.3]], np.float32)
+    poses = pipeline.chain_poses(rel, Tr).astype(np.float64)
+    R_Tr, T_Tr = odometry.GetRtFromOnePose(Tr.astype(np.float64))
+    R_Tr_inv = np.linalg.inv(R_Tr)
+    T_Tr_inv = -np.dot(R_Tr_inv, T_Tr)
+    for i in range(5):      # the LiDAR-frame relative motion of the chained poses is the relative pose that went in
+        R, T = odometry.GetLidarRelRtBetween2Poses(poses[i], poses[i + 1], R_Tr, T_Tr, R_Tr_inv, T_Tr_inv)
+        assert np.allclose(R, rel[i, :9].reshape(3, 3), atol=1e-5) and np.allclose(T.ravel(), rel[i, 9:12], atol=1e-5)
+    relRs = np.zeros((5, 3, 3)); relTs = np.zeros((5, 3))
+    for i in range(5):
+        R, T = odometry.GetRelRtBetween2Poses(poses[i], poses[i + 1])
+        relRs[i], relTs[i] = R, T.ravel()
+    new2 = poses[2].copy(); new2[3] += 1.0
+    p2, r2, t2 = odometry.ForwardUpdatePoses(poses, 2, new2, relRs, relTs)
+    assert np.array_equal(p2[:2], poses[:2]) and np.array_equal(p2[2], new2)
+    assert np.allclose(r2[2:], relRs[2:]) and np.allclose(t2[2:], relTs[2:])          # later relative motions kept
+    for i in range(2, 5):
+        R, T = odometry.GetRelRtBetween2Poses(p2[i], p2[i + 1])
+        assert np.allclose(R, relRs[i]) and np.allclose(T.ravel(), relTs[i])
