@@ -29,6 +29,19 @@ pipe._collect(pending)
 torch.cuda.synchronize()
 print("wall per step %.3f ms" % ((time.perf_counter() - t_all) / 20 * 1e3))
 for k, v in acc.items(): print("%-8s host %.3f ms (median)" % (k, 1e3 * float(np.median(v))))
+# per-kernel device time inside the streamed steps (H2D of the next batch running underneath) vs isolated steps
+def per_kernel(fn, n):
+    ctx.profile(True); ctx.profile_fetch(); fn(); prof = ctx.profile_fetch(); ctx.profile(False)
+    return {k: v[1] / n for k, v in prof.items()}
+def streamed():
+    for _ in pipe.run_host_stream([batch] * 10): pass
+dev = {k: torch.from_numpy(d[k]).cuda() for k in ("ring3", "counter", "vox")}
+def isolated():
+    for _ in range(10): pipe.run_device(dev["ring3"], dev["counter"], dev["vox"], voff, None, ids)
+a, b = per_kernel(streamed, 10), per_kernel(isolated, 10)
+print("kernel                         streamed  isolated (ms/step)")
+for k in b: print("%-30s %8.4f  %8.4f" % (k, a.get(k, 0), b[k]))
+print("%-30s %8.4f  %8.4f" % ("sum", sum(a.values()), sum(b.values())))
 # finer: the calls inside _enqueue
 import cProfile, pstats
 pr = cProfile.Profile(); pr.enable()
