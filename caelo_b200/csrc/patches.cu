@@ -128,27 +128,52 @@ struct ScanBuildArgs {
     int *status;                 // dev [F] or null
 };
 
-// returns true iff this call set a bit that was clear (a voxel seen for the first time).  Most points of a
-// scan fall into a voxel that is already recorded: plain loads filter those before any atomic is issued.
-__device__ __forceinline__ bool brick_set(const Table &t, const Table &ts, int x, int y, int z)
+// Insert of one voxel, split in two so that a thread can have the first probes of all three scales in flight at
+// once (the tables are far larger than L2: a probe is a DRAM round trip).  brick_probe issues ONE 16-byte load of
+// the home slot {key, ~mask}; brick_set finishes the insert from it and returns true iff this call set a bit that
+// was clear (a voxel seen for the first time).  Most points of a scan fall into a voxel that is already recorded:
+// the loaded slot shows it and no atomic is issued.  (A stale load can only show LESS than the truth — bits are
+// only ever set — and then the atomic's own return value decides.)
+struct Probe {
+    unsigned long long key, bit;
+    unsigned slot;
+    ulonglong2 kv;
+};
+
+__device__ __forceinline__ Probe brick_probe(const Table &t, int x, int y, int z)
 {
-    const unsigned long long key = brick_key(x >> 2, y >> 2, z >> 2);
-    const unsigned long long bit = 1ull << (((x & 3) * 4 + (y & 3)) * 4 + (z & 3));
-    unsigned slot = hash64(key) & t.cap_mask;
+    Probe p;
+    p.key = brick_key(x >> 2, y >> 2, z >> 2);
+    p.bit = 1ull << (((x & 3) * 4 + (y & 3)) * 4 + (z & 3));
+    p.slot = hash64(p.key) & t.cap_mask;
+    p.kv = __ldcg(reinterpret_cast<const ulonglong2 *>(key_of(t, p.slot)));
+    return p;
+}
+
+__device__ __forceinline__ bool brick_set(const Table &t, const Table &ts, int x, int y, int z, const Probe &p)
+{
+    const unsigned long long key = p.key, bit = p.bit;
+    unsigned slot = p.slot;
+    ulonglong2 kv = p.kv;
     while (true) {
-        unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(key_of(t, slot));
+        unsigned long long k = kv.x;
+        bool fresh = false;                      // this thread just claimed the slot: its mask is still empty
         if (k == EMPTY) {
             k = atomicCAS(key_of(t, slot), EMPTY, key);
             if (k == EMPTY) {
                 k = key;
+                fresh = true;
                 super_set(ts, x >> 2, y >> 2, z >> 2);
+            } else {
+                kv.y = ~0ull;                    // someone else took it: nothing known about its mask
             }
         }
         if (k == key) {
-            if (!(*reinterpret_cast<volatile unsigned long long *>(inv_mask_of(t, slot)) & bit)) return false;   // already set
+            if (!fresh && !(kv.y & bit)) return false;   // already set
             return (atomicAnd(inv_mask_of(t, slot), ~bit) & bit) != 0ull;
         }
         slot = (slot + 1) & t.cap_mask;
+        kv = __ldcg(reinterpret_cast<const ulonglong2 *>(key_of(t, slot)));
     }
 }
 
@@ -171,9 +196,11 @@ __global__ void __launch_bounds__(256) scan_brick_insert_kernel(const ScanBuildA
             const int st = voxel_of_point(p.x, p.y, p.z, v);
             bad += st < 0;
             if (st > 0) {
-                n0 = brick_set(t0, s0, v.g0[0], v.g0[1], v.g0[2]);
-                n1 = brick_set(t1, s1, v.g1[0], v.g1[1], v.g1[2]);
-                n2 = brick_set(t2, s2, v.g2[0], v.g2[1], v.g2[2]);
+                const Probe p0 = brick_probe(t0, v.g0[0], v.g0[1], v.g0[2]), p1 = brick_probe(t1, v.g1[0], v.g1[1], v.g1[2]),
+                            p2 = brick_probe(t2, v.g2[0], v.g2[1], v.g2[2]);     // three DRAM round trips side by side
+                n0 = brick_set(t0, s0, v.g0[0], v.g0[1], v.g0[2], p0);
+                n1 = brick_set(t1, s1, v.g1[0], v.g1[1], v.g1[2], p1);
+                n2 = brick_set(t2, s2, v.g2[0], v.g2[1], v.g2[2], p2);
             }
         }
         // warp-aggregated voxel counters (one atomic per warp and scale instead of one per new voxel)
