@@ -7,19 +7,22 @@
 // Input is the 512-byte bit-packed occupancy patch produced by patches.cu (values are exactly
 // {0,1}); max-pool commutes with the monotonic tanh, so tanh is applied after pooling.
 //
-//   conv12_tc_kernel   persistent CTAs (2 per SM).  Per patch: conv1 on CUDA cores as an exact sum of
-//                      selected weights (64-bit neighbourhood windows) + max-pool + tanh, written as
-//                      split fp16 (hi+lo) into a zero-haloed 10^3 x 8ch volume in shared memory;
-//                      conv2 as an IMPLICIT GEMM on tcgen05: for every x-slice (M = 64 positions) and
-//                      tap pair (K = 16) the A operand is a shifted view of that volume described by
-//                      a no-swizzle K-major smem descriptor (SBO = 160 B = one padded y-row, LBO =
-//                      distance between the two taps), B = [W_hi | W_lo] (N = 32) for A_hi and W_hi
-//                      (N = 16) for A_lo, fp32 accumulation in TMEM (double-buffered, 2 x 128 columns);
-//                      epilogue: tcgen05.ld, hi/lo halves added, bias, 2x2x2 max-pool by warp
+//   conv12_tc_kernel   persistent CTAs (2 per SM), warp-specialised: eight PRODUCER warps run conv1 on CUDA
+//                      cores as an exact sum of selected weights (table of partial sums per 3-bit dz pattern,
+//                      eight lanes per non-empty pooled cell) + max-pool + tanh, written as split fp16
+//                      (hi+lo) into a zero-haloed 10^3 x 8ch volume in shared memory; one ISSUER warp runs
+//                      conv2 as an IMPLICIT GEMM on tcgen05: for every x-slice (M = 64 positions) and tap
+//                      pair (K = 16) the A operand is a shifted view of that volume described by a
+//                      no-swizzle K-major smem descriptor (SBO = 160 B = one padded y-row, LBO = distance
+//                      between the two taps), B = [W_hi | W_lo] (N = 32) for A_hi and W_hi (N = 16) for
+//                      A_lo, fp32 accumulation in TMEM (double-buffered, 2 x 128 columns), x-slice pairs
+//                      whose whole neighbourhood is background skipped; four EPILOGUE warps (one per TMEM
+//                      lane quarter): tcgen05.ld, hi/lo halves added, bias, 2x2x2 max-pool by warp
 //                      shuffles (two interleaved M=64 tiles per 32-lane quarter), tanh -> act2.
-//                      One warp issues MMAs; eight warps produce operands / drain accumulators.
-//   conv3_kernel       fp32 CUDA cores (weights in smem) -> act3 [P,2048]
-//   dense_kernel       64-patch tiles: dense1 (register-tiled SGEMM) + tanh + dense2 + tanh
+//   conv3_tc_kernel    one CTA per SM: implicit GEMM over 9 (dy,dz)-shifted compact copies of the 4^3 x 16ch
+//                      input (4 producer warps, issuer warp, 8 epilogue warps) -> act3 as split fp16
+//   dense_tc_kernel    256 patches x 208 outputs x K = 2048 per CTA, operands by TMA (cp.async.bulk.tensor.3d),
+//                      3-stage mbarrier pipeline, epilogue tanh + dense2 (200 -> 20) + tanh in registers
 #include <cuda.h>
 
 #include "common.cuh"
