@@ -754,3 +754,90 @@ def ICP(PC0, PC1, maxIterTimes=50, minIterTimes=20 - 1, inlierThreshold=0.5, sma
     if info is not None:
         info.update(iters=iIter + 1, inliers=n_in, threshold=inlierThreshold)
     return R_star, T_star, True
+
+
+def _nn3_inliers(ctx, pc0_dev, pc1_host, thr):
+    """(idx0 of the inlier pairs, bool mask over pc1) for dist < thr (MyICP.py:77-82)."""
+    idx, _dist, mask, _ = ctx.nn3(pc0_dev, _dev(np.ascontiguousarray(pc1_host, np.float32)), thr, want_mask=True)
+    m = mask.cpu().numpy().astype(bool)
+    return idx.cpu().numpy()[m], m
+
+
+def GetPlanarPtsInliners(PtsWithNorm0, PtsWithNorm1, inlierThreshold0, inlierThreshold1):
+    """MyICP.py:88-113 — nearest frame-0 planar point of every frame-1 planar point (device), then the foot point
+    of the frame-0 point on the frame-1 tangent plane and the point-to-plane gate, evaluated with the reference's
+    own numpy expressions on the host (at most 2000 rows)."""
+    ctx = default_context()
+    PC0, PC1, Norms1 = PtsWithNorm0[:, 0:3], PtsWithNorm1[:, 0:3], PtsWithNorm1[:, 3:6]
+    idx0, idx1 = _nn3_inliers(ctx, _dev(np.ascontiguousarray(PC0, np.float32)), PC1, inlierThreshold1)
+    inliers0 = PC0[idx0, :]
+    inliers1 = PC1[idx1, :]
+    norms1 = Norms1[idx1, :]
+    vetors = inliers0 - inliers1
+    dist2Planes = np.sum(norms1 * vetors, axis=1)
+    pedals = inliers1 + norms1 * np.tile(dist2Planes.reshape(dist2Planes.shape[0], 1), [1, 3])
+    distances = np.linalg.norm((pedals - inliers1), axis=1)
+    idx = (distances < inlierThreshold0).flatten()
+    return pedals[idx, :], inliers1[idx, :]
+
+
+def ICP_Pt2PtAndPt2Plane(PC0, PC1, PtsWithNorm0, PtsWithNorm1, maxIterTimes=50, minIterTimes=20 - 1,
+                         inlierThreshold0=0.5, decay_rate0=0.9, inlierThreshold1=2.0, decay_rate1=0.5,
+                         smallShiftThreshold=0.1, ep=0.01, info=None):
+    """MyICP.py:127-201, same arguments, return values, progress line, use of the global np.random stream (planar
+    points beyond 2000 are subsampled) and in-place update of PtsWithNorm1's coordinates.  The two nearest-neighbour
+    searches, SolveRT on the stacked pairs and the point updates run on the device.  With EMPTY planar arrays — what
+    the shipped pipeline produces — the reference raises (IndexError on the 1-D array); so does this."""
+    ctx = default_context()
+    R_star = np.eye(3, dtype=np.float64)
+    T_star = np.zeros((3, 1), dtype=np.float64)
+    nMaxPts = 2000
+    if PtsWithNorm1.shape[0] > nMaxPts:
+        RandIdxes = np.random.random((nMaxPts,))
+        RandIdxes = RandIdxes * (PtsWithNorm1.shape[0])
+        RandIdxes = np.array(RandIdxes, dtype=np.int32)
+        PtsWithNorm1 = PtsWithNorm1[RandIdxes, :]
+    PtsWithNorm0[:, 0:3], PtsWithNorm1[:, 0:3]           # raises like the reference on the empty 1-D arrays
+    pc0_host = np.ascontiguousarray(PC0, np.float32)
+    pc0 = _dev(pc0_host)
+    pc1 = _dev(np.ascontiguousarray(PC1, np.float32)).clone()
+    isSuccess = True
+    minNumOfInputPts = 200
+    n_pts = n_pl = 0
+    iIter = -1
+    for iIter in range(maxIterTimes):
+        idx, _dist, mask, _ = ctx.nn3(pc0, pc1, inlierThreshold0, want_mask=True)
+        m = mask.cpu().numpy().astype(bool)
+        pc1_host = pc1.cpu().numpy()
+        inliers0_pts, inliers1_pts = pc0_host[idx.cpu().numpy()[m], :], pc1_host[m, :]
+        inliers0_planarPts, inliers1_planarPts = GetPlanarPtsInliners(PtsWithNorm0, PtsWithNorm1, inlierThreshold0,
+                                                                      inlierThreshold1)
+        n_pts, n_pl = inliers0_pts.shape[0], inliers0_planarPts.shape[0]
+        inliers0 = np.r_[inliers0_pts, inliers0_planarPts]
+        inliers1 = np.r_[inliers1_pts, inliers1_planarPts]
+        if inliers0.shape[0] < minNumOfInputPts:
+            if iIter < 1:
+                isSuccess = False
+            break
+        R, T, _isCredible = SolveRT(inliers0, inliers1)
+        rt = _dev(np.r_[R.ravel(), T.ravel()].astype(np.float32))
+        ctx.transform_points(rt, pc1)
+        pl = _dev(np.ascontiguousarray(PtsWithNorm1[:, 0:3], np.float32))
+        ctx.transform_points(rt, pl)
+        PtsWithNorm1[:, 0:3] = pl.cpu().numpy()
+        R_star = np.dot(R, R_star)
+        T_star = np.dot(R, T_star) + T
+        eulers = RotateMat2EulerAngle_XYZ(R)
+        normEulers = np.linalg.norm(eulers)
+        normT = np.linalg.norm(T)
+        if iIter >= minIterTimes:
+            if normEulers < ep and normT < ep:
+                break
+        if normEulers < smallShiftThreshold and normT < smallShiftThreshold:
+            inlierThreshold0 *= decay_rate0
+            inlierThreshold1 *= decay_rate1
+    print('ICP iters:', iIter + 1, ', inliers0:', n_pts, ', inliers1:', n_pl,
+          ', th0:', round(inlierThreshold0, 5), ', th1:', round(inlierThreshold1, 5))
+    if info is not None:
+        info.update(iters=iIter + 1, inliers0=n_pts, inliers1=n_pl, th0=inlierThreshold0, th1=inlierThreshold1)
+    return R_star, T_star, isSuccess

@@ -32,7 +32,8 @@ HOT = {
     "Match": {"GetFeaturesFromPatches": api.GetFeaturesFromPatches, "SolveRT": api.SolveRT, "RANSAC4RT": api.RANSAC4RT,
               "SolveRelativePose": api.SolveRelativePose, "LoadVoxelModelAndKeyPts": odometry.LoadVoxelModelAndKeyPts,
               "LoadKeyPtsAndFeatures": odometry.LoadKeyPtsAndFeatures},
-    "MyICP": {"ICP": api.ICP, "GetPtsInliners": api.GetPtsInliners},      # f4 (RefinePoses.py does `from MyICP import *`)
+    "MyICP": {"ICP": api.ICP, "GetPtsInliners": api.GetPtsInliners, "GetPlanarPtsInliners": api.GetPlanarPtsInliners,
+              "ICP_Pt2PtAndPt2Plane": api.ICP_Pt2PtAndPt2Plane},      # f4 (RefinePoses.py does `from MyICP import *`)
 }
 
 # module-level constants the drivers read after ``from X import *`` (Voxel.py:15-52, SphericalRing.py:28-62, Dirs.py:29-30)

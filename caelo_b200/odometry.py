@@ -240,15 +240,17 @@ def extended_key_points(scans: Sequence[np.ndarray], batch: int = 16, ctx: Optio
     return out
 
 
-def RefinementCore(poses, KeyPts0, KeyPts1, iFrame0, iFrame1, relRs, relTs, Tr, inlierThreshold0=0.5):
+def RefinementCore(poses, KeyPts0, KeyPts1, iFrame0, iFrame1, relRs, relTs, Tr, inlierThreshold0=0.5,
+                   PlanarPts0=None, PlanarPts1=None):
     """RefinePoses.py:273-334 for one frame pair: move frame 1's extended key points by the odometry pose, register
     them against frame 0's with ICP, reject the result if it moves the pose by more than 10 degrees / 5 m, otherwise
     replace pose ``iFrame1`` and forward-update the rest.  Returns (code, poses, relRs, relTs) with the reference's
     codes: -1 = ICP failed, 0 = change too large, 1 = refined.
-    The reference calls ICP_Pt2PtAndPt2Plane here with the frames' planar points, which are always empty in the
-    shipped pipeline (SphericalRing.py:219,285) and make that function raise; this is the point-to-point variant the
-    reference keeps commented out next to it (``R_ICP, T_ICP, isSuccess = ICP(KeyPts0, KeyPts1_)``, :297) with the
-    thresholds of the call it replaces."""
+    With planar points (N x 6: point + normal) the reference's call is made: ICP_Pt2PtAndPt2Plane with frame 1's
+    planar coordinates moved by the odometry pose as well (:289-296).  The shipped pipeline never produces planar
+    points (SphericalRing.py:219,285: always empty, and the reference's call raises on them); without them this is
+    the point-to-point variant the reference keeps commented out next to it (``R_ICP, T_ICP, isSuccess =
+    ICP(KeyPts0, KeyPts1_)``, :297) with the thresholds of the call it replaces."""
     Tr = np.asarray(Tr, np.float32).reshape(3, 4)
     R_Tr, T_Tr = GetRtFromOnePose(Tr)
     R_Tr_inv = np.linalg.inv(R_Tr)
@@ -256,8 +258,18 @@ def RefinementCore(poses, KeyPts0, KeyPts1, iFrame0, iFrame1, relRs, relTs, Tr, 
     pose0, pose1 = poses[iFrame0, :], poses[iFrame1, :]
     oriRelR, oriRelT = GetLidarRelRtBetween2Poses(pose0, pose1, R_Tr, T_Tr, R_Tr_inv, T_Tr_inv)
     KeyPts1_ = np.array(((np.dot(oriRelR, KeyPts1.T) + oriRelT).T), dtype=np.float32)
-    R_ICP, T_ICP, isSuccess = api.ICP(KeyPts0, KeyPts1_, maxIterTimes=50, minIterTimes=20 - 1,
-                                      inlierThreshold=inlierThreshold0, decay_rate=0.9, smallShiftThreshold=0.1, ep=0.001)
+    if PlanarPts0 is not None and PlanarPts1 is not None and PlanarPts0.ndim == 2 and PlanarPts1.ndim == 2 \
+            and PlanarPts0.shape[0] and PlanarPts1.shape[0]:
+        PlanarPts1_ = PlanarPts1.copy()
+        PlanarPts1_[:, 0:3] = np.array(((np.dot(oriRelR, PlanarPts1[:, 0:3].T) + oriRelT).T), dtype=np.float32)
+        R_ICP, T_ICP, isSuccess = api.ICP_Pt2PtAndPt2Plane(KeyPts0, KeyPts1_, PlanarPts0, PlanarPts1_, maxIterTimes=50,
+                                                           minIterTimes=20 - 1, inlierThreshold0=inlierThreshold0,
+                                                           decay_rate0=0.9, inlierThreshold1=5.0, decay_rate1=0.9,
+                                                           smallShiftThreshold=0.1, ep=0.001)
+    else:
+        R_ICP, T_ICP, isSuccess = api.ICP(KeyPts0, KeyPts1_, maxIterTimes=50, minIterTimes=20 - 1,
+                                          inlierThreshold=inlierThreshold0, decay_rate=0.9, smallShiftThreshold=0.1,
+                                          ep=0.001)
     if not isSuccess:
         return -1, poses.copy(), relRs, relTs
     relativeR = np.dot(R_ICP, oriRelR)

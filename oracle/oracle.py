@@ -494,3 +494,79 @@ def icp(PC0, PC1, maxIterTimes=50, minIterTimes=20 - 1, inlierThreshold=0.5, sma
     if info is not None:
         info.update(iters=it_done, inliers=n_in, threshold=inlierThreshold)
     return R_star, T_star, True
+
+
+def get_pts_inliers(PC0, PC1, inlierThreshold):
+    """GetPtsInliners (MyICP.py:76-85)."""
+    idx, dist = nn3(PC0, PC1)
+    m = dist < inlierThreshold
+    return PC0[idx[m], :], PC1[m, :]
+
+
+def planar_pedals(inliers0, inliers1, norms1):
+    """The point-to-plane part of GetPlanarPtsInliners (MyICP.py:103-109) exactly as numpy evaluates it on the
+    input dtype: foot points of frame-0 points on the frame-1 tangent planes, and their distance to the plane point."""
+    vetors = inliers0 - inliers1
+    dist2Planes = np.sum(norms1 * vetors, axis=1)
+    pedals = inliers1 + norms1 * np.tile(dist2Planes.reshape(dist2Planes.shape[0], 1), [1, 3])
+    distances = np.linalg.norm((pedals - inliers1), axis=1)
+    return pedals, distances
+
+
+def get_planar_pts_inliers(PtsWithNorm0, PtsWithNorm1, inlierThreshold0, inlierThreshold1):
+    """GetPlanarPtsInliners (MyICP.py:88-113)."""
+    PC0, PC1, Norms1 = PtsWithNorm0[:, 0:3], PtsWithNorm1[:, 0:3], PtsWithNorm1[:, 3:6]
+    idx, dist = nn3(PC0, PC1)
+    m = dist < inlierThreshold1
+    inliers0, inliers1 = PC0[idx[m], :], PC1[m, :]
+    pedals, distances = planar_pedals(inliers0, inliers1, Norms1[m, :])
+    keep = (distances < inlierThreshold0).flatten()
+    return pedals[keep, :], inliers1[keep, :]
+
+
+def icp_pt2pt_and_pt2plane(PC0, PC1, PtsWithNorm0, PtsWithNorm1, maxIterTimes=50, minIterTimes=20 - 1,
+                           inlierThreshold0=0.5, decay_rate0=0.9, inlierThreshold1=2.0, decay_rate1=0.5,
+                           smallShiftThreshold=0.1, ep=0.01, info=None):
+    """ICP_Pt2PtAndPt2Plane (MyICP.py:127-201) restated: point pairs + planar foot-point pairs stacked into one
+    SolveRT per iteration; more than 2000 planar points are subsampled from the global np.random stream (:135-139);
+    PtsWithNorm1's coordinates are updated IN PLACE (its normals are not rotated), as the reference does."""
+    R_star = np.eye(3, dtype=np.float64)
+    T_star = np.zeros((3, 1), dtype=np.float64)
+    PC0 = np.ascontiguousarray(PC0, np.float32)
+    PC1 = np.ascontiguousarray(PC1, np.float32)
+    nMaxPts = 2000
+    if PtsWithNorm1.shape[0] > nMaxPts:
+        RandIdxes = np.random.random((nMaxPts,))
+        RandIdxes = RandIdxes * (PtsWithNorm1.shape[0])
+        RandIdxes = np.array(RandIdxes, dtype=np.int32)
+        PtsWithNorm1 = PtsWithNorm1[RandIdxes, :]
+    isSuccess = True
+    n_pts = n_pl = 0
+    it_done = 0
+    for iIter in range(maxIterTimes):
+        it_done = iIter + 1
+        in0_pts, in1_pts = get_pts_inliers(PC0, PC1, inlierThreshold0)
+        in0_pl, in1_pl = get_planar_pts_inliers(PtsWithNorm0, PtsWithNorm1, inlierThreshold0, inlierThreshold1)
+        n_pts, n_pl = in0_pts.shape[0], in0_pl.shape[0]
+        inliers0 = np.r_[in0_pts, in0_pl]
+        inliers1 = np.r_[in1_pts, in1_pl]
+        if inliers0.shape[0] < 200:
+            if iIter < 1:
+                isSuccess = False
+            break
+        R, T, _ = solve_rt(inliers0, inliers1)
+        PC1 = transform_points(R, T, PC1)
+        PtsWithNorm1[:, 0:3] = transform_points(R, T, PtsWithNorm1[:, 0:3])
+        R_star = np.dot(R, R_star)
+        T_star = np.dot(R, T_star) + T
+        normEulers = np.linalg.norm(rotate_mat_to_euler_xyz(R))
+        normT = np.linalg.norm(T)
+        if iIter >= minIterTimes:
+            if normEulers < ep and normT < ep:
+                break
+        if normEulers < smallShiftThreshold and normT < smallShiftThreshold:
+            inlierThreshold0 *= decay_rate0
+            inlierThreshold1 *= decay_rate1
+    if info is not None:
+        info.update(iters=it_done, inliers0=n_pts, inliers1=n_pl, th0=inlierThreshold0, th1=inlierThreshold1)
+    return R_star, T_star, isSuccess

@@ -40,6 +40,18 @@ def icp_inputs(seq):
     return k0, k1, k1_
 
 
+def planar_inputs(k, n_max=3000):
+    """A deterministic stand-in for the planar points the shipped pipeline never produces (SphericalRing.py:219):
+    every 4th extended key point with a plausible unit normal — up for ground points, towards the sensor otherwise."""
+    p = k[::4][:n_max].astype(np.float32)
+    n = np.zeros_like(p)
+    ground = p[:, 2] < -1.3
+    n[ground, 2] = 1.0
+    h = -p[~ground, 0:2]
+    n[~ground, 0:2] = h / np.linalg.norm(h, axis=1, keepdims=True)
+    return np.ascontiguousarray(np.c_[p, n].astype(np.float32))
+
+
 def main():
     reference_stub.load()
     sys.path.insert(0, reference_stub.REFERENCE_DIR)
@@ -54,6 +66,19 @@ def main():
             out["R_" + name], out["T_" + name], out["ok_" + name] = R, T, ok
             out["log_" + name] = buf.getvalue().strip()
             print(seq, name, k0.shape, pc1.shape, ok, buf.getvalue().strip())
+        # ICP_Pt2PtAndPt2Plane (MyICP.py:127-201) with the arguments of RefinementCore (RefinePoses.py:293-296);
+        # frame 1's planar coordinates are moved by the odometry pose like its key points (:289-290)
+        pl0, pl1 = planar_inputs(k0), planar_inputs(k1)
+        p = G.pose(seq)
+        pl1[:, 0:3] = np.array((np.dot(p["R_0"], pl1[:, 0:3].T) + p["T_0"].reshape(3, 1)).T, dtype=np.float32)
+        np.random.seed(7)
+        with contextlib.redirect_stdout(io.StringIO()) as buf:
+            R, T, ok = MyICP.ICP_Pt2PtAndPt2Plane(k0.copy(), k1_.copy(), pl0.copy(), pl1.copy(), maxIterTimes=50,
+                                                  minIterTimes=20 - 1, inlierThreshold0=0.5, decay_rate0=0.9,
+                                                  inlierThreshold1=5.0, decay_rate1=0.9, smallShiftThreshold=0.1, ep=0.001)
+        out["R_plane"], out["T_plane"], out["ok_plane"], out["log_plane"] = R, T, ok, buf.getvalue().strip()
+        out["next_random_plane"] = np.random.random()
+        print(seq, "plane", pl0.shape, pl1.shape, ok, buf.getvalue().strip())
         np.savez_compressed(os.path.join(HERE, "icp_%s.npz" % seq), **out)
 
 

@@ -30,7 +30,7 @@ assert GetKeyPtsByAE is api.GetKeyPtsByAE and GetKeyPtsFromRawFileName is api.Ge
 assert ExtendKeyPtsInShpericalRing is api.ExtendKeyPtsInShpericalRing
 assert LoadVoxelModelAndKeyPts is odometry.LoadVoxelModelAndKeyPts
 from MyICP import *
-assert ICP is api.ICP and GetPtsInliners is api.GetPtsInliners
+assert ICP is api.ICP and GetPtsInliners is api.GetPtsInliners and ICP_Pt2PtAndPt2Plane is api.ICP_Pt2PtAndPt2Plane
 assert (nLines, ImgH, ImgW, CropWidth_SphericalRing, Channels4AE) == (64, 69, 1800, 8, [0, 1, 2])
 assert abs(VisibleLength - 99.84) < 1e-12 and VoxelSizes == [0.02, 0.16, 0.64] and PatchSize == 16
 assert strVoxelPatchEncoderPath.endswith('EncoderModel4VoxelPatch.h5')
@@ -60,7 +60,7 @@ assert Match.SolveRelativePose is api.SolveRelativePose and Match.GetPatchesList
 assert SphericalRing.GetKeyPtsByAE is api.GetKeyPtsByAE and SphericalRing.Voxelization is api.Voxelization
 assert Voxel.GetPatchesList is api.GetPatchesList
 import MyICP
-assert MyICP.ICP is api.ICP and MyICP.SolveRT is api.SolveRT and callable(MyICP.ICP_Pt2PtAndPt2Plane)
+assert MyICP.ICP is api.ICP and MyICP.SolveRT is api.SolveRT and MyICP.ICP_Pt2PtAndPt2Plane is api.ICP_Pt2PtAndPt2Plane
 # untouched helpers of the reference are still the reference's
 assert Match.GetKeyVoxelsAroundKeyPts.__module__ == 'Match' and callable(SphericalRing.LocateKeyPixels)
 assert Voxel.nBlocksL == 156 and SphericalRing.ImgW == 1800

@@ -270,3 +270,33 @@ def test_forward_update_and_relative_pose_helpers():
     for i in range(2, 5):
         R, T = odometry.GetRelRtBetween2Poses(p2[i], p2[i + 1])
         assert np.allclose(R, relRs[i]) and np.allclose(T.ravel(), relTs[i])
+
+
+@pytest.mark.parametrize("seq", ["00", "01"])
+def test_icp_pt2plane_matches_oracle(api, oracle_mod, seq, capsys):
+    """api.ICP_Pt2PtAndPt2Plane / GetPlanarPtsInliners == the oracle restatement (bit-identical pose, counts,
+    thresholds, np.random position, in-place side effect) with RefinementCore's arguments; empty planar arrays raise
+    as in the reference."""
+    import sys
+    import golden_data as G
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_oracle_golden import _plane_inputs, PLANE_KW
+    k0, k1_, pl0, pl1 = _plane_inputs(seq)
+    a, b = api.GetPlanarPtsInliners(pl0, pl1[:1500], 0.5, 5.0)
+    ao, bo = oracle_mod.get_planar_pts_inliers(pl0, pl1[:1500], 0.5, 5.0)
+    assert np.array_equal(a, ao) and np.array_equal(b, bo) and a.shape[0] > 100
+    gi, oi = {}, {}
+    np.random.seed(7)
+    R, T, ok = api.ICP_Pt2PtAndPt2Plane(k0, k1_, pl0, pl1.copy(), info=gi, **PLANE_KW)
+    r_after = np.random.random()
+    np.random.seed(7)
+    Ro, To, oko = oracle_mod.icp_pt2pt_and_pt2plane(k0, k1_, pl0, pl1.copy(), info=oi, **PLANE_KW)
+    assert r_after == np.random.random() and ok == oko and gi == oi, (gi, oi)
+    assert np.array_equal(R, Ro) and np.array_equal(T, To)
+    s1, s2 = pl1[:800].copy(), pl1[:800].copy()
+    api.ICP_Pt2PtAndPt2Plane(k0, k1_, pl0, s1, **PLANE_KW)
+    oracle_mod.icp_pt2pt_and_pt2plane(k0, k1_, pl0, s2, **PLANE_KW)
+    assert np.array_equal(s1, s2) and not np.array_equal(s1, pl1[:800])
+    assert "inliers0:" in capsys.readouterr().out
+    with pytest.raises(IndexError):                    # what the shipped pipeline hands over (SphericalRing.py:219)
+        api.ICP_Pt2PtAndPt2Plane(k0, k1_, np.array([], np.float32), np.array([], np.float32))

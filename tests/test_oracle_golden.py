@@ -200,3 +200,45 @@ def test_nn3_and_transform_contracts(oracle_mod):
     T = np.array([[0.5], [-0.25], [0.125]], np.float32)
     got = oracle_mod.transform_points(R, T, p1)
     assert got.dtype == np.float32 and np.abs(got - (p1.astype(np.float64) @ R.astype(np.float64).T + T.T.astype(np.float64))).max() < 4e-6
+
+
+def _plane_inputs(seq):
+    import sys
+    sys.path.insert(0, G.GOLDEN)
+    import make_icp_golden as M
+    k0, k1, k1_ = M.icp_inputs(seq)
+    pl0, pl1 = M.planar_inputs(k0), M.planar_inputs(k1)
+    p = G.pose(seq)
+    pl1[:, 0:3] = np.array((np.dot(p["R_0"], pl1[:, 0:3].T) + p["T_0"].reshape(3, 1)).T, dtype=np.float32)
+    return k0, k1_, pl0, pl1
+
+
+PLANE_KW = dict(maxIterTimes=50, minIterTimes=20 - 1, inlierThreshold0=0.5, decay_rate0=0.9, inlierThreshold1=5.0,
+                decay_rate1=0.9, smallShiftThreshold=0.1, ep=0.001)       # RefinePoses.py:293-296
+
+
+@pytest.mark.parametrize("seq", ["00", "01"])
+def test_icp_pt2plane_vs_reference_run(oracle_mod, seq):
+    """oracle.icp_pt2pt_and_pt2plane vs the UNMODIFIED reference ICP_Pt2PtAndPt2Plane (MyICP.py:127-201) with
+    RefinementCore's arguments on the demo pairs (planar points: tests/golden/make_icp_golden.planar_inputs, more
+    than 2000 of them so that the np.random subsampling is exercised).  Pair 00: same iteration count, inlier
+    counts and thresholds, pose to 1e-6 / 2e-5; pair 01 ends one iteration apart in the ~1 cm tail (see
+    test_icp_vs_reference_run) — flag and pose only.  The global np.random stream ends at the same position."""
+    z = np.load(os.path.join(G.GOLDEN, "icp_%s.npz" % seq))
+    k0, k1_, pl0, pl1 = _plane_inputs(seq)
+    before = pl1.copy()
+    np.random.seed(7)
+    info = {}
+    R, T, ok = oracle_mod.icp_pt2pt_and_pt2plane(k0, k1_, pl0, pl1, info=info, **PLANE_KW)
+    assert np.random.random() == float(z["next_random_plane"])
+    assert ok == bool(z["ok_plane"]) and np.array_equal(pl1, before)        # > 2000 rows: the caller's array is not touched
+    if seq == "00":
+        want = "ICP iters: %d , inliers0: %d , inliers1: %d , th0: %s , th1: %s" % (
+            info["iters"], info["inliers0"], info["inliers1"], round(info["th0"], 5), round(info["th1"], 5))
+        assert want == str(z["log_plane"])
+        assert np.abs(R - z["R_plane"]).max() < 1e-6 and np.abs(T - z["T_plane"]).max() < 2e-5
+    else:
+        assert np.abs(R - z["R_plane"]).max() < 1e-4 and np.abs(T - z["T_plane"]).max() < 2e-3
+    small = pl1[:500].copy()                                                 # <= 2000 rows: updated in place, normals untouched
+    oracle_mod.icp_pt2pt_and_pt2plane(k0, k1_, pl0, small, **PLANE_KW)
+    assert not np.array_equal(small[:, 0:3], pl1[:500, 0:3]) and np.array_equal(small[:, 3:6], pl1[:500, 3:6])
