@@ -163,7 +163,9 @@ def make_frames(n_frames: int, seed: int = 0, first_frame: int = 0):
     npts = []
     from concurrent.futures import ThreadPoolExecutor
     import os
-    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+    # one generator per rank runs at the same time on the box: share the host cores
+    n_ranks = max(1, int(os.environ.get("WORLD_SIZE", "1")))
+    with ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 1) // n_ranks))) as ex:
         scans = list(ex.map(lambda f: scan(world, first_frame + f, seed * 100003 + first_frame + f),
                             range(n_frames)))
     for f in range(n_frames):

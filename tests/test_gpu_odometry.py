@@ -241,37 +241,6 @@ def test_odometry_and_refinement_accuracy_on_known_motion(api, sequence, capsys)
     assert "ICP iters:" in capsys.readouterr().out
 
 
-def test_forward_update_and_relative_pose_helpers():
-    """ForwardUpdatePoses / GetRelRtBetween2Poses / GetLidarRelRtBetween2Poses round trips (pure host math)."""
-    from caelo_b200 import odometry, pipeline
-    rng = np.random.default_rng(2)
-    rel = np.zeros((5, 16), np.float32)
-    for i in range(5):
-        a = 0.01 * (i + 1)
-        rel[i, :9] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], np.float32).ravel()
-        rel[i, 9:12] = rng.normal(0, 0.5, 3)
-        rel[i, 12] = 1
-    Tr = np.array([[0, -1, 0, 0.1], [0, 0, -1, -0.2], [1, 0, 0, 0.3]], np.float32)
-    poses = pipeline.chain_poses(rel, Tr).astype(np.float64)
-    R_Tr, T_Tr = odometry.GetRtFromOnePose(Tr.astype(np.float64))
-    R_Tr_inv = np.linalg.inv(R_Tr)
-    T_Tr_inv = -np.dot(R_Tr_inv, T_Tr)
-    for i in range(5):      # the LiDAR-frame relative motion of the chained poses is the relative pose that went in
-        R, T = odometry.GetLidarRelRtBetween2Poses(poses[i], poses[i + 1], R_Tr, T_Tr, R_Tr_inv, T_Tr_inv)
-        assert np.allclose(R, rel[i, :9].reshape(3, 3), atol=1e-5) and np.allclose(T.ravel(), rel[i, 9:12], atol=1e-5)
-    relRs = np.zeros((5, 3, 3)); relTs = np.zeros((5, 3))
-    for i in range(5):
-        R, T = odometry.GetRelRtBetween2Poses(poses[i], poses[i + 1])
-        relRs[i], relTs[i] = R, T.ravel()
-    new2 = poses[2].copy(); new2[3] += 1.0
-    p2, r2, t2 = odometry.ForwardUpdatePoses(poses, 2, new2, relRs, relTs)
-    assert np.array_equal(p2[:2], poses[:2]) and np.array_equal(p2[2], new2)
-    assert np.allclose(r2[2:], relRs[2:]) and np.allclose(t2[2:], relTs[2:])          # later relative motions kept
-    for i in range(2, 5):
-        R, T = odometry.GetRelRtBetween2Poses(p2[i], p2[i + 1])
-        assert np.allclose(R, relRs[i]) and np.allclose(T.ravel(), relTs[i])
-
-
 @pytest.mark.parametrize("seq", ["00", "01"])
 def test_icp_pt2plane_matches_oracle(api, oracle_mod, seq, capsys):
     """api.ICP_Pt2PtAndPt2Plane / GetPlanarPtsInliners == the oracle restatement (bit-identical pose, counts,

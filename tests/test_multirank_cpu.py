@@ -118,3 +118,78 @@ def test_synthetic_world_does_not_run_out_down_the_road():
         assert v0.shape[0] > 50000 and v1.shape[0] > 15000 and v2.shape[0] > 3000
         ring, counter = synth.project_ring(pc)
         assert (counter[:64, :1792] > 0).sum() > 60000
+
+
+def test_forward_update_and_relative_pose_helpers():
+    """ForwardUpdatePoses / GetRelRtBetween2Poses / GetLidarRelRtBetween2Poses round trips (pure host math)."""
+    from caelo_b200 import odometry, pipeline
+    rng = np.random.default_rng(2)
+    rel = np.zeros((5, 16), np.float32)
+    for i in range(5):
+        a = 0.01 * (i + 1)
+        rel[i, :9] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], np.float32).ravel()
+        rel[i, 9:12] = rng.normal(0, 0.5, 3)
+        rel[i, 12] = 1
+    Tr = np.array([[0, -1, 0, 0.1], [0, 0, -1, -0.2], [1, 0, 0, 0.3]], np.float32)
+    poses = pipeline.chain_poses(rel, Tr).astype(np.float64)
+    R_Tr, T_Tr = odometry.GetRtFromOnePose(Tr.astype(np.float64))
+    R_Tr_inv = np.linalg.inv(R_Tr)
+    T_Tr_inv = -np.dot(R_Tr_inv, T_Tr)
+    for i in range(5):      # the LiDAR-frame relative motion of the chained poses is the relative pose that went in
+        R, T = odometry.GetLidarRelRtBetween2Poses(poses[i], poses[i + 1], R_Tr, T_Tr, R_Tr_inv, T_Tr_inv)
+        assert np.allclose(R, rel[i, :9].reshape(3, 3), atol=1e-5) and np.allclose(T.ravel(), rel[i, 9:12], atol=1e-5)
+    relRs = np.zeros((5, 3, 3)); relTs = np.zeros((5, 3))
+    for i in range(5):
+        R, T = odometry.GetRelRtBetween2Poses(poses[i], poses[i + 1])
+        relRs[i], relTs[i] = R, T.ravel()
+    new2 = poses[2].copy(); new2[3] += 1.0
+    p2, r2, t2 = odometry.ForwardUpdatePoses(poses, 2, new2, relRs, relTs)
+    assert np.array_equal(p2[:2], poses[:2]) and np.array_equal(p2[2], new2)
+    assert np.allclose(r2[2:], relRs[2:]) and np.allclose(t2[2:], relTs[2:])          # later relative motions kept
+    for i in range(2, 5):
+        R, T = odometry.GetRelRtBetween2Poses(p2[i], p2[i + 1])
+        assert np.allclose(R, relRs[i]) and np.allclose(T.ravel(), relTs[i])
+
+
+@pytest.mark.reference
+def test_pose_helpers_equal_the_reference_functions():
+    """odometry.GetRelRtBetween2Poses / GetLidarRelRtBetween2Poses / ForwardUpdatePoses and api.RotateMat2EulerAngle_XYZ
+    against the UNMODIFIED reference: Transformations.py imported through the stub loader, ForwardUpdatePoses
+    (RefinePoses.py:120-143) executed from its own source text (the module itself is a script that cannot be imported)."""
+    import ast
+    import copy
+    from oracle import reference_stub
+    if not reference_stub.available():
+        pytest.skip("reference tree not mounted")
+    from caelo_b200 import api, odometry
+    Tf = reference_stub.load()["Transformations"]
+    src = open(os.path.join(reference_stub.REFERENCE_DIR, "RefinePoses.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "ForwardUpdatePoses")
+    ns = dict(np=np, copy=copy, GetRelRtBetween2Poses=Tf.GetRelRtBetween2Poses, GetRtFromOnePose=Tf.GetRtFromOnePose)
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "RefinePoses.py", "exec"), ns)
+    rng = np.random.default_rng(4)
+
+    def rand_pose():
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        q *= np.sign(np.linalg.det(q))
+        return np.c_[q, rng.normal(0, 5, (3, 1))].reshape(12)
+
+    poses = np.array([rand_pose() for _ in range(6)])
+    Tr = rand_pose()
+    R_Tr, T_Tr = Tf.GetRtFromOnePose(Tr)
+    R_Tr_inv = np.linalg.inv(R_Tr)
+    T_Tr_inv = -np.dot(R_Tr_inv, T_Tr)
+    for i in range(5):
+        for ours, ref in ((odometry.GetRelRtBetween2Poses(poses[i], poses[i + 1]), Tf.GetRelRtBetween2Poses(poses[i], poses[i + 1])),
+                          (odometry.GetLidarRelRtBetween2Poses(poses[i], poses[i + 1], R_Tr, T_Tr, R_Tr_inv, T_Tr_inv),
+                           Tf.GetLidarRelRtBetween2Poses(poses[i], poses[i + 1], R_Tr, T_Tr, R_Tr_inv, T_Tr_inv))):
+            assert np.array_equal(ours[0], ref[0]) and np.array_equal(ours[1], ref[1])
+        R = poses[i].reshape(3, 4)[:, :3]
+        assert np.array_equal(api.RotateMat2EulerAngle_XYZ(R), Tf.RotateMat2EulerAngle_XYZ(R))
+    relRs = np.array([Tf.GetRelRtBetween2Poses(poses[i], poses[i + 1])[0] for i in range(5)])
+    relTs = np.array([Tf.GetRelRtBetween2Poses(poses[i], poses[i + 1])[1].ravel() for i in range(5)])
+    new = rand_pose()
+    ours = odometry.ForwardUpdatePoses(poses, 2, new, relRs, relTs)
+    ref = ns["ForwardUpdatePoses"](poses, 2, new, relRs, relTs)
+    for o, r in zip(ours, ref):
+        assert np.array_equal(o, r)
