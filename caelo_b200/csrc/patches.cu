@@ -528,8 +528,8 @@ extern "C" int caelo_bricks_build(caelo_ctx *ctx, const int16_t *vox, const int6
     if (rc) return rc;
     BuildArgs b;
     b.vox = vox; b.offsets = d_off; b.tables = d_tables; b.nlists = nl;
-    int bx = (int)((maxlen + 255) / 256);
-    if (bx > 64) bx = 64;
+    int bx = (int)((maxlen + 255) / 256);   // one voxel per thread: the kernel is latency-bound, parallelism is what it needs
+    if (bx > 1024) bx = 1024;
     { ProfScope ps_(ctx, "brick_insert_kernel", st); brick_insert_kernel<<<dim3(bx, nl), 256, 0, st>>>(b); }
     CAELO_LAUNCH_CHECK(ctx);
     ctx->bricks_tables = d_tables;
@@ -567,8 +567,8 @@ extern "C" int caelo_bricks_build_scans(caelo_ctx *ctx, const float *pts, const 
     CAELO_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)F * 4, st));
     ScanBuildArgs b;
     b.pts = pts; b.offsets = d_off; b.tables = d_tables; b.nlists = nl; b.nvox = nvox; b.status = status;
-    int bx = (int)((maxn + 255) / 256);
-    if (bx > 128) bx = 128;
+    int bx = (int)((maxn + 255) / 256);     // one point per thread
+    if (bx > 1024) bx = 1024;
     if (bx < 1) bx = 1;
     { ProfScope ps_(ctx, "scan_brick_insert_kernel", st); scan_brick_insert_kernel<<<dim3(bx, F), 256, 0, st>>>(b); }
     CAELO_LAUNCH_CHECK(ctx);
