@@ -471,7 +471,7 @@ __host__ __device__ constexpr int c3_smem(int nbuf) { return sm3_bar(nbuf) + 64;
 struct Conv3Args {
     const float *act2;     // [P,64,16]
     const float *k3, *b3;  // (27,16,32), (32)
-    __half *act3_hi, *act3_lo;  // [P,2048] split fp16 (dense1 operands)
+    __half *act3_hi, *act3_lo;  // split fp16 dense1 operands, tile-major: [ceil(P/256)][256 chunks][256 patches][8]
     int P;
 };
 
@@ -597,8 +597,11 @@ __global__ void __launch_bounds__(C3_THREADS, 3 - NBUF) conv3_tc_kernel(const Co
             umma::mbar_arrive(&tempty[b]);
             if (lane < 16) {  // M=64 accumulator: rows 16q..16q+15 live in lanes 0..15 of quarter q
                 const int pos = 16 * q + lane;
-                const size_t o = (size_t)patch_of(i) * 2048 + pos * 32 + hc * 16;
-                uint4 *dh = reinterpret_cast<uint4 *>(a.act3_hi + o), *dl = reinterpret_cast<uint4 *>(a.act3_lo + o);
+                // act3 is stored TILE-MAJOR for dense1: [tile of 256 patches][chunk of 8 k (256 of them)][patch][8 halves],
+                // so that a K stage of a dense1 CTA is one contiguous block (a single bulk copy, no 16-byte gather)
+                const int p = patch_of(i);
+                const size_t row8 = ((size_t)(p >> 8) * 256 * 256 + (size_t)(p & 255)) * 8;   // halves
+                const int c0 = pos * 4 + hc * 2;                                               // chunk of channel hc*16 at this position
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {   // 8 channels at a time
                     __half2 hh[4], ll[4];
@@ -609,8 +612,9 @@ __global__ void __launch_bounds__(C3_THREADS, 3 - NBUF) conv3_tc_kernel(const Co
                         const float o1 = fast_tanh((__uint_as_float(v0[ch + 1]) + __uint_as_float(v1[ch + 1])) + b3s[hc * 16 + ch + 1]);
                         umma::split_f16x2(o0, o1, hh[c], ll[c]);
                     }
-                    dh[g] = *reinterpret_cast<uint4 *>(hh);
-                    dl[g] = *reinterpret_cast<uint4 *>(ll);
+                    const size_t o = row8 + (size_t)(c0 + g) * 256 * 8;
+                    *reinterpret_cast<uint4 *>(a.act3_hi + o) = *reinterpret_cast<uint4 *>(hh);
+                    *reinterpret_cast<uint4 *>(a.act3_lo + o) = *reinterpret_cast<uint4 *>(ll);
                 }
             }
         }
@@ -626,10 +630,13 @@ __global__ void __launch_bounds__(C3_THREADS, 3 - NBUF) conv3_tc_kernel(const Co
 //   D_t += A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T   (one fp32 accumulator per tile in TMEM, 2 x 208 columns),
 //   h = tanh(D_t + b).  The kernel is bound by the L2 -> smem operand stream (the 1.7 MB of weights are
 //   re-streamed per CTA), hence the tall CTA tile: weights are fetched once per 256 patches.
-// Operands stream L2 -> smem by TMA (cp.async.bulk.tensor.3d): each row-major [rows][2048] fp16 matrix is
-// described as a 3-D tensor (8 elements, rows, 256 16-byte chunks) so that a box {8, R, 4} lands in shared
-// memory as [chunk][row][16 B] — exactly the canonical K-major no-swizzle UMMA layout (SBO = 128 B,
-// LBO = R*16 B).  Three-stage mbarrier pipeline: 1 TMA-producer thread, 1 MMA-issuer thread, 4 epilogue warps.
+// Operands stream to smem by 1-D bulk copies (cp.async.bulk + mbarrier complete_tx).  Both are stored TILE-MAJOR in
+// global memory — act3 by conv3's epilogue as [tile of 256 patches][chunk of 8 k][patch][16 B], the weights once at
+// load time as [chunk][row][16 B] — so a K stage (4 chunks) of each operand is ONE contiguous block that lands in
+// shared memory already in the canonical K-major no-swizzle UMMA layout (SBO = 128 B, LBO = rows*16 B).  (The first
+// version described the row-major matrices to the TMA as (8 elements, rows, chunks) tensors: correct, but the copy
+// engine then moved 16-byte pieces 4 KB apart.)  Three-stage mbarrier pipeline: 1 producer thread, 1 MMA-issuer
+// thread, 8 epilogue warps.
 constexpr int DN = 208;                       // dense1 outputs padded to a multiple of 16
 constexpr int DM = 256;                       // patches per CTA
 constexpr int DK_STAGE = 32;                  // K elements per stage (4 chunks of 16 B)
@@ -643,6 +650,8 @@ constexpr int D_THREADS = 320;                // warps 0-3 and 6-9: epilogue of 
 
 struct DenseArgs {
     const float *bd1, *d2, *bd2;  // (200), (200,20), (20)
+    const __half *act3_hi, *act3_lo;   // tile-major A operands (conv3_tc_kernel)
+    const __half *w_hi, *w_lo;         // dense1 weights, [256 chunks][208 rows][8] (prep_dense_weights_kernel)
     float *feat;
     int P, feat_stride, feat_col0;
     // frame mode: packed order is [F,3,K]; row p -> feat[(f*K+k)*60 + s*20]
@@ -650,17 +659,16 @@ struct DenseArgs {
     long long *timeline;  // debug: [grid][8] clock64 stamps or null
 };
 
-__device__ __forceinline__ void tma_load_3d(uint32_t sdst, const CUtensorMap *map, uint32_t mbar, int c0, int c1, int c2)
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t sdst, const void *gsrc, uint32_t bytes, uint32_t mbar)
 {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(sdst),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst),
+                 "l"(gsrc), "r"(bytes), "r"(mbar)
+                 : "memory");
 }
 
 __global__ void __launch_bounds__(D_THREADS, 1)
-dense_tc_kernel(const DenseArgs a, const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
-                const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl)
+dense_tc_kernel(const DenseArgs a)
 {
     extern __shared__ __align__(128) unsigned char dsm[];
     uint64_t *full = reinterpret_cast<uint64_t *>(dsm + D_SM_BAR), *empty = full + D_STAGES, *accum = full + 2 * D_STAGES;
@@ -694,11 +702,14 @@ dense_tc_kernel(const DenseArgs a, const __grid_constant__ CUtensorMap map_ah, c
                 if (kt >= D_STAGES) umma::mbar_wait(&empty[s], (uint32_t)(((kt / D_STAGES) - 1) & 1));
                 const uint32_t st = sbase + s * D_STAGE, mb = umma::smem_u32(&full[s]);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(D_STAGE) : "memory");
-                const int kc = kt * (DK_STAGE / 8);
-                tma_load_3d(st, &map_ah, mb, 0, row0, kc);
-                tma_load_3d(st + D_A_BYTES, &map_al, mb, 0, row0, kc);
-                tma_load_3d(st + 2 * D_A_BYTES, &map_wh, mb, 0, 0, kc);
-                tma_load_3d(st + 2 * D_A_BYTES + D_W_BYTES, &map_wl, mb, 0, 0, kc);
+                // operands are stored tile-major ([tile][chunk][row][16 B]): the stage's 4 chunks of each operand are one
+                // contiguous block that lands in shared memory already in the canonical K-major layout
+                const size_t a_off = ((size_t)blockIdx.x * 256 + (size_t)kt * (DK_STAGE / 8)) * DM * 8;   // halves
+                const size_t w_off = (size_t)kt * (DK_STAGE / 8) * DN * 8;
+                bulk_g2s(st, a.act3_hi + a_off, D_A_BYTES, mb);
+                bulk_g2s(st + D_A_BYTES, a.act3_lo + a_off, D_A_BYTES, mb);
+                bulk_g2s(st + 2 * D_A_BYTES, a.w_hi + w_off, D_W_BYTES, mb);
+                bulk_g2s(st + 2 * D_A_BYTES + D_W_BYTES, a.w_lo + w_off, D_W_BYTES, mb);
             }
         }
         __syncwarp();
@@ -790,34 +801,6 @@ dense_tc_kernel(const DenseArgs a, const __grid_constant__ CUtensorMap map_ah, c
     if (warp == 4) umma::tmem_dealloc(tbase, 512);
 }
 
-// [rows][2048] fp16 row-major matrix as the 3-D tensor (8 elems, rows, 256 chunks of 16 B); box {8, box_rows, 4}
-int make_kmajor_map(caelo_ctx *ctx, CUtensorMap *map, const __half *base, uint64_t rows, uint32_t box_rows)
-{
-    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    if (!encode) {
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        CAELO_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (!fn || qres != cudaDriverEntryPointSuccess) return CAELO_ERR_UNSUPPORTED;
-        encode = reinterpret_cast<EncodeFn>(fn);
-    }
-    const cuuint64_t dims[3] = {8, rows, 256};
-    const cuuint64_t strides[2] = {4096, 16};  // bytes: rows, chunks
-    const cuuint32_t box[3] = {8, box_rows, DK_STAGE / 8};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half *>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        ctx->last_err = cudaErrorInvalidValue;
-        return CAELO_ERR_CUDA;
-    }
-    return CAELO_OK;
-}
-
 // conv12 tables, computed once per weight set.
 //   T1 [9 (dx,dy)][8 dz-patterns][8 ch]: partial conv1 sums  sum_{dz in pattern} k1[(dx,dy,dz)][ch]
 //   BG [27 classes][16 ch]: conv2 + max-pool + tanh where the whole neighbourhood is background.  If every
@@ -860,15 +843,16 @@ __global__ void prep_conv12_tables_kernel(const float *k1, const float *b1, cons
     }
 }
 
-// dense1 weights (2048,200) f32 -> transposed split fp16 [208][2048] (rows 200..207 zero)
+// dense1 weights (2048,200) f32 -> split fp16 in the operand layout [chunk of 8 k (256)][row n (208)][8] (rows 200..207 zero)
 __global__ void prep_dense_weights_kernel(const float *d1, __half *w_hi, __half *w_lo)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < DN * 2048; i += gridDim.x * blockDim.x) {
         int n = i / 2048, k = i % 2048;
         __half h = __float2half_rn(0.f), l = h;
         if (n < 200) umma::split_f16(d1[(size_t)k * 200 + n], h, l);
-        w_hi[i] = h;
-        w_lo[i] = l;
+        const size_t o = ((size_t)(k >> 3) * DN + n) * 8 + (k & 7);
+        w_hi[o] = h;
+        w_lo[o] = l;
     }
 }
 
@@ -922,16 +906,12 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
         conv3_tc_kernel<2><<<grid3, C3_THREADS, c3_smem(2), st>>>(c3);
     }
     CAELO_LAUNCH_CHECK(ctx);
-    CUtensorMap m_ah, m_al, m_wh, m_wl;
-    if ((rc = make_kmajor_map(ctx, &m_ah, act3_hi, Ppad, DM))) return rc;
-    if ((rc = make_kmajor_map(ctx, &m_al, act3_lo, Ppad, DM))) return rc;
-    if ((rc = make_kmajor_map(ctx, &m_wh, ctx->enc_w1t_hi, DN, DN))) return rc;
-    if ((rc = make_kmajor_map(ctx, &m_wl, ctx->enc_w1t_lo, DN, DN))) return rc;
     DenseArgs d;
     d.bd1 = ctx->enc.bd1; d.d2 = ctx->enc.d2; d.bd2 = ctx->enc.bd2;
+    d.act3_hi = act3_hi; d.act3_lo = act3_lo; d.w_hi = ctx->enc_w1t_hi; d.w_lo = ctx->enc_w1t_lo;
     d.feat = feat; d.P = P; d.feat_stride = feat_stride; d.feat_col0 = feat_col0;
     d.frame_mode = frame_mode; d.K = K; d.timeline = ctx->dbg_timeline ? ctx->dbg_timeline + (size_t)2 * ctx->num_sms * 64 * 16 : nullptr;
-    { ProfScope ps_(ctx, "dense_tc_kernel", st); dense_tc_kernel<<<(unsigned)(Ppad / DM), D_THREADS, D_SMEM, st>>>(d, m_ah, m_al, m_wh, m_wl); }
+    { ProfScope ps_(ctx, "dense_tc_kernel", st); dense_tc_kernel<<<(unsigned)(Ppad / DM), D_THREADS, D_SMEM, st>>>(d); }
     CAELO_LAUNCH_CHECK(ctx);
     return CAELO_OK;
 }
