@@ -674,7 +674,7 @@ def _ransac(ctx, pc0, pc1, pair_idx, N, verbose=False):
         print('cntItersRANSAC =', used)
         print('residualThreshold =', thr)
         print('nInliers/nFilteredKeyPts1 =', best_n, '/', N, '=', round(best_n / N, 3))
-    return R_star, T_star, ok, mask_star, thr
+    return R_star, T_star, ok, mask_star, thr, used
 
 
 def RANSAC4RT(Pairs0, Pairs1, Weights0=None, Weights1=None):
@@ -682,7 +682,7 @@ def RANSAC4RT(Pairs0, Pairs1, Weights0=None, Weights1=None):
     ctx = default_context()
     P0 = np.asarray(Pairs0, np.float32)
     N = P0.shape[0]
-    R, T, ok, mask, thr = _ransac(ctx, _dev(P0[None]), _dev(np.asarray(Pairs1, np.float32)[None]), None, N)
+    R, T, ok, mask, thr, _used = _ransac(ctx, _dev(P0[None]), _dev(np.asarray(Pairs1, np.float32)[None]), None, N)
     m = np.zeros((N,), dtype=bool) if mask is None else mask[0].cpu().numpy().astype(bool)
     return R, T, ok, m, thr
 
@@ -690,26 +690,28 @@ def RANSAC4RT(Pairs0, Pairs1, Weights0=None, Weights1=None):
 def SolveRelativePose(OriPC0, OriCodes0, Weights0, OriPC1, OriCodes1, Weights1):
     """Match.py:241 — (R, T, isSuccess, inliersIdx0, inliersIdx1, residualThreshold);
     x0 ~= R x1 + T.  Weights are ignored, as in the reference (overwritten with ones, :265-266)."""
-    ctx = default_context()
-    pc0 = _dev(np.asarray(OriPC0, np.float32)[None])
-    pc1 = _dev(np.asarray(OriPC1, np.float32)[None])
-    c0 = _dev(np.asarray(OriCodes0, np.float32)[None])
-    c1 = _dev(np.asarray(OriCodes1, np.float32)[None])
+    return solve_relative_pose(default_context(), OriPC0, OriCodes0, OriPC1, OriCodes1)[:6]
+
+
+def solve_relative_pose(ctx, OriPC0, OriCodes0, OriPC1, OriCodes1):
+    """SolveRelativePose on a given context; also returns the number of RANSAC trials of the last ladder round."""
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, np.float32)[None])).to(ctx.device)
+    pc0, pc1, c0, c1 = dev(OriPC0), dev(OriPC1), dev(OriCodes0), dev(OriCodes1)
     N = pc1.shape[1]
     pair_idx = ctx.nn_match(c0, c1)
-    R, T, ok, mask, thr = _ransac(ctx, pc0, pc1, pair_idx, N)
+    R, T, ok, mask, thr, used = _ransac(ctx, pc0, pc1, pair_idx, N)
     if mask is None:
         e = np.zeros((0,), np.int64)
-        return R, T, ok, e, e.copy(), thr
+        return R, T, ok, e, e.copy(), thr, used
     m = mask[0].cpu().numpy().astype(bool)
     pidx = pair_idx[0].cpu().numpy()
     inliersIdx0 = pidx[m]
     inliersIdx1 = np.arange(N)[m]
     if inliersIdx0.shape[0] == 0:
-        return R, T, ok, inliersIdx0, inliersIdx1, thr
+        return R, T, ok, inliersIdx0, inliersIdx1, thr, used
     rt, _ = ctx.kabsch(pc0, pc1, pair_idx, mask)
     rt = rt.cpu().numpy()[0]
-    return rt[:9].reshape(3, 3).copy(), rt[9:].reshape(3, 1).copy(), ok, inliersIdx0, inliersIdx1, thr
+    return rt[:9].reshape(3, 3).copy(), rt[9:].reshape(3, 1).copy(), ok, inliersIdx0, inliersIdx1, thr, used
 
 
 # ------------------------------------------------------------------------------------------

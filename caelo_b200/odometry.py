@@ -86,18 +86,21 @@ def preprocess_sequence(seq_dir: str, frames: Optional[Sequence[int]] = None, ri
         pts = host.to(ctx.device)
         ring = cnt = None
         if rings or keypts:
-            r = ctx.project_ring(pts, off, want=("ring5", "counter_i32"))
+            want = (("ring5", "counter_i32") if rings else ()) + (("ring3", "counter_i8") if keypts else ())
+            r = ctx.project_ring(pts, off, want=want)
             if r["status"].any().item():
                 raise IndexError("index %d is out of bounds for axis 1 with size %d" % (api.ImgW, api.ImgW))
-            ring, cnt = r["ring5"], r["counter_i32"]
+            ring, cnt = r.get("ring5"), r.get("counter_i32")
         if voxels:
             v = ctx.voxelize(pts, off, want_blocks=True)
             if v["status"].any().item():
                 raise IndexError("a point indexes outside the block grid")
             counts = v["counts"].cpu().numpy()
         if keypts:
-            kp, px, n = ctx.select_keypoints(ring, cnt, None, max_kpts=api.nFixedKeyPts)
-            ext, n_ext = ctx.extend_keypoints(ring, cnt, px, n)
+            # BatchPreprocess.py:97-105,136-141: the key points come from the CROPPED 3-channel ring and the int8
+            # counter (the range gate of SphericalRing.py:197 is then r >= 10 m, quirk 3), and so do the extended ones
+            kp, px, n = ctx.select_keypoints(r["ring3"], r["counter_i8"], None, max_kpts=api.nFixedKeyPts)
+            ext, n_ext = ctx.extend_keypoints(r["ring3"], r["counter_i8"], px, n)
         for j, i in enumerate(ids):
             name = os.path.basename(files[i]) + ".mat"
             if rings:
@@ -121,19 +124,33 @@ def preprocess_sequence(seq_dir: str, frames: Optional[Sequence[int]] = None, ri
 
 
 # ---- one sequence of odometry ---------------------------------------------------------------
-def estimate_sequence(raw_dir: str, Tr: Optional[np.ndarray] = None, poses_path: Optional[str] = None,
+def estimate_sequence(raw_dir: Optional[str] = None, Tr: Optional[np.ndarray] = None, poses_path: Optional[str] = None,
                       features_dir: Optional[str] = None, inliers_dir: Optional[str] = None, batch_pairs: int = 32,
                       rank: int = 0, world: int = 1, pipe: Optional[pipeline.OdometryPipeline] = None,
-                      scans: Optional[Sequence[np.ndarray]] = None):
+                      scans: Optional[Sequence[np.ndarray]] = None, stacked=None, in_flight: int = 3,
+                      stacked_first_frame: int = 0, n_frames: Optional[int] = None):
     """PoseEstimation.py:185-310 for one sequence: every consecutive frame pair -> relative [R|t] ->
     chained absolute poses -> ``poses_/SS.txt``; optionally the per-frame ``Features`` and per-pair
     ``InliersIdx`` .mat files (:283-310).  Frame pairs are sharded contiguously over ``world`` ranks
     (one-frame halo recomputed), each rank works in batches of ``batch_pairs`` pairs straight from the
-    raw scans, and rank 0 gathers the pose rows and runs the sequential chain.  Returns (poses [F,12]
-    float32, rel [P,16]) on rank 0 and (None, local rel) elsewhere."""
+    raw scans, and rank 0 gathers the pose rows — ONE collective per sequence — and runs the sequential chain.
+    Input: ``raw_dir`` (velodyne/*.bin files), ``scans`` (list of (N,4) arrays) or ``stacked`` = (pts [sumN,4] f32
+    torch tensor, row offsets): a pinned host tensor is streamed batch by batch (H2D of batch i+1 under the kernels
+    of batch i), a CUDA tensor is used in place (``in_flight`` batches queued ahead, no host wait in between).
+    ``stacked`` holds the whole sequence, or — with ``stacked_first_frame`` and ``n_frames`` (frames of the whole
+    sequence) — only the frames this rank needs, starting at that frame (a rank loads its own shard).  Returns (poses [F,12] float32, rel [P,16]) on rank 0 and (None, local rel)
+    elsewhere.  A rank that fails (a scan the reference would raise on) still takes part in the gather, so the
+    other ranks never block; the error is raised on every rank afterwards."""
     pipe = pipe or pipeline.OdometryPipeline()
-    files = None if scans is not None else list_scans(raw_dir)
-    F = len(scans) if scans is not None else len(files)
+    files = None
+    if stacked is not None:
+        pts_all, off_all = stacked[0], np.asarray(stacked[1], np.int64)
+        F = n_frames if n_frames is not None else off_all.shape[0] - 1
+    elif scans is not None:
+        F = len(scans)
+    else:
+        files = list_scans(raw_dir)
+        F = len(files)
     P = F - 1
     lo, hi = pipeline.shard_pairs(P, rank, world)
     want_files = features_dir is not None or inliers_dir is not None
@@ -146,31 +163,43 @@ def estimate_sequence(raw_dir: str, Tr: Optional[np.ndarray] = None, poses_path:
 
     def batches():                                                          # read one batch ahead of the device
         for b0, b1 in ranges:
-            chunk = [scans[i] if scans is not None else read_scan(files[i]) for i in range(b0, b1 + 1)]
-            host, off = _stack_scans(chunk)
-            yield ("scans", host.pin_memory(), off, list(range(b0, b1)))
+            if stacked is not None:
+                j0, j1 = b0 - stacked_first_frame, b1 - stacked_first_frame
+                assert j0 >= 0 and j1 + 1 < off_all.shape[0], "stacked scans do not cover this rank's frames"
+                host, off = pts_all[int(off_all[j0]):int(off_all[j1 + 1])], off_all[j0:j1 + 2] - off_all[j0]
+            else:
+                chunk = [scans[i] if scans is not None else read_scan(files[i]) for i in range(b0, b1 + 1)]
+                host, off = _stack_scans(chunk)
+                host = host.pin_memory()
+            yield ("scans", host, off, list(range(b0, b1)))
 
-    for (b0, b1), poses_b in zip(ranges, pipe.run_host_stream(batches())):
-        ids = list(range(b0, b1 + 1))                                   # frames b0..b1 -> pairs b0..b1-1
-        rows.append(poses_b)
-        if want_files:
-            d = pipe.last_details
-            kp, ft = d["kpts"].cpu().numpy(), d["feat"].cpu().numpy()
-            pidx, mask, ok = d["pair_idx"].cpu().numpy(), d["mask"].cpu().numpy().astype(bool), d["ok"].cpu().numpy()
-            if features_dir:
-                first = 0 if b0 == lo else 1                             # the halo frame was written by the previous batch
-                for j in range(first, len(ids)):
-                    io.savemat(os.path.join(features_dir, str(ids[j]).zfill(6) + ".bin.mat"),
-                               {"KeyPts": kp[j], "Features": ft[j],
-                                "Weights": np.ones((kp[j].shape[0], 1), dtype=np.float32)})
-            if inliers_dir:
-                for j in range(b1 - b0):
-                    m = mask[j] if ok[j] else np.zeros_like(mask[j])
-                    io.savemat(os.path.join(inliers_dir, "%s-%s.bin.mat" % (str(ids[j]).zfill(6), str(ids[j + 1]).zfill(6))),
-                               {"iFrame0": ids[j], "iFrame1": ids[j + 1], "inliersIdx0": pidx[j][m],
-                                "inliersIdx1": np.arange(mask.shape[1])[m]})
+    def results():
+        if stacked is not None and stacked[0].is_cuda:                      # whole sequence resident in HBM
+            pending = []
+            for _k, pts, off, ids in batches():
+                pending.append(pipe.enqueue_device_scans(pts, off, None, ids))
+                if len(pending) > in_flight:
+                    yield pipe.collect(pending.pop(0))
+            for h in pending:
+                yield pipe.collect(h)
+        else:
+            yield from pipe.run_host_stream(batches())
+
+    error = None
+    try:
+        for (b0, b1), poses_b in zip(ranges, results()):
+            rows.append(poses_b)
+            if want_files:
+                _write_batch_files(pipe.last_details, b0, b1, lo, features_dir, inliers_dir)
+    except Exception as e:                                                  # noqa: BLE001 — re-raised after the collective
+        error = e
     rel_local = np.concatenate(rows, 0) if rows else np.zeros((0, 16), np.float32)
-    rel = pipeline.gather_poses(rel_local, pipe.dev, cap=-(-P // world))
+    rel, failed_ranks = pipeline.gather_poses(rel_local, pipe.dev, cap=-(-P // world), failed=error is not None,
+                                              return_failed=True)
+    if error is not None:
+        raise error
+    if failed_ranks:
+        raise api._lib.CaeloError("rank(s) %s failed on their part of the sequence" % failed_ranks)
     if rel is None:
         return None, rel_local
     poses = pipeline.chain_poses(rel, Tr)
@@ -178,6 +207,25 @@ def estimate_sequence(raw_dir: str, Tr: Optional[np.ndarray] = None, poses_path:
         os.makedirs(os.path.dirname(os.path.abspath(poses_path)), exist_ok=True)
         np.savetxt(poses_path, poses)
     return poses, rel
+
+
+def _write_batch_files(d, b0, b1, lo, features_dir, inliers_dir):
+    """Features/NNNNNN.bin.mat and InliersIdx/A-B.bin.mat of one batch (PoseEstimation.py:283-310)."""
+    ids = list(range(b0, b1 + 1))                                       # frames b0..b1 -> pairs b0..b1-1
+    kp, ft = d["kpts"].cpu().numpy(), d["feat"].cpu().numpy()
+    pidx, mask, ok = d["pair_idx"].cpu().numpy(), d["mask"].cpu().numpy().astype(bool), d["ok"].cpu().numpy()
+    if features_dir:
+        first = 0 if b0 == lo else 1                                     # the halo frame was written by the previous batch
+        for j in range(first, len(ids)):
+            io.savemat(os.path.join(features_dir, str(ids[j]).zfill(6) + ".bin.mat"),
+                       {"KeyPts": kp[j], "Features": ft[j],
+                        "Weights": np.ones((kp[j].shape[0], 1), dtype=np.float32)})
+    if inliers_dir:
+        for j in range(b1 - b0):
+            m = mask[j] if ok[j] else np.zeros_like(mask[j])
+            io.savemat(os.path.join(inliers_dir, "%s-%s.bin.mat" % (str(ids[j]).zfill(6), str(ids[j + 1]).zfill(6))),
+                       {"iFrame0": ids[j], "iFrame1": ids[j + 1], "inliersIdx0": pidx[j][m],
+                        "inliersIdx1": np.arange(mask.shape[1])[m]})
 
 
 # ---- f4: pose refinement on the extended key points (RefinePoses.py:120-143, 273-334) -------------------------
@@ -232,9 +280,9 @@ def extended_key_points(scans: Sequence[np.ndarray], batch: int = 16, ctx: Optio
     out = []
     for b0 in range(0, len(scans), batch):
         host, off = _stack_scans(scans[b0:b0 + batch])
-        r = ctx.project_ring(host.to(ctx.device), off, want=("ring5", "counter_i32"))
-        _kp, px, n = ctx.select_keypoints(r["ring5"], r["counter_i32"], None, max_kpts=api.nFixedKeyPts)
-        ext, n_ext = ctx.extend_keypoints(r["ring5"], r["counter_i32"], px, n)
+        r = ctx.project_ring(host.to(ctx.device), off, want=("ring3", "counter_i8"))
+        _kp, px, n = ctx.select_keypoints(r["ring3"], r["counter_i8"], None, max_kpts=api.nFixedKeyPts)
+        ext, n_ext = ctx.extend_keypoints(r["ring3"], r["counter_i8"], px, n)
         ne = n_ext.cpu().numpy()
         out += [ext[j, :int(ne[j])].cpu().numpy() for j in range(ext.shape[0])]
     return out

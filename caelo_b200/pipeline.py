@@ -98,20 +98,18 @@ class OdometryPipeline:
         host.copy_(packed, non_blocking=True)
         done = torch.cuda.Event()
         done.record()
-        return dict(host=host, done=done, kpts=kpts, pair_idx=pair_idx, pair_ids=list(pair_ids),
+        return dict(host=host, done=done, kpts=kpts, feat=feat, pair_idx=pair_idx, pair_ids=list(pair_ids),
                     rounds=rounds.shape[0], details=details)
 
     def _result_slot(self, shape):
-        """Pinned host buffer for one batch's result rows, from a ring of four (a batch is collected before the
-        ring comes round: the stream pipeline is two deep) — no pinned allocation on the hot path."""
-        if not hasattr(self, "_res_ring"):
-            self._res_ring, self._res_next = [None] * 4, 0
-        i = self._res_next
-        self._res_next = (i + 1) % 4
-        buf = self._res_ring[i]
-        if buf is None or tuple(buf.shape) != tuple(shape):
-            buf = self._res_ring[i] = torch.empty(tuple(shape), dtype=torch.float32, pin_memory=True)
-        return buf
+        """Pinned host buffer for one batch's result rows, from a free list that ``_collect`` refills — no pinned
+        allocation on the hot path once as many buffers exist as batches are ever in flight."""
+        if not hasattr(self, "_res_free"):
+            self._res_free = []
+        for i, buf in enumerate(self._res_free):
+            if tuple(buf.shape) == tuple(shape):
+                return self._res_free.pop(i)
+        return torch.empty(tuple(shape), dtype=torch.float32, pin_memory=True)
 
     def _collect(self, h):
         """Waits for one queued batch (the one sync point of the batch); returns poses [P,16] float32 (host):
@@ -120,13 +118,12 @@ class OdometryPipeline:
         if self.keep_details:
             self.last_details = h["details"]
         host = h["host"].numpy().copy()                 # the pinned slot is reused by a later batch
+        self._res_free.append(h["host"])
         P = host.shape[0]
         res, rt_h = host[:, :16], host[:, 16:28]
         if host[:, 31].any():
             raise api._lib.CaeloError("a scan has points outside the voxel grid / ring image or fewer than 496 "
                                       "occupied voxels at some scale (the reference raises on it too)")
-        if (host[:, 29] != self.K).any() or (host[:, 30] != self.K).any():
-            raise api._lib.CaeloError("a frame yielded fewer than %d keypoints; use the per-pair API" % self.K)
         poses = np.zeros((P, 16), np.float32)
         poses[:, :12] = rt_h
         poses[:, 12] = res[:, 12]
@@ -139,25 +136,58 @@ class OdometryPipeline:
         elif failed.size:                               # total failure: R=I, T=0 (Match.py:277-278)
             poses[failed, :12] = [1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]
             poses[failed, 13] = 0
+        short = np.flatnonzero((host[:, 29] != self.K) | (host[:, 30] != self.K))
+        if short.size:
+            self._short_pairs(short, host[:, 29].astype(int), host[:, 30].astype(int), h, poses)
         return poses
 
-    def _finish(self, kpts, feat, n, samples, pair_ids, status=None):
-        return self._collect(self._enqueue_pairs(kpts, feat, n, samples, pair_ids, status))
+    def _short_pairs(self, short, n0s, n1s, h, poses):
+        """Pairs with a frame that yielded fewer than K key points (a sparse scan): the batched kernels assume K
+        rows, so these pairs are redone through the per-pair path on the rows that exist — exactly what the
+        reference does with whatever GetKeyPtsByAE returned (it only asserts n > 50, SphericalRing.py:286) — with
+        np.random.seed(pair_id) as everywhere in the pipeline; the caller's global stream is left untouched."""
+        state = np.random.get_state()
+        try:
+            for p in short:
+                n0, n1 = int(n0s[p]), int(n1s[p])
+                assert n0 > 50 and n1 > 50                              # SphericalRing.py:286
+                kp0, kp1 = h["kpts"][p, :n0].cpu().numpy(), h["kpts"][p + 1, :n1].cpu().numpy()
+                ft0, ft1 = h["feat"][p, :n0].cpu().numpy(), h["feat"][p + 1, :n1].cpu().numpy()
+                np.random.seed(int(h["pair_ids"][p]))
+                R, T, ok, i0, _i1, thr, used = api.solve_relative_pose(self.ctx, kp0, ft0, kp1, ft1)
+                poses[p, :9] = np.asarray(R, np.float32).ravel()
+                poses[p, 9:12] = np.asarray(T, np.float32).ravel()
+                poses[p, 12:] = [1.0 if ok else 0.0, len(i0), thr, used]
+        finally:
+            np.random.set_state(state)
 
-    def run_device(self, ring, counter, vox, vox_offsets, samples, pair_ids):
-        """Inputs already in HBM.  ``samples`` None: the RANSAC indices of all three ladder rounds are generated
-        on the device from the pair ids (np.random.seed(pair_id) streams)."""
+    def enqueue_device(self, ring, counter, vox, vox_offsets, samples, pair_ids):
+        """Queues one batch whose inputs are already in HBM and returns a handle for ``collect`` — nothing waits for
+        the device, so consecutive batches run back to back.  ``samples`` None: the RANSAC indices of all three
+        ladder rounds are generated on the device from the pair ids (np.random.seed(pair_id) streams)."""
         kpts, feat, n = self.frames_to_descriptors(ring, counter, vox, vox_offsets)
         if samples is None:
             samples = self.ctx.draw_samples(pair_ids, self.K, rounds=3)
-        return self._finish(kpts, feat, n, samples, pair_ids)
+        return self._enqueue_pairs(kpts, feat, n, samples, pair_ids)
 
-    def run_device_scans(self, pts, pts_offsets, samples, pair_ids):
-        """Raw scans already in HBM."""
+    def enqueue_device_scans(self, pts, pts_offsets, samples, pair_ids):
+        """The same from raw scans already in HBM."""
         kpts, feat, n, st = self.scans_to_descriptors(pts, pts_offsets)
         if samples is None:
             samples = self.ctx.draw_samples(pair_ids, self.K, rounds=3)
-        return self._finish(kpts, feat, n, samples, pair_ids, st)
+        return self._enqueue_pairs(kpts, feat, n, samples, pair_ids, st)
+
+    def collect(self, handle):
+        """Waits for a queued batch -> poses [P,16] float32 (host)."""
+        return self._collect(handle)
+
+    def run_device(self, ring, counter, vox, vox_offsets, samples, pair_ids):
+        """Inputs already in HBM: enqueue_device + collect."""
+        return self._collect(self.enqueue_device(ring, counter, vox, vox_offsets, samples, pair_ids))
+
+    def run_device_scans(self, pts, pts_offsets, samples, pair_ids):
+        """Raw scans already in HBM."""
+        return self._collect(self.enqueue_device_scans(pts, pts_offsets, samples, pair_ids))
 
     # ---- host (pinned) inputs -----------------------------------------------------------------
     def _copy_stream_(self):
@@ -321,16 +351,19 @@ class OdometryPipeline:
 _comm_streams = {}
 
 
-def gather_poses(poses: np.ndarray, device: torch.device, cap: Optional[int] = None):
+def gather_poses(poses: np.ndarray, device: torch.device, cap: Optional[int] = None, failed: bool = False,
+                 return_failed: bool = False):
     """NCCL gather of the per-rank [P_local,16] pose rows to rank 0 (the only collective on the
     path; PoseEstimation.py:254-267's pose chain then runs on rank 0).  Returns the concatenated
     array on rank 0, None elsewhere.  Works without torch.distributed initialised (1 rank).
     ``cap``: an upper bound of P_local that every rank knows (e.g. ceil(P_total / world)); then ONE gather of
     [cap+1,16] rows moves everything (row 0 carries the row count) instead of a count exchange first.  The
-    collective runs on its own CUDA stream, so it never waits for kernels queued on the compute stream."""
+    collective runs on its own CUDA stream, so it never waits for kernels queued on the compute stream.
+    ``failed``: this rank hit an error on its part — it still takes part (so nobody blocks) and flags it in row 0;
+    with ``return_failed`` the call returns (rows, [failed ranks]) (the list is only known on rank 0)."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return poses
+        return (poses, [0] if failed else []) if return_failed else poses
     world, rank = dist.get_world_size(), dist.get_rank()
     import contextlib
     if device.type == "cuda":
@@ -350,14 +383,17 @@ def gather_poses(poses: np.ndarray, device: torch.device, cap: Optional[int] = N
         assert rows.shape[0] <= cap
         buf = np.zeros((cap + 1, 16), np.float32)
         buf[0, 0] = rows.shape[0]
+        buf[0, 1] = 1.0 if failed else 0.0
         buf[1:1 + rows.shape[0]] = rows
         t = torch.from_numpy(buf).to(device)
         bufs = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
         dist.gather(t, bufs, dst=0)
         if rank != 0:
-            return None
+            return (None, []) if return_failed else None
         allr = torch.stack(bufs).cpu().numpy()          # waits for the comm stream only
-    return np.concatenate([allr[r, 1:1 + int(allr[r, 0, 0])] for r in range(world)], 0)
+    out = np.concatenate([allr[r, 1:1 + int(allr[r, 0, 0])] for r in range(world)], 0)
+    bad = [r for r in range(world) if allr[r, 0, 1] != 0]
+    return (out, bad) if return_failed else out
 
 
 def chain_poses(rel: np.ndarray, Tr: Optional[np.ndarray] = None):

@@ -67,49 +67,92 @@ class World:
         return np.concatenate(los), np.concatenate(his)
 
 
+# Beam pattern of the sensor KITTI was recorded with (Velodyne HDL-64E): 64 lasers in two blocks — the upper 32 are
+# 1/3 degree apart, the lower 32 are 1/2 degree apart — firing 2083 times per revolution (0.1728 degrees).  The ring
+# image has 0.2-degree columns and 0.425-degree rows, so ~16 % of a beam's shots share a column with the previous
+# shot and neighbouring upper beams share rows: ~120 k points per scan, ~25-30 k pixels hit by more than one point
+# (124,668 points, 27,959 multi-hit pixels on demo frame 00/000000) — the load that
+# ProjectPC2SphericalRing's last-writer-wins rule and Voxelization's duplicate handling see on real data.
+N_AZIMUTH = 2083
+BEAM_ELEVATION_DEG = np.r_[1.9 - np.arange(32) / 3.0, -8.83 - np.arange(32) / 2.0]
+DROPOUT = 0.06
+
+
 def _rays():
-    el = VerticalViewDown + VerticalResolution * (np.arange(64) + 0.5)   # beam centred in its ring row
-    az = math.pi - AzimuthResolution * (np.arange(1800) + 0.5)
+    el = BEAM_ELEVATION_DEG * _DEG
+    az = math.pi - (2 * math.pi / N_AZIMUTH) * (np.arange(N_AZIMUTH) + 0.5)
     ce, se = np.cos(el)[:, None], np.sin(el)[:, None]
-    d = np.stack([ce * np.cos(az)[None], ce * np.sin(az)[None], np.broadcast_to(se, (64, 1800))], -1)
-    return d.reshape(-1, 3).astype(np.float32)
+    d = np.stack([ce * np.cos(az)[None], ce * np.sin(az)[None], np.broadcast_to(se, (64, N_AZIMUTH))], -1)
+    return d.reshape(-1, 3).astype(np.float32)      # file order: beam by beam, each a full revolution
 
 
-_RAYS = None
+_RAYS = {}
+
+
+def _rays_on(device):
+    import torch
+    key = str(device)
+    if key not in _RAYS:
+        _RAYS[key] = torch.from_numpy(_rays()).to(device)
+    return _RAYS[key]
+
+
+def sensor_pose(frame: int, step: float = 0.7, yaw_step_deg: float = 0.3):
+    """World pose of the sensor at ``frame``: x_world = Rz(yaw) x_sensor + pos."""
+    yaw = math.radians(yaw_step_deg) * frame
+    cy, sy = math.cos(yaw), math.sin(yaw)
+    return (np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]], np.float32),
+            np.array([step * frame, 0.02 * frame, 0.0], np.float32))
+
+
+def scan_torch(world: World, frame: int, seed: int, device="cpu", step: float = 0.7, yaw_step_deg: float = 0.3):
+    """One LiDAR scan as a torch tensor [N,4] f32 (x, y, z in the sensor frame, intensity) on ``device``: every ray
+    of the beam pattern is cast against the ground plane and the boxes of the tiles in reach (slab test), returns
+    outside [3, 80] m and a random 6 % are dropped, 2 cm range noise.  The random numbers come from numpy
+    (``default_rng(seed)``) whatever the device, so the CPU and the GPU produce the same scan up to the rounding
+    of the ray casting."""
+    import torch
+    rays = _rays_on(device)
+    Rw, pos = sensor_pose(frame, step, yaw_step_deg)
+    rng = np.random.default_rng(seed)
+    nr = rays.shape[0]
+    u = torch.from_numpy(rng.random(nr, dtype=np.float32)).to(device)
+    noise = torch.from_numpy(rng.standard_normal(nr, dtype=np.float32) * np.float32(0.02)).to(device)
+    inten = torch.from_numpy(rng.random(nr, dtype=np.float32)).to(device)
+    pos_t = torch.from_numpy(pos).to(device)
+    d = rays @ torch.from_numpy(np.ascontiguousarray(Rw.T)).to(device)
+    t = torch.full((nr,), float("inf"), dtype=torch.float32, device=device)
+    down = d[:, 2] < -1e-6
+    t = torch.where(down, (-1.73 - pos_t[2]) / d[:, 2], t)
+    inv = 1.0 / d
+    wlo, whi = world.boxes_near(float(pos[0]))
+    lo_t, hi_t = torch.from_numpy(wlo).to(device), torch.from_numpy(whi).to(device)
+    for b0 in range(0, lo_t.shape[0], 32):
+        t1 = (lo_t[None, b0:b0 + 32] - pos_t) * inv[:, None, :]
+        t2 = (hi_t[None, b0:b0 + 32] - pos_t) * inv[:, None, :]
+        tn = torch.minimum(t1, t2).amax(-1)
+        tf = torch.maximum(t1, t2).amin(-1)
+        hit = (tf >= tn) & (tn > 0)
+        t = torch.minimum(t, torch.where(hit, tn, torch.full_like(tn, float("inf"))).amin(1))
+    ok = torch.isfinite(t) & (t >= 3.0) & (t <= 80.0) & (u > DROPOUT)
+    pts = rays[ok] * (t[ok] + noise[ok])[:, None]
+    return torch.cat([pts, inten[ok][:, None]], 1)
 
 
 def scan(world: World, frame: int, seed: int, step: float = 0.7, yaw_step_deg: float = 0.3):
     """One LiDAR scan (N,4) f32 in the sensor frame; sensor moves ``step`` m forward per frame."""
-    global _RAYS
-    if _RAYS is None:
-        _RAYS = _rays()
-    rng = np.random.default_rng(seed)
-    yaw = math.radians(yaw_step_deg) * frame
-    pos = np.array([step * frame, 0.02 * frame, 0.0], np.float32)
-    cy, sy = math.cos(yaw), math.sin(yaw)
-    Rw = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]], np.float32)
-    d = _RAYS @ Rw.T
-    t = np.full(d.shape[0], np.inf, np.float32)
-    down = d[:, 2] < -1e-6
-    t[down] = (-1.73 - pos[2]) / d[down, 2]
-    with np.errstate(divide="ignore", invalid="ignore"):
-        inv = (1.0 / d).astype(np.float32)
-        wlo, whi = world.boxes_near(float(pos[0]))
-        for b0 in range(0, wlo.shape[0], 16):
-            lo = wlo[b0:b0 + 16][None]
-            hi = whi[b0:b0 + 16][None]
-            t1 = (lo - pos) * inv[:, None, :]
-            t2 = (hi - pos) * inv[:, None, :]
-            tn = np.minimum(t1, t2).max(-1)
-            tf = np.maximum(t1, t2).min(-1)
-            hit = (tf >= tn) & (tn > 0)
-            tb = np.where(hit, tn, np.inf).min(1)
-            t = np.minimum(t, tb)
-    ok = np.isfinite(t) & (t >= 3.0) & (t <= 80.0) & (rng.random(t.shape[0]) > 0.25)
-    rng_t = t[ok] + rng.normal(0, 0.02, int(ok.sum())).astype(np.float32)   # 2 cm range noise
-    pts = (_RAYS[ok] * rng_t[:, None]).astype(np.float32)                    # sensor frame
-    inten = rng.random((pts.shape[0], 1)).astype(np.float32)
-    return np.concatenate([pts, inten], 1)
+    return scan_torch(world, frame, seed, "cpu", step, yaw_step_deg).numpy()
+
+
+def make_scans(n_frames: int, seed: int = 0, first_frame: int = 0, device="cpu"):
+    """Frames first_frame .. first_frame+n_frames-1 of the drive through World(seed) -> (pts [sumN,4] f32 tensor on
+    ``device``, row offsets int64 [F+1]).  On a GPU a 4541-frame sequence (configs[2]) takes seconds."""
+    import torch
+    world = World(seed)
+    parts = [scan_torch(world, first_frame + f, seed * 100003 + first_frame + f, device) for f in range(n_frames)]
+    off = np.zeros(n_frames + 1, np.int64)
+    off[1:] = np.cumsum([p.shape[0] for p in parts])
+    return torch.cat(parts, 0), off
 
 
 def project_ring(pc: np.ndarray):
@@ -124,12 +167,15 @@ def project_ring(pc: np.ndarray):
     row = ImgH - (beta / VerticalResolution + VerticalPixelsOffset).astype(np.int64)
     ok = (row >= 0) & (row < ImgH) & (col >= 0) & (col < ImgW)
     row, col, pc, r = row[ok], col[ok], pc[ok], r[ok]
-    ring = np.zeros((ImgH, ImgW, 5), np.float32)
-    counter = np.zeros((ImgH, ImgW), np.int32)
-    ring[row, col, 0:4] = pc[:, 0:4]
-    ring[row, col, 4] = r
-    np.add.at(counter, (row, col), 1)
-    return ring, counter
+    ring = np.zeros((ImgH * ImgW, 5), np.float32)
+    flat = row * ImgW + col
+    counter = np.bincount(flat, minlength=ImgH * ImgW).astype(np.int32).reshape(ImgH, ImgW)
+    # the LAST point in file order wins a pixel (SphericalRing.py:91-92): first occurrence in the reversed order
+    pix, first_rev = np.unique(flat[::-1], return_index=True)
+    last = flat.shape[0] - 1 - first_rev
+    ring[pix, 0:4] = pc[last, 0:4]
+    ring[pix, 4] = r[last]
+    return ring.reshape(ImgH, ImgW, 5), counter
 
 
 def voxelize(pc: np.ndarray):
@@ -153,21 +199,19 @@ def voxelize(pc: np.ndarray):
     return out
 
 
-def make_frames(n_frames: int, seed: int = 0, first_frame: int = 0):
+def make_frames(n_frames: int, seed: int = 0, first_frame: int = 0, device=None):
     """-> dict(ring3 [F,64,1792,3] f32, counter [F,69,1800] i8, vox int16 [sumV,3], vox_offsets int64 [3F+1],
-    scans list)."""
+    scans list).  ``device``: where the rays are cast (default: the GPU when there is one)."""
     world = World(seed)
+    if device is None:
+        import torch
+        device = "cuda" if torch.cuda.is_available() else "cpu"
     ring3 = np.zeros((n_frames, 64, 1792, 3), np.float32)
     counter = np.zeros((n_frames, ImgH, ImgW), np.int8)
     vox, off = [], [0]
     npts = []
-    from concurrent.futures import ThreadPoolExecutor
-    import os
-    # one generator per rank runs at the same time on the box: share the host cores
-    n_ranks = max(1, int(os.environ.get("WORLD_SIZE", "1")))
-    with ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 1) // n_ranks))) as ex:
-        scans = list(ex.map(lambda f: scan(world, first_frame + f, seed * 100003 + first_frame + f),
-                            range(n_frames)))
+    scans = [scan_torch(world, first_frame + f, seed * 100003 + first_frame + f, device).cpu().numpy()
+             for f in range(n_frames)]
     for f in range(n_frames):
         pc = scans[f]
         ring, cnt = project_ring(pc)

@@ -117,6 +117,13 @@ def test_preprocess_sequence_writes_what_the_loaders_read(api, sequence, oracle_
         assert kp.shape == (1024, 3) and np.array_equal(v0, want[3]) and np.array_equal(v2, want[5])
         k = io.loadmat(os.path.join(sequence["root"], "KeyPts", name))
         assert k["ExtendedKeyPts"].shape[1] == 3 and k["ExtendedKeyPts"].shape[0] >= 1024
+        # BatchPreprocess.py:97-105,136-141: key points are selected on the CROPPED 3-channel ring + int8 counter
+        # (range gate r >= 10 m), not on the 5-channel image
+        ring3, cnt8 = np.ascontiguousarray(ring[0:64, 0:1792, 0:3]), counter.astype(np.int8)
+        kpo, pxo = oracle_mod.select_keypoints(ring3, cnt8, oracle_mod.respond_predict(ring3[None])[0])
+        assert np.array_equal(k["KeyPts"], kpo)
+        assert np.array_equal(k["ExtendedKeyPts"], oracle_mod.extend_keypoints(ring3, cnt8.copy(), pxo))
+        assert np.array_equal(odometry.extended_key_points([pc])[0], k["ExtendedKeyPts"])
 
 
 @pytest.mark.parametrize("n,d", [(1024, 128), (4096, 128), (16384, 128), (3000, 60)])
