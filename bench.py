@@ -586,11 +586,17 @@ def run_ours(args, rank, local_rank, world):
 
     extras = {}
     if not args.no_extras:
-        extras["seq00"] = seq00(pipe, args, rank, world, dev, dist)
+        def extra(name, fn, *a):
+            # a sub-run never takes the headline down (every rank runs the same sub-runs, so collectives still pair up)
+            try:
+                extras[name] = fn(*a)
+            except Exception as e:                                      # noqa: BLE001
+                extras[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        extra("seq00", seq00, pipe, args, rank, world, dev, dist)
         if rank == 0:
-            extras["single_pair"] = single_pair_latency(pipe, data, dev)
-            extras["nn_match"] = nn_match_microbench(ctx, dev, _peaks())
-        extras["refine"] = refine_bench(ctx, pipe, data, dev, rank, world, dist)
+            extra("single_pair", single_pair_latency, pipe, data, dev)
+            extra("nn_match", nn_match_microbench, ctx, dev, _peaks())
+        extra("refine", refine_bench, ctx, pipe, data, dev, rank, world, dist)
 
     if rank == 0:
         peaks = _peaks()

@@ -399,6 +399,24 @@ class Context:
         self.check(self.lib.caelo_transform_points(self.h, _ptr(rt), _ptr(pc), pc.shape[0], _stream()),
                    "caelo_transform_points")
 
+    def icp_batch(self, pc0: torch.Tensor, off0: np.ndarray, pc1: torch.Tensor, off1: np.ndarray, thr0: float, decay: float,
+                  small_shift: float, ep: float, max_iter: int, min_iter: int, min_inliers: int = 100):
+        """Whole ICPs of B pairs on the device (caelo_icp_batch): pc0 [S0,3] / pc1 [S1,3] f32 = the B target / source
+        clouds concatenated (pc1 is updated IN PLACE), off0 / off1 host int64 [B+1].  -> hist [B,max_iter,12] f32,
+        hist_n [B,max_iter] int32, state [B,4] float64 (success, iterations, last inlier count, final threshold)."""
+        o0, o1 = np.ascontiguousarray(off0, np.int64), np.ascontiguousarray(off1, np.int64)
+        B = o0.shape[0] - 1
+        assert pc0.dtype == torch.float32 and pc1.dtype == torch.float32 and pc0.is_contiguous() and pc1.is_contiguous()
+        assert o1.shape[0] == B + 1 and int(o0[-1]) == pc0.shape[0] and int(o1[-1]) == pc1.shape[0]
+        hist = torch.empty((B, max_iter, 12), dtype=torch.float32, device=self.device)
+        hist_n = torch.empty((B, max_iter), dtype=torch.int32, device=self.device)
+        state = torch.empty((B, 4), dtype=torch.float64, device=self.device)
+        self.check(self.lib.caelo_icp_batch(self.h, _ptr(pc0), o0.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _ptr(pc1),
+                                            o1.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), B, float(thr0), float(decay),
+                                            float(small_shift), float(ep), int(max_iter), int(min_iter), int(min_inliers),
+                                            _ptr(hist), _ptr(hist_n), _ptr(state), _stream()), "caelo_icp_batch")
+        return hist, hist_n, state
+
     def kabsch(self, pc0, pc1, pair_idx=None, mask=None, skip_if_ok=None, out_rt=None):
         P, N0, _ = pc0.shape
         N = pc1.shape[1]
@@ -740,46 +758,106 @@ def GetPtsInliners(PC0, PC1, inlierThreshold):
     return PC0[idx0, :], PC1[idx1, :]
 
 
-def ICP(PC0, PC1, maxIterTimes=50, minIterTimes=20 - 1, inlierThreshold=0.5, smallShiftThreshold=0.05, decay_rate=0.9,
-        ep=0.001, info=None):
-    """MyICP.py:28-73, same arguments and return values (R_star (3,3) f64, T_star (3,1) f64, isSuccess) and the
-    same progress line on stdout.  Per iteration the device does the exact 1-NN search (caelo_nn3), SolveRT on the
-    inlier pairs (caelo_kabsch) and the update of PC1 (caelo_transform_points); ONE small D2H (R, T, inlier count)
-    feeds the reference's own loop control here: fewer than 100 inliers -> failure, Euler-angle / translation
-    convergence test after minIterTimes, threshold decay while the step is small."""
-    ctx = default_context()
+def _icp_replay(hist, hist_n, maxIterTimes, minIterTimes, inlierThreshold, smallShiftThreshold, decay_rate, ep, min_inliers=100):
+    """The reference's loop (MyICP.py:31-70) over the [R|T] and inlier count the device recorded for every iteration:
+    R*, T* accumulated with the reference's own numpy expressions (float32 R, T into float64 R*, T*), and every
+    decision — failure, convergence, threshold decay — taken again on the host.
+    -> (R_star, T_star, isSuccess, iterations, last inlier count, final threshold)."""
     R_star = np.eye(3, dtype=np.float64)
     T_star = np.zeros((3, 1), dtype=np.float64)
-    pc0 = _dev(np.ascontiguousarray(PC0, np.float32))
-    pc1 = _dev(np.ascontiguousarray(PC1, np.float32)).clone()
-    n_in = 0
-    iIter = -1
+    n_in, it_done = 0, 0
     for iIter in range(maxIterTimes):
-        idx, _dist, mask, count = ctx.nn3(pc0, pc1, inlierThreshold, want_mask=True)
-        rt, _cred = ctx.kabsch(pc0[None], pc1[None], idx[None], mask[None])
-        host = torch.cat([rt[0], count.to(torch.float32)]).cpu().numpy()          # the iteration's one sync
-        n_in = int(host[12])
-        if n_in < 100:
-            print('ICP iters:', iIter + 1, ',  inliers:', n_in, ',  inlierThreshold:', round(inlierThreshold, 5))
-            if info is not None:
-                info.update(iters=iIter + 1, inliers=n_in, threshold=inlierThreshold)
-            return R_star, T_star, False
-        R, T = host[:9].reshape(3, 3).copy(), host[9:12].reshape(3, 1).copy()
-        ctx.transform_points(rt[0], pc1)
+        n_in, it_done = int(hist_n[iIter]), iIter + 1
+        if n_in < min_inliers:
+            return R_star, T_star, False, it_done, n_in, inlierThreshold
+        R, T = hist[iIter, :9].reshape(3, 3), hist[iIter, 9:12].reshape(3, 1)
         R_star = np.dot(R, R_star)
         T_star = np.dot(R, T_star) + T
-        eulers = RotateMat2EulerAngle_XYZ(R)
-        normEulers = np.linalg.norm(eulers)
+        normEulers = np.linalg.norm(RotateMat2EulerAngle_XYZ(R))
         normT = np.linalg.norm(T)
-        if iIter >= minIterTimes:
-            if normEulers < ep and normT < ep:
-                break
+        if iIter >= minIterTimes and normEulers < ep and normT < ep:
+            break
         if normEulers < smallShiftThreshold and normT < smallShiftThreshold:
             inlierThreshold *= decay_rate
-    print('ICP iters:', iIter + 1, ',  inliers:', n_in, ',  inlierThreshold:', round(inlierThreshold, 5))
+    return R_star, T_star, True, it_done, n_in, inlierThreshold
+
+
+def icp_batch(PC0s, PC1s, maxIterTimes=50, minIterTimes=20 - 1, inlierThreshold=0.5, smallShiftThreshold=0.05,
+              decay_rate=0.9, ep=0.001, ctx: Optional[Context] = None):
+    """MyICP.ICP (MyICP.py:28-73) for a whole batch of cloud pairs at once: ONE call runs every pair's iterations on the
+    device (nearest neighbours through a grid index, SolveRT, point update, loop control) and ONE copy brings the
+    per-iteration [R|T] back; the host then accumulates R*, T* as the reference does and re-takes every loop decision
+    from the recorded data.  Should a decision differ from the device's (its Euler angles come from CUDA's atan2, the
+    host's from libm — they can only disagree when a norm sits within an ulp of a threshold) that pair is redone
+    with the host-driven iteration of ``_icp_stepwise``.  -> [(R_star (3,3) f64, T_star (3,1) f64, isSuccess, info)]."""
+    ctx = ctx or default_context()
+    p0 = [np.ascontiguousarray(p, np.float32).reshape(-1, 3) for p in PC0s]
+    p1 = [np.ascontiguousarray(p, np.float32).reshape(-1, 3) for p in PC1s]
+    assert len(p0) == len(p1) and len(p0) > 0 and all(a.shape[0] > 0 and b.shape[0] > 0 for a, b in zip(p0, p1))
+    off0, off1 = np.zeros(len(p0) + 1, np.int64), np.zeros(len(p0) + 1, np.int64)
+    off0[1:], off1[1:] = np.cumsum([a.shape[0] for a in p0]), np.cumsum([a.shape[0] for a in p1])
+    d0 = torch.from_numpy(np.concatenate(p0, 0)).to(ctx.device)
+    d1 = torch.from_numpy(np.concatenate(p1, 0)).to(ctx.device)
+    hist, hist_n, state = ctx.icp_batch(d0, off0, d1, off1, inlierThreshold, decay_rate, smallShiftThreshold, ep,
+                                        maxIterTimes, minIterTimes)
+    hist, hist_n, state = hist.cpu().numpy(), hist_n.cpu().numpy(), state.cpu().numpy()      # the batch's one sync
+    out = []
+    for b in range(len(p0)):
+        R, T, ok, iters, n_in, thr = _icp_replay(hist[b], hist_n[b], maxIterTimes, minIterTimes, inlierThreshold,
+                                                 smallShiftThreshold, decay_rate, ep)
+        if (ok, iters, n_in, thr) != (bool(state[b, 0]), int(state[b, 1]), int(state[b, 2]), float(state[b, 3])):
+            info = {}
+            R, T, ok = _icp_stepwise(ctx, p0[b], p1[b], maxIterTimes, minIterTimes, inlierThreshold, smallShiftThreshold,
+                                     decay_rate, ep, info)
+            info["redone_on_host"] = True
+        else:
+            info = dict(iters=iters, inliers=n_in, threshold=thr)
+        out.append((R, T, ok, info))
+    return out
+
+
+def ICP(PC0, PC1, maxIterTimes=50, minIterTimes=20 - 1, inlierThreshold=0.5, smallShiftThreshold=0.05, decay_rate=0.9,
+        ep=0.001, info=None):
+    """MyICP.py:28-73, same arguments and return values (R_star (3,3) f64, T_star (3,1) f64, isSuccess) and the same
+    progress line on stdout; a batch of one through ``icp_batch``."""
+    R_star, T_star, ok, inf = icp_batch([PC0], [PC1], maxIterTimes, minIterTimes, inlierThreshold, smallShiftThreshold,
+                                        decay_rate, ep)[0]
+    print('ICP iters:', inf["iters"], ',  inliers:', inf["inliers"], ',  inlierThreshold:', round(inf["threshold"], 5))
     if info is not None:
-        info.update(iters=iIter + 1, inliers=n_in, threshold=inlierThreshold)
-    return R_star, T_star, True
+        info.update(iters=inf["iters"], inliers=inf["inliers"], threshold=inf["threshold"])
+    return R_star, T_star, ok
+
+
+def _icp_stepwise(ctx, PC0, PC1, maxIterTimes, minIterTimes, inlierThreshold, smallShiftThreshold, decay_rate, ep, info=None):
+    """One ICP with the loop on the host (one small D2H per iteration): brute-force exact 1-NN (caelo_nn3), SolveRT
+    (caelo_kabsch), point update (caelo_transform_points).  The fallback of ``icp_batch`` and its cross-check in the
+    tests."""
+    pc0 = torch.from_numpy(np.ascontiguousarray(PC0, np.float32)).to(ctx.device)
+    pc1 = torch.from_numpy(np.ascontiguousarray(PC1, np.float32)).to(ctx.device).clone()
+    hist = np.zeros((maxIterTimes, 12), np.float32)
+    hist_n = np.zeros((maxIterTimes,), np.int32)
+    thr = inlierThreshold
+    for iIter in range(maxIterTimes):
+        idx, _dist, mask, count = ctx.nn3(pc0, pc1, thr, want_mask=True)
+        rt, _cred = ctx.kabsch(pc0[None], pc1[None], idx[None], mask[None])
+        host = torch.cat([rt[0], count.to(torch.float32)]).cpu().numpy()
+        hist_n[iIter] = int(host[12])
+        if hist_n[iIter] < 100:
+            break
+        hist[iIter] = host[:12]
+        ctx.transform_points(rt[0], pc1)
+        # the decisions that steer the next search (same expressions as _icp_replay)
+        R, T = hist[iIter, :9].reshape(3, 3), hist[iIter, 9:12].reshape(3, 1)
+        normEulers, normT = np.linalg.norm(RotateMat2EulerAngle_XYZ(R)), np.linalg.norm(T)
+        if iIter >= minIterTimes and normEulers < ep and normT < ep:
+            break
+        if normEulers < smallShiftThreshold and normT < smallShiftThreshold:
+            thr *= decay_rate
+    R_star, T_star, ok, iters, n_in, thr = _icp_replay(hist, hist_n, maxIterTimes, minIterTimes, inlierThreshold,
+                                                       smallShiftThreshold, decay_rate, ep)
+    if info is not None:
+        info.update(iters=iters, inliers=n_in, threshold=thr)
+    return R_star, T_star, ok
 
 
 def _nn3_inliers(ctx, pc0_dev, pc1_host, thr):

@@ -62,7 +62,7 @@ extern "C" int caelo_destroy(caelo_ctx *ctx)
     if (!ctx) return CAELO_ERR_ARG;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    Scratch *all[] = {&ctx->cand, &ctx->bricks, &ctx->enc_ws, &ctx->pose_ws, &ctx->misc, &ctx->scan_ws, &ctx->seed_ws, &ctx->match_ops};
+    Scratch *all[] = {&ctx->cand, &ctx->bricks, &ctx->enc_ws, &ctx->pose_ws, &ctx->misc, &ctx->scan_ws, &ctx->seed_ws, &ctx->match_ops, &ctx->icp_ws};
     for (Scratch *s : all)
         if (s->ptr) cudaFree(s->ptr);
     for (int i = 0; i < caelo_ctx::kStageSlots; ++i) {

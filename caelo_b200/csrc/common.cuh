@@ -66,6 +66,7 @@ struct caelo_ctx {
     Scratch scan_ws;   // projection / voxelisation: pixel owners, hash tables, compaction lists
     Scratch seed_ws;   // ransac: per-pair generator seeds
     Scratch match_ops; // nn match: split-fp16 operand tiles + padded norms
+    Scratch icp_ws;    // batched ICP: grid index over PC0, nearest-neighbour indices, per-pair state
 };
 
 #define CAELO_CUDA(ctx, call)                         \

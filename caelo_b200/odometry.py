@@ -228,130 +228,16 @@ def _write_batch_files(d, b0, b1, lo, features_dir, inliers_dir):
                         "inliersIdx1": np.arange(mask.shape[1])[m]})
 
 
-# ---- f4: pose refinement on the extended key points (RefinePoses.py:120-143, 273-334) -------------------------
-def GetRtFromOnePose(pose):
-    """Transformations.py:164-168."""
-    pose = pose.reshape(3, 4)
-    return pose[:, 0:3], pose[:, 3].reshape(3, 1)
-
-
-def GetRelRtBetween2Poses(pose0, pose1):
-    """Transformations.py:106-113 — from pose1 to pose0."""
-    R0, T0 = GetRtFromOnePose(pose0)
-    R0_inv = np.linalg.inv(R0)
-    T0_inv = -np.dot(R0_inv, T0)
-    R1, T1 = GetRtFromOnePose(pose1)
-    return np.dot(R0_inv, R1), np.dot(R0_inv, T1) + T0_inv
-
-
-def GetLidarRelRtBetween2Poses(pose0, pose1, R_Tr, T_Tr, R_Tr_inv, T_Tr_inv):
-    """Transformations.py:118-125 — the same in the LiDAR frame (Tr = velodyne -> camera)."""
-    R0, T0 = GetRtFromOnePose(pose0)
-    R0_inv = np.linalg.inv(R0)
-    T0_inv = -np.dot(R0_inv, T0)
-    R1, T1 = GetRtFromOnePose(pose1)
-    R = np.dot(R_Tr_inv, np.dot(R0_inv, np.dot(R1, R_Tr)))
-    T = np.dot(R_Tr_inv, np.dot(R0_inv, np.dot(R1, T_Tr) + T1) + T0_inv) + T_Tr_inv
-    return R, T
-
-
-def ForwardUpdatePoses(poses, frameNum, newPose, relRs, relTs):
-    """RefinePoses.py:120-143: replace pose ``frameNum`` and re-chain every later pose with the stored relative
-    motions."""
-    poses_, relRs_, relTs_ = poses.copy(), relRs.copy(), relTs.copy()
-    poses_[frameNum, :] = newPose
-    relR, relT = GetRelRtBetween2Poses(poses_[frameNum - 1, :], newPose)
-    relRs_[frameNum - 1, :, :] = relR
-    relTs_[frameNum - 1, :] = relT.reshape(3,)
-    for iFrame in range(frameNum + 1, poses_.shape[0], 1):
-        R0, T0 = GetRtFromOnePose(poses_[iFrame - 1])
-        relativeR = relRs_[iFrame - 1, :, :]
-        relativeT = relTs_[iFrame - 1, :].reshape(3, 1)
-        R = np.dot(R0, relativeR)
-        T = np.dot(R0, relativeT) + T0
-        poses_[iFrame, :] = np.c_[R, T].reshape((1, 12))
-    return poses_, relRs_, relTs_
-
-
-def extended_key_points(scans: Sequence[np.ndarray], batch: int = 16, ctx: Optional[api.Context] = None):
-    """ExtendedKeyPts of every scan (BatchPreprocess.py:136-141: GetKeyPtsByAE on the 3-channel ring, then
-    ExtendKeyPtsInShpericalRing), batched on the device."""
-    ctx = ctx or api.default_context()
-    out = []
-    for b0 in range(0, len(scans), batch):
-        host, off = _stack_scans(scans[b0:b0 + batch])
-        r = ctx.project_ring(host.to(ctx.device), off, want=("ring3", "counter_i8"))
-        _kp, px, n = ctx.select_keypoints(r["ring3"], r["counter_i8"], None, max_kpts=api.nFixedKeyPts)
-        ext, n_ext = ctx.extend_keypoints(r["ring3"], r["counter_i8"], px, n)
-        ne = n_ext.cpu().numpy()
-        out += [ext[j, :int(ne[j])].cpu().numpy() for j in range(ext.shape[0])]
-    return out
-
-
-def RefinementCore(poses, KeyPts0, KeyPts1, iFrame0, iFrame1, relRs, relTs, Tr, inlierThreshold0=0.5,
-                   PlanarPts0=None, PlanarPts1=None):
-    """RefinePoses.py:273-334 for one frame pair: move frame 1's extended key points by the odometry pose, register
-    them against frame 0's with ICP, reject the result if it moves the pose by more than 10 degrees / 5 m, otherwise
-    replace pose ``iFrame1`` and forward-update the rest.  Returns (code, poses, relRs, relTs) with the reference's
-    codes: -1 = ICP failed, 0 = change too large, 1 = refined.
-    With planar points (N x 6: point + normal) the reference's call is made: ICP_Pt2PtAndPt2Plane with frame 1's
-    planar coordinates moved by the odometry pose as well (:289-296).  The shipped pipeline never produces planar
-    points (SphericalRing.py:219,285: always empty, and the reference's call raises on them); without them this is
-    the point-to-point variant the reference keeps commented out next to it (``R_ICP, T_ICP, isSuccess =
-    ICP(KeyPts0, KeyPts1_)``, :297) with the thresholds of the call it replaces."""
-    Tr = np.asarray(Tr, np.float32).reshape(3, 4)
-    R_Tr, T_Tr = GetRtFromOnePose(Tr)
-    R_Tr_inv = np.linalg.inv(R_Tr)
-    T_Tr_inv = -np.dot(R_Tr_inv, T_Tr)
-    pose0, pose1 = poses[iFrame0, :], poses[iFrame1, :]
-    oriRelR, oriRelT = GetLidarRelRtBetween2Poses(pose0, pose1, R_Tr, T_Tr, R_Tr_inv, T_Tr_inv)
-    KeyPts1_ = np.array(((np.dot(oriRelR, KeyPts1.T) + oriRelT).T), dtype=np.float32)
-    if PlanarPts0 is not None and PlanarPts1 is not None and PlanarPts0.ndim == 2 and PlanarPts1.ndim == 2 \
-            and PlanarPts0.shape[0] and PlanarPts1.shape[0]:
-        PlanarPts1_ = PlanarPts1.copy()
-        PlanarPts1_[:, 0:3] = np.array(((np.dot(oriRelR, PlanarPts1[:, 0:3].T) + oriRelT).T), dtype=np.float32)
-        R_ICP, T_ICP, isSuccess = api.ICP_Pt2PtAndPt2Plane(KeyPts0, KeyPts1_, PlanarPts0, PlanarPts1_, maxIterTimes=50,
-                                                           minIterTimes=20 - 1, inlierThreshold0=inlierThreshold0,
-                                                           decay_rate0=0.9, inlierThreshold1=5.0, decay_rate1=0.9,
-                                                           smallShiftThreshold=0.1, ep=0.001)
-    else:
-        R_ICP, T_ICP, isSuccess = api.ICP(KeyPts0, KeyPts1_, maxIterTimes=50, minIterTimes=20 - 1,
-                                          inlierThreshold=inlierThreshold0, decay_rate=0.9, smallShiftThreshold=0.1,
-                                          ep=0.001)
-    if not isSuccess:
-        return -1, poses.copy(), relRs, relTs
-    relativeR = np.dot(R_ICP, oriRelR)
-    relativeT = np.dot(R_ICP, oriRelT) + T_ICP
-    diffRelEulers = np.linalg.norm(api.RotateMat2EulerAngle_XYZ(oriRelR) - api.RotateMat2EulerAngle_XYZ(relativeR))
-    diffRelT = np.linalg.norm(oriRelT - relativeT)
-    if diffRelEulers > 10 or diffRelT > 5:
-        return 0, poses.copy(), relRs, relTs
-    R0, T0 = GetRtFromOnePose(pose0)
-    R_poseDiff = np.dot(R_Tr, np.dot(relativeR, R_Tr_inv))
-    T_poseDiff = np.dot(R_Tr, np.dot(relativeR, T_Tr_inv) + relativeT) + T_Tr
-    R = np.dot(R0, R_poseDiff)
-    T = np.dot(R0, T_poseDiff) + T0
-    pose1 = np.c_[R, T].reshape((12,))
-    poses_, relRs, relTs = ForwardUpdatePoses(poses, iFrame1, pose1, relRs, relTs)
-    return 1, poses_, relRs, relTs
-
-
-def refine_sequence(scans: Sequence[np.ndarray], poses: np.ndarray, Tr: Optional[np.ndarray] = None,
-                    inlierThreshold0: float = 0.5):
-    """Frame-to-frame refinement of a whole pose file (the iRefineOdometry stage of RefinePoses.py with key frames =
-    consecutive frames): RefinementCore for every pair (i, i+1) on the device-computed extended key points.
-    Returns (poses [F,12] float64, codes [F-1])."""
-    Tr = np.asarray(np.c_[np.eye(3), np.zeros(3)] if Tr is None else Tr, np.float32).reshape(3, 4)
-    poses = np.asarray(poses, np.float64).copy()
-    F = poses.shape[0]
-    relRs = np.zeros((F - 1, 3, 3), np.float64)
-    relTs = np.zeros((F - 1, 3), np.float64)
-    for i in range(F - 1):
-        R, T = GetRelRtBetween2Poses(poses[i], poses[i + 1])
-        relRs[i], relTs[i] = R, T.reshape(3,)
-    ext = extended_key_points(scans)
-    codes = []
-    for i in range(F - 1):
-        code, poses, relRs, relTs = RefinementCore(poses, ext[i], ext[i + 1], i, i + 1, relRs, relTs, Tr, inlierThreshold0)
-        codes.append(code)
-    return poses, np.asarray(codes)
+# ---- f4: pose refinement on the extended key points lives in caelo_b200/refine.py ----------------------------------
+def __getattr__(name):
+    """Names that moved to ``caelo_b200.refine`` (kept importable from here)."""
+    from . import refine
+    moved = {"GetRtFromOnePose": "split_pose", "GetRelRtBetween2Poses": "relative_motion"}
+    if name in moved:
+        return getattr(refine, moved[name])
+    if name in ("ForwardUpdatePoses", "extended_key_points", "RefinementCore", "refine_sequence", "RefineOdometry"):
+        return getattr(refine, name)
+    if name == "GetLidarRelRtBetween2Poses":
+        return lambda pose0, pose1, R_Tr, T_Tr, R_Tr_inv, T_Tr_inv: refine.lidar_relative_motion(
+            pose0, pose1, (R_Tr, T_Tr, R_Tr_inv, T_Tr_inv))
+    raise AttributeError(name)

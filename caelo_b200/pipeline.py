@@ -352,7 +352,7 @@ _comm_streams = {}
 
 
 def gather_poses(poses: np.ndarray, device: torch.device, cap: Optional[int] = None, failed: bool = False,
-                 return_failed: bool = False):
+                 return_failed: bool = False, dtype=np.float32):
     """NCCL gather of the per-rank [P_local,16] pose rows to rank 0 (the only collective on the
     path; PoseEstimation.py:254-267's pose chain then runs on rank 0).  Returns the concatenated
     array on rank 0, None elsewhere.  Works without torch.distributed initialised (1 rank).
@@ -360,7 +360,8 @@ def gather_poses(poses: np.ndarray, device: torch.device, cap: Optional[int] = N
     [cap+1,16] rows moves everything (row 0 carries the row count) instead of a count exchange first.  The
     collective runs on its own CUDA stream, so it never waits for kernels queued on the compute stream.
     ``failed``: this rank hit an error on its part — it still takes part (so nobody blocks) and flags it in row 0;
-    with ``return_failed`` the call returns (rows, [failed ranks]) (the list is only known on rank 0)."""
+    with ``return_failed`` the call returns (rows, [failed ranks]) (the list is only known on rank 0).
+    ``dtype``: float32 pose rows of the odometry, float64 for the refinement's rows (caelo_b200.refine)."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return (poses, [0] if failed else []) if return_failed else poses
@@ -373,7 +374,7 @@ def gather_poses(poses: np.ndarray, device: torch.device, cap: Optional[int] = N
         on_comm = torch.cuda.stream(comm)
     else:                                   # gloo (the CPU tests of the sharding logic)
         on_comm = contextlib.nullcontext()
-    rows = np.ascontiguousarray(poses, np.float32)
+    rows = np.ascontiguousarray(poses, dtype)
     with on_comm:
         if cap is None:
             n_loc = torch.tensor([rows.shape[0]], dtype=torch.int64, device=device)
@@ -381,7 +382,7 @@ def gather_poses(poses: np.ndarray, device: torch.device, cap: Optional[int] = N
             dist.all_gather(counts, n_loc)
             cap = max(int(c.item()) for c in counts)
         assert rows.shape[0] <= cap
-        buf = np.zeros((cap + 1, 16), np.float32)
+        buf = np.zeros((cap + 1, 16), dtype)
         buf[0, 0] = rows.shape[0]
         buf[0, 1] = 1.0 if failed else 0.0
         buf[1:1 + rows.shape[0]] = rows

@@ -98,11 +98,13 @@ def _rays_on(device):
 
 
 def sensor_pose(frame: int, step: float = 0.7, yaw_step_deg: float = 0.3):
-    """World pose of the sensor at ``frame``: x_world = Rz(yaw) x_sensor + pos."""
+    """World pose of the sensor at ``frame``: x_world = Rz(yaw) x_sensor + pos.  ``step`` metres forward and
+    ``yaw_step_deg`` of heading per frame, weaving +-2 m across the road (2 cm per frame at the start) — bounded, so a
+    4541-frame drive stays on the road."""
     yaw = math.radians(yaw_step_deg) * frame
     cy, sy = math.cos(yaw), math.sin(yaw)
     return (np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]], np.float32),
-            np.array([step * frame, 0.02 * frame, 0.0], np.float32))
+            np.array([step * frame, 2.0 * math.sin(0.01 * frame), 0.0], np.float32))
 
 
 def scan_torch(world: World, frame: int, seed: int, device="cpu", step: float = 0.7, yaw_step_deg: float = 0.3):

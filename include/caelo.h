@@ -236,6 +236,21 @@ int caelo_nn3(caelo_ctx *ctx, const float *pc0, int N, const float *pc1, int M, 
               double thr, uint8_t *mask, int32_t *count, void *stream);
 int caelo_transform_points(caelo_ctx *ctx, const float *Rt, float *pc, int M, void *stream);
 
+/* f4, batched — WHOLE ICPs (MyICP.py:28-73) for B frame pairs in one call, no host round trip per iteration (what
+ * RefinePoses.py:273-334 `RefinementCore` runs per key-frame pair; configs[4] shards the pairs of seq 00-10 over ranks).
+ * pc0 dev [S0,3] f32 = the B target clouds concatenated, off0 HOST int64 [B+1] row offsets; pc1 dev [S1,3] f32 = the B
+ * source clouds (already moved by the odometry pose), off1 likewise — pc1 is the work copy and is updated in place.
+ * Per iteration and pair: exact nearest neighbour within the current inlier threshold (uniform grid over pc0, same
+ * pairs as the brute-force search of caelo_nn3), SolveRT on them (caelo_kabsch's arithmetic), pc1 <- R pc1 + T, then
+ * the reference's loop control on the device: fewer than min_inliers -> failure; Euler-angle / translation norms below
+ * ep after min_iter iterations -> converged; both below small_shift -> thr *= decay.
+ * Out: hist dev [B,max_iter,12] f32 = [R|T] of every iteration run (zeros beyond), hist_n dev int32 [B,max_iter] = its
+ * inlier count, state dev float64 [B,4] = success flag, iterations run, last inlier count, final threshold.  The host
+ * accumulates R*, T* from hist with the reference's own numpy expressions (api.icp_batch). */
+int caelo_icp_batch(caelo_ctx *ctx, const float *pc0, const int64_t *off0, float *pc1, const int64_t *off1, int B,
+                    double thr0, double decay, double small_shift, double ep, int max_iter, int min_iter,
+                    int min_inliers, float *hist, int32_t *hist_n, double *state, void *stream);
+
 /* Debug: device buffer [grid][64][16] int64 (+ [1024][8] for dense) receiving clock64 stamps of the encoder's per-patch
  * phases (NULL disables).  Used by tools/encoder_timeline.py. */
 int caelo_debug_set_timeline(caelo_ctx *ctx, long long *buf);

@@ -22,7 +22,7 @@ import numpy as np
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STAGED_DIR = os.path.join(_ROOT, "baseline", "_ref")       # git-ignored working copy that travels to the GPU box
 STAGED_FILES = ("Dirs.py", "Voxel.py", "SphericalRing.py", "Transformations.py", "Match.py", "MyICP.py",
-                "PoseEstimation.py", "TrainedModels/SphericalRingPCRespondLayer.h5",
+                "PoseEstimation.py", "RefinePoses.py", "TrainedModels/SphericalRingPCRespondLayer.h5",
                 "TrainedModels/EncoderModel4VoxelPatch.h5")
 
 

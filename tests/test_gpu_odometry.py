@@ -189,25 +189,58 @@ def test_icp_matches_oracle_and_reference_run(api, oracle_mod, seq, capsys):
     for pc1, kw, tag in ((k1_, dict(inlierThreshold=0.3, smallShiftThreshold=0.1, ep=0.01), "tight"), (k1_, {}, "aligned"),
                          (k1, {}, "raw")):
         gi, oi = {}, {}
-        R, T, ok = api.ICP(k0, pc1, info=gi, **kw)
+        R, T, ok = api.ICP(k0, pc1, info=gi, **kw)                # a batch of one through the device-side ICP
         Ro, To, oko = oracle_mod.icp(k0, pc1, info=oi, **kw)
         assert ok == oko and gi == oi, (tag, gi, oi)
         assert np.array_equal(R, Ro) and np.array_equal(T, To)
         assert R.dtype == np.float64 and T.shape == (3, 1)
+        si = {}
+        full = dict(maxIterTimes=50, minIterTimes=19, inlierThreshold=0.5, smallShiftThreshold=0.05, decay_rate=0.9, ep=0.001)
+        full.update(kw)
+        Rs, Ts, oks = api._icp_stepwise(api.default_context(), k0, pc1, info=si, **full)   # host-driven loop, brute-force search
+        assert oks == ok and si == gi and np.array_equal(Rs, R) and np.array_equal(Ts, T)
         if tag == "tight":
             assert ok and np.abs(R - z["R_tight"]).max() < 1e-5 and np.abs(T - z["T_tight"]).max() < 2e-4
     assert "ICP iters:" in capsys.readouterr().out          # the reference's progress line
 
 
+def test_icp_batch_equals_single_icps_and_oracle(api, oracle_mod):
+    """caelo_icp_batch: seven ICPs of different sizes in ONE call (grid-indexed search, loop control on the device) ==
+    the oracle's ICP pair by pair — incl. a pair that fails (< 100 inliers), one that starts far off, one with
+    duplicated points (distance ties -> lowest index) and a tiny cloud."""
+    import sys
+    import golden_data as G
+    sys.path.insert(0, G.GOLDEN)
+    import make_icp_golden as M
+    rng = np.random.default_rng(5)
+    k0, k1, k1_ = M.icp_inputs("00")
+    j0, j1, j1_ = M.icp_inputs("01")
+    far = (k1_ + np.float32([0.0, 0.0, 200.0])).astype(np.float32)              # nothing within the threshold -> failure
+    dup0 = np.r_[k0[:4000], k0[:4000]].astype(np.float32)                       # every target point twice
+    tiny0, tiny1 = k0[:300].copy(), (k0[:300] + rng.normal(0, 0.01, (300, 3))).astype(np.float32)
+    P0 = [k0, k0, j0, k0, dup0, tiny0, j0]
+    P1 = [k1_, k1, j1_, far, k1_[:6000], tiny1, j1]
+    kw = dict(inlierThreshold=1.0, smallShiftThreshold=0.1, ep=0.001)          # RefineOdometry's setting
+    got = api.icp_batch(P0, P1, **kw)
+    assert not any(g[3].get("redone_on_host") for g in got)
+    for (R, T, ok, info), p0, p1 in zip(got, P0, P1):
+        oi = {}
+        Ro, To, oko = oracle_mod.icp(p0, p1, info=oi, **kw)
+        assert ok == oko and info == oi, (info, oi)
+        assert np.array_equal(R, Ro) and np.array_equal(T, To)
+    assert [g[2] for g in got][3] is False and got[0][2] is True
+    one = api.icp_batch([j0], [j1_], **kw)[0]                                 # batch composition does not matter
+    assert np.array_equal(one[0], got[2][0]) and np.array_equal(one[1], got[2][1]) and one[3] == got[2][3]
+
+
 # ---- accuracy on a drive with known motion + the f4 refinement flow -------------------------------------------
-def _ground_truth(n_frames, step=0.7, yaw_step_deg=0.3):
+def _ground_truth(n_frames):
     """Absolute sensor poses of synth.scan (x_world = Rz(yaw_f) x_f + pos_f) as [F,12] rows."""
+    from caelo_b200 import synth
     out = []
     for f in range(n_frames):
-        a = np.radians(yaw_step_deg) * f
-        R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
-        T = np.array([[step * f], [0.02 * f], [0.0]])
-        out.append(np.c_[R, T].reshape(12))
+        R, T = synth.sensor_pose(f)
+        out.append(np.c_[R.astype(np.float64), T.astype(np.float64).reshape(3, 1)].reshape(12))
     return np.asarray(out)
 
 
@@ -245,7 +278,60 @@ def test_odometry_and_refinement_accuracy_on_known_motion(api, sequence, capsys)
     assert rre2.max() < 0.5 and rte2.max() < 0.2 and rte2.mean() <= rte.mean() + 0.01, (rte, rte2)
     print('RTE odometry %.3f m -> refined %.3f m; RRE %.3f -> %.3f deg' % (rte.mean(), rte2.mean(), rre.mean(), rre2.mean()))
     assert np.array_equal(refined[0], poses[0].astype(np.float64))          # the first pose is never touched
-    assert "ICP iters:" in capsys.readouterr().out
+    # the batched refinement == RefinementCore + ForwardUpdatePoses pair after pair (the reference's own sequence of
+    # calls, RefinePoses.py:273-334), up to the float64 rounding of re-chaining the poses F times instead of once
+    from caelo_b200 import refine
+    seq = poses.astype(np.float64)
+    relRs, relTs = refine.all_relative_motions(seq)
+    for i in range(len(scans) - 1):
+        code, seq, relRs, relTs = refine.RefinementCore(seq, ext[i], ext[i + 1], i, i + 1, relRs, relTs, None)
+        assert code == 1
+    assert np.abs(seq - refined).max() < 1e-9
+    # sharded over two 'ranks' (one-frame halo of extended key points recomputed) == single rank
+    rows = [refine.refine_pairs(ext[lo:hi + 1], poses.astype(np.float64), [(i, i + 1) for i in range(lo, hi)], None, 0.5,
+                                frame0=lo) for lo, hi in (pipeline_shard(len(scans) - 1, r, 2) for r in range(2))]
+    assert np.array_equal(refine.chain_refined(poses, np.concatenate(rows, 0)), refined)
+
+
+def pipeline_shard(n, r, w):
+    from caelo_b200 import pipeline
+    return pipeline.shard_pairs(n, r, w)
+
+
+def test_refine_odometry_key_frames(api, sequence, tmp_path):
+    """RefineOdometry (RefinePoses.py:338-475): option 0 walks consecutive pairs, option 1 the key-frame pairs found by
+    transferring the inlier key points from pair to pair (GetTransferPairIdx, :102-114) — planned ahead and registered
+    as one batch.  The InliersIdx files PoseEstimation.py writes (:296-309) feed the transfer, as in the reference."""
+    from scipy import io
+    from caelo_b200 import odometry, refine
+    scans = sequence["scans"]
+    idir = str(tmp_path / "InliersIdx")
+    poses, rel = odometry.estimate_sequence(sequence["raw"], scans=scans, inliers_dir=idir, batch_pairs=8)
+    F = len(scans)
+    inl = []
+    for i in range(F - 1):
+        m = io.loadmat(os.path.join(idir, "%06d-%06d.bin.mat" % (i, i + 1)))
+        inl.append((m["inliersIdx0"].ravel(), m["inliersIdx1"].ravel()))
+    # transfer_pairs == the reference's cdist / argmin / == 0 formulation
+    from scipy.spatial.distance import cdist
+    a, b = inl[0][1], inl[1][0]
+    D = cdist(np.c_[a, a], np.c_[b, b])
+    want = [[i, int(D[i].argmin())] for i in range(D.shape[0]) if D[i, D[i].argmin()] == 0]
+    assert refine.transfer_pairs(a, b) == want and len(want) > 0
+    assert refine.transfer_pairs(np.zeros(0), b) == []
+    ext = refine.extended_key_points(scans)
+    gt = _ground_truth(F)
+    p0, walk0 = refine.RefineOdometry(ext, poses, None, 0)
+    assert [w[:2] for w in walk0] == [(i, i + 1) for i in range(F - 2)] and all(w[2] == 1 for w in walk0)   # :364: the last pair is never visited
+    p1, walk1 = refine.RefineOdometry(ext, poses, None, 1, inliers=inl)
+    assert walk1[0][0] == 0 and walk1[-1][1] >= F - 2 and all(w[2] == 1 for w in walk1)
+    assert all(a[1] == b[0] for a, b in zip(walk1, walk1[1:])) and max(w[1] - w[0] for w in walk1) > 1      # real key frames
+    lp = refine.longest_pair(inl, 0, F)
+    assert lp == walk1[0][:2] and refine.longest_pair(inl, 0, F, nMaxTransferFrames=1) == (0, 1)
+    for p in (p0, p1):
+        rre, rte = _pose_errors(p, gt)
+        assert rre.max() < 0.5 and rte.max() < 0.2
+        assert np.array_equal(p[0], poses[0].astype(np.float64))
 
 
 @pytest.mark.parametrize("seq", ["00", "01"])

@@ -133,10 +133,25 @@ def test_patches_too_few_voxels_raises(api):
 
 
 # ---- a3 ------------------------------------------------------------------------------------
-DESC_RTOL = 1e-4  # north_star: descriptors within 1e-4 relative fp32 (|err| <= rtol * max|ref|, max|ref| ~ 1)
+# north_star: descriptors within 1e-4 relative fp32.  The contract tested here is ELEMENTWISE:
+#     |d - d_ref| <= DESC_RTOL * |d_ref| + DESC_ATOL          for every one of the 60 components,
+# and additionally the global form |d - d_ref| <= DESC_RTOL * max|d_ref|.  The absolute floor is needed by any
+# two fp32 implementations (descriptor components cross zero; TF 1.14 vs torch-CPU already differ by 8.7e-7 on the
+# golden files); ours is 1e-5 because the tensor cores truncate their fp32 accumulation (dense1 adds 384 MMAs
+# into one accumulator): measured max |err| 8.0e-6 on the demo frames, independent of |d_ref| (profiles/r2_desc_err.txt:
+# atol 5e-6 leaves 7 of 245,760 components outside, atol 1e-5 none).
+DESC_RTOL = 1e-4
+DESC_ATOL = 1e-5
 
 
-@pytest.mark.parametrize("tag", G.FRAMES[:2])
+def assert_descriptors_close(got, want):
+    err = np.abs(got - want)
+    assert err.max() <= DESC_RTOL * np.abs(want).max()
+    bad = err > DESC_RTOL * np.abs(want) + DESC_ATOL
+    assert not bad.any(), (int(bad.sum()), float(err.max()))
+
+
+@pytest.mark.parametrize("tag", G.FRAMES)
 def test_descriptors_vs_oracle_and_golden(api, oracle_mod, tag):
     f, rr = G.frame(tag), G.refrun(tag)
     enc = api.load_model(api.WEIGHT_DIR + "/encoder.npz")
@@ -144,7 +159,7 @@ def test_descriptors_vs_oracle_and_golden(api, oracle_mod, tag):
     feat = api.GetFeaturesFromPatches(enc, ref_patches)          # predict() boundary: float32 patches
     want = oracle_mod.get_features_from_patches(ref_patches)
     assert feat.shape == (1024, 60) and feat.dtype == np.float32
-    assert np.abs(feat - want).max() <= DESC_RTOL * np.abs(want).max()
+    assert_descriptors_close(feat, want)
     # golden Features/*.mat (TF 1.14): <1e-5 except rows whose patch hit a k-th-neighbour tie
     err = np.abs(feat - f["golden_Features"]).max(1)
     assert (err < 1e-5).sum() >= 1022
@@ -161,7 +176,7 @@ def test_encoder_dense_random_patches(api, oracle_mod):
     x[1] = 1
     enc = api.load_model(api.WEIGHT_DIR + "/encoder.npz")
     got, want = enc.predict(x), oracle_mod.encoder_predict(x)
-    assert np.abs(got - want).max() <= DESC_RTOL * np.abs(want).max()
+    assert_descriptors_close(got, want)
     assert enc.predict(x[:0]).shape == (0, 20)
 
 
@@ -340,6 +355,95 @@ def test_pipeline_batch_matches_oracle(api, oracle_mod):
             assert np.abs(poses_dev[i, 9:12] - T.ravel()).max() <= 1e-4 * max(1.0, np.abs(T).max())
         else:
             assert abs(int(poses_dev[i, 13]) - len(i0)) <= 3
+
+
+def _bench_cpu_frames(d, n_frames):
+    """Oracle frame stage (respond -> select -> patches -> encoder) for frames 0..n-1 on a pool of host processes."""
+    import multiprocessing as mp
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    off = d["vox_offsets"]
+    jobs = [("port", d["ring3"][f], d["counter"][f], *[d["vox"][off[3 * f + s]:off[3 * f + s + 1]] for s in range(3)])
+            for f in range(n_frames)]
+    workers = min(os.cpu_count() or 1, 8)
+    with mp.get_context("spawn").Pool(workers, initializer=bench._cpu_init, initargs=("port", 2)) as pool:
+        return pool.map(bench._cpu_frame, jobs)
+
+
+def test_pipeline_on_the_bench_config_is_exact_stage_by_stage(api, oracle_mod):
+    """The batch bench.py times (33 synthetic frames, seed 1, pair ids 0..31) against the oracle, closing the chain
+    stage by stage: key points of every frame bit-identical; descriptors of every frame inside the contract; and for
+    EVERY pair the oracle's SolveRelativePose on the pipeline's own key points + descriptors with np.random.seed(pair)
+    gives the pipeline's row bit for bit (R, T, success, inlier count, threshold, trial count)."""
+    import torch
+    from caelo_b200 import pipeline, synth
+    F = 33
+    d = synth.make_frames(F, seed=1, first_frame=0)
+    pipe = pipeline.OdometryPipeline(api.default_context())
+    pipe.keep_details = True
+    ids = list(range(F - 1))
+    poses = pipe.run_device(*(torch.from_numpy(d[k]).cuda() for k in ("ring3", "counter", "vox")), d["vox_offsets"], None, ids)
+    det = pipe.last_details
+    kp_g, ft_g = det["kpts"].cpu().numpy(), det["feat"].cpu().numpy()
+    cpu = _bench_cpu_frames(d, F)
+    for f in range(F):
+        assert np.array_equal(kp_g[f], cpu[f][0]), f
+        assert_descriptors_close(ft_g[f], cpu[f][1])
+    assert (poses[:, 12] == 1).all()
+    for p in ids:
+        np.random.seed(p)
+        info = {}
+        R, T, ok, i0, i1, thr = oracle_mod.solve_relative_pose(kp_g[p], ft_g[p], None, kp_g[p + 1], ft_g[p + 1], None, info)
+        assert np.array_equal(poses[p, :9], np.asarray(R, np.float32).ravel()), p
+        assert np.array_equal(poses[p, 9:12], np.asarray(T, np.float32).ravel()), p
+        assert bool(poses[p, 12]) == ok and int(poses[p, 13]) == len(i0) and abs(poses[p, 14] - thr) < 1e-6
+        assert int(poses[p, 15]) == info["trials"]
+        m = det["mask"][p].cpu().numpy().astype(bool)
+        assert np.array_equal(np.flatnonzero(m), i1) and np.array_equal(det["pair_idx"][p].cpu().numpy()[m], i0)
+    # the raw-scan entry (f1, f2+a6 on the device) gives the same rows
+    soff = np.zeros(F + 1, np.int64)
+    soff[1:] = np.cumsum([s.shape[0] for s in d["scans"]])
+    poses_s = pipe.run_device_scans(torch.from_numpy(np.concatenate(d["scans"], 0)).cuda(), soff, None, ids)
+    assert np.array_equal(poses_s, poses)
+
+
+def test_pipeline_frames_with_few_keypoints(api, oracle_mod):
+    """A sparse scan (fewer than 1024 candidates, SphericalRing.py:286 only asserts > 50) must not abort the batch:
+    its pairs go through the per-pair path on the rows that exist — the reference's behaviour — and every other
+    pair is untouched."""
+    import torch
+    from caelo_b200 import pipeline, synth
+    d = synth.make_frames(4, seed=9)
+    ring, cnt = d["ring3"].copy(), d["counter"].copy()
+    ring[2, :, 110:] = 0                                   # frame 2: only 110 of 1792 columns return anything
+    cnt[2, :, 110:] = 0
+    pipe = pipeline.OdometryPipeline(api.default_context())
+    pipe.keep_details = True
+    ids = [10, 11, 12]
+    full = pipe.run_device(*(torch.from_numpy(x).cuda() for x in (d["ring3"], d["counter"], d["vox"])), d["vox_offsets"], None, ids)
+    np.random.seed(1234)
+    before = np.random.get_state()[1].copy()
+    poses = pipe.run_device(*(torch.from_numpy(x).cuda() for x in (ring, cnt, d["vox"])), d["vox_offsets"], None, ids)
+    assert np.array_equal(np.random.get_state()[1], before)            # the caller's global stream is untouched
+    det = pipe.last_details
+    resp = oracle_mod.respond_predict(ring[2][None])[0]
+    kp2, _ = oracle_mod.select_keypoints(ring[2], cnt[2], resp)
+    n2 = kp2.shape[0]
+    assert 50 < n2 < 1024
+    assert np.array_equal(det["kpts"][2, :n2].cpu().numpy(), kp2)
+    assert np.array_equal(poses[0], full[0])                             # pair (0,1) does not involve frame 2
+    kp, ft = det["kpts"].cpu().numpy(), det["feat"].cpu().numpy()
+    for p, (na, nb) in ((1, (1024, n2)), (2, (n2, 1024))):
+        np.random.seed(ids[p])
+        info = {}
+        R, T, ok, i0, i1, thr = oracle_mod.solve_relative_pose(kp[p, :na], ft[p, :na], None, kp[p + 1, :nb], ft[p + 1, :nb],
+                                                               None, info)
+        assert bool(poses[p, 12]) == ok and int(poses[p, 13]) == len(i0) and abs(poses[p, 14] - thr) < 1e-6
+        assert np.array_equal(poses[p, :9], np.asarray(R, np.float32).ravel())
+        assert np.array_equal(poses[p, 9:12], np.asarray(T, np.float32).ravel())
+        assert int(poses[p, 15]) == info["trials"]
 
 
 def test_device_sample_stream_is_numpys(api):

@@ -65,6 +65,34 @@ def test_shard_gather_chain_world2(tmp_path, n_pairs, use_cap):
     assert poses.shape == (n_pairs + 1, 12)
 
 
+def _worker_failing(rank, world, port, out):
+    """Rank 1 'fails' on its shard: it must still take part in the one collective (nobody blocks) and rank 0 must
+    learn which rank failed (a raising rank used to leave the others waiting in the NCCL gather)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = pipeline.shard_pairs(9, rank, world)
+    rows = _fake_pose_rows(list(range(lo, hi)))
+    if rank == 1:
+        rows = rows[:2]                                   # what it had finished before the error
+    got, bad = pipeline.gather_poses(rows, torch.device("cpu"), cap=5, failed=(rank == 1), return_failed=True)
+    if rank == 0:
+        np.save(out, got)
+        assert bad == [1]
+    else:
+        assert got is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_with_a_failed_rank_does_not_block(tmp_path):
+    out = str(tmp_path / "gathered.npy")
+    mp.spawn(_worker_failing, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    assert got.shape == (5 + 2, 16)
+    rows, bad = pipeline.gather_poses(_fake_pose_rows([0, 1]), torch.device("cpu"), failed=True, return_failed=True)
+    assert bad == [0] and rows.shape == (2, 16)           # single process: same contract
+
+
 def test_shard_pairs_cover_everything():
     for n in (1, 5, 32, 4540):
         for world in (1, 2, 3, 8):
