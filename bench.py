@@ -291,10 +291,33 @@ def cpu_baseline_and_parity(data, gpu_rows, gpu_details):
     arm.close()
     oracle.build()
     kp_g, ft_g = gpu_details["kpts"], gpu_details["feat"]
-    kp_same = all(np.array_equal(kp_g[f], arm.frames[f][0]) for f in range(n + 1))
-    desc_err = max(float(np.abs(ft_g[f] - arm.frames[f][1]).max()) for f in range(n + 1))
-    desc_ok = all(bool((np.abs(ft_g[f] - arm.frames[f][1]) <= 1e-4 * np.abs(arm.frames[f][1]) + 1e-5).all())
-                  for f in range(n + 1))
+    # (a) against the CPU arm: its predict is a torch-CPU stand-in for Keras, NOT the arithmetic contract the kernels
+    #     and the oracle share, so near-tied scores may order differently: report the overlap, compare descriptors on
+    #     the key points both sides selected
+    common, same_order, desc_err, desc_ok = [], True, 0.0, True
+    for f in range(n + 1):
+        kc, fc = arm.frames[f]
+        idx = {tuple(r): i for i, r in enumerate(kc.view(np.uint32).tolist())}
+        m = [(i, idx[tuple(r)]) for i, r in enumerate(kp_g[f].view(np.uint32).tolist()) if tuple(r) in idx]
+        common.append(len(m) / max(1, kp_g[f].shape[0]))
+        same_order &= kc.shape == kp_g[f].shape and bool(np.array_equal(kc, kp_g[f]))
+        if m:
+            gi, ci = np.array(m).T
+            e = np.abs(ft_g[f][gi] - fc[ci])
+            desc_err = max(desc_err, float(e.max()))
+            desc_ok &= bool((e <= 1e-4 * np.abs(fc[ci]) + 1e-5).all())
+    # (b) against the ORACLE (the contract arithmetic) on the first frames: key points bit-identical, descriptors
+    #     inside the contract
+    n_or = 3
+    off = data["vox_offsets"]
+    or_kp, or_desc = True, True
+    for f in range(n_or):
+        ko, _ = oracle.select_keypoints(data["ring3"][f], data["counter"][f], oracle.respond_predict(data["ring3"][f][None])[0])
+        _, pl = oracle.get_patches_list(ko, *[data["vox"][off[3 * f + s]:off[3 * f + s + 1]] for s in range(3)])
+        fo = oracle.get_features_from_patches(pl)
+        or_kp &= bool(np.array_equal(ko, kp_g[f]))
+        or_desc &= bool(ko.shape == kp_g[f].shape and (np.abs(ft_g[f] - fo) <= 1e-4 * np.abs(fo) + 1e-5).all())
+    # (c) match + RANSAC + refit: the oracle's SolveRelativePose on the GPU's own key points + descriptors, same seed
     exact = 0
     for p in range(n):
         np.random.seed(p)
@@ -307,10 +330,14 @@ def cpu_baseline_and_parity(data, gpu_rows, gpu_details):
     base = {"value": n / sec, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
             "sample": arm.describe("%d pairs (%d new frames) of rank 0's step, every frame processed once; 1 warm-up pass"
                                    % (n, n))}
-    parity = {"parity_checked_pairs": n, "keypoints_bit_exact": bool(kp_same), "descriptors_within_contract": bool(desc_ok),
-              "descriptor_max_abs_err": desc_err, "pose_bit_exact_vs_oracle_on_gpu_descriptors": exact,
-              "pose_max_abs_diff_vs_cpu_arm": dpose, "inliers_gpu": [int(x) for x in gpu_rows[:n, 13]],
-              "inliers_cpu_arm": [int(x) for x in rows[:, 13]]}
+    parity = {"parity_checked_pairs": n,
+              "vs_oracle": {"frames": n_or, "keypoints_bit_exact": or_kp, "descriptors_within_contract": or_desc,
+                            "pairs_pose_bit_exact_on_gpu_descriptors": exact},
+              "vs_cpu_arm": {"keypoints_in_common_min": float(min(common)), "keypoints_identical_incl_order": bool(same_order),
+                             "descriptors_within_contract_on_common_keypoints": bool(desc_ok),
+                             "descriptor_max_abs_err": desc_err, "pose_max_abs_diff": dpose,
+                             "inliers_gpu": [int(x) for x in gpu_rows[:n, 13]], "inliers_cpu_arm": [int(x) for x in rows[:, 13]]},
+              "descriptor_contract": "|d - d_ref| <= 1e-4 |d_ref| + 1e-5 per component"}
     return base, parity
 
 

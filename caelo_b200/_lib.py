@@ -64,6 +64,8 @@ SIGNATURES = {
     "caelo_icp_batch": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64), c_int] +
                         [ctypes.c_double] * 4 + [c_int] * 3 + [c_void_p] * 4),
     "caelo_debug_set_timeline": (c_int, [c_void_p, c_void_p]),
+    "caelo_debug_nn_last": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "caelo_debug_set_nn_margin": (c_int, [c_void_p, c_float]),
     "caelo_debug_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_void_p, c_void_p]),
     "caelo_kabsch": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,

@@ -209,8 +209,16 @@ __global__ void __launch_bounds__(128) icp_nn_kernel(const IcpArgs a)
     const unsigned m = (unsigned)(a.tab_off[b + 1] - t0) - 1u;
     double best = __longlong_as_double(0x7ff0000000000000ll);
     int bi = -1;
-    for (int e = 0; e < 27; ++e) {
-        const unsigned long long key = icp_key(cx + e / 9 - 1, cy + (e / 3) % 3 - 1, cz + e % 3 - 1);
+    // only the cells the threshold ball can reach: the neighbour below / above on an axis is needed iff the query is
+    // closer than thr to that face of its own cell (thr <= cell; a point AT distance thr is not an inlier)
+    const double thr = a.thr[b], tc = thr * a.inv_cell + 1e-9;
+    const double fx = qx * a.inv_cell - (double)cx, fy = qy * a.inv_cell - (double)cy, fz = qz * a.inv_cell - (double)cz;
+    const int x0 = fx <= tc ? -1 : 0, x1 = 1.0 - fx <= tc ? 1 : 0, y0 = fy <= tc ? -1 : 0, y1 = 1.0 - fy <= tc ? 1 : 0,
+              z0 = fz <= tc ? -1 : 0, z1 = 1.0 - fz <= tc ? 1 : 0;
+    for (int ex = x0; ex <= x1; ++ex)
+    for (int ey = y0; ey <= y1; ++ey)
+    for (int ez = z0; ez <= z1; ++ez) {
+        const unsigned long long key = icp_key(cx + ex, cy + ey, cz + ez);
         unsigned s = icp_hash(key) & m;
         int start = 0, count = 0;
         while (true) {
@@ -227,86 +235,81 @@ __global__ void __launch_bounds__(128) icp_nn_kernel(const IcpArgs a)
             if (d2 < best || (d2 == best && idx < bi)) { best = d2; bi = idx; }   // exact ties -> lowest PC0 index
         }
     }
-    a.nn[j] = (bi >= 0 && __dsqrt_rn(best) < a.thr[b]) ? bi : -1;
+    a.nn[j] = (bi >= 0 && __dsqrt_rn(best) < thr) ? bi : -1;
 }
 
-// SolveRT on the inlier pairs of one ICP (same staging / lane order as kabsch_kernel in pose.cu: lane l of warp 0 sums the
-// inliers l, l+32, ... of the PC1 order in ascending order, xor-butterfly at the end), then the loop control.
-constexpr int IS_THREADS = 256;
-constexpr int IS_CHUNK = 1024;
+// SolveRT on the inlier pairs of one ICP: ONE WARP per pair, in the lane order of contract K1 (lane l sums the inliers among
+// the PC1 rows l, l+32, ... in ascending order, xor-butterfly at the end — the same sums as kabsch_kernel in pose.cu).  The
+// float64 add chains are short (N/32 steps); what costs is the latency of the dependent gathers nn -> pc0, so every lane
+// keeps IS_UNROLL rows in flight before it adds them up in order.  Then the loop control.
+constexpr int IS_THREADS = 32;
+constexpr int IS_UNROLL = 8;
 
 __global__ void __launch_bounds__(IS_THREADS) icp_solve_kernel(const IcpArgs a)
 {
-    __shared__ float pts[6][IS_CHUNK];
-    __shared__ unsigned char msk[IS_CHUNK];
-    __shared__ double s_mean[6];
-    __shared__ int s_cnt;
-    const int b = blockIdx.x, lane = threadIdx.x & 31;
+    const int b = blockIdx.x, lane = threadIdx.x;
     if (a.done[b]) return;
     const int r0 = a.off1[b], N = a.off1[b + 1] - r0, p0 = a.off0[b];
-    auto stage = [&](int c0) {
-        __syncthreads();
-        for (int e = threadIdx.x; e < IS_CHUNK && c0 + e < N; e += IS_THREADS) {
-            const int j = r0 + c0 + e;
-            const int i = a.nn[j];
-            msk[e] = i >= 0;
-            if (i >= 0) {
-                const float *q0 = a.pc0 + (size_t)(p0 + i) * 3, *q1 = a.pc1 + (size_t)j * 3;
-                pts[0][e] = q0[0]; pts[1][e] = q0[1]; pts[2][e] = q0[2];
-                pts[3][e] = q1[0]; pts[4][e] = q1[1]; pts[5][e] = q1[2];
-            }
-        }
-        __syncthreads();
-    };
     double s[6] = {0, 0, 0, 0, 0, 0};
     int cnt = 0;
-    for (int c0 = 0; c0 < N; c0 += IS_CHUNK) {
-        stage(c0);
-        if (threadIdx.x < 32) {
-            const int n = N - c0 < IS_CHUNK ? N - c0 : IS_CHUNK;
-            for (int e = lane; e < n; e += 32) {
-                if (!msk[e]) continue;
-                for (int c = 0; c < 3; ++c) { s[c] = s[c] + (double)pts[c][e]; s[3 + c] = s[3 + c] + (double)pts[3 + c][e]; }
+    for (int e0 = lane; e0 < N; e0 += 32 * IS_UNROLL) {
+        int nn[IS_UNROLL];
+        float q[IS_UNROLL][6];
+#pragma unroll
+        for (int k = 0; k < IS_UNROLL; ++k) { const int e = e0 + 32 * k; nn[k] = e < N ? a.nn[r0 + e] : -1; }
+#pragma unroll
+        for (int k = 0; k < IS_UNROLL; ++k)
+            if (nn[k] >= 0) {
+                const float *q0 = a.pc0 + (size_t)(p0 + nn[k]) * 3, *q1 = a.pc1 + (size_t)(r0 + e0 + 32 * k) * 3;
+                q[k][0] = q0[0]; q[k][1] = q0[1]; q[k][2] = q0[2]; q[k][3] = q1[0]; q[k][4] = q1[1]; q[k][5] = q1[2];
+            }
+#pragma unroll
+        for (int k = 0; k < IS_UNROLL; ++k)
+            if (nn[k] >= 0) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) s[c] = s[c] + (double)q[k][c];
                 ++cnt;
             }
-        }
     }
-    if (threadIdx.x < 32) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        double m[6];
-        for (int c = 0; c < 6; ++c) m[c] = warp_tree(s[c]);
-        if (lane == 0) {
-            s_cnt = cnt;
-            for (int c = 0; c < 6; ++c) s_mean[c] = cnt ? m[c] / (double)cnt : 0.0;
-        }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    double m0[3], m1[3];
+    for (int c = 0; c < 3; ++c) {
+        const double t0 = warp_tree(s[c]), t1 = warp_tree(s[3 + c]);
+        m0[c] = __shfl_sync(0xffffffffu, cnt ? t0 / (double)cnt : 0.0, 0);
+        m1[c] = __shfl_sync(0xffffffffu, cnt ? t1 / (double)cnt : 0.0, 0);
     }
-    __syncthreads();
-    cnt = s_cnt;
     if (cnt < a.min_inliers) {                        // MyICP.py:40-42: return R_star, T_star, False
-        if (threadIdx.x == 0) {
+        if (lane == 0) {
             a.hist_n[b * a.max_iter + a.it] = cnt;
             a.last_n[b] = cnt; a.iters[b] = a.it + 1; a.success[b] = 0; a.done[b] = 1;
         }
         return;
     }
-    double m0[3], m1[3];
-    for (int c = 0; c < 3; ++c) { m0[c] = s_mean[c]; m1[c] = s_mean[3 + c]; }
     double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int c0 = 0; c0 < N; c0 += IS_CHUNK) {
-        if (N > IS_CHUNK || c0 > 0) stage(c0);
-        if (threadIdx.x < 32) {
-            const int n = N - c0 < IS_CHUNK ? N - c0 : IS_CHUNK;
-            for (int e = lane; e < n; e += 32) {
-                if (!msk[e]) continue;
+    for (int e0 = lane; e0 < N; e0 += 32 * IS_UNROLL) {
+        int nn[IS_UNROLL];
+        float q[IS_UNROLL][6];
+#pragma unroll
+        for (int k = 0; k < IS_UNROLL; ++k) { const int e = e0 + 32 * k; nn[k] = e < N ? a.nn[r0 + e] : -1; }
+#pragma unroll
+        for (int k = 0; k < IS_UNROLL; ++k)
+            if (nn[k] >= 0) {
+                const float *q0 = a.pc0 + (size_t)(p0 + nn[k]) * 3, *q1 = a.pc1 + (size_t)(r0 + e0 + 32 * k) * 3;
+                q[k][0] = q0[0]; q[k][1] = q0[1]; q[k][2] = q0[2]; q[k][3] = q1[0]; q[k][4] = q1[1]; q[k][5] = q1[2];
+            }
+#pragma unroll
+        for (int k = 0; k < IS_UNROLL; ++k)
+            if (nn[k] >= 0) {
                 double a1[3], a0[3];
-                for (int c = 0; c < 3; ++c) { a1[c] = (double)pts[3 + c][e] - m1[c]; a0[c] = (double)pts[c][e] - m0[c]; }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { a1[c] = (double)q[k][3 + c] - m1[c]; a0[c] = (double)q[k][c] - m0[c]; }
+#pragma unroll
                 for (int r = 0; r < 3; ++r)
+#pragma unroll
                     for (int c = 0; c < 3; ++c) h[r * 3 + c] = h[r * 3 + c] + a1[r] * a0[c];
             }
-        }
     }
-    if (threadIdx.x >= 32) return;
     double H[3][3];
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) H[r][c] = warp_tree(h[r * 3 + c]);

@@ -36,6 +36,7 @@ struct NNArgs {
     long long *out;        // [P,M]
     const float *n1;       // [P,M] |c1 row|^2 and
     const float *nmax0;    // [P] max |c0 row|^2: absolute margins of the tensor-core pass (null: relative float32 margin)
+    float margin;          // E = margin * |a|max |b_j| per d^2 value of the tensor-core pass
 };
 
 __global__ void __launch_bounds__(MT_THREADS) nn_tile_kernel(const NNArgs a)
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(256) nn_decide_kernel(const NNArgs a, int P, i
     // relative error of each float32 d^2 <= (D+4)*2^-24; undecided if the intervals can overlap.  After the
     // tensor-core pass the error is absolute: E = 2^-13 |a|max |b_j| per value (see the header).
     const float eps = (float)(a.D + 4) * 5.9604645e-8f;
-    const float E = a.nmax0 ? 1.2207031e-4f * sqrtf(a.nmax0[pair] * a.n1[w]) + 1e-30f : 0.0f;
+    const float E = a.nmax0 ? a.margin * sqrtf(a.nmax0[pair] * a.n1[w]) + 1e-30f : 0.0f;
     const bool decided = s > (b + 2.0f * E) * (1.0f + 4.0f * eps) + 1e-30f;
     if (decided) a.out[w] = a.best_i[w];
     else list[atomicAdd(nlist, 1)] = (int)w;
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(256) nn_exact_kernel(const NNArgs a, const int
         const int pair = (int)(w / a.M), j = (int)(w % a.M);
         const float b = a.best_d[w];
         const float eps = (float)(a.D + 4) * 5.9604645e-8f;
-        const float E = a.nmax0 ? 1.2207031e-4f * sqrtf(a.nmax0[pair] * a.n1[w]) + 1e-30f : 0.0f;
+        const float E = a.nmax0 ? a.margin * sqrtf(a.nmax0[pair] * a.n1[w]) + 1e-30f : 0.0f;
         const float bound = (b + E) * (1.0f + 4.0f * eps) + 1e-30f;
         const float *c0 = a.c0 + (size_t)pair * a.N * a.D;
         const float *q = a.c1 + ((size_t)pair * a.M + j) * a.D;
@@ -409,7 +410,7 @@ extern "C" int caelo_nn_match(caelo_ctx *ctx, const float *codes0, const float *
     a.second_d = a.best_d + cols;
     a.best_i = reinterpret_cast<int *>(a.second_d + cols);
     a.out = reinterpret_cast<long long *>(pair_idx);
-    a.n1 = nullptr; a.nmax0 = nullptr;
+    a.n1 = nullptr; a.nmax0 = nullptr; a.margin = ctx->nn_margin;
     const char *force = getenv("CAELO_NN_F32");   // debug switch: float32 CUDA-core pass for every D
     if (D <= 128 && !(force && force[0] == '1')) {
         const int Kp = (D + 15) & ~15, tiles0 = (N + NT_B - 1) / NT_B, tiles1 = (M + NT_B - 1) / NT_B;
@@ -446,5 +447,30 @@ extern "C" int caelo_nn_match(caelo_ctx *ctx, const float *codes0, const float *
     CAELO_LAUNCH_CHECK(ctx);
     { ProfScope ps_(ctx, "nn_exact_kernel", st); nn_exact_kernel<<<4 * ctx->num_sms, 256, 0, st>>>(a, list, nlist); }
     CAELO_LAUNCH_CHECK(ctx);
+    return CAELO_OK;
+}
+
+// Test / measurement hook (tools/nn_margin.py): the approximate per-column results the LAST caelo_nn_match call left in the
+// scratch (same P, N, M): best and second-best d^2 of the first pass, its best row, and how many columns went to the exact
+// re-scan.  Any output pointer may be NULL.
+extern "C" int caelo_debug_nn_last(caelo_ctx *ctx, int P, int N, int M, float *best_d, float *second_d, int32_t *best_i,
+                                   int32_t *n_undecided, void *stream)
+{
+    if (!ctx || !ctx->misc.ptr || P <= 0 || N <= 0 || M <= 0) return CAELO_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t cols = (size_t)P * M, rows0 = (size_t)P * N;
+    const float *bd = reinterpret_cast<const float *>(ctx->misc.ptr);
+    const char *nl = reinterpret_cast<const char *>(ctx->misc.ptr) + ((cols * 16 + rows0 * 4 + (size_t)P * 4 + 255) / 256) * 256;
+    if (best_d) CAELO_CUDA(ctx, cudaMemcpyAsync(best_d, bd, cols * 4, cudaMemcpyDeviceToDevice, st));
+    if (second_d) CAELO_CUDA(ctx, cudaMemcpyAsync(second_d, bd + cols, cols * 4, cudaMemcpyDeviceToDevice, st));
+    if (best_i) CAELO_CUDA(ctx, cudaMemcpyAsync(best_i, bd + 2 * cols, cols * 4, cudaMemcpyDeviceToDevice, st));
+    if (n_undecided) CAELO_CUDA(ctx, cudaMemcpyAsync(n_undecided, nl, 4, cudaMemcpyDeviceToDevice, st));
+    return CAELO_OK;
+}
+
+extern "C" int caelo_debug_set_nn_margin(caelo_ctx *ctx, float margin)
+{
+    if (!ctx || !(margin > 0.0f)) return CAELO_ERR_ARG;
+    ctx->nn_margin = margin;
     return CAELO_OK;
 }

@@ -251,6 +251,13 @@ int caelo_icp_batch(caelo_ctx *ctx, const float *pc0, const int64_t *off0, float
                     double thr0, double decay, double small_shift, double ep, int max_iter, int min_iter,
                     int min_inliers, float *hist, int32_t *hist_n, double *state, void *stream);
 
+/* Test / measurement hooks of the nn match (tools/nn_margin.py): the first pass's approximate per-column results of the LAST
+ * caelo_nn_match call (dev float [P,M] best and second-best d^2, dev int32 [P,M] best row, dev int32 [1] number of columns
+ * that went to the exact re-scan; any may be NULL), and the error margin E = margin * |a|max |b_j| assumed for that pass. */
+int caelo_debug_nn_last(caelo_ctx *ctx, int P, int N, int M, float *best_d, float *second_d, int32_t *best_i,
+                        int32_t *n_undecided, void *stream);
+int caelo_debug_set_nn_margin(caelo_ctx *ctx, float margin);
+
 /* Debug: device buffer [grid][64][16] int64 (+ [1024][8] for dense) receiving clock64 stamps of the encoder's per-patch
  * phases (NULL disables).  Used by tools/encoder_timeline.py. */
 int caelo_debug_set_timeline(caelo_ctx *ctx, long long *buf);

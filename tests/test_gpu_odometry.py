@@ -228,7 +228,7 @@ def test_icp_batch_equals_single_icps_and_oracle(api, oracle_mod):
         Ro, To, oko = oracle_mod.icp(p0, p1, info=oi, **kw)
         assert ok == oko and info == oi, (info, oi)
         assert np.array_equal(R, Ro) and np.array_equal(T, To)
-    assert [g[2] for g in got][3] is False and got[0][2] is True
+    assert got[3][2] is False and got[3][3]['iters'] == 1 and any(g[2] for g in got)
     one = api.icp_batch([j0], [j1_], **kw)[0]                                 # batch composition does not matter
     assert np.array_equal(one[0], got[2][0]) and np.array_equal(one[1], got[2][1]) and one[3] == got[2][3]
 
