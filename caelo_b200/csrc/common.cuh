@@ -44,7 +44,7 @@ struct caelo_ctx {
     int64_t launches = 0;
     cudaError_t last_err = cudaSuccess;
     bool have_respond = false, have_encoder = false;
-    float nn_margin = 1.2207031e-4f;    // nn match: E = nn_margin |a|max |b| (2^-13; see match.cu)
+    float nn_margin = 1.5258789e-5f;    // nn match: proportional term of the margin, 2^-16 (see nn_margin_E in match.cu)
     RespondWeights respond_host;
     EncoderWeightsDev enc;
     float *enc_blob = nullptr;

@@ -171,12 +171,18 @@ __device__ __forceinline__ void conv1_to_smem(const unsigned short *rows, const 
         for (int j = 0; j < 9; ++j) {
             const unsigned gj = (j < 3) ? g0 : ((j < 6) ? g1 : g2);
             const unsigned pat = (gj >> (4 * (j % 3))) & 7u;
-            const float4 *row = reinterpret_cast<const float4 *>(t1 + j * T1_ROW + pat * T1_PAT);
-            const float4 w0 = row[0], w1 = row[1];
-            acc2[0] = __fadd2_rn(acc2[0], make_float2(w0.x, w0.y));
-            acc2[1] = __fadd2_rn(acc2[1], make_float2(w0.z, w0.w));
-            acc2[2] = __fadd2_rn(acc2[2], make_float2(w1.x, w1.y));
-            acc2[3] = __fadd2_rn(acc2[3], make_float2(w1.z, w1.w));
+            // the patches are sparse: most (dx,dy) groups of a listed sub-position are empty, and the empty pattern's
+            // row is all zeros (x + 0 = x exactly) — lanes with pat == 0 skip the two 16-byte loads, which cuts the
+            // shared-memory wavefronts the tensor core's operand fetch competes with (ncu round 2: the LSU took 60 %
+            // of the shared-memory pipe next to the tensor core's 74 %, three quarters of it these table rows)
+            if (pat) {
+                const float4 *row = reinterpret_cast<const float4 *>(t1 + j * T1_ROW + pat * T1_PAT);
+                const float4 w0 = row[0], w1 = row[1];
+                acc2[0] = __fadd2_rn(acc2[0], make_float2(w0.x, w0.y));
+                acc2[1] = __fadd2_rn(acc2[1], make_float2(w0.z, w0.w));
+                acc2[2] = __fadd2_rn(acc2[2], make_float2(w1.x, w1.y));
+                acc2[3] = __fadd2_rn(acc2[3], make_float2(w1.z, w1.w));
+            }
         }
         const float acc[8] = {acc2[0].x, acc2[0].y, acc2[1].x, acc2[1].y, acc2[2].x, acc2[2].y, acc2[3].x, acc2[3].y};
         // max over the eight sub-position lanes, halving the channel set a lane carries at each exchange:
@@ -625,6 +631,182 @@ __global__ void __launch_bounds__(C3_THREADS, 3 - NBUF) conv3_tc_kernel(const Co
     if (warp == C3_ISSUER) umma::tmem_dealloc(tbase, 128);
 }
 
+// ---- conv3, two patches per MMA (M = 128) ----------------------------------------------------------------------
+// The M = 64 kernel above leaves half of the tensor datapath idle and fetches the 2 KB weight tile of every tap once per
+// patch; an MMA at this size is bound by its shared-memory operand fetch (A 2 KB + B 2 / 1 KB per MMA at ~128 B/clk), so
+// 189 KB of operands per patch cost ~1.5 k cycles.  Here TWO patches share every MMA: each (dy,dz)-shifted compact copy is
+// stored as [xi 6][patch 2][yz 16] x 16 B, so the 128 rows (x, patch, yz) of tap (dx,dy,dz) are again ONE contiguous run
+// (2048 B, SBO = 128 B) starting dx*512 B into the copy.  Operands per patch pair: 27 x (4+2) + 27 x (4+1) KB = 297 KB, i.e.
+// 148 KB per patch (-22 %), half the MMA count, all 128 TMEM lanes used.
+// The pair's operands take 108 KB, so there is ONE operand buffer, pipelined copy by copy: the nine copies are nine
+// stages with their own full / empty mbarriers; the issuer commits after the six MMAs of a stage (3 dx x {hi, lo}), which
+// lets the producers overwrite that copy with the NEXT pair while the later stages of this pair are still being multiplied.
+constexpr int C3P_COPY = 6 * 2 * 16 * 16;             // 3072 B: [xi 6][patch 2][yz 16] x 16 B
+constexpr int C3P_HALF = 9 * C3P_COPY;                // 27648 B: nine copies of one channel half
+constexpr int C3P_PART = 2 * C3P_HALF;                // 55296 B: both halves (the two K chunks)
+constexpr int C3P_BUF = 2 * C3P_PART;                 // 110592 B: hi + lo
+constexpr int C3P_SM_W = C3P_BUF;                     // W3 [kc 54][n 64][16 B]
+constexpr int C3P_SM_B3 = C3P_SM_W + 54 * 1024;
+constexpr int C3P_SM_BAR = C3P_SM_B3 + 128;           // full[9] empty[9] tfull[2] tempty[2] + tmem slot
+constexpr int C3P_SMEM = C3P_SM_BAR + 22 * 8 + 16;
+constexpr int C3P_PROD = 8;                           // warps 0-7 produce (thread = patch x position x channel half)
+constexpr int C3P_EPI = 8;                            // warps 8-15 drain the accumulators (lane quarter x channel half)
+constexpr int C3P_ISSUER = C3P_PROD + C3P_EPI;        // warp 16 issues the MMAs
+constexpr int C3P_THREADS = (C3P_ISSUER + 1) * 32;
+
+__global__ void __launch_bounds__(C3P_THREADS, 1) conv3_pair_kernel(const Conv3Args a)
+{
+    extern __shared__ __align__(128) unsigned char sm[];
+    float *b3s = reinterpret_cast<float *>(sm + C3P_SM_B3);
+    uint64_t *full = reinterpret_cast<uint64_t *>(sm + C3P_SM_BAR), *empty = full + 9, *tfull = full + 18, *tempty = full + 20;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + C3P_SM_BAR + 22 * 8);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+    for (int i = tid; i < C3P_BUF / 16; i += C3P_THREADS) reinterpret_cast<uint4 *>(sm)[i] = make_uint4(0, 0, 0, 0);
+    for (int e = tid; e < 27 * 16 * 32; e += C3P_THREADS) {     // B operand as in conv3_tc_kernel
+        int t = e / 512, ci = (e / 32) % 16, co = e % 32;
+        __half h, l;
+        umma::split_f16(a.k3[e], h, l);
+        unsigned char *w = sm + C3P_SM_W + (t * 2 + ci / 8) * 1024 + (ci % 8) * 2;
+        *reinterpret_cast<__half *>(w + (co / 8) * 128 + (co % 8) * 16) = h;
+        *reinterpret_cast<__half *>(w + ((32 + co) / 8) * 128 + (co % 8) * 16) = l;
+    }
+    if (tid < 32) b3s[tid] = a.b3[tid];
+    if (warp == C3P_ISSUER) umma::tmem_alloc(tmem_slot, 128);
+    if (tid == 0) {
+        for (int c = 0; c < 9; ++c) {
+            umma::mbar_init(&full[c], C3P_PROD * 32);
+            umma::mbar_init(&empty[c], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            umma::mbar_init(&tfull[b], 1);
+            umma::mbar_init(&tempty[b], C3P_EPI * 32);
+        }
+        umma::fence_mbar_init();
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t sC = umma::smem_u32(sm), sW = umma::smem_u32(sm + C3P_SM_W);
+    const int n_pairs = (a.P + 1) / 2;
+    const int n_my = (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // patch pairs of this CTA
+    auto pair_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
+
+    if (warp == C3P_ISSUER) {
+        const uint32_t idesc64 = umma::idesc_f16_f32(128, 64), idesc32 = umma::idesc_f16_f32(128, 32);
+        for (int j = 0; j < n_my; ++j) {
+            const int b = j & 1;
+            if (j >= 2) umma::mbar_wait(&tempty[b], (uint32_t)(((j >> 1) - 1) & 1));
+            const uint32_t d = tbase + b * 64;
+#pragma unroll 1
+            for (int c = 0; c < 9; ++c) {          // stage = (dy,dz) copy
+                umma::mbar_wait(&full[c], (uint32_t)(j & 1));
+                umma::fence_after_thread_sync();
+                if (umma::elect_one()) {
+                    const int dy = c / 3, dz = c % 3;
+#pragma unroll
+                    for (int part = 0; part < 2; ++part)
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const int t = dx * 9 + dy * 3 + dz;
+                            uint64_t da = umma::smem_desc(sC + part * C3P_PART + c * C3P_COPY + dx * 512, C3P_HALF, 128);
+                            uint64_t db = umma::smem_desc(sW + t * 2048, 1024, 128);
+                            umma::mma_f16(d, da, db, part ? idesc32 : idesc64, (c | part | dx) ? 1u : 0u);
+                        }
+                    umma::commit(&empty[c]);
+                    if (c == 8) umma::commit(&tfull[b]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < C3P_PROD) {
+        // ===== producers: thread = (patch of the pair, position, channel half); hi and lo written into every copy whose
+        // shifted window holds this position, each copy as soon as the previous pair's MMAs on it have completed =====
+        // consecutive threads = consecutive positions of one (patch, channel half): their 16-byte stores are contiguous
+        // (the M = 64 kernel interleaves the halves, whose copies are a multiple of 128 B apart: two-way bank conflicts)
+        const int pp = tid >> 7, half = (tid >> 6) & 1, pos = tid & 63;
+        const int x = pos >> 4, y = (pos >> 2) & 3, z = pos & 3;
+        float4 nv0 = make_float4(0.f, 0.f, 0.f, 0.f), nv1 = nv0;
+        auto fetch = [&](int i) {
+            if (i >= n_my) return;
+            int p = 2 * pair_of(i) + pp;
+            if (p >= a.P) p = a.P - 1;                 // odd patch count: the last pair's second half repeats the first
+            const float4 *src = reinterpret_cast<const float4 *>(a.act2 + (size_t)p * 1024 + pos * 16 + half * 8);
+            nv0 = __ldg(src);
+            nv1 = __ldg(src + 1);
+        };
+        fetch(0);
+        for (int i = 0; i < n_my; ++i) {
+            const float4 v0 = nv0, v1 = nv1;
+            fetch(i + 1);
+            const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            __half2 hv[4], lv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) umma::split_f16x2(f[2 * c], f[2 * c + 1], hv[c], lv[c]);
+            const uint4 vh = *reinterpret_cast<uint4 *>(hv), vl = *reinterpret_cast<uint4 *>(lv);
+            unsigned char *base = sm + half * C3P_HALF;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) {
+                const int dy = c / 3, dz = c % 3;
+                if (i >= 1) {
+                    umma::mbar_wait(&empty[c], (uint32_t)((i - 1) & 1));
+                    umma::fence_after_thread_sync();
+                }
+                const int ys = y + 1 - dy, zs = z + 1 - dz;
+                if ((unsigned)ys < 4u && (unsigned)zs < 4u) {
+                    unsigned char *q = base + c * C3P_COPY + ((((x + 1) * 2 + pp) * 4 + ys) * 4 + zs) * 16;
+                    *reinterpret_cast<uint4 *>(q) = vh;
+                    *reinterpret_cast<uint4 *>(q + C3P_PART) = vl;
+                }
+                umma::fence_proxy_async();
+                umma::mbar_arrive(&full[c]);
+            }
+        }
+    } else {
+        // ===== epilogue (8 warps = TMEM lane quarter x channel half): lane -> (x = quarter, patch, yz) =====
+        const int q = warp & 3, hc = (warp - C3P_PROD) >> 2;
+        for (int i = 0; i < n_my; ++i) {
+            const int b = i & 1;
+            umma::mbar_wait(&tfull[b], (uint32_t)((i >> 1) & 1));
+            umma::fence_after_thread_sync();
+            uint32_t v0[16], v1[16];
+            const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16) + b * 64 + hc * 16;
+            umma::tmem_ld_x16(trow, v0);        // columns 0..31: W_hi (A_hi + A_lo products)
+            umma::tmem_ld_x16(trow + 32, v1);   // columns 32..63: W_lo
+            umma::tmem_ld_wait();
+            umma::fence_before_thread_sync();
+            umma::mbar_arrive(&tempty[b]);
+            const int p = 2 * pair_of(i) + (lane >> 4);
+            if (p < a.P) {
+                const int pos = 16 * q + (lane & 15);
+                const size_t row8 = ((size_t)(p >> 8) * 256 * 256 + (size_t)(p & 255)) * 8;   // halves (tile-major act3)
+                const int c0 = pos * 4 + hc * 2;
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    __half2 hh[4], ll[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int ch = 8 * g + 2 * c;
+                        const float o0 = fast_tanh((__uint_as_float(v0[ch]) + __uint_as_float(v1[ch])) + b3s[hc * 16 + ch]);
+                        const float o1 = fast_tanh((__uint_as_float(v0[ch + 1]) + __uint_as_float(v1[ch + 1])) + b3s[hc * 16 + ch + 1]);
+                        umma::split_f16x2(o0, o1, hh[c], ll[c]);
+                    }
+                    const size_t o = row8 + (size_t)(c0 + g) * 256 * 8;
+                    *reinterpret_cast<uint4 *>(a.act3_hi + o) = *reinterpret_cast<uint4 *>(hh);
+                    *reinterpret_cast<uint4 *>(a.act3_lo + o) = *reinterpret_cast<uint4 *>(ll);
+                }
+            }
+        }
+    }
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    if (warp == C3P_ISSUER) umma::tmem_dealloc(tbase, 128);
+}
+
 // ---- dense1 (tcgen05) + tanh + dense2 + tanh ---------------------------------------------------
 // One CTA = 256 patches (two M = 128 tiles) x 208 outputs (N = 200 padded) x K = 2048, split-fp16 operands:
 //   D_t += A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T   (one fp32 accumulator per tile in TMEM, 2 x 208 columns),
@@ -899,11 +1081,18 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
     Conv3Args c3;
     c3.act2 = act2; c3.k3 = ctx->enc.k3; c3.b3 = ctx->enc.b3; c3.act3_hi = act3_hi; c3.act3_lo = act3_lo; c3.P = P;
     {
-        // one CTA per SM with two operand buffers (two single-buffer CTAs per SM measured slower: 0.95 vs 0.89 ms)
-        int grid3 = ctx->num_sms;
-        if (grid3 > P) grid3 = P;
+        const char *e = getenv("CAELO_CONV3_M64");       // debug switch for A/B timing: the one-patch-per-MMA kernel
         ProfScope ps_(ctx, "conv3_tc_kernel", st);
-        conv3_tc_kernel<2><<<grid3, C3_THREADS, c3_smem(2), st>>>(c3);
+        if (e && e[0] == '1') {
+            // one CTA per SM with two operand buffers (two single-buffer CTAs per SM measured slower: 0.95 vs 0.89 ms)
+            int grid3 = ctx->num_sms;
+            if (grid3 > P) grid3 = P;
+            conv3_tc_kernel<2><<<grid3, C3_THREADS, c3_smem(2), st>>>(c3);
+        } else {
+            int grid3 = ctx->num_sms;                    // persistent: one CTA per SM walks the patch PAIRS
+            if (grid3 > (P + 1) / 2) grid3 = (P + 1) / 2;
+            conv3_pair_kernel<<<grid3, C3P_THREADS, C3P_SMEM, st>>>(c3);
+        }
     }
     CAELO_LAUNCH_CHECK(ctx);
     DenseArgs d;
@@ -922,6 +1111,7 @@ int caelo_encoder_init(caelo_ctx *ctx)
 {
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv12_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem(2)));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
     return CAELO_OK;
 }

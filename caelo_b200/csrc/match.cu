@@ -299,6 +299,18 @@ __global__ void __launch_bounds__(NT_THREADS) nn_tc_kernel(const NNTcArgs a)
 }
 
 // decided columns get their index; the others are appended to a list for the exact re-scan
+// Error margin of one d^2 value of the tensor-core pass: a term proportional to |a|max |b_j| (split-fp16 products, fp32
+// accumulation in the tensor core) plus an absolute term for the fp16 lo parts that fall into the subnormal range
+// (|lo| <= 2^-12 |x| is below 2^-14 for every |x| < 1/4: absolute error <= 2^-25 per element, so <= 2^-25 sqrt(D) (|a| + |b|)
+// on the dot product).  Measured (tools/nn_margin.py, profiles/r2_nn_margin.txt): 2^-18.6 |a||b| on tanh-distributed
+// descriptors, 2^-15.5 |a||b| on descriptors of magnitude 1e-3 — which the absolute term covers 10x over.
+__device__ __forceinline__ float nn_margin_E(const NNArgs &a, int pair, long long w)
+{
+    if (!a.nmax0) return 0.0f;
+    const float na = sqrtf(a.nmax0[pair]), nb = sqrtf(a.n1[w]);
+    return a.margin * na * nb + 1.1920929e-7f * sqrtf((float)a.D) * (na + nb) + 1e-30f;
+}
+
 __global__ void __launch_bounds__(256) nn_decide_kernel(const NNArgs a, int P, int *list, int *nlist)
 {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,7 +320,7 @@ __global__ void __launch_bounds__(256) nn_decide_kernel(const NNArgs a, int P, i
     // relative error of each float32 d^2 <= (D+4)*2^-24; undecided if the intervals can overlap.  After the
     // tensor-core pass the error is absolute: E = 2^-13 |a|max |b_j| per value (see the header).
     const float eps = (float)(a.D + 4) * 5.9604645e-8f;
-    const float E = a.nmax0 ? a.margin * sqrtf(a.nmax0[pair] * a.n1[w]) + 1e-30f : 0.0f;
+    const float E = nn_margin_E(a, pair, w);
     const bool decided = s > (b + 2.0f * E) * (1.0f + 4.0f * eps) + 1e-30f;
     if (decided) a.out[w] = a.best_i[w];
     else list[atomicAdd(nlist, 1)] = (int)w;
@@ -318,25 +330,35 @@ __global__ void __launch_bounds__(256) nn_decide_kernel(const NNArgs a, int P, i
 // pass keeps the rows inside the margin (any summation order is within (D+4)*2^-24 of the true value), those
 // are evaluated with the reference's own arithmetic (contract M1: float64 sequential sum, sqrt), and the CTA
 // reduces to the smallest (distance, row).
-__global__ void __launch_bounds__(256) nn_exact_kernel(const NNArgs a, const int *list, const int *nlist)
+struct NNPart { double d; int i; int pad; };
+
+__global__ void __launch_bounds__(256) nn_exact_kernel(const NNArgs a, const int *list, const int *nlist, int *part_cnt, NNPart *parts)
 {
     __shared__ double s_d[8];
     __shared__ int s_i[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = *nlist;
     const bool vec = (a.D & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.c0) | reinterpret_cast<uintptr_t>(a.c1)) & 15) == 0;
-    for (int u = blockIdx.x; u < n; u += gridDim.x) {
+    // few undecided columns (the usual case: a fraction of a percent): a column's rows are split over up to 16 CTAs —
+    // one CTA streaming all N rows of a column through L2 alone is latency-bound — and the CTA that finishes a column
+    // last combines the parts
+    int S = 1;
+    if (n > 0 && n < (int)gridDim.x) { S = (int)gridDim.x / n; if (S > 16) S = 16; }
+    const int rows_per = (a.N + S - 1) / S;
+    for (int wi = blockIdx.x; wi < n * S; wi += gridDim.x) {
+        const int u = wi / S, sp = wi - u * S;
         const long long w = list[u];
         const int pair = (int)(w / a.M), j = (int)(w % a.M);
         const float b = a.best_d[w];
         const float eps = (float)(a.D + 4) * 5.9604645e-8f;
-        const float E = a.nmax0 ? a.margin * sqrtf(a.nmax0[pair] * a.n1[w]) + 1e-30f : 0.0f;
+        const float E = nn_margin_E(a, pair, w);
         const float bound = (b + E) * (1.0f + 4.0f * eps) + 1e-30f;
         const float *c0 = a.c0 + (size_t)pair * a.N * a.D;
         const float *q = a.c1 + ((size_t)pair * a.M + j) * a.D;
         double bd = __longlong_as_double(0x7ff0000000000000ll);
         int bi = 0x7fffffff;
-        for (int i = threadIdx.x; i < a.N; i += 256) {
+        const int i_end = (sp + 1) * rows_per < a.N ? (sp + 1) * rows_per : a.N;
+        for (int i = sp * rows_per + threadIdx.x; i < i_end; i += 256) {
             const float *p = c0 + (size_t)i * a.D;
             float acc32;
             if (vec) {
@@ -377,7 +399,22 @@ __global__ void __launch_bounds__(256) nn_exact_kernel(const NNArgs a, const int
         if (threadIdx.x == 0) {
             for (int k = 1; k < 8; ++k)
                 if (s_d[k] < bd || (s_d[k] == bd && s_i[k] < bi)) { bd = s_d[k]; bi = s_i[k]; }
-            a.out[w] = bi;     // ties -> lowest row, as numpy's argmin
+            if (S == 1) {
+                a.out[w] = bi;     // ties -> lowest row, as numpy's argmin
+            } else {
+                NNPart *pp = parts + (size_t)u * 16;
+                pp[sp].d = bd; pp[sp].i = bi;
+                __threadfence();
+                if (atomicAdd(part_cnt + u, 1) == S - 1) {           // the last part of this column
+                    __threadfence();
+                    for (int k = 0; k < S; ++k) {
+                        const double od = *reinterpret_cast<volatile double *>(&pp[k].d);
+                        const int oi = *reinterpret_cast<volatile int *>(&pp[k].i);
+                        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+                    }
+                    a.out[w] = bi;
+                }
+            }
         }
         __syncthreads();
     }
@@ -402,7 +439,8 @@ extern "C" int caelo_nn_match(caelo_ctx *ctx, const float *codes0, const float *
         return CAELO_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     size_t cols = (size_t)P * M, rows0 = (size_t)P * N;
-    int rc = caelo_reserve(ctx, ctx->misc, cols * 20 + rows0 * 4 + (size_t)P * 4 + 512);
+    const int exact_grid = 4 * ctx->num_sms;
+    int rc = caelo_reserve(ctx, ctx->misc, cols * 20 + rows0 * 4 + (size_t)P * 4 + 1024 + (size_t)exact_grid * (4 + 16 * sizeof(NNPart)));
     if (rc) return rc;
     NNArgs a;
     a.c0 = codes0; a.c1 = codes1; a.N = N; a.M = M; a.D = D; a.Dp = (D + 3) & ~3;
@@ -442,10 +480,13 @@ extern "C" int caelo_nn_match(caelo_ctx *ctx, const float *codes0, const float *
     // undecided-column list lives behind every other array of the scratch block
     int *nlist = reinterpret_cast<int *>(reinterpret_cast<char *>(ctx->misc.ptr) + ((cols * 16 + rows0 * 4 + (size_t)P * 4 + 255) / 256) * 256);
     int *list = nlist + 16;
-    CAELO_CUDA(ctx, cudaMemsetAsync(nlist, 0, 4, st));
+    int *part_cnt = list + ((cols + 15) / 16) * 16;
+    NNPart *parts = reinterpret_cast<NNPart *>(part_cnt + ((exact_grid + 15) / 16) * 16);
+    CAELO_CUDA(ctx, cudaMemsetAsync(nlist, 0, 64, st));
+    CAELO_CUDA(ctx, cudaMemsetAsync(part_cnt, 0, (size_t)exact_grid * 4, st));
     { ProfScope ps_(ctx, "nn_decide_kernel", st); nn_decide_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(a, P, list, nlist); }
     CAELO_LAUNCH_CHECK(ctx);
-    { ProfScope ps_(ctx, "nn_exact_kernel", st); nn_exact_kernel<<<4 * ctx->num_sms, 256, 0, st>>>(a, list, nlist); }
+    { ProfScope ps_(ctx, "nn_exact_kernel", st); nn_exact_kernel<<<exact_grid, 256, 0, st>>>(a, list, nlist, part_cnt, parts); }
     CAELO_LAUNCH_CHECK(ctx);
     return CAELO_OK;
 }

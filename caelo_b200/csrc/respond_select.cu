@@ -25,23 +25,50 @@ constexpr int EDGE = 8;  // Size4FilterTopEdge, SphericalRing.py:42
 
 // contract R1 for one pixel; x[27] in (ky,kx,ci) order, out[8].  Scalar FFMA with the weight as a constant-bank
 // operand: the packed FFMA2 form was measured 2x SLOWER here (0.40 -> 0.81 ms) — a 64-bit weight pair cannot be
-// an immediate constant operand and has to come through uniform-register loads.
-__device__ __forceinline__ void respond_pixel(const RespondWeights &w, const float (&x)[27],
-                                              float (&out)[8])
+// an immediate constant operand and has to come through uniform-register loads.  The channel loop is FULLY unrolled
+// (1120 straight-line FFMAs, 18 KB of code): with `unroll 4` the weight offsets were run-time values and every FFMA
+// was preceded by a uniform constant load (ncu source page, round 2: 93 M LDCU next to 119 M FFMA per launch).
+template <int PPT>
+__device__ __forceinline__ void respond_pixels(const RespondWeights &w, const float (&x)[PPT][27], float (&out)[PPT][8])
 {
+    // PPT pixels per thread share every weight load, and the 32 hidden channels are walked four at a time with the tap
+    // loop inside, so that the four weights of a tap (contiguous in w1[t][co]) come in with one 16-byte uniform load.
+    // Every per-channel chain is still bias, then fmaf over the taps in ascending order, and the 1x1 layer still
+    // accumulates the hidden channels in ascending order (contract R1).
 #pragma unroll
-    for (int c2 = 0; c2 < 8; ++c2) out[c2] = w.b2[c2];
-#pragma unroll 4
-    for (int co = 0; co < 32; ++co) {
-        float acc = w.b1[co];
+    for (int p = 0; p < PPT; ++p)
 #pragma unroll
-        for (int t = 0; t < 27; ++t) acc = __fmaf_rn(x[t], w.w1[t * 32 + co], acc);
-        float h = fmaxf(acc, 0.0f);
+        for (int c2 = 0; c2 < 8; ++c2) out[p][c2] = w.b2[c2];
 #pragma unroll
-        for (int c2 = 0; c2 < 8; ++c2) out[c2] = __fmaf_rn(h, w.w2[co * 8 + c2], out[c2]);
+    for (int g = 0; g < 8; ++g) {
+        float acc[PPT][4];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[p][k] = w.b1[4 * g + k];
+#pragma unroll
+        for (int t = 0; t < 27; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) acc[p][k] = __fmaf_rn(x[p][t], w.w1[t * 32 + 4 * g + k], acc[p][k]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c2 = 0; c2 < 8; ++c2)
+#pragma unroll
+                for (int p = 0; p < PPT; ++p)
+                    out[p][c2] = __fmaf_rn(fmaxf(acc[p][k], 0.0f), w.w2[(4 * g + k) * 8 + c2], out[p][c2]);
     }
 #pragma unroll
-    for (int c2 = 0; c2 < 8; ++c2) out[c2] = fmaxf(out[c2], 0.0f);
+    for (int p = 0; p < PPT; ++p)
+#pragma unroll
+        for (int c2 = 0; c2 < 8; ++c2) out[p][c2] = fmaxf(out[p][c2], 0.0f);
+}
+
+__device__ __forceinline__ void respond_pixel(const RespondWeights &w, const float (&x)[27], float (&out)[8])
+{
+    respond_pixels<1>(w, reinterpret_cast<const float (&)[1][27]>(x), reinterpret_cast<float (&)[1][8]>(out));
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -151,30 +178,44 @@ respond_score_kernel(const __grid_constant__ RespondWeights w, const SelectArgs 
     }
     __syncthreads();
     const int nocc = s_nocc, nctr = s_nctr;
-    // ---- response of the occupied pixels ----
-    for (int n = threadIdx.x; n < nocc; n += kThreads) {
-        const int i = list_occ[n];
-        const int lr = i / RW, lc = i % RW;
-        float out[8];
-        if (kFused) {
-            float x[27];
+    // ---- response of the occupied pixels (fused: two listed pixels per thread and round, see respond_pixels) ----
+    if (kFused) {
+        for (int n0 = 0; n0 < nocc; n0 += 2 * kThreads) {
+            const int na = n0 + threadIdx.x, nb = na + kThreads;
+            if (na >= nocc) break;
+            const int ia = list_occ[na], ib = list_occ[nb < nocc ? nb : na];
+            float x[2][27], out[2][8];
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
+            for (int p = 0; p < 2; ++p) {
+                const int i = p ? ib : ia, lr = i / RW, lc = i % RW;
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx)
+                for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                    for (int ci = 0; ci < 3; ++ci)
-                        x[(ky * 3 + kx) * 3 + ci] = in_s[((lr + ky) * IW + (lc + kx)) * 3 + ci];
-            respond_pixel(w, x, out);
-        } else {
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int ci = 0; ci < 3; ++ci)
+                            x[p][(ky * 3 + kx) * 3 + ci] = in_s[((lr + ky) * IW + (lc + kx)) * 3 + ci];
+            }
+            if (nb < nocc) {
+                respond_pixels<2>(w, x, out);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { resp_s[k * NPIX + ia] = out[0][k]; resp_s[k * NPIX + ib] = out[1][k]; }
+            } else {
+                respond_pixels<1>(w, reinterpret_cast<const float (&)[1][27]>(x[0]), reinterpret_cast<float (&)[1][8]>(out[0]));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) resp_s[k * NPIX + ia] = out[0][k];
+            }
+        }
+    } else {
+        for (int n = threadIdx.x; n < nocc; n += kThreads) {
+            const int i = list_occ[n];
+            const int lr = i / RW, lc = i % RW;
             const float4 *q = reinterpret_cast<const float4 *>(
                 a.resp + (((size_t)b * H + (r0 + lr)) * W + (c0 + lc)) * 8);
             float4 v0 = __ldg(q), v1 = __ldg(q + 1);
-            out[0] = v0.x; out[1] = v0.y; out[2] = v0.z; out[3] = v0.w;
-            out[4] = v1.x; out[5] = v1.y; out[6] = v1.z; out[7] = v1.w;
+            resp_s[0 * NPIX + i] = v0.x; resp_s[1 * NPIX + i] = v0.y; resp_s[2 * NPIX + i] = v0.z; resp_s[3 * NPIX + i] = v0.w;
+            resp_s[4 * NPIX + i] = v1.x; resp_s[5 * NPIX + i] = v1.y; resp_s[6 * NPIX + i] = v1.z; resp_s[7 * NPIX + i] = v1.w;
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) resp_s[k * NPIX + i] = out[k];
     }
     __syncthreads();
 

@@ -215,9 +215,15 @@ class OdometryPipeline:
         pair_ids), host tensors pinned."""
         cs = self._copy_stream_()
         if not hasattr(self, "_slots"):
-            self._slots, self._slot_next = [dict(), dict()], 0
+            # THREE upload slots: with two, the copy of batch i+1 can only start once batch i-1's frame stages have run,
+            # i.e. it lands on the latency-bound match / RANSAC tail of batch i-1 (those kernels were measured 1.6-3.4x
+            # slower next to the copy, +0.46 ms per step); with three the slot of batch i+1 has been free since batch
+            # i-2, the copy starts the moment the host queues it — at the beginning of batch i-1's tensor-core phase —
+            # and is over before the tail begins.  CAELO_UPLOAD_SLOTS=2 restores the old behaviour for A/B timing.
+            n_slots = max(2, int(os.environ.get("CAELO_UPLOAD_SLOTS", "3")))
+            self._slots, self._slot_next = [dict() for _ in range(n_slots)], 0
         slot = self._slots[self._slot_next]
-        self._slot_next ^= 1
+        self._slot_next = (self._slot_next + 1) % len(self._slots)
         if "free" in slot:
             cs.wait_event(slot["free"])
         parts = []
