@@ -649,10 +649,10 @@ constexpr int C3P_SM_W = C3P_BUF;                     // W3 [kc 54][n 64][16 B]
 constexpr int C3P_SM_B3 = C3P_SM_W + 54 * 1024;
 constexpr int C3P_SM_BAR = C3P_SM_B3 + 128;           // full[9] empty[9] tfull[2] tempty[2] + tmem slot
 constexpr int C3P_SMEM = C3P_SM_BAR + 22 * 8 + 16;
-constexpr int C3P_PROD = 8;                           // warps 0-7 produce (thread = patch x position x channel half)
-constexpr int C3P_EPI = 8;                            // warps 8-15 drain the accumulators (lane quarter x channel half)
-constexpr int C3P_ISSUER = C3P_PROD + C3P_EPI;        // warp 16 issues the MMAs
-constexpr int C3P_THREADS = (C3P_ISSUER + 1) * 32;
+constexpr int C3P_PROD = 9;                           // warps 0-8 produce: warp c owns the (dy,dz) copy c
+constexpr int C3P_ISSUER = 9;                         // warp 9 issues the MMAs (warps 10, 11 idle: the epilogue warps must start at a multiple of 4)
+constexpr int C3P_EPI0 = 12, C3P_EPI = 8;             // warps 12-19 drain the accumulators (lane quarter x channel half)
+constexpr int C3P_THREADS = (C3P_EPI0 + C3P_EPI) * 32;
 
 __global__ void __launch_bounds__(C3P_THREADS, 1) conv3_pair_kernel(const Conv3Args a)
 {
@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(C3P_THREADS, 1) conv3_pair_kernel(const Conv3A
     if (warp == C3P_ISSUER) umma::tmem_alloc(tmem_slot, 128);
     if (tid == 0) {
         for (int c = 0; c < 9; ++c) {
-            umma::mbar_init(&full[c], C3P_PROD * 32);
+            umma::mbar_init(&full[c], 32);      // the copy's producer warp
             umma::mbar_init(&empty[c], 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -723,51 +723,47 @@ __global__ void __launch_bounds__(C3P_THREADS, 1) conv3_pair_kernel(const Conv3A
             }
         }
     } else if (warp < C3P_PROD) {
-        // ===== producers: thread = (patch of the pair, position, channel half); hi and lo written into every copy whose
-        // shifted window holds this position, each copy as soon as the previous pair's MMAs on it have completed =====
-        // consecutive threads = consecutive positions of one (patch, channel half): their 16-byte stores are contiguous
-        // (the M = 64 kernel interleaves the halves, whose copies are a multiple of 128 B apart: two-way bank conflicts)
-        const int pp = tid >> 7, half = (tid >> 6) & 1, pos = tid & 63;
-        const int x = pos >> 4, y = (pos >> 2) & 3, z = pos & 3;
-        float4 nv0 = make_float4(0.f, 0.f, 0.f, 0.f), nv1 = nv0;
-        auto fetch = [&](int i) {
-            if (i >= n_my) return;
-            int p = 2 * pair_of(i) + pp;
-            if (p >= a.P) p = a.P - 1;                 // odd patch count: the last pair's second half repeats the first
-            const float4 *src = reinterpret_cast<const float4 *>(a.act2 + (size_t)p * 1024 + pos * 16 + half * 8);
-            nv0 = __ldg(src);
-            nv1 = __ldg(src + 1);
-        };
-        fetch(0);
+        // ===== producers: warp c owns copy c = (dy,dz).  Per pair it loads the pair's whole act2 (2 x 4 KB; eight
+        // (patch, channel half, position) elements per lane, all loads issued before anything waits), and once the previous
+        // pair's MMAs on its copy have completed it writes hi and lo of every position the shifted window holds: one
+        // proxy fence and one arrive per lane and pair.  (A first version had thread = element writing all nine copies:
+        // nine proxy fences per thread and pair made the producers slower than the tensor core, 0.89 ms.) =====
+        const int c = warp, dy = c / 3, dz = c % 3;
         for (int i = 0; i < n_my; ++i) {
-            const float4 v0 = nv0, v1 = nv1;
-            fetch(i + 1);
-            const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            __half2 hv[4], lv[4];
+            float4 v[8][2];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) umma::split_f16x2(f[2 * c], f[2 * c + 1], hv[c], lv[c]);
-            const uint4 vh = *reinterpret_cast<uint4 *>(hv), vl = *reinterpret_cast<uint4 *>(lv);
-            unsigned char *base = sm + half * C3P_HALF;
-#pragma unroll
-            for (int c = 0; c < 9; ++c) {
-                const int dy = c / 3, dz = c % 3;
-                if (i >= 1) {
-                    umma::mbar_wait(&empty[c], (uint32_t)((i - 1) & 1));
-                    umma::fence_after_thread_sync();
-                }
-                const int ys = y + 1 - dy, zs = z + 1 - dz;
-                if ((unsigned)ys < 4u && (unsigned)zs < 4u) {
-                    unsigned char *q = base + c * C3P_COPY + ((((x + 1) * 2 + pp) * 4 + ys) * 4 + zs) * 16;
-                    *reinterpret_cast<uint4 *>(q) = vh;
-                    *reinterpret_cast<uint4 *>(q + C3P_PART) = vl;
-                }
-                umma::fence_proxy_async();
-                umma::mbar_arrive(&full[c]);
+            for (int k = 0; k < 8; ++k) {
+                const int e = lane + 32 * k, pp = e >> 7, half = (e >> 6) & 1, pos = e & 63;
+                int p = 2 * pair_of(i) + pp;
+                if (p >= a.P) p = a.P - 1;             // odd patch count: the last pair's second half repeats the first
+                const float4 *src = reinterpret_cast<const float4 *>(a.act2 + (size_t)p * 1024 + pos * 16 + half * 8);
+                v[k][0] = __ldg(src);
+                v[k][1] = __ldg(src + 1);
             }
+            if (i >= 1) {
+                umma::mbar_wait(&empty[c], (uint32_t)((i - 1) & 1));
+                umma::fence_after_thread_sync();
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int e = lane + 32 * k, pp = e >> 7, half = (e >> 6) & 1, pos = e & 63;
+                const int x = pos >> 4, ys = ((pos >> 2) & 3) + 1 - dy, zs = (pos & 3) + 1 - dz;
+                if ((unsigned)ys < 4u && (unsigned)zs < 4u) {
+                    const float f[8] = {v[k][0].x, v[k][0].y, v[k][0].z, v[k][0].w, v[k][1].x, v[k][1].y, v[k][1].z, v[k][1].w};
+                    __half2 hv[4], lv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) umma::split_f16x2(f[2 * j], f[2 * j + 1], hv[j], lv[j]);
+                    unsigned char *q = sm + half * C3P_HALF + c * C3P_COPY + ((((x + 1) * 2 + pp) * 4 + ys) * 4 + zs) * 16;
+                    *reinterpret_cast<uint4 *>(q) = *reinterpret_cast<uint4 *>(hv);
+                    *reinterpret_cast<uint4 *>(q + C3P_PART) = *reinterpret_cast<uint4 *>(lv);
+                }
+            }
+            umma::fence_proxy_async();
+            umma::mbar_arrive(&full[c]);
         }
-    } else {
+    } else if (warp >= C3P_EPI0) {
         // ===== epilogue (8 warps = TMEM lane quarter x channel half): lane -> (x = quarter, patch, yz) =====
-        const int q = warp & 3, hc = (warp - C3P_PROD) >> 2;
+        const int q = warp & 3, hc = (warp - C3P_EPI0) >> 2;
         for (int i = 0; i < n_my; ++i) {
             const int b = i & 1;
             umma::mbar_wait(&tfull[b], (uint32_t)((i >> 1) & 1));

@@ -12,6 +12,10 @@
 //                         reaches HBM.  <!fused>: same scoring from a response tile in HBM.
 //   topk_kernel           per frame: radix-select the (maxk+1) largest (score,index) keys,
 //                         bitonic-sort them, drop the best (quirk 1), emit points + pixels.
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -28,37 +32,63 @@ constexpr int EDGE = 8;  // Size4FilterTopEdge, SphericalRing.py:42
 // an immediate constant operand and has to come through uniform-register loads.  The channel loop is FULLY unrolled
 // (1120 straight-line FFMAs, 18 KB of code): with `unroll 4` the weight offsets were run-time values and every FFMA
 // was preceded by a uniform constant load (ncu source page, round 2: 93 M LDCU next to 119 M FFMA per launch).
-template <int PPT>
-__device__ __forceinline__ void respond_pixels(const RespondWeights &w, const float (&x)[PPT][27], float (&out)[PPT][8])
+// where the weights come from: the kernel-parameter constant bank (uniform loads) or a copy in shared memory
+// (16-byte broadcast loads into ordinary registers)
+struct WConst {
+    const RespondWeights &w;
+    __device__ __forceinline__ float4 w1(int t, int g) const { return make_float4(w.w1[t * 32 + 4 * g], w.w1[t * 32 + 4 * g + 1], w.w1[t * 32 + 4 * g + 2], w.w1[t * 32 + 4 * g + 3]); }
+    __device__ __forceinline__ float4 b1(int g) const { return make_float4(w.b1[4 * g], w.b1[4 * g + 1], w.b1[4 * g + 2], w.b1[4 * g + 3]); }
+    __device__ __forceinline__ float4 w2(int co, int h) const { return make_float4(w.w2[co * 8 + 4 * h], w.w2[co * 8 + 4 * h + 1], w.w2[co * 8 + 4 * h + 2], w.w2[co * 8 + 4 * h + 3]); }
+    __device__ __forceinline__ float4 b2(int h) const { return make_float4(w.b2[4 * h], w.b2[4 * h + 1], w.b2[4 * h + 2], w.b2[4 * h + 3]); }
+};
+constexpr int WS_B1 = 27 * 32, WS_W2 = WS_B1 + 32, WS_B2 = WS_W2 + 256, WS_FLOATS = WS_B2 + 8;   // smem copy: w1 | b1 | w2 | b2
+struct WSmem {
+    const float *p;
+    __device__ __forceinline__ float4 w1(int t, int g) const { return *reinterpret_cast<const float4 *>(p + t * 32 + 4 * g); }
+    __device__ __forceinline__ float4 b1(int g) const { return *reinterpret_cast<const float4 *>(p + WS_B1 + 4 * g); }
+    __device__ __forceinline__ float4 w2(int co, int h) const { return *reinterpret_cast<const float4 *>(p + WS_W2 + co * 8 + 4 * h); }
+    __device__ __forceinline__ float4 b2(int h) const { return *reinterpret_cast<const float4 *>(p + WS_B2 + 4 * h); }
+};
+
+template <int PPT, class W>
+__device__ __forceinline__ void respond_pixels(const W &w, const float (&x)[PPT][27], float (&out)[PPT][8])
 {
     // PPT pixels per thread share every weight load, and the 32 hidden channels are walked four at a time with the tap
-    // loop inside, so that the four weights of a tap (contiguous in w1[t][co]) come in with one 16-byte uniform load.
+    // loop inside, so that the four weights of a tap (contiguous in w1[t][co]) come in with one 16-byte load.
     // Every per-channel chain is still bias, then fmaf over the taps in ascending order, and the 1x1 layer still
     // accumulates the hidden channels in ascending order (contract R1).
+    {
+        const float4 c0 = w.b2(0), c1 = w.b2(1);
 #pragma unroll
-    for (int p = 0; p < PPT; ++p)
-#pragma unroll
-        for (int c2 = 0; c2 < 8; ++c2) out[p][c2] = w.b2[c2];
+        for (int p = 0; p < PPT; ++p) {
+            out[p][0] = c0.x; out[p][1] = c0.y; out[p][2] = c0.z; out[p][3] = c0.w;
+            out[p][4] = c1.x; out[p][5] = c1.y; out[p][6] = c1.z; out[p][7] = c1.w;
+        }
+    }
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
         float acc[PPT][4];
+        const float4 bb = w.b1(g);
 #pragma unroll
-        for (int p = 0; p < PPT; ++p)
+        for (int p = 0; p < PPT; ++p) { acc[p][0] = bb.x; acc[p][1] = bb.y; acc[p][2] = bb.z; acc[p][3] = bb.w; }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc[p][k] = w.b1[4 * g + k];
-#pragma unroll
-        for (int t = 0; t < 27; ++t)
+        for (int t = 0; t < 27; ++t) {
+            const float4 wv = w.w1(t, g);
+            const float wk[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k)
 #pragma unroll
-                for (int p = 0; p < PPT; ++p) acc[p][k] = __fmaf_rn(x[p][t], w.w1[t * 32 + 4 * g + k], acc[p][k]);
+                for (int p = 0; p < PPT; ++p) acc[p][k] = __fmaf_rn(x[p][t], wk[k], acc[p][k]);
+        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 4; ++k) {
+            const float4 u0 = w.w2(4 * g + k, 0), u1 = w.w2(4 * g + k, 1);
+            const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
             for (int c2 = 0; c2 < 8; ++c2)
 #pragma unroll
-                for (int p = 0; p < PPT; ++p)
-                    out[p][c2] = __fmaf_rn(fmaxf(acc[p][k], 0.0f), w.w2[(4 * g + k) * 8 + c2], out[p][c2]);
+                for (int p = 0; p < PPT; ++p) out[p][c2] = __fmaf_rn(fmaxf(acc[p][k], 0.0f), uu[c2], out[p][c2]);
+        }
     }
 #pragma unroll
     for (int p = 0; p < PPT; ++p)
@@ -66,9 +96,16 @@ __device__ __forceinline__ void respond_pixels(const RespondWeights &w, const fl
         for (int c2 = 0; c2 < 8; ++c2) out[p][c2] = fmaxf(out[p][c2], 0.0f);
 }
 
+template <int P, int kVar>
+__device__ __forceinline__ void conv_px(const RespondWeights &w, const float *w_s, const float (&x)[P][27], float (&out)[P][8])
+{
+    if constexpr (kVar >= 2) respond_pixels<P>(WSmem{w_s}, x, out);
+    else respond_pixels<P>(WConst{w}, x, out);
+}
+
 __device__ __forceinline__ void respond_pixel(const RespondWeights &w, const float (&x)[27], float (&out)[8])
 {
-    respond_pixels<1>(w, reinterpret_cast<const float (&)[1][27]>(x), reinterpret_cast<float (&)[1][8]>(out));
+    respond_pixels<1>(WConst{w}, reinterpret_cast<const float (&)[1][27]>(x), reinterpret_cast<float (&)[1][8]>(out));
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -117,11 +154,18 @@ __device__ __forceinline__ bool occupied(const SelectArgs &a, int b, int r, int 
                                           : (reinterpret_cast<const int32_t *>(a.counter)[i] > 0);
 }
 
-template <bool kFused>
-__global__ void __launch_bounds__(kThreads)
+// kVar (fused only): 0 = one pixel per thread and round, weights from the constant bank; 1 = two pixels, constant bank;
+// 2 = two pixels, weights from shared memory; 3 = one pixel, shared memory
+template <bool kFused, int kVar>
+__global__ void __launch_bounds__(kThreads, !kFused ? 1 : ((kVar == 0 || kVar == 3) ? 3 : 2))
 respond_score_kernel(const __grid_constant__ RespondWeights w, const SelectArgs a)
 {
     extern __shared__ float smem[];
+    __shared__ __align__(16) float w_s[(kFused && kVar >= 2) ? WS_FLOATS : 4];
+    if (kFused && kVar >= 2) {
+        for (int i = threadIdx.x; i < WS_FLOATS; i += kThreads)
+            w_s[i] = i < WS_B1 ? w.w1[i] : (i < WS_W2 ? w.b1[i - WS_B1] : (i < WS_B2 ? w.w2[i - WS_W2] : w.b2[i - WS_B2]));
+    }
     float *resp_s = smem;                                   // [8][NPIX]
     unsigned char *occ_s = reinterpret_cast<unsigned char *>(resp_s + 8 * NPIX);  // [NPIX]
     float *in_s = reinterpret_cast<float *>(occ_s + ((NPIX + 15) / 16) * 16);      // [IH*IW*3]
@@ -180,13 +224,14 @@ respond_score_kernel(const __grid_constant__ RespondWeights w, const SelectArgs 
     const int nocc = s_nocc, nctr = s_nctr;
     // ---- response of the occupied pixels (fused: two listed pixels per thread and round, see respond_pixels) ----
     if (kFused) {
-        for (int n0 = 0; n0 < nocc; n0 += 2 * kThreads) {
+        constexpr int PPT = (kVar == 1 || kVar == 2) ? 2 : 1;
+        for (int n0 = 0; n0 < nocc; n0 += PPT * kThreads) {
             const int na = n0 + threadIdx.x, nb = na + kThreads;
             if (na >= nocc) break;
-            const int ia = list_occ[na], ib = list_occ[nb < nocc ? nb : na];
-            float x[2][27], out[2][8];
+            const int ia = list_occ[na], ib = (PPT == 2) ? list_occ[nb < nocc ? nb : na] : ia;
+            float x[PPT][27], out[PPT][8];
 #pragma unroll
-            for (int p = 0; p < 2; ++p) {
+            for (int p = 0; p < PPT; ++p) {
                 const int i = p ? ib : ia, lr = i / RW, lc = i % RW;
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
@@ -196,12 +241,12 @@ respond_score_kernel(const __grid_constant__ RespondWeights w, const SelectArgs 
                         for (int ci = 0; ci < 3; ++ci)
                             x[p][(ky * 3 + kx) * 3 + ci] = in_s[((lr + ky) * IW + (lc + kx)) * 3 + ci];
             }
-            if (nb < nocc) {
-                respond_pixels<2>(w, x, out);
+            if (PPT == 2 && nb < nocc) {
+                conv_px<PPT, kVar>(w, w_s, x, out);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { resp_s[k * NPIX + ia] = out[0][k]; resp_s[k * NPIX + ib] = out[1][k]; }
+                for (int k = 0; k < 8; ++k) { resp_s[k * NPIX + ia] = out[0][k]; resp_s[k * NPIX + ib] = out[PPT - 1][k]; }
             } else {
-                respond_pixels<1>(w, reinterpret_cast<const float (&)[1][27]>(x[0]), reinterpret_cast<float (&)[1][8]>(out[0]));
+                conv_px<1, kVar>(w, w_s, reinterpret_cast<const float (&)[1][27]>(x), reinterpret_cast<float (&)[1][8]>(out));
 #pragma unroll
                 for (int k = 0; k < 8; ++k) resp_s[k * NPIX + ia] = out[0][k];
             }
@@ -467,10 +512,18 @@ int launch_select(caelo_ctx *ctx, bool fused, const float *resp, int H, int W, c
     dim3 grid((W - 2 * EDGE + TW - 1) / TW, (H - 2 * EDGE + TH - 1) / TH, B);
     size_t smem = (size_t)8 * NPIX * 4 + ((NPIX + 15) / 16) * 16 + (fused ? (size_t)IH * IW * 3 * 4 : 0) + (NPIX + TH * TW) * 2;
     if (fused) {
-        { ProfScope ps_(ctx, "respond_score_kernel<fused>", st); respond_score_kernel<true><<<grid, kThreads, smem, st>>>(ctx->respond_host, a); }
+        static int var = -1;
+        if (var < 0) { const char *e = getenv("CAELO_RESPOND_VARIANT"); var = e ? atoi(e) : 2; }
+        ProfScope ps_(ctx, "respond_score_kernel<fused>", st);
+        switch (var) {
+        case 0: respond_score_kernel<true, 0><<<grid, kThreads, smem, st>>>(ctx->respond_host, a); break;
+        case 1: respond_score_kernel<true, 1><<<grid, kThreads, smem, st>>>(ctx->respond_host, a); break;
+        case 3: respond_score_kernel<true, 3><<<grid, kThreads, smem, st>>>(ctx->respond_host, a); break;
+        default: respond_score_kernel<true, 2><<<grid, kThreads, smem, st>>>(ctx->respond_host, a); break;
+        }
     } else {
         if (!resp) return CAELO_ERR_ARG;
-        { ProfScope ps_(ctx, "respond_score_kernel<from_resp>", st); respond_score_kernel<false><<<grid, kThreads, smem, st>>>(ctx->respond_host, a); }
+        { ProfScope ps_(ctx, "respond_score_kernel<from_resp>", st); respond_score_kernel<false, 0><<<grid, kThreads, smem, st>>>(ctx->respond_host, a); }
     }
     CAELO_LAUNCH_CHECK(ctx);
 
@@ -491,9 +544,11 @@ int launch_select(caelo_ctx *ctx, bool fused, const float *resp, int H, int W, c
 int caelo_select_init(caelo_ctx *ctx)
 {
     const int smem = 8 * NPIX * 4 + ((NPIX + 15) / 16) * 16 + IH * IW * 3 * 4 + (NPIX + TH * TW) * 2;
-    CAELO_CUDA(ctx, cudaFuncSetAttribute(respond_score_kernel<true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CAELO_CUDA(ctx, cudaFuncSetAttribute(respond_score_kernel<false>,
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(respond_score_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(respond_score_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(respond_score_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(respond_score_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(respond_score_kernel<false, 0>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + TOPK_CAND) * 8));
     return CAELO_OK;
