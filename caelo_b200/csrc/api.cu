@@ -11,6 +11,53 @@ int caelo_match_init(caelo_ctx *ctx);
 int caelo_pose_init(caelo_ctx *ctx);
 int caelo_select_init(caelo_ctx *ctx);
 
+namespace {
+__global__ void __launch_bounds__(256) fill_kernel(unsigned char *p, unsigned char v, size_t head, size_t n16, size_t tail)
+{
+    // [head bytes][n16 aligned 16-byte words][tail bytes]
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    const unsigned w = v * 0x01010101u;
+    uint4 *q = reinterpret_cast<uint4 *>(p + head);
+    for (size_t k = i; k < n16; k += stride) q[k] = make_uint4(w, w, w, w);
+    if (i < head) p[i] = v;
+    if (i < tail) p[head + n16 * 16 + i] = v;
+}
+}  // namespace
+
+namespace {
+__global__ void __launch_bounds__(256) stage_copy_kernel(unsigned *dst, const unsigned *src, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+}  // namespace
+
+cudaError_t caelo_stage_copy_async(void *dst, const void *pinned_src, size_t nbytes, cudaStream_t st)
+{
+    if (!nbytes) return cudaSuccess;
+    void *dsrc = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&dsrc, const_cast<void *>(pinned_src), 0);
+    if (e != cudaSuccess) return e;
+    const size_t n = (nbytes + 3) / 4;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 64) blocks = 64;
+    stage_copy_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<unsigned *>(dst), static_cast<const unsigned *>(dsrc), n);
+    return cudaGetLastError();
+}
+
+cudaError_t caelo_fill_async(void *ptr, int byte_value, size_t nbytes, cudaStream_t st)
+{
+    if (!nbytes) return cudaSuccess;
+    unsigned char *p = static_cast<unsigned char *>(ptr);
+    size_t head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
+    if (head > nbytes) head = nbytes;
+    const size_t n16 = (nbytes - head) / 16, tail = nbytes - head - n16 * 16;
+    size_t blocks = (n16 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    fill_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, (unsigned char)byte_value, head, n16, tail);
+    return cudaGetLastError();
+}
+
 extern "C" int caelo_version(void) { return 100; }
 
 extern "C" const char *caelo_error_string(int code)

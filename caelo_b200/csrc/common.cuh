@@ -95,6 +95,16 @@ static inline int caelo_reserve(caelo_ctx *ctx, Scratch &s, size_t bytes)
     return CAELO_OK;
 }
 
+// Device-memory fill by a KERNEL on the stream.  cudaMemsetAsync may be executed by a copy engine: behind a long
+// host->device transfer on another stream it then waits for that transfer (measured in round 2: with the next batch's
+// 84 MB upload in flight the memsets of a step stalled the compute stream by ~1 ms per step).
+cudaError_t caelo_fill_async(void *ptr, int byte_value, size_t nbytes, cudaStream_t st);
+// Small host -> device copy by a KERNEL that reads the pinned staging slot (caelo_stage_acquire) over PCIe: a
+// cudaMemcpyAsync of a few hundred bytes on the compute stream queues on the host->device copy engine BEHIND the next
+// batch's 65-85 MB upload and holds the compute stream up until that has finished.  `pinned_src` must be a slot
+// returned by caelo_stage_acquire (device-accessible pinned memory), nbytes a multiple of 4.
+cudaError_t caelo_stage_copy_async(void *dst, const void *pinned_src, size_t nbytes, cudaStream_t st);
+
 #define CAELO_LAUNCH_CHECK(ctx)                       \
     do {                                              \
         (ctx)->launches++;                            \

@@ -1077,9 +1077,9 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
     Conv3Args c3;
     c3.act2 = act2; c3.k3 = ctx->enc.k3; c3.b3 = ctx->enc.b3; c3.act3_hi = act3_hi; c3.act3_lo = act3_lo; c3.P = P;
     {
-        const char *e = getenv("CAELO_CONV3_M64");       // debug switch for A/B timing: the one-patch-per-MMA kernel
+        const char *e = getenv("CAELO_CONV3_PAIR");      // switch for A/B timing: "1" = the two-patches-per-MMA kernel
         ProfScope ps_(ctx, "conv3_tc_kernel", st);
-        if (e && e[0] == '1') {
+        if (!(e && e[0] == '1')) {
             // one CTA per SM with two operand buffers (two single-buffer CTAs per SM measured slower: 0.95 vs 0.89 ms)
             int grid3 = ctx->num_sms;
             if (grid3 > P) grid3 = P;
@@ -1151,7 +1151,7 @@ extern "C" int caelo_encode_patches(caelo_ctx *ctx, const float *patches, int P,
     int rc = caelo_reserve(ctx, ctx->misc, (size_t)P * 512);
     if (rc) return rc;
     unsigned *packed = reinterpret_cast<unsigned *>(ctx->misc.ptr);
-    if (status) CAELO_CUDA(ctx, cudaMemsetAsync(status, 0, 4, st));
+    if (status) CAELO_CUDA(ctx, caelo_fill_async(status, 0, 4, st));
     long long nwords = (long long)P * 128;
     long long blocks = (nwords * 32 + 255) / 256;
     if (blocks > (long long)ctx->num_sms * 32) blocks = (long long)ctx->num_sms * 32;

@@ -165,7 +165,7 @@ extern "C" int caelo_extend_keypoints(caelo_ctx *ctx, const float *ring, int rin
     a.ext = ext; a.n_ext = n_ext;
     a.ring_C = ring_C; a.ring_H = ring_H; a.ring_W = ring_W; a.cnt_kind = counter_dtype; a.cnt_H = cnt_H; a.cnt_W = cnt_W;
     a.B = B; a.max_kpts = max_kpts; a.ext_cap = ext_cap;
-    CAELO_CUDA(ctx, cudaMemsetAsync(a.owner, 0x7F, npx * 4, st));
+    CAELO_CUDA(ctx, caelo_fill_async(a.owner, 0x7F, npx * 4, st));
     { ProfScope ps_(ctx, "extend_claim_kernel", st); extend_claim_kernel<<<dim3((max_kpts + 7) / 8, B), 256, 0, st>>>(a); }
     CAELO_LAUNCH_CHECK(ctx);
     const size_t smem = (size_t)(max_kpts + 1) * 4;

@@ -345,7 +345,7 @@ extern "C" int caelo_nn3(caelo_ctx *ctx, const float *pc0, int N, const float *p
 {
     if (!ctx || !pc0 || !pc1 || !idx || !dist || N <= 0 || M <= 0) return CAELO_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (count) CAELO_CUDA(ctx, cudaMemsetAsync(count, 0, 4, st));
+    if (count) CAELO_CUDA(ctx, caelo_fill_async(count, 0, 4, st));
     { ProfScope ps_(ctx, "nn3_kernel", st);
       nn3_kernel<<<(M + NN3_THREADS - 1) / NN3_THREADS, NN3_THREADS, 0, st>>>(pc0, N, pc1, M, reinterpret_cast<long long *>(idx),
                                                                               dist, thr, mask, count); }
@@ -400,7 +400,7 @@ extern "C" int caelo_icp_batch(caelo_ctx *ctx, const float *pc0, const int64_t *
     rc = caelo_reserve(ctx, ctx->icp_ws, o_end);
     if (rc) return rc;
     unsigned char *ws = static_cast<unsigned char *>(ctx->icp_ws.ptr);
-    CAELO_CUDA(ctx, cudaMemcpyAsync(ws + o_off, h_stage, n_int * 4, cudaMemcpyHostToDevice, st));
+    CAELO_CUDA(ctx, caelo_stage_copy_async(ws + o_off, h_stage, n_int * 4, st));
     CAELO_CUDA(ctx, cudaEventRecord(ev, st));
     IcpArgs a;
     a.pc0 = pc0; a.pc1 = pc1; a.B = B; a.S0 = S0; a.S1 = S1;
@@ -418,12 +418,12 @@ extern "C" int caelo_icp_batch(caelo_ctx *ctx, const float *pc0, const int64_t *
     a.rt = reinterpret_cast<float *>(sp);
     a.hist = hist; a.hist_n = hist_n; a.max_iter = max_iter; a.min_iter = min_iter; a.min_inliers = min_inliers;
     a.decay = decay; a.small_shift = small_shift; a.ep = ep; a.it = 0;
-    CAELO_CUDA(ctx, cudaMemsetAsync(a.keys, 0xFF, (size_t)slots * 8, st));
-    CAELO_CUDA(ctx, cudaMemsetAsync(a.meta, 0, (size_t)slots * 16, st));
-    CAELO_CUDA(ctx, cudaMemsetAsync(a.done, 0, (size_t)B * 6 * 4, st));
-    CAELO_CUDA(ctx, cudaMemsetAsync(a.apply_it, 0xFF, (size_t)B * 4, st));
-    CAELO_CUDA(ctx, cudaMemsetAsync(hist_n, 0, (size_t)B * max_iter * 4, st));
-    CAELO_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)B * max_iter * 48, st));
+    CAELO_CUDA(ctx, caelo_fill_async(a.keys, 0xFF, (size_t)slots * 8, st));
+    CAELO_CUDA(ctx, caelo_fill_async(a.meta, 0, (size_t)slots * 16, st));
+    CAELO_CUDA(ctx, caelo_fill_async(a.done, 0, (size_t)B * 6 * 4, st));
+    CAELO_CUDA(ctx, caelo_fill_async(a.apply_it, 0xFF, (size_t)B * 4, st));
+    CAELO_CUDA(ctx, caelo_fill_async(hist_n, 0, (size_t)B * max_iter * 4, st));
+    CAELO_CUDA(ctx, caelo_fill_async(hist, 0, (size_t)B * max_iter * 48, st));
     { ProfScope ps_(ctx, "icp_init_kernel", st); icp_init_kernel<<<(B + 255) / 256, 256, 0, st>>>(a.thr, B, thr0); }
     CAELO_LAUNCH_CHECK(ctx);
     { ProfScope ps_(ctx, "icp_grid_count_kernel", st); icp_grid_count_kernel<<<(S0 + 255) / 256, 256, 0, st>>>(a); }

@@ -458,7 +458,7 @@ extern "C" int caelo_nn_match(caelo_ctx *ctx, const float *codes0, const float *
         unsigned char *ops0 = reinterpret_cast<unsigned char *>(ctx->match_ops.ptr), *ops1 = ops0 + (size_t)P * tiles0 * blk;
         float *n0p = reinterpret_cast<float *>(ops1 + (size_t)P * tiles1 * blk);
         float *n1 = reinterpret_cast<float *>(a.best_i + cols), *nmax = n1 + cols + rows0;
-        CAELO_CUDA(ctx, cudaMemsetAsync(nmax, 0, (size_t)P * 4, st));
+        CAELO_CUDA(ctx, caelo_fill_async(nmax, 0, (size_t)P * 4, st));
         { ProfScope ps_(ctx, "desc_prep_kernel", st);
           desc_prep_kernel<<<dim3(tiles0, P), NT_B, 0, st>>>(codes0, N, D, Kp, tiles0, ops0, nullptr, n0p, nmax);
           desc_prep_kernel<<<dim3(tiles1, P), NT_B, 0, st>>>(codes1, M, D, Kp, tiles1, ops1, n1, nullptr, nullptr); }
@@ -482,8 +482,8 @@ extern "C" int caelo_nn_match(caelo_ctx *ctx, const float *codes0, const float *
     int *list = nlist + 16;
     int *part_cnt = list + ((cols + 15) / 16) * 16;
     NNPart *parts = reinterpret_cast<NNPart *>(part_cnt + ((exact_grid + 15) / 16) * 16);
-    CAELO_CUDA(ctx, cudaMemsetAsync(nlist, 0, 64, st));
-    CAELO_CUDA(ctx, cudaMemsetAsync(part_cnt, 0, (size_t)exact_grid * 4, st));
+    CAELO_CUDA(ctx, caelo_fill_async(nlist, 0, 64, st));
+    CAELO_CUDA(ctx, caelo_fill_async(part_cnt, 0, (size_t)exact_grid * 4, st));
     { ProfScope ps_(ctx, "nn_decide_kernel", st); nn_decide_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(a, P, list, nlist); }
     CAELO_LAUNCH_CHECK(ctx);
     { ProfScope ps_(ctx, "nn_exact_kernel", st); nn_exact_kernel<<<exact_grid, 256, 0, st>>>(a, list, nlist, part_cnt, parts); }

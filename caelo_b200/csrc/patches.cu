@@ -150,11 +150,9 @@ __device__ __forceinline__ Probe brick_probe(const Table &t, int x, int y, int z
     return p;
 }
 
-// `bits`: the voxel bits of every lane of the warp that fell into this brick (merged by the caller); returns how many of
-// them were clear before, i.e. how many voxels were seen for the first time.
-__device__ __forceinline__ int brick_set(const Table &t, const Table &ts, int x, int y, int z, const Probe &p, unsigned long long bits)
+__device__ __forceinline__ bool brick_set(const Table &t, const Table &ts, int x, int y, int z, const Probe &p)
 {
-    const unsigned long long key = p.key, bit = bits;
+    const unsigned long long key = p.key, bit = p.bit;
     unsigned slot = p.slot;
     ulonglong2 kv = p.kv;
     while (true) {
@@ -171,8 +169,8 @@ __device__ __forceinline__ int brick_set(const Table &t, const Table &ts, int x,
             }
         }
         if (k == key) {
-            if (!fresh && !(kv.y & bit)) return 0;       // all already set
-            return __popcll(atomicAnd(inv_mask_of(t, slot), ~bit) & bit);
+            if (!fresh && !(kv.y & bit)) return false;   // already set
+            return (atomicAnd(inv_mask_of(t, slot), ~bit) & bit) != 0ull;
         }
         slot = (slot + 1) & t.cap_mask;
         kv = __ldcg(reinterpret_cast<const ulonglong2 *>(key_of(t, slot)));
@@ -191,47 +189,27 @@ __global__ void __launch_bounds__(256) scan_brick_insert_kernel(const ScanBuildA
     // warp-uniform trip count: the ballots below need every lane
     for (long long i0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {
         const long long i = i0 + lane;
-        // Consecutive points of a scan are neighbours in space: at the 16 cm and 64 cm scales most lanes of a warp fall
-        // into the same few bricks.  Lanes with equal brick keys merge their voxel bits first and only the group leader
-        // probes / updates the table (12 M single-voxel probes per 33-frame step before; round 2 ncu: 0.60 ms against
-        // 0.23 ms for the list-based insert, which has always merged).  The three leaders' home-slot loads are still
-        // issued side by side.
-        int g[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-        bool ok = false;
+        bool n0 = false, n1 = false, n2 = false;
         if (i < n) {
             const float4 p = p4[i];
             VoxelOfPoint v;
             const int st = voxel_of_point(p.x, p.y, p.z, v);
             bad += st < 0;
-            ok = st > 0;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { g[0][c] = v.g0[c]; g[1][c] = v.g1[c]; g[2][c] = v.g2[c]; }
+            if (st > 0) {
+                const Probe p0 = brick_probe(t0, v.g0[0], v.g0[1], v.g0[2]), p1 = brick_probe(t1, v.g1[0], v.g1[1], v.g1[2]),
+                            p2 = brick_probe(t2, v.g2[0], v.g2[1], v.g2[2]);     // three DRAM round trips side by side
+                n0 = brick_set(t0, s0, v.g0[0], v.g0[1], v.g0[2], p0);
+                n1 = brick_set(t1, s1, v.g1[0], v.g1[1], v.g1[2], p1);
+                n2 = brick_set(t2, s2, v.g2[0], v.g2[1], v.g2[2], p2);
+            }
         }
-        unsigned long long bits[3];
-        bool leader[3];
-#pragma unroll
-        for (int sc = 0; sc < 3; ++sc) {
-            const unsigned long long key = ok ? brick_key(g[sc][0] >> 2, g[sc][1] >> 2, g[sc][2] >> 2) : EMPTY;
-            const unsigned long long bit = ok ? 1ull << (((g[sc][0] & 3) * 4 + (g[sc][1] & 3)) * 4 + (g[sc][2] & 3)) : 0ull;
-            const unsigned grp = __match_any_sync(0xffffffffu, key);
-            const unsigned lo = __reduce_or_sync(grp, (unsigned)bit), hi = __reduce_or_sync(grp, (unsigned)(bit >> 32));
-            bits[sc] = ((unsigned long long)hi << 32) | lo;
-            leader[sc] = ok && lane == __ffs(grp) - 1;
-        }
-        Probe p0, p1, p2;
-        if (leader[0]) p0 = brick_probe(t0, g[0][0], g[0][1], g[0][2]);
-        if (leader[1]) p1 = brick_probe(t1, g[1][0], g[1][1], g[1][2]);
-        if (leader[2]) p2 = brick_probe(t2, g[2][0], g[2][1], g[2][2]);
-        const int n0 = leader[0] ? brick_set(t0, s0, g[0][0], g[0][1], g[0][2], p0, bits[0]) : 0;
-        const int n1 = leader[1] ? brick_set(t1, s1, g[1][0], g[1][1], g[1][2], p1, bits[1]) : 0;
-        const int n2 = leader[2] ? brick_set(t2, s2, g[2][0], g[2][1], g[2][2], p2, bits[2]) : 0;
-        // warp-aggregated voxel counters (one atomic per warp and scale)
-        const int w0 = __reduce_add_sync(0xffffffffu, n0), w1 = __reduce_add_sync(0xffffffffu, n1),
-                  w2 = __reduce_add_sync(0xffffffffu, n2);
+        // warp-aggregated voxel counters (one atomic per warp and scale instead of one per new voxel)
+        const unsigned m0 = __ballot_sync(0xffffffffu, n0), m1 = __ballot_sync(0xffffffffu, n1),
+                       m2 = __ballot_sync(0xffffffffu, n2);
         if (lane == 0) {
-            if (w0) atomicAdd(a.nvox + f * 3, w0);
-            if (w1) atomicAdd(a.nvox + f * 3 + 1, w1);
-            if (w2) atomicAdd(a.nvox + f * 3 + 2, w2);
+            if (m0) atomicAdd(a.nvox + f * 3, __popc(m0));
+            if (m1) atomicAdd(a.nvox + f * 3 + 1, __popc(m1));
+            if (m2) atomicAdd(a.nvox + f * 3 + 2, __popc(m2));
         }
     }
     if (bad && a.status) atomicAdd(a.status + f, bad);
@@ -485,9 +463,9 @@ static int setup_tables(caelo_ctx *ctx, int nl, const size_t *caps, const int64_
         cur += caps[l];
     }
     memcpy(reinterpret_cast<char *>(h_stage) + (size_t)nl * sizeof(Table), offsets, (size_t)n_off * 8);
-    CAELO_CUDA(ctx, cudaMemcpyAsync(*d_tables, h_stage, stage_bytes, cudaMemcpyHostToDevice, st));
+    CAELO_CUDA(ctx, caelo_stage_copy_async(*d_tables, h_stage, stage_bytes, st));
     CAELO_CUDA(ctx, cudaEventRecord(ev, st));
-    CAELO_CUDA(ctx, cudaMemsetAsync(d_slots, 0xFF, total_slots * 16, st));
+    CAELO_CUDA(ctx, caelo_fill_async(d_slots, 0xFF, total_slots * 16, st));
     return CAELO_OK;
 }
 
@@ -585,8 +563,8 @@ extern "C" int caelo_bricks_build_scans(caelo_ctx *ctx, const float *pts, const 
     long long *d_off;
     int rc = setup_tables(ctx, 2 * nl, caps.data(), pts_offsets, F + 1, &d_tables, &d_off, st);
     if (rc) return rc;
-    CAELO_CUDA(ctx, cudaMemsetAsync(nvox, 0, (size_t)nl * 4, st));
-    CAELO_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)F * 4, st));
+    CAELO_CUDA(ctx, caelo_fill_async(nvox, 0, (size_t)nl * 4, st));
+    CAELO_CUDA(ctx, caelo_fill_async(status, 0, (size_t)F * 4, st));
     ScanBuildArgs b;
     b.pts = pts; b.offsets = d_off; b.tables = d_tables; b.nlists = nl; b.nvox = nvox; b.status = status;
     int bx = (int)((maxn + 255) / 256);     // one point per thread

@@ -555,7 +555,7 @@ extern "C" int caelo_ransac_draw_samples(caelo_ctx *ctx, const int64_t *seeds, i
     cudaEvent_t ev;
     if ((rc = caelo_stage_acquire(ctx, (size_t)P * 8, &h_stage, &ev))) return rc;
     memcpy(h_stage, seeds, (size_t)P * 8);
-    CAELO_CUDA(ctx, cudaMemcpyAsync(ctx->seed_ws.ptr, h_stage, (size_t)P * 8, cudaMemcpyHostToDevice, st));
+    CAELO_CUDA(ctx, caelo_stage_copy_async(ctx->seed_ws.ptr, h_stage, (size_t)P * 8, st));
     CAELO_CUDA(ctx, cudaEventRecord(ev, st));
     DrawArgs a;
     a.seeds = reinterpret_cast<const long long *>(ctx->seed_ws.ptr); a.samples = samples; a.P = P;

@@ -503,7 +503,7 @@ int launch_select(caelo_ctx *ctx, bool fused, const float *resp, int H, int W, c
     if (rc) return rc;
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(ctx->cand.ptr);
     int *count = reinterpret_cast<int *>(keys + (size_t)B * cap);
-    CAELO_CUDA(ctx, cudaMemsetAsync(count, 0, (size_t)B * 4, st));
+    CAELO_CUDA(ctx, caelo_fill_async(count, 0, (size_t)B * 4, st));
 
     SelectArgs a;
     a.ring = ring; a.counter = counter; a.resp = resp; a.keys = keys; a.count = count;
@@ -513,13 +513,13 @@ int launch_select(caelo_ctx *ctx, bool fused, const float *resp, int H, int W, c
     size_t smem = (size_t)8 * NPIX * 4 + ((NPIX + 15) / 16) * 16 + (fused ? (size_t)IH * IW * 3 * 4 : 0) + (NPIX + TH * TW) * 2;
     if (fused) {
         static int var = -1;
-        if (var < 0) { const char *e = getenv("CAELO_RESPOND_VARIANT"); var = e ? atoi(e) : 2; }
+        if (var < 0) { const char *e = getenv("CAELO_RESPOND_VARIANT"); var = e ? atoi(e) : 0; }
         ProfScope ps_(ctx, "respond_score_kernel<fused>", st);
         switch (var) {
-        case 0: respond_score_kernel<true, 0><<<grid, kThreads, smem, st>>>(ctx->respond_host, a); break;
         case 1: respond_score_kernel<true, 1><<<grid, kThreads, smem, st>>>(ctx->respond_host, a); break;
         case 3: respond_score_kernel<true, 3><<<grid, kThreads, smem, st>>>(ctx->respond_host, a); break;
-        default: respond_score_kernel<true, 2><<<grid, kThreads, smem, st>>>(ctx->respond_host, a); break;
+        case 2: respond_score_kernel<true, 2><<<grid, kThreads, smem, st>>>(ctx->respond_host, a); break;
+        default: respond_score_kernel<true, 0><<<grid, kThreads, smem, st>>>(ctx->respond_host, a); break;
         }
     } else {
         if (!resp) return CAELO_ERR_ARG;

@@ -366,7 +366,7 @@ int upload_offsets(caelo_ctx *ctx, const int64_t *host, int n, long long *dev, c
     int rc = caelo_stage_acquire(ctx, (size_t)n * 8, &h, &ev);
     if (rc) return rc;
     memcpy(h, host, (size_t)n * 8);
-    CAELO_CUDA(ctx, cudaMemcpyAsync(dev, h, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CAELO_CUDA(ctx, caelo_stage_copy_async(dev, h, (size_t)n * 8, st));
     CAELO_CUDA(ctx, cudaEventRecord(ev, st));
     return CAELO_OK;
 }
@@ -405,9 +405,9 @@ extern "C" int caelo_project_ring(caelo_ctx *ctx, const float *pts, const int64_
     a.v_off = -vdown / a.v_res;
     a.ring5 = ring5; a.counter_i32 = counter_i32; a.ring3 = ring3; a.counter_i8 = reinterpret_cast<signed char *>(counter_i8);
     a.F = F;
-    CAELO_CUDA(ctx, cudaMemsetAsync(a.winner, 0xFF, npx * 4, st));
-    CAELO_CUDA(ctx, cudaMemsetAsync(a.hits, 0, npx * 4, st));
-    if (status) CAELO_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)F * 4, st));
+    CAELO_CUDA(ctx, caelo_fill_async(a.winner, 0xFF, npx * 4, st));
+    CAELO_CUDA(ctx, caelo_fill_async(a.hits, 0, npx * 4, st));
+    if (status) CAELO_CUDA(ctx, caelo_fill_async(status, 0, (size_t)F * 4, st));
     int bx = (int)((maxn + 255) / 256);
     if (bx > 128) bx = 128;
     if (bx < 1) bx = 1;
@@ -465,10 +465,10 @@ extern "C" int caelo_voxelize(caelo_ctx *ctx, const float *pts, const int64_t *p
     a.vox = vox; a.local0 = local0; a.blocks = blocks;
     a.cnt = cnt ? cnt : reinterpret_cast<int *>(base + o_cnt);
     a.counts = counts; a.status = status; a.cap = cap; a.F = F;
-    CAELO_CUDA(ctx, cudaMemsetAsync(a.keys, 0xFF, (size_t)F * 4 * capT * 8, st));
-    CAELO_CUDA(ctx, cudaMemsetAsync(a.vals, 0x7F, (size_t)F * 4 * capT * 4, st));
-    CAELO_CUDA(ctx, cudaMemsetAsync(a.bcount, 0, 2 * fc * 4, st));
-    if (status) CAELO_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)F * 4, st));
+    CAELO_CUDA(ctx, caelo_fill_async(a.keys, 0xFF, (size_t)F * 4 * capT * 8, st));
+    CAELO_CUDA(ctx, caelo_fill_async(a.vals, 0x7F, (size_t)F * 4 * capT * 4, st));
+    CAELO_CUDA(ctx, caelo_fill_async(a.bcount, 0, 2 * fc * 4, st));
+    if (status) CAELO_CUDA(ctx, caelo_fill_async(status, 0, (size_t)F * 4, st));
     int bx = (int)((maxn + 255) / 256);
     if (bx > 128) bx = 128;
     if (bx < 1) bx = 1;

@@ -181,23 +181,23 @@ def test_encoder_dense_random_patches(api, oracle_mod):
 
 
 def test_conv3_pair_kernel_matches_single_patch_kernel(api, oracle_mod):
-    """conv3 with two patches per MMA (M = 128, the default) against the one-patch kernel (M = 64, CAELO_CONV3_M64=1) and
+    """conv3 with two patches per MMA (M = 128, CAELO_CONV3_PAIR=1) against the one-patch kernel (M = 64, the default) and
     the oracle, on odd and tiny patch counts (the last pair of an odd count is half empty)."""
     import os
     rng = np.random.default_rng(17)
     enc = api.load_model(api.WEIGHT_DIR + "/encoder.npz")
     for n in (1, 2, 3, 255, 257, 600):
         x = (rng.random((n, 16, 16, 16, 1)) < rng.choice([0.002, 0.02, 0.2])).astype(np.float32)
-        got = enc.predict(x)
-        os.environ["CAELO_CONV3_M64"] = "1"
+        old = enc.predict(x)
+        os.environ["CAELO_CONV3_PAIR"] = "1"
         try:
-            old = enc.predict(x)
+            got = enc.predict(x)
         finally:
-            del os.environ["CAELO_CONV3_M64"]
+            del os.environ["CAELO_CONV3_PAIR"]
         assert np.abs(got - old).max() < 2e-6, n                 # same products, another accumulation order
         if n <= 257:
             assert_descriptors_close(got, oracle_mod.encoder_predict(x))
-        assert np.array_equal(got, enc.predict(x))               # deterministic
+        assert np.array_equal(old, enc.predict(x))               # deterministic
 
 
 def test_encoder_rejects_non_binary(api):
