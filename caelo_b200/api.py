@@ -123,6 +123,22 @@ class Context:
             out[name] = (int(n), float(ms))
         return out
 
+    def _scratch(self, name: str, shape, dtype) -> torch.Tensor:
+        """A persistent device buffer for a TRANSIENT result of the batched pipeline (ring images, packed patches):
+        the same tensor is handed out call after call.  Safe because every kernel that touches it is queued on the one
+        compute stream; it spares the hot path its large torch allocations — with several batches queued ahead the
+        caching allocator kept carving the freed 45-52 MB blocks up for the small per-batch results and went back to
+        cudaMalloc (which synchronises the device) for the big ones: 6 ms of host time per step."""
+        if not hasattr(self, "_scratch_bufs"):
+            self._scratch_bufs = {}
+        key = (name, tuple(shape), dtype)
+        buf = self._scratch_bufs.get(key)
+        if buf is None:
+            if len(self._scratch_bufs) > 32:                      # many different batch shapes: start over
+                self._scratch_bufs.clear()
+            buf = self._scratch_bufs[key] = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+        return buf
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.caelo_destroy(self.h)
@@ -164,7 +180,7 @@ class Context:
         self.check(rc, "caelo_select_keypoints")
         return kpts, kpix, n
 
-    def project_ring(self, pts: torch.Tensor, pts_offsets: np.ndarray, want=("ring3", "counter_i8")):
+    def project_ring(self, pts: torch.Tensor, pts_offsets: np.ndarray, want=("ring3", "counter_i8"), reuse: bool = False):
         """f1: pts [sumN,4] f32, pts_offsets host int64 [F+1] -> dict of the requested outputs
         (ring5 [F,69,1800,5], counter_i32 [F,69,1800], ring3 [F,64,1792,3], counter_i8) + status [F]."""
         off = np.ascontiguousarray(pts_offsets, np.int64)
@@ -173,7 +189,9 @@ class Context:
         shapes = {"ring5": ((F, ImgH, ImgW, 5), torch.float32), "counter_i32": ((F, ImgH, ImgW), torch.int32),
                   "ring3": ((F, nLines, ImgW - CropWidth_SphericalRing, 3), torch.float32),
                   "counter_i8": ((F, ImgH, ImgW), torch.int8)}
-        out = {k: torch.empty(shapes[k][0], dtype=shapes[k][1], device=self.device) for k in want}
+        new = (lambda k, sh, dt: self._scratch("ring_" + k, sh, dt)) if reuse else \
+            (lambda k, sh, dt: torch.empty(sh, dtype=dt, device=self.device))
+        out = {k: new(k, shapes[k][0], shapes[k][1]) for k in want}
         out["status"] = torch.empty((F,), dtype=torch.int32, device=self.device)
         self.check(self.lib.caelo_project_ring(self.h, _ptr(pts), off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), F,
                                                _ptr(out.get("ring5")), _ptr(out.get("counter_i32")),
@@ -220,7 +238,7 @@ class Context:
 
     def gather_patches(self, kpts: torch.Tensor, vox: torch.Tensor, vox_offsets: np.ndarray,
                        n_kpts: Optional[torch.Tensor] = None, want_f32: bool = False, want_trunc: bool = False,
-                       group: Optional[int] = None):
+                       group: Optional[int] = None, reuse: bool = False):
         """kpts [F,K,3] f32|f64; vox int16 [sumV,3]; vox_offsets host int64 [F*3+1] (rows).
         ``group``: frames per C call (0 / default = the whole batch in one call).  Building and querying the brick
         tables a few frames at a time keeps them in L2 (one frame's tables are ~10 MB, a 33-frame batch's ~340 MB) —
@@ -230,7 +248,8 @@ class Context:
         assert kpts.is_contiguous() and vox.dtype == torch.int16 and vox.is_contiguous()
         off = np.ascontiguousarray(vox_offsets, np.int64)
         assert off.shape == (F * 3 + 1,)
-        packed = torch.empty((F, 3, K, 128), dtype=torch.int32, device=self.device)
+        packed = self._scratch("packed", (F, 3, K, 128), torch.int32) if reuse else \
+            torch.empty((F, 3, K, 128), dtype=torch.int32, device=self.device)
         f32 = torch.empty((F, 3, K, 16, 16, 16), dtype=torch.float32, device=self.device) if want_f32 else None
         trunc = torch.empty((F, 3, K), dtype=torch.uint8, device=self.device) if want_trunc else None
         if group is None:
@@ -250,13 +269,14 @@ class Context:
 
     def gather_patches_scans(self, kpts: torch.Tensor, pts: torch.Tensor, pts_offsets: np.ndarray,
                              n_kpts: Optional[torch.Tensor] = None, want_f32: bool = False, want_trunc: bool = False,
-                             group: Optional[int] = None):
+                             group: Optional[int] = None, reuse: bool = False):
         """f2+a6 fused: kpts [F,K,3]; pts [sumN,4] f32 raw scans; -> packed, f32, trunc, nvox [F,3], status [F].
         ``group`` as in gather_patches."""
         F, K, _ = kpts.shape
         off = np.ascontiguousarray(pts_offsets, np.int64)
         assert off.shape == (F + 1,) and pts.dtype == torch.float32 and pts.is_contiguous() and kpts.is_contiguous()
-        packed = torch.empty((F, 3, K, 128), dtype=torch.int32, device=self.device)
+        packed = self._scratch("packed", (F, 3, K, 128), torch.int32) if reuse else \
+            torch.empty((F, 3, K, 128), dtype=torch.int32, device=self.device)
         f32 = torch.empty((F, 3, K, 16, 16, 16), dtype=torch.float32, device=self.device) if want_f32 else None
         trunc = torch.empty((F, 3, K), dtype=torch.uint8, device=self.device) if want_trunc else None
         nvox = torch.empty((F, 3), dtype=torch.int32, device=self.device)

@@ -62,7 +62,7 @@ class OdometryPipeline:
         # (building the a6 index on a second stream under the selection was measured: the two compete for the same SMs,
         #  brick_insert 0.19 -> 0.45 ms, respond_score 0.40 -> 0.60 ms, step 4.69 -> 4.75 ms — so one stream)
         kpts, _kpix, n = self.ctx.select_keypoints(ring, counter, None, max_kpts=self.K)
-        packed, _, _ = self.ctx.gather_patches(kpts, vox, vox_offsets, n)
+        packed, _, _ = self.ctx.gather_patches(kpts, vox, vox_offsets, n, reuse=True)
         feat = self.ctx.encode_frames(packed)
         return kpts, feat, n
 
@@ -70,9 +70,9 @@ class OdometryPipeline:
         """Raw scans (pts [sumN,4] f32 + host row offsets [F+1]) -> kpts, feat, n_kpts, status [F]:
         f1 projection -> a1+a2 -> f2+a6 fused (bricks straight from the points) -> a3.  ``status`` is
         non-zero for a frame the reference would have raised on (IndexError / sklearn ValueError)."""
-        r = self.ctx.project_ring(pts, pts_offsets, want=("ring3", "counter_i8"))
+        r = self.ctx.project_ring(pts, pts_offsets, want=("ring3", "counter_i8"), reuse=True)
         kpts, _kpix, n = self.ctx.select_keypoints(r["ring3"], r["counter_i8"], None, max_kpts=self.K)
-        packed, _, _, _nvox, st = self.ctx.gather_patches_scans(kpts, pts, pts_offsets, n)
+        packed, _, _, _nvox, st = self.ctx.gather_patches_scans(kpts, pts, pts_offsets, n, reuse=True)
         feat = self.ctx.encode_frames(packed)
         return kpts, feat, n, st | r["status"]
 
