@@ -654,8 +654,10 @@ constexpr int C3P_ISSUER = 9;                         // warp 9 issues the MMAs 
 constexpr int C3P_EPI0 = 12, C3P_EPI = 8;             // warps 12-19 drain the accumulators (lane quarter x channel half)
 constexpr int C3P_THREADS = (C3P_EPI0 + C3P_EPI) * 32;
 
+template <int NST>   // pipeline stages of the operand ring: 9 (one per copy) or 3 (three copies each)
 __global__ void __launch_bounds__(C3P_THREADS, 1) conv3_pair_kernel(const Conv3Args a)
 {
+    constexpr int CPS = 9 / NST;   // copies per stage
     extern __shared__ __align__(128) unsigned char sm[];
     float *b3s = reinterpret_cast<float *>(sm + C3P_SM_B3);
     uint64_t *full = reinterpret_cast<uint64_t *>(sm + C3P_SM_BAR), *empty = full + 9, *tfull = full + 18, *tempty = full + 20;
@@ -675,8 +677,8 @@ __global__ void __launch_bounds__(C3P_THREADS, 1) conv3_pair_kernel(const Conv3A
     if (tid < 32) b3s[tid] = a.b3[tid];
     if (warp == C3P_ISSUER) umma::tmem_alloc(tmem_slot, 128);
     if (tid == 0) {
-        for (int c = 0; c < 9; ++c) {
-            umma::mbar_init(&full[c], 32);      // the copy's producer warp
+        for (int c = 0; c < NST; ++c) {
+            umma::mbar_init(&full[c], 32 * CPS);   // the producer warps of the stage's copies
             umma::mbar_init(&empty[c], 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -696,28 +698,36 @@ __global__ void __launch_bounds__(C3P_THREADS, 1) conv3_pair_kernel(const Conv3A
     auto pair_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
 
     if (warp == C3P_ISSUER) {
+        // Every descriptor is a constant offset from two base descriptors (the loops below are fully unrolled): the issuer
+        // thread's instruction stream must stay well below the tensor core's ~44 cycles per MMA — with run-time (dy,dz) and
+        // descriptors rebuilt per MMA the first version spent ~100 cycles of dependent uniform-datapath code per MMA and the
+        // tensor pipe idled at 25 %.
         const uint32_t idesc64 = umma::idesc_f16_f32(128, 64), idesc32 = umma::idesc_f16_f32(128, 32);
+        const uint64_t a_base = umma::smem_desc(sC, C3P_HALF, 128), b_base = umma::smem_desc(sW, 1024, 128);
         for (int j = 0; j < n_my; ++j) {
             const int b = j & 1;
             if (j >= 2) umma::mbar_wait(&tempty[b], (uint32_t)(((j >> 1) - 1) & 1));
             const uint32_t d = tbase + b * 64;
-#pragma unroll 1
-            for (int c = 0; c < 9; ++c) {          // stage = (dy,dz) copy
-                umma::mbar_wait(&full[c], (uint32_t)(j & 1));
+#pragma unroll
+            for (int sg = 0; sg < NST; ++sg) {
+                umma::mbar_wait(&full[sg], (uint32_t)(j & 1));
                 umma::fence_after_thread_sync();
                 if (umma::elect_one()) {
-                    const int dy = c / 3, dz = c % 3;
 #pragma unroll
-                    for (int part = 0; part < 2; ++part)
+                    for (int cc = 0; cc < CPS; ++cc) {
+                        const int c = sg * CPS + cc, dy = c / 3, dz = c % 3;
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            const int t = dx * 9 + dy * 3 + dz;
-                            uint64_t da = umma::smem_desc(sC + part * C3P_PART + c * C3P_COPY + dx * 512, C3P_HALF, 128);
-                            uint64_t db = umma::smem_desc(sW + t * 2048, 1024, 128);
-                            umma::mma_f16(d, da, db, part ? idesc32 : idesc64, (c | part | dx) ? 1u : 0u);
-                        }
-                    umma::commit(&empty[c]);
-                    if (c == 8) umma::commit(&tfull[b]);
+                        for (int part = 0; part < 2; ++part)
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx) {
+                                const int t = dx * 9 + dy * 3 + dz;
+                                const uint64_t da = a_base + (uint64_t)((part * C3P_PART + c * C3P_COPY + dx * 512) >> 4);
+                                const uint64_t db = b_base + (uint64_t)((t * 2048) >> 4);
+                                umma::mma_f16(d, da, db, part ? idesc32 : idesc64, (c | part | dx) ? 1u : 0u);
+                            }
+                    }
+                    umma::commit(&empty[sg]);
+                    if (sg == NST - 1) umma::commit(&tfull[b]);
                 }
                 __syncwarp();
             }
@@ -741,7 +751,7 @@ __global__ void __launch_bounds__(C3P_THREADS, 1) conv3_pair_kernel(const Conv3A
                 v[k][1] = __ldg(src + 1);
             }
             if (i >= 1) {
-                umma::mbar_wait(&empty[c], (uint32_t)((i - 1) & 1));
+                umma::mbar_wait(&empty[c / CPS], (uint32_t)((i - 1) & 1));
                 umma::fence_after_thread_sync();
             }
 #pragma unroll
@@ -759,7 +769,7 @@ __global__ void __launch_bounds__(C3P_THREADS, 1) conv3_pair_kernel(const Conv3A
                 }
             }
             umma::fence_proxy_async();
-            umma::mbar_arrive(&full[c]);
+            umma::mbar_arrive(&full[c / CPS]);
         }
     } else if (warp >= C3P_EPI0) {
         // ===== epilogue (8 warps = TMEM lane quarter x channel half): lane -> (x = quarter, patch, yz) =====
@@ -1087,7 +1097,8 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
         } else {
             int grid3 = ctx->num_sms;                    // persistent: one CTA per SM walks the patch PAIRS
             if (grid3 > (P + 1) / 2) grid3 = (P + 1) / 2;
-            conv3_pair_kernel<<<grid3, C3P_THREADS, C3P_SMEM, st>>>(c3);
+            if (e[1] == '9') conv3_pair_kernel<9><<<grid3, C3P_THREADS, C3P_SMEM, st>>>(c3);
+            else conv3_pair_kernel<3><<<grid3, C3P_THREADS, C3P_SMEM, st>>>(c3);
         }
     }
     CAELO_LAUNCH_CHECK(ctx);
@@ -1107,7 +1118,8 @@ int caelo_encoder_init(caelo_ctx *ctx)
 {
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv12_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem(2)));
-    CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_pair_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
     return CAELO_OK;
 }
