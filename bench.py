@@ -572,6 +572,7 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(2):
         poses_s = pipe.collect(enqueue_scans())
     same = bool(np.array_equal(poses_s, poses))
+    pipeline.gather_poses(np.concatenate([poses] * K, 0), dev, cap=K * P)      # warm-up of the collective (NCCL sets its communicator up lazily)
 
     # ---- timed region: K steps from ring images + voxel lists resident in HBM ----
     sampler = ClockSampler(local_rank) if rank == 0 else None

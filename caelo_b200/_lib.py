@@ -7,7 +7,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libcaelo_b200.so")
+SO_PATH = os.environ.get("CAELO_SO_PATH") or os.path.join(_HERE, "libcaelo_b200.so")   # CAELO_SO_PATH: an experimental build (A/B timing)
 
 
 class CaeloError(RuntimeError):

@@ -42,18 +42,20 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out_path: str = OUT, objdir_name: str = "build") -> str:
+    """``extra_flags`` / ``out_path`` / ``objdir_name``: an experimental variant next to the product library (A/B timing on
+    the GPU box: CAELO_SO_PATH selects the library _lib.load() opens)."""
+    if not force and not extra_flags and not needs_build():
         return OUT
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, objdir_name)
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []
     for src, extra in SOURCES.items():
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *ARCH, *COMMON, *extra, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False
@@ -67,8 +69,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed (see above)")
-    subprocess.check_call([nvcc, *ARCH, "-shared", "-o", OUT, *objs, "-lcudart"])
-    return OUT
+    subprocess.check_call([nvcc, *ARCH, "-shared", "-o", out_path, *objs, "-lcudart"])
+    return out_path
 
 
 if __name__ == "__main__":

@@ -105,9 +105,25 @@ __device__ __forceinline__ void fence_mbar_init()
 {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+#ifndef CAELO_MBAR_HINT_NS
+#define CAELO_MBAR_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *mbar, uint32_t parity)
 {
     uint32_t ok;
+#if CAELO_MBAR_HINT_NS > 0
+    // with a suspend-time hint the hardware parks the thread until the phase completes (or the hint expires) instead
+    // of returning after its short default time-out: far fewer polls of the barrier word in shared memory
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(mbar)), "r"(parity), "r"((uint32_t)CAELO_MBAR_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -117,6 +133,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *mbar, uint32_t parity)
         : "=r"(ok)
         : "r"(smem_u32(mbar)), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity)
@@ -124,7 +141,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity)
     // try_wait already suspends for a hardware-chosen time; back off a little more so that parked
     // warps do not take issue slots from the warps still producing (15% of all issued instructions
     // of conv12 were this loop before)
+#if CAELO_MBAR_HINT_NS > 0
+    while (!mbar_try_wait(mbar, parity)) {}
+#else
     while (!mbar_try_wait(mbar, parity)) __nanosleep(40);
+#endif
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *mbar)
 {

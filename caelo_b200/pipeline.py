@@ -414,18 +414,26 @@ def chain_poses(rel: np.ndarray, Tr: Optional[np.ndarray] = None):
     R_Tr_inv = np.linalg.inv(R_Tr)
     T_Tr = Tr[:, 3].reshape(3, 1)
     T_Tr_inv = -np.dot(R_Tr_inv, T_Tr)
-    poses = [np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], dtype=np.float32).reshape(12, 1)]
-    for i in range(rel.shape[0]):
-        ok = rel[i, 12] != 0
-        dt = np.float32 if ok else np.float64
-        relativeR = np.asarray(rel[i, :9], dtype=dt).reshape(3, 3)
-        relativeT = np.asarray(rel[i, 9:12], dtype=dt).reshape(3, 1)
-        pose0 = poses[i].reshape(3, 4)
-        R0, T0 = pose0[:, 0:3], pose0[:, 3].reshape(3, 1)
-        R_poseDiff = np.dot(R_Tr, np.dot(relativeR, R_Tr_inv))
-        T_poseDiff = np.dot(R_Tr, np.dot(relativeR, T_Tr_inv) + relativeT) + T_Tr
-        R = np.dot(R0, R_poseDiff)
-        T = np.dot(R0, T_poseDiff) + T0
-        poses.append(np.c_[R, T].reshape((12, 1)))
-    out = np.array(poses, dtype=np.float32)
-    return out.reshape(out.shape[0], 12)
+    # the recurrence is inherently sequential and its float32 np.dot calls are kept exactly as the reference makes them
+    # (a batched np.matmul rounds differently); only the Python overhead around them is trimmed — for seq 00 this loop
+    # is what rank 0 does alone after the one gather
+    P = rel.shape[0]
+    ok = rel[:, 12] != 0
+    out = np.empty((P + 1, 3, 4), dtype=np.float32)
+    R0 = np.eye(3, dtype=np.float32)
+    T0 = np.zeros((3, 1), dtype=np.float32)
+    out[0, :, :3], out[0, :, 3:] = R0, T0
+    rel32 = np.ascontiguousarray(rel[:, :12], dtype=np.float32)
+    rel64 = rel32.astype(np.float64) if not ok.all() else None
+    dot = np.dot
+    for i in range(P):
+        src = rel32[i] if ok[i] else rel64[i]
+        relativeR = src[:9].reshape(3, 3)
+        relativeT = src[9:12].reshape(3, 1)
+        R_poseDiff = dot(R_Tr, dot(relativeR, R_Tr_inv))
+        T_poseDiff = dot(R_Tr, dot(relativeR, T_Tr_inv) + relativeT) + T_Tr
+        R = dot(R0, R_poseDiff)
+        T = dot(R0, T_poseDiff) + T0
+        out[i + 1, :, :3], out[i + 1, :, 3:] = R, T            # stored as float32 (np.array(poses, float32) at :272) ...
+        R0, T0 = R, T                                             # ... but chained in the dtype the reference chains in
+    return out.reshape(P + 1, 12)
