@@ -575,6 +575,10 @@ def run_ours(args, rank, local_rank, world):
     pipeline.gather_poses(np.concatenate([poses] * K, 0), dev, cap=K * P)      # warm-up of the collective (NCCL sets its communicator up lazily)
 
     # ---- timed region: K steps from ring images + voxel lists resident in HBM ----
+    # one untimed round in exactly the shape of the timed one (K steps queued ahead, handles alive): afterwards the caching
+    # allocator owns every block the timed round needs — a cudaMalloc inside the timed region synchronises the device
+    timed_steps(enqueue_rings)
+    timed_steps(enqueue_scans)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ctx.profile(True)
     ctx.profile_fetch()
