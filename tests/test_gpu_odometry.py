@@ -93,6 +93,36 @@ def test_estimate_sequence_sharded_equals_single_rank(api, sequence):
     assert np.array_equal(np.concatenate(parts, 0), rel_all)
 
 
+def test_long_drive_sharded_equals_single_rank_and_stays_on_track(api):
+    """configs[2] at a size that exercises many batches: a 258-frame synthetic drive (257 pairs) from scans resident in
+    HBM — the pair ranges of 2 and of 8 'ranks' (every rank holding only its own frames + the one-frame halo) concatenate
+    to exactly the single-rank result; every pair registers, and the chained trajectory stays close to the known motion."""
+    import torch
+    from caelo_b200 import odometry, pipeline, synth
+    F = 258
+    pts, off = synth.make_scans(F, seed=7, device="cuda")
+    pipe = pipeline.OdometryPipeline(api.default_context())
+    poses, rel = odometry.estimate_sequence(stacked=(pts, off), batch_pairs=32, pipe=pipe)
+    assert rel.shape == (F - 1, 16) and (rel[:, 12] == 1).all()
+    for world in (2, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = pipeline.shard_pairs(F - 1, r, world)
+            sl = (pts[int(off[lo]):int(off[hi + 1])], off[lo:hi + 2] - off[lo])          # this rank's frames only
+            parts.append(odometry.estimate_sequence(stacked=sl, stacked_first_frame=lo, n_frames=F, batch_pairs=32, rank=r,
+                                                    world=world, pipe=pipe)[1])
+        assert np.array_equal(np.concatenate(parts, 0), rel), world
+    # host-resident input (pinned, streamed batch by batch) gives the same rows
+    host = torch.empty(pts.shape, dtype=torch.float32, pin_memory=True)
+    host.copy_(pts)
+    _, rel_h = odometry.estimate_sequence(stacked=(host, off), batch_pairs=32, pipe=pipe)
+    assert np.array_equal(rel_h, rel)
+    gt = _ground_truth(F)
+    rre, rte = _pose_errors(poses.astype(np.float64), gt)
+    assert rre.max() < 1.0 and rte.max() < 0.5                        # the reference's success criterion, every pair
+    assert np.linalg.norm(poses[-1].reshape(3, 4)[:, 3] - gt[-1].reshape(3, 4)[:, 3]) < 0.1 * 0.7 * (F - 1)
+
+
 def test_preprocess_sequence_writes_what_the_loaders_read(api, sequence, oracle_mod):
     """BatchPreprocess.py:44-67 / BatchVoxelization.py:42-64 outputs for two frames: .mat contents == the oracle's
     ProjectPC2SphericalRing / Voxelization, and LoadVoxelModelAndKeyPts (Match.py:46-61) reads them back."""
