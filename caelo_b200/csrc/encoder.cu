@@ -96,10 +96,15 @@ __device__ __forceinline__ constexpr int tap_off(int t)  // byte offset of tap t
 //           conv is 9 table rows added up: no data-dependent loop, every load independent.  Max over the
 //           sub-positions by three channel-halving exchanges, tanh, split to fp16 hi/lo — each lane
 //           finishes one channel.
+//   The operand cell of pooled position (px,py,pz) is  px*SX + py*SY + pz + c0  (16 B each): the one-patch kernel keeps a
+//   10^3 volume (SX = 100, SY = 10, c0 = 111), the pair kernel an [x 8][y 10][patch 2][z 10] volume (SX = 200, SY = 20,
+//   c0 = 21 + 10*patch).  `barid` = the named barrier of the 256 threads that work on this patch.
+template <int SX, int SY>
 __device__ __forceinline__ void conv1_to_smem(const unsigned short *rows, const unsigned char *t1, const float *b1s,
                                               unsigned char *a_hi, unsigned char *a_lo,
                                               unsigned long long *lwin, unsigned short *lcell, int *lcount,
-                                              unsigned char *xs_any, int tid, int &n_listed, long long *tl)
+                                              unsigned char *xs_any, int tid, int &n_listed, long long *tl,
+                                              int c0 = 111, int barid = 1)
 {
     const int lane = tid & 31;
     {
@@ -141,13 +146,13 @@ __device__ __forceinline__ void conv1_to_smem(const unsigned short *rows, const 
                 if (nz) {
                     const int k = base + __popc(m & ((1u << lane) - 1u));
                     lwin[k] = ((unsigned long long)whi << 32) | wlo;
-                    lcell[k] = (unsigned short)(((px + 1) * 10 + (py + 1)) * 10 + (pz + 1));
+                    lcell[k] = (unsigned short)(px * SX + py * SY + pz + c0);
                 }
             }
         }
         if (lane == 0) xs_any[tid >> 5] = cells != 0u;   // warp w owns the cells of x-slice px = w
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync %0, 256;" ::"r"(barid) : "memory");
     if (tl && tid == 0) tl[7] = clock64();
     // pass 2: eight consecutive lanes share a listed cell, lane s = (sx,sy,sz); a warp takes 4 cells per round
     // (warp-uniform trip count: the shuffles below need every lane)
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
             long long *tl = (a.timeline && i < 64) ? a.timeline + ((size_t)blockIdx.x * 64 + i) * 16 : nullptr;
             if (tl && tid == 0) tl[2] = clock64();
             int n_listed;
-            conv1_to_smem(rows, sm + SM_T1, b1s, a_hi, a_lo, lwin, lc, lcnt + b, sm + SM_XS + 8 * (i & 3), tid, n_listed, tl);
+            conv1_to_smem<100, 10>(rows, sm + SM_T1, b1s, a_hi, a_lo, lwin, lc, lcnt + b, sm + SM_XS + 8 * (i & 3), tid, n_listed, tl);
             if (b) n_dirty1 = n_listed; else n_dirty0 = n_listed;
             umma::fence_proxy_async();
             umma::mbar_arrive(&full[b]);
@@ -450,6 +455,430 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
     __syncthreads();
     umma::fence_after_thread_sync();
     if (warp == TC_ISSUER) umma::tmem_dealloc(tbase, 256);
+}
+
+// ---- conv1 + conv2, two patches per MMA (M = 128) and dx folded into N -------------------------------------------------
+// conv12_tc_kernel above is bound by the tensor core's shared-memory operand fetch (ncu round 2: its wavefronts take 79 % of
+// the shared-memory pipe, the tensor pipe is 44 % active): with only 16 output channels every M = 64 x N = 32 MMA fetches
+// 2 KB of A for 1 KB of B, 616 KB per patch.  Two changes cut the operand bytes per patch to 280 KB:
+//   * TWO patches share every MMA (M = 128): the operand volume is [x 8][y 10 (halo)][patch 2][z 10 (halo)] x 16 B, so
+//     the 128 rows (y, patch, z) of tap (dy,dz) in slab x are 16 eight-row groups 160 B apart — one K-major descriptor.
+//   * the three dx taps are folded into N: slab x is multiplied ONCE per (dy,dz) tap pair by B = [dx=2 | dx=1 | dx=0] x
+//     [W_hi | W_lo] (N = 96) and accumulates into the 32-column blocks of the output slices x-1, x, x+1, which lie side by
+//     side in TMEM (slabs 0 and 7 use the N = 64 sub-matrix).  The 9 (dy,dz) taps of the hi and of the lo volume are 4 + 4 K-steps
+//     of two taps plus ONE step whose two K chunks are tap 8 of the hi and of the lo volume: 9 MMAs per slab.
+// A_hi and A_lo both go through the same B: D[:, hi columns] + D[:, lo columns] = (A_hi + A_lo)(W_hi + W_lo).
+// Because one MMA now touches three output blocks of which one may be fresh, the pair's 256 accumulator columns are cleared
+// by ONE N = 256 MMA against a zero B operand and everything else accumulates.
+// One CTA per SM (all 512 TMEM columns = two pairs in flight): 16 producer warps, 1 issuer warp, 8 epilogue warps.  An output
+// slice pair is skipped when it is background in BOTH patches; a slab is multiplied when one of its three output slices is
+// wanted.
+// conv1 of a pair, by all 16 producer warps (the tensor side above needs ~4 k cycles per pair, so conv1 has to stay below):
+//   pass 1  thread = (patch, (px,py) column, z quarter): ORs the 4x4 occupancy rows around the column and appends the cells
+//           whose 4x4x4 window is non-empty to ONE list for both patches (cell index + coordinates, 4 bytes);
+//   pass 2  a warp takes 8 listed cells per round as two independent groups of 4 (eight lanes per cell = the pooled
+//           sub-positions).  The 8 lanes first assemble the cell's 64-bit window (each loads two of its 16 rows, three
+//           xor-shuffle ORs), then a sub-position's 27 neighbourhood bits are three 9-bit (dy,dz) patterns, one per dx, each
+//           indexing a table of precomputed partial weight sums (3 x 512 patterns x 8 channels, built per CTA from the 9 x 8
+//           partial-sum table): three table rows added up, max over the eight lanes by channel-halving shuffles, tanh, split.
+// Only listed cells cost anything (10 % of the cells on the benchmark's patches): the first version built every cell's window
+// in pass 1 (2.4 k warp instructions per patch, now ~0.3 k) and ran the two patches on separate halves of the producers (a
+// pair took the slower patch's time).
+constexpr int P2_PROD_WARPS = 16;
+constexpr int P2_PROD = P2_PROD_WARPS * 32;           // warps 0-15: conv1
+constexpr int P2_ISSUER = 16;
+constexpr int P2_EPI0 = 17, P2_EPI_WARPS = 8;         // warps 17-24: (lane quarter = warp % 4) x (output slice pairs 0-1 / 2-3)
+constexpr int P2_THREADS = (P2_EPI0 + P2_EPI_WARPS) * 32;
+constexpr int P2_VOL = 8 * 10 * 2 * 10 * 16;          // 25600 B
+constexpr int P2_SM_A = 0;                            // [buf 2][hi, lo][P2_VOL]
+constexpr int P2_W_S = 2 * 96 * 16;                   // one K-step of B: [chunk 2][row 96][16 B]
+constexpr int P2_SM_W = 4 * P2_VOL;
+constexpr int P2_SM_Z = P2_SM_W + 5 * P2_W_S;         // zero B operand [chunk 2][row 256][16 B]
+constexpr int P2_SM_T3 = P2_SM_Z + 2 * 256 * 16;      // conv1 partial sums [ch half 2][dx 3][512 (dy,dz) patterns][4] f32
+constexpr int P2_T3_HALF = 3 * 512 * 16;
+constexpr int P2_SM_B12 = P2_SM_T3 + 2 * P2_T3_HALF;
+constexpr int P2_SM_BG = P2_SM_B12 + (8 + 16) * 4;
+constexpr int P2_SM_PK = P2_SM_BG + 32;               // staged occupancy rows [buf 2][patch 2][PK_BYTES]
+constexpr int P2_SM_LST = P2_SM_PK + 4 * PK_BYTES;    // listed cells [buf 2][1024] u32: cell | patch<<16 | px<<20 | py<<24 | pz<<28
+constexpr int P2_SM_LCNT = P2_SM_LST + 2 * 1024 * 4;  // [buf 2]
+constexpr int P2_SM_XS = P2_SM_LCNT + 16;             // ring of 4 pairs x 2 patches x 8 slice flags
+constexpr int P2_SM_BGP = P2_SM_XS + 64;
+constexpr int P2_SM_BAR = P2_SM_BGP + 27 * 16 * 4;
+constexpr int P2_SMEM = P2_SM_BAR + 64;
+static_assert(P2_SM_T3 % 16 == 0 && P2_SM_B12 % 16 == 0 && P2_SM_PK % 16 == 0 && P2_SM_LST % 16 == 0 && P2_SM_XS % 8 == 0 &&
+              P2_SM_BGP % 16 == 0 && P2_SM_BAR % 8 == 0 && P2_SMEM <= 227 * 1024, "smem layout");
+
+// conv1 of four listed cells per warp (eight lanes each): window -> three table rows -> max-pool -> tanh -> split fp16
+__device__ __forceinline__ void conv1_cells(const unsigned *lst, int k, int n, const unsigned char *pk, const unsigned char *t3,
+                                            const float *b1s, unsigned char *a_hi, unsigned char *a_lo, int sub)
+{
+    const bool valid = k < n;
+    const unsigned ent = valid ? lst[k] : 0u;
+    const int pp = (ent >> 16) & 1, px = (ent >> 20) & 7, py = (ent >> 24) & 7, pz = ent >> 28;
+    // the cell's window = rows x = 2px-1 .. 2px+2, y = 2py-1 .. 2py+2 (staged with a halo: row (x,y) at [(x+1)*PITCH + y+1]),
+    // bits z = 2pz-1 .. 2pz+2; nibble (ix,iy) at bits 16*ix + 4*iy.  This lane loads rows (ix = sub>>1, iy = 2*(sub&1), +1).
+    const int ix = sub >> 1, yh = sub & 1;
+    const unsigned v = *reinterpret_cast<const unsigned *>(pk + pp * PK_BYTES + ((2 * px + ix) * PK_PITCH + 2 * py + 2 * yh) * 2);
+    const unsigned n01 = ((((v & 0xFFFFu) << 1) >> (2 * pz)) & 0xFu) | (((((v >> 16) << 1) >> (2 * pz)) & 0xFu) << 4);
+    const unsigned sh = n01 << (16 * (ix & 1) + 8 * yh);
+    unsigned wlo = ix < 2 ? sh : 0u, whi = ix < 2 ? 0u : sh;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        wlo |= __shfl_xor_sync(0xffffffffu, wlo, d);
+        whi |= __shfl_xor_sync(0xffffffffu, whi, d);
+    }
+    const int sx = sub >> 2, sy = (sub >> 1) & 1, sz = sub & 1;
+    const unsigned long long w2 = (((unsigned long long)whi << 32) | wlo) >> (16 * sx + 4 * sy + sz);
+    float2 acc2[4];
+    {
+        const float4 c0 = *reinterpret_cast<const float4 *>(b1s), c1 = *reinterpret_cast<const float4 *>(b1s + 4);
+        acc2[0] = make_float2(c0.x, c0.y); acc2[1] = make_float2(c0.z, c0.w);
+        acc2[2] = make_float2(c1.x, c1.y); acc2[3] = make_float2(c1.z, c1.w);
+    }
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+        const unsigned g = (unsigned)(w2 >> (16 * dx)) & 0x777u;                       // (dy,dz) bits at 4*dy + dz
+        const unsigned idx = (g & 7u) | ((g >> 1) & 0x38u) | ((g >> 2) & 0x1C0u);
+        if (idx) {   // the empty pattern's row is all zeros; most patterns of a sparse patch are empty
+            const float4 w0 = *reinterpret_cast<const float4 *>(t3 + (dx * 512 + idx) * 16);
+            const float4 w1 = *reinterpret_cast<const float4 *>(t3 + P2_T3_HALF + (dx * 512 + idx) * 16);
+            acc2[0] = __fadd2_rn(acc2[0], make_float2(w0.x, w0.y));
+            acc2[1] = __fadd2_rn(acc2[1], make_float2(w0.z, w0.w));
+            acc2[2] = __fadd2_rn(acc2[2], make_float2(w1.x, w1.y));
+            acc2[3] = __fadd2_rn(acc2[3], make_float2(w1.z, w1.w));
+        }
+    }
+    const float acc[8] = {acc2[0].x, acc2[0].y, acc2[1].x, acc2[1].y, acc2[2].x, acc2[2].y, acc2[3].x, acc2[3].y};
+    // max over the eight sub-position lanes, halving the channel set a lane carries at each exchange: lane `sub` ends with
+    // channel 4*sx + 2*sy + sz = sub
+    float h4[4], h2[2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float recv = __shfl_xor_sync(0xffffffffu, sx ? acc[c] : acc[4 + c], 4);
+        h4[c] = fmaxf(sx ? acc[4 + c] : acc[c], recv);
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const float recv = __shfl_xor_sync(0xffffffffu, sy ? h4[c] : h4[2 + c], 2);
+        h2[c] = fmaxf(sy ? h4[2 + c] : h4[c], recv);
+    }
+    const float recv = __shfl_xor_sync(0xffffffffu, sz ? h2[0] : h2[1], 1);
+    const float o = fmaxf(sz ? h2[1] : h2[0], recv);
+    if (valid) {
+        const int pi = ent & 0xFFFFu;
+        __half h, l;
+        umma::split_f16(fast_tanh(o), h, l);
+        *reinterpret_cast<__half *>(a_hi + pi * 16 + sub * 2) = h;
+        *reinterpret_cast<__half *>(a_lo + pi * 16 + sub * 2) = l;
+    }
+}
+
+__global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12Args a)
+{
+    extern __shared__ __align__(128) unsigned char sm[];
+    float *b1s = reinterpret_cast<float *>(sm + P2_SM_B12), *b2s = b1s + 8;
+    const uint4 *bg = reinterpret_cast<const uint4 *>(sm + P2_SM_BG);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sm + P2_SM_BAR);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + P2_SM_BAR + 48);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+    // ---- one-time setup ----
+    for (int i = tid; i < P2_SM_T3 / 16; i += P2_THREADS) reinterpret_cast<uint4 *>(sm)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 4 * PK_BYTES / 16; i += P2_THREADS) reinterpret_cast<uint4 *>(sm + P2_SM_PK)[i] = make_uint4(0, 0, 0, 0);
+    // T3[half][dx][(dy,dz) pattern][4 ch] = sum over dy of the (dx,dy) partial sums of the pattern's three dz bits
+    for (int e = tid; e < 3 * 512 * 8; e += P2_THREADS) {
+        const int c = e & 7, idx = (e >> 3) & 511, dx = e >> 12;
+        float s = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) s += a.tables[((dx * 3 + dy) * 8 + ((idx >> (3 * dy)) & 7)) * 8 + c];
+        *reinterpret_cast<float *>(sm + P2_SM_T3 + (c >> 2) * P2_T3_HALF + (dx * 512 + idx) * 16 + (c & 3) * 4) = s;
+    }
+    for (int e = tid; e < 27 * 16; e += P2_THREADS) reinterpret_cast<float *>(sm + P2_SM_BGP)[e] = a.tables[576 + e];
+    if (tid < 8) {
+        b1s[tid] = a.b1[tid];
+        __half h, l;
+        umma::split_f16(tanhf(a.b1[tid]), h, l);
+        reinterpret_cast<__half *>(sm + P2_SM_BG)[tid] = h;
+        reinterpret_cast<__half *>(sm + P2_SM_BG + 16)[tid] = l;
+    }
+    if (tid < 16) b2s[tid] = a.b2[tid];
+    __syncthreads();
+    for (int e = tid; e < 4 * 1024; e += P2_THREADS) {     // interior cells start as the background value tanh(b1)
+        const int vol = e >> 10, c = e & 1023;
+        const int pi = (((c >> 7) * 10 + ((c >> 4) & 7) + 1) * 2 + ((c >> 3) & 1)) * 10 + (c & 7) + 1;
+        *reinterpret_cast<uint4 *>(sm + P2_SM_A + vol * P2_VOL + pi * 16) = bg[vol & 1];
+    }
+    // B: K-step s < 4 holds the (dy,dz) taps j = 2s (chunk 0) and 2s+1 (chunk 1); step 4 holds tap 8 in BOTH chunks (its A chunks
+    // are tap 8 of the hi and of the lo volume: one MMA serves both parts).  Row n = blk*32 + h*16 + co with blk = 2 - dx (the
+    // output slice x + 1 - dx in ascending order), h = 0: W_hi, 1: W_lo.
+    for (int e = tid; e < 27 * 8 * 16; e += P2_THREADS) {
+        const int t = e / 128, ci = (e / 16) % 8, co = e % 16;
+        const int dx = t / 9, j = t % 9, blk = 2 - dx;
+        __half h, l;
+        umma::split_f16(a.k2[e], h, l);
+        const int nh = blk * 32 + co, nl = nh + 16;
+        for (int rep = 0; rep < (j < 8 ? 1 : 2); ++rep) {
+            const int s = j < 8 ? j >> 1 : 4, chunk = j < 8 ? j & 1 : rep;
+            unsigned char *w = sm + P2_SM_W + s * P2_W_S + chunk * (96 * 16) + ci * 2;
+            *reinterpret_cast<__half *>(w + (nh >> 3) * 128 + (nh & 7) * 16) = h;
+            *reinterpret_cast<__half *>(w + (nl >> 3) * 128 + (nl & 7) * 16) = l;
+        }
+    }
+    if (warp == P2_ISSUER) umma::tmem_alloc(tmem_slot, 512);
+    uint64_t *full = mbar, *tfull = mbar + 2, *tempty = mbar + 4;
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            umma::mbar_init(&full[b], P2_PROD);
+            umma::mbar_init(&tfull[b], 1);
+            umma::mbar_init(&tempty[b], P2_EPI_WARPS * 32);
+        }
+        umma::fence_mbar_init();
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t sA = umma::smem_u32(sm + P2_SM_A), sW = umma::smem_u32(sm + P2_SM_W), sZ = umma::smem_u32(sm + P2_SM_Z);
+
+    // patch pairs: in frame mode with an even K a pair = two consecutive key points of one scale, and consecutive pairs of
+    // a CTA cycle through the scales (their conv1 work differs a lot, their conv2 work does not)
+    const bool by_scale = a.K3 != 0 && ((a.K3 / 3) & 1) == 0;
+    const int n_pairs = (a.P + 1) / 2;
+    const int n_my = (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto patch_of = [&](int i, int g) {
+        const int v = (int)blockIdx.x + i * (int)gridDim.x;
+        int p = 2 * v + g;
+        if (by_scale) {
+            const int hp = a.K3 / 2, f = v / hp, r = v - f * hp;
+            p = f * a.K3 + (r % 3) * (a.K3 / 3) + 2 * (r / 3) + g;
+        }
+        return p;
+    };
+    auto stamp = [&](int i, int slot) {
+        if (a.timeline && i < 64) a.timeline[((size_t)blockIdx.x * 64 + i) * 16 + slot] = clock64();
+    };
+    // output slice pairs (pooled x) that need conv2 in at least one patch of the pair `ord & 3`
+    auto active_pairs = [&](int ord) -> unsigned {
+        if (!a.skip_bg) return 0xFu;
+        const unsigned long long *fp = reinterpret_cast<const unsigned long long *>(sm + P2_SM_XS + 16 * ord);
+        const unsigned long long f = fp[0] | fp[1];
+        unsigned m = 0;
+#pragma unroll
+        for (int xs = 0; xs < 8; ++xs) m |= (unsigned)((f >> (8 * xs)) & 1ull) << xs;
+        const unsigned near = m | (m << 1) | (m >> 1);
+        unsigned act = 0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) act |= ((near >> (2 * p)) & 3u) ? (1u << p) : 0u;
+        return act;
+    };
+
+    if (warp == P2_ISSUER) {
+        // ===== MMA issuer =====
+        const uint32_t id96 = umma::idesc_f16_f32(128, 96), id64 = umma::idesc_f16_f32(128, 64), id256 = umma::idesc_f16_f32(128, 256);
+        const uint64_t a_base = umma::smem_desc(sA, 0, 160), b_base = umma::smem_desc(sW, 96 * 16, 128);
+        const uint64_t z_desc = umma::smem_desc(sZ, 256 * 16, 128);
+        for (int j = 0; j < n_my; ++j) {
+            const int b = j & 1, k = j >> 1;
+            umma::mbar_wait(&full[b], (uint32_t)(k & 1));
+            if (k >= 1) umma::mbar_wait(&tempty[b], (uint32_t)((k - 1) & 1));
+            umma::fence_after_thread_sync();
+            if (lane == 0) stamp(j, 5);
+            const unsigned act = active_pairs(j & 3);
+            unsigned need = 0;   // slab x feeds the output slices x-1 .. x+1
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                if ((act >> p) & 1u) need |= ((0xFu << (2 * p)) >> 1) & 0xFFu;
+            if (umma::elect_one()) {
+                const uint32_t d0 = tbase + b * 256;
+                if (act) umma::mma_f16(d0, a_base | (1ull << 16), z_desc, id256, 0u);   // clear the pair's accumulators
+#pragma unroll 1
+                for (int x = 0; x < 8; ++x) {
+                    if (!((need >> x) & 1u)) continue;
+                    const uint32_t d = d0 + (x == 0 ? 0 : x - 1) * 32;
+                    const uint32_t idesc = (x == 0 || x == 7) ? id64 : id96;
+                    const uint64_t bx = b_base + (uint64_t)(x == 0 ? (32 * 16) >> 4 : 0);   // slab 0: rows 32..95 (dx = 1, 0)
+#pragma unroll
+                    for (int part = 0; part < 2; ++part) {
+                        const uint64_t ax = a_base + (uint64_t)(((2 * b + part) * P2_VOL + x * 3200) >> 4);
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) {
+                            // taps (2s, 2s+1): tap j = dy*3+dz sits dy*320 + dz*16 bytes into the slab
+                            const int j0 = 2 * s, j1 = j0 + 1;
+                            const int o0 = (j0 / 3) * 320 + (j0 % 3) * 16, o1 = (j1 / 3) * 320 + (j1 % 3) * 16;
+                            const uint64_t da = ax + (uint64_t)(o0 >> 4) + ((uint64_t)((o1 - o0) >> 4) << 16);
+                            const uint64_t db = bx + (uint64_t)((s * P2_W_S) >> 4);
+                            umma::mma_f16(d, da, db, idesc, 1u);
+                        }
+                    }
+                    {   // tap 8 of the hi volume (chunk 0) and of the lo volume (chunk 1, LBO = the distance between the volumes)
+                        const uint64_t da = a_base + (uint64_t)(((2 * b) * P2_VOL + x * 3200 + 2 * 320 + 2 * 16) >> 4) + ((uint64_t)(P2_VOL >> 4) << 16);
+                        umma::mma_f16(d, da, bx + (uint64_t)((4 * P2_W_S) >> 4), idesc, 1u);
+                    }
+                }
+                umma::commit(&tfull[b]);
+            }
+            __syncwarp();
+            if (lane == 0) stamp(j, 6);
+        }
+    } else if (warp < P2_ISSUER) {
+        // ===== producers (16 warps): conv1 of both patches of pair i into operand buffer i&1 =====
+        const int g = tid >> 8, t = tid & 255;          // pass 1: this thread's patch of the pair, its thread within the patch
+        unsigned *lst_all = reinterpret_cast<unsigned *>(sm + P2_SM_LST);
+        int *lcnt = reinterpret_cast<int *>(sm + P2_SM_LCNT);
+        unsigned pk_next = 0u;
+        int n_dirty0 = 0, n_dirty1 = 0;
+        auto fetch = [&](int i) {
+            if (i < n_my) {
+                int p = patch_of(i, g);
+                if (p >= a.P) p = a.P - 1;              // odd patch count: the last pair's second half repeats the first
+                if (t < 128) pk_next = __ldg(a.packed + (size_t)p * 128 + t);
+            }
+        };
+        fetch(0);
+        for (int i = 0; i < n_my; ++i) {
+            const int b = i & 1;
+            if (tid == 0) stamp(i, 0);
+            if (i >= 2) {   // the MMAs of pair i-2 must have finished reading operand buffer b
+                umma::mbar_wait(&tfull[b], (uint32_t)(((i - 2) >> 1) & 1));
+                umma::fence_after_thread_sync();
+            }
+            unsigned char *a_hi = sm + P2_SM_A + (2 * b) * P2_VOL, *a_lo = a_hi + P2_VOL;
+            unsigned *lst = lst_all + b * 1024;
+            // restore the cells the previous pair of this buffer wrote to the background value
+            const int nd = b ? n_dirty1 : n_dirty0;
+            for (int k = tid; k < nd; k += P2_PROD) {
+                const int pi = lst[k] & 0xFFFFu;
+                *reinterpret_cast<uint4 *>(a_hi + pi * 16) = bg[0];
+                *reinterpret_cast<uint4 *>(a_lo + pi * 16) = bg[1];
+            }
+            // (staged rows are double-buffered like the operands: other warps may still be in pass 2 of the previous pair)
+            unsigned short *rows = reinterpret_cast<unsigned short *>(sm + P2_SM_PK + (2 * b + g) * PK_BYTES);
+            if (t < 128) {  // word t = occupancy rows (x, y) and (x, y+1), x = t/8, y = 2*(t%8)
+                unsigned short *dst = rows + ((t >> 3) + 1) * PK_PITCH + 2 * (t & 7) + 1;
+                dst[0] = (unsigned short)(pk_next & 0xFFFFu);
+                dst[1] = (unsigned short)(pk_next >> 16);
+            }
+            fetch(i + 1);
+            asm volatile("bar.sync 1, 512;" ::: "memory");   // rows staged, restore done, the previous pass 2 has left the list
+            if (tid == 0) lcnt[b] = 0;                     // (the other buffer's counter is the one pass 2 just read)
+            long long *tl = (a.timeline && i < 64) ? a.timeline + ((size_t)blockIdx.x * 64 + i) * 16 : nullptr;
+            if (tl && tid == 0) tl[2] = clock64();
+            // ---- pass 1: list the cells with a non-empty window ----
+            unsigned found[2];
+            {
+                const int col = t >> 2, zq = t & 3, px = col >> 3, py = col & 7;
+                const unsigned *rp = reinterpret_cast<const unsigned *>(rows + (2 * px) * PK_PITCH + 2 * py);
+                unsigned any = 0;
+#pragma unroll
+                for (int ix = 0; ix < 4; ++ix) any |= rp[ix * (PK_PITCH / 2)] | rp[ix * (PK_PITCH / 2) + 1];
+                any = ((any | (any >> 16)) & 0xFFFFu) << 1;   // bit z+1 <-> some row of the column has voxel z
+                unsigned cells = 0;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int pz = 2 * zq + half;
+                    const bool nz = ((any >> (2 * pz)) & 0xFu) != 0u;   // a voxel at z = 2pz-1 .. 2pz+2
+                    found[half] = __ballot_sync(0xffffffffu, nz);
+                    cells |= found[half];
+                }
+                if (lane == 0) sm[P2_SM_XS + 16 * (i & 3) + 8 * g + (t >> 5)] = cells != 0u;   // the warp = x-slice px of patch g
+                asm volatile("bar.sync 2, 512;" ::: "memory");                                   // counter reset visible
+                const int cnt = __popc(found[0]) + __popc(found[1]);
+                if (cnt) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(lcnt + b, cnt);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        if ((found[half] >> lane) & 1u) {
+                            const int pz = 2 * zq + half;
+                            const int k = base + __popc(found[half] & ((1u << lane) - 1u)) + (half ? __popc(found[0]) : 0);
+                            lst[k] = (unsigned)(((px * 10 + py + 1) * 2 + g) * 10 + pz + 1) | ((unsigned)g << 16) | ((unsigned)px << 20) |
+                                     ((unsigned)py << 24) | ((unsigned)pz << 28);
+                        }
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (tl && tid == 0) tl[7] = clock64();
+            // ---- pass 2: eight listed cells per warp and round, as two independent groups of four ----
+            const int n = lcnt[b];
+            if (b) n_dirty1 = n; else n_dirty0 = n;
+            const int sub = lane & 7;
+            for (int k0 = warp * 8 + (lane >> 3); k0 - (lane >> 3) < n; k0 += P2_PROD_WARPS * 8) {
+                conv1_cells(lst, k0, n, sm + P2_SM_PK + 2 * b * PK_BYTES, sm + P2_SM_T3, b1s, a_hi, a_lo, sub);
+                conv1_cells(lst, k0 + 4, n, sm + P2_SM_PK + 2 * b * PK_BYTES, sm + P2_SM_T3, b1s, a_hi, a_lo, sub);
+            }
+            if (tl && tid == 0) tl[8] = clock64();
+            umma::fence_proxy_async();
+            umma::mbar_arrive(&full[b]);
+            if (tid == 0) stamp(i, 1);
+        }
+    } else {
+        // ===== epilogue (8 warps): TMEM lane = (y, patch, z); warp -> lane quarter q (pooled y = q) and two of the four
+        // output slice pairs =====
+        const int q = warp & 3, xh = (warp - P2_EPI0) >> 2;
+        const int yb = (lane >> 4) & 1, pp = (lane >> 3) & 1, zb = lane & 1, z2 = (lane & 7) >> 1;
+        const int jq = yb * 2 + zb;                      // the lane ends with channels 4*jq .. 4*jq+3 of its pooled cell
+        const float4 bias4 = *reinterpret_cast<const float4 *>(b2s + 4 * jq);
+        for (int i = 0; i < n_my; ++i) {
+            const int b = i & 1;
+            umma::mbar_wait(&tfull[b], (uint32_t)((i >> 1) & 1));
+            umma::fence_after_thread_sync();
+            if (warp == P2_EPI0 && lane == 0) stamp(i, 3);
+            const int p = patch_of(i, pp);
+            const bool valid = p < a.P;
+            float *out = a.act2 + (size_t)(valid ? p : 0) * 1024;
+            const unsigned act = active_pairs(i & 3);
+#pragma unroll 1
+            for (int px = 2 * xh; px < 2 * xh + 2; ++px) {
+                const int pos = (px * 4 + q) * 4 + z2;
+                if (!((act >> px) & 1u)) {
+                    const int cls = (px == 0 ? 0 : (px == 3 ? 2 : 1)) * 9 + (q == 0 ? 0 : (q == 3 ? 2 : 1)) * 3 +
+                                    (z2 == 0 ? 0 : (z2 == 3 ? 2 : 1));
+                    if (valid)
+                        *reinterpret_cast<float4 *>(out + pos * 16 + 4 * jq) =
+                            *reinterpret_cast<const float4 *>(sm + P2_SM_BGP + (cls * 16 + 4 * jq) * 4);
+                    continue;
+                }
+                const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16) + b * 256 + px * 64;
+                uint32_t v[32];
+                float m[16];
+                umma::tmem_ld_x32(trow, v);              // slice 2px: 16 hi + 16 lo columns
+                umma::tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 16; ++c) m[c] = __uint_as_float(v[c]) + __uint_as_float(v[16 + c]);
+                umma::tmem_ld_x32(trow + 32, v);         // slice 2px+1
+                umma::tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 16; ++c) m[c] = fmaxf(m[c], __uint_as_float(v[c]) + __uint_as_float(v[16 + c]));
+                // y partner = lane ^ 16, z partner = lane ^ 1; every exchange halves the channels a lane carries
+                float m8[8], m4[4];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float recv = __shfl_xor_sync(0xffffffffu, yb ? m[c] : m[8 + c], 16);
+                    m8[c] = fmaxf(yb ? m[8 + c] : m[c], recv);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float recv = __shfl_xor_sync(0xffffffffu, zb ? m8[c] : m8[4 + c], 1);
+                    m4[c] = fmaxf(zb ? m8[4 + c] : m8[c], recv);
+                }
+                if (valid)   // the bias is common to the pooled cells: added after the max
+                    *reinterpret_cast<float4 *>(out + pos * 16 + 4 * jq) =
+                        make_float4(fast_tanh(m4[0] + bias4.x), fast_tanh(m4[1] + bias4.y), fast_tanh(m4[2] + bias4.z),
+                                    fast_tanh(m4[3] + bias4.w));
+            }
+            umma::fence_before_thread_sync();
+            umma::mbar_arrive(&tempty[b]);
+            if (warp == P2_EPI0 && lane == 0) stamp(i, 4);
+        }
+    }
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    if (warp == P2_ISSUER) umma::tmem_dealloc(tbase, 512);
 }
 
 // ---- conv3 (tcgen05) ---------------------------------------------------------------------------
@@ -1081,8 +1510,17 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
         const char *e = getenv("CAELO_CONV12_SKIP_BG");   // debug switch for A/B timing; default on
         c.skip_bg = !(e && e[0] == '0');
     }
-    int grid = 2 * ctx->num_sms < P ? 2 * ctx->num_sms : P;
-    { ProfScope ps_(ctx, "conv12_tc_kernel", st); conv12_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(c); }
+    {
+        const char *e = getenv("CAELO_CONV12_PAIR");      // switch for A/B timing: "0" = the one-patch-per-MMA kernel (M = 64)
+        ProfScope ps_(ctx, "conv12_tc_kernel", st);
+        if (e && e[0] == '0') {
+            int grid = 2 * ctx->num_sms < P ? 2 * ctx->num_sms : P;
+            conv12_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(c);
+        } else {
+            int grid = ctx->num_sms < (P + 1) / 2 ? ctx->num_sms : (P + 1) / 2;   // persistent: one CTA per SM walks the patch PAIRS
+            conv12_pair_kernel<<<grid, P2_THREADS, P2_SMEM, st>>>(c);
+        }
+    }
     CAELO_LAUNCH_CHECK(ctx);
     Conv3Args c3;
     c3.act2 = act2; c3.k3 = ctx->enc.k3; c3.b3 = ctx->enc.b3; c3.act3_hi = act3_hi; c3.act3_lo = act3_lo; c3.P = P;
@@ -1117,6 +1555,7 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
 int caelo_encoder_init(caelo_ctx *ctx)
 {
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv12_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(conv12_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem(2)));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_pair_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM));

@@ -200,6 +200,45 @@ def test_conv3_pair_kernel_matches_single_patch_kernel(api, oracle_mod):
         assert np.array_equal(old, enc.predict(x))               # deterministic
 
 
+def test_conv12_pair_kernel_matches_single_patch_kernel(api, oracle_mod):
+    """conv1+conv2 with two patches per MMA and dx folded into N (the default) against the one-patch kernel
+    (CAELO_CONV12_PAIR=0) and the oracle: odd and tiny patch counts, all-empty / all-full / one-voxel patches (background
+    skipping in one or both patches of a pair), and the frame-ordered entry point with an even and an odd K."""
+    import os
+    import torch
+    rng = np.random.default_rng(23)
+    enc = api.load_model(api.WEIGHT_DIR + "/encoder.npz")
+
+    def both(fn):
+        got = fn()
+        os.environ["CAELO_CONV12_PAIR"] = "0"
+        try:
+            old = fn()
+        finally:
+            del os.environ["CAELO_CONV12_PAIR"]
+        return got, old
+
+    for n in (1, 2, 3, 9, 255, 600):
+        x = (rng.random((n, 16, 16, 16, 1)) < rng.choice([0.0005, 0.01, 0.2], size=(n, 1, 1, 1, 1))).astype(np.float32)
+        x[0] = 0                                                  # an all-background patch next to whatever patch 1 is
+        if n > 2:
+            x[2] = 0
+            x[2, 15, 0, 7, 0] = 1                                 # one voxel in a corner
+        if n > 8:
+            x[7] = 1
+        got, old = both(lambda: enc.predict(x))
+        assert np.abs(got - old).max() < 4e-6, n                  # (A_hi + A_lo)(W_hi + W_lo) vs three of the four products
+        assert_descriptors_close(got, oracle_mod.encoder_predict(x))
+        assert np.array_equal(got, enc.predict(x))                # deterministic
+    ctx = api.default_context()
+    for F, K in ((2, 6), (1, 7), (3, 1)):                        # [F,3,K] order: pairs by scale when K is even
+        bits = rng.random((F, 3, K, 16, 16, 16)) < 0.02
+        packed = torch.from_numpy(np.packbits(bits.reshape(F, 3, K, 128, 32), axis=-1, bitorder="little")
+                                  .view(np.uint32).reshape(F, 3, K, 128).copy()).cuda()
+        got, old = both(lambda: ctx.encode_frames(packed).cpu().numpy())
+        assert got.shape == (F, K, 60) and np.abs(got - old).max() < 4e-6, (F, K)
+
+
 def test_encoder_rejects_non_binary(api):
     from caelo_b200._lib import CaeloError
     x = np.zeros((2, 16, 16, 16, 1), np.float32)

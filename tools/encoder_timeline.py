@@ -21,7 +21,9 @@ tl = tl_all[:grid * 64 * 16].view(grid, 64, 16)
 dn = tl_all[grid * 64 * 16:].view(-1, 8).cpu().numpy().astype(np.float64)
 dn = dn[dn[:, 0] > 0]
 print("dense_tc per-CTA cycles: start->accum-done %.0f  W2 fill+Hs fill %.0f  dense2 %.0f  total %.0f (n=%d)" % ((dn[:,3]-dn[:,0]).mean(), (dn[:,4]-dn[:,3]).mean(), (dn[:,5]-dn[:,4]).mean(), (dn[:,5]-dn[:,0]).mean(), len(dn)))
-t = tl.cpu().numpy()[:, 4:60, :].astype(np.float64)
+t = tl.cpu().numpy()
+t = t[t[:, 10, 0] > 0][:, 4:60, :].astype(np.float64)          # CTAs that ran (the pair kernel launches one per SM)
+print("CTAs with stamps:", t.shape[0])
 def stat(x): return "mean %8.0f  p50 %8.0f  p90 %8.0f" % (x.mean(), np.median(x), np.percentile(x, 90))
 print("conv1            1-0 :", stat(t[..., 1] - t[..., 0]))
 print("  restore+stage  2-0 :", stat(t[..., 2] - t[..., 0]))
@@ -34,8 +36,13 @@ print("mbar wait        3-1 :", stat(t[..., 3] - t[..., 1]))
 print("epilogue         4-3 :", stat(t[..., 4] - t[..., 3]))
 
 print("iteration  next0-0 :", stat(t[:, 1:, 0] - t[:, :-1, 0]))
+for r in range(3):
+    sel = [i for i in range(t.shape[1] - 1) if (i + 4) % 3 == r]
+    print("  iterations with i %% 3 == %d: iteration %s | pass1 %6.0f pass2 %6.0f mma %6.0f epi %6.0f" % (
+        r, stat((t[:, 1:, 0] - t[:, :-1, 0])[:, sel]), (t[..., 7] - t[..., 2])[:, sel].mean(), (t[..., 8] - t[..., 7])[:, sel].mean(),
+        (t[..., 6] - t[..., 5])[:, sel].mean(), (t[..., 4] - t[..., 3])[:, sel].mean()))
 raw = tl.cpu().numpy()
-for cta in (0, 150):
+for cta in (0, 100):
     print("CTA", cta, "(cycles relative to iteration-10 start; columns = stamps 0..7)")
     base = raw[cta, 10, 0]
     for i in range(10, 15):
