@@ -75,6 +75,7 @@ struct Conv12Args {
     int P;
     int K3;                  // frame mode: 3*K (patch order [F][3][K]) — CTAs then walk the patches scale-interleaved; 0 = as stored
     int skip_bg;             // 1: x-slice pairs whose whole conv2 neighbourhood is background skip their MMAs
+    int dbg;                 // measurement only (CAELO_CONV12_DBG): bit 0 = no MMAs, bit 1 = no conv1 pass 2 (results are wrong)
     long long *timeline;     // debug: [gridDim.x][64][16] clock64 stamps, or null
 };
 
@@ -508,69 +509,118 @@ constexpr int P2_SMEM = P2_SM_BAR + 64;
 static_assert(P2_SM_T3 % 16 == 0 && P2_SM_B12 % 16 == 0 && P2_SM_PK % 16 == 0 && P2_SM_LST % 16 == 0 && P2_SM_XS % 8 == 0 &&
               P2_SM_BGP % 16 == 0 && P2_SM_BAR % 8 == 0 && P2_SMEM <= 227 * 1024, "smem layout");
 
-// conv1 of four listed cells per warp (eight lanes each): window -> three table rows -> max-pool -> tanh -> split fp16
+// Row of pattern idx inside a 512-row table.  The eight lanes of a quarter warp (= the eight sub-positions of one cell) read
+// their rows with one 16-byte load each, and the patterns of a sparse patch are mostly single bits: 2^k is a multiple of 8
+// for k >= 3, so with slot = idx six of the nine one-voxel patterns share a 16-byte bank group (measured: 3.4 wavefronts per
+// ideal one, half of all the kernel's shared-memory wavefronts).  The low three bits are therefore XORed with a hash of the
+// upper six (a bijection); K = 23, shift 2 was the best of a search over the windows of real patches (tools: 2.05 -> 1.23
+// wavefronts per quarter-warp load).
+__device__ __forceinline__ unsigned t3_slot(unsigned idx) { return idx ^ ((((idx >> 3) * 23u) >> 2) & 7u); }
+
+// conv1 of U x four listed cells per warp (eight lanes each): window -> three table rows -> max-pool -> tanh -> split fp16.
+// The U groups advance in lockstep, stage by stage: one group is a chain of ~150 dependent instructions (shared-memory loads,
+// two shuffle butterflies), and with only 16 producer warps on the SM it is their latency, not the issue rate, that bounds
+// conv1 — two calls one after the other were not interleaved by the compiler (the shuffles keep their order).
+template <int U>
 __device__ __forceinline__ void conv1_cells(const unsigned *lst, int k, int n, const unsigned char *pk, const unsigned char *t3,
-                                            const float *b1s, unsigned char *a_hi, unsigned char *a_lo, int sub)
+                                            const float4 &bias_lo, const float4 &bias_hi, unsigned char *a_hi, unsigned char *a_lo,
+                                            int sub)
 {
-    const bool valid = k < n;
-    const unsigned ent = valid ? lst[k] : 0u;
-    const int pp = (ent >> 16) & 1, px = (ent >> 20) & 7, py = (ent >> 24) & 7, pz = ent >> 28;
+    const int ix = sub >> 1, yh = sub & 1;
+    const int sx = sub >> 2, sy = (sub >> 1) & 1, sz = sub & 1;
+    unsigned ent[U], v[U], wlo[U], whi[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) ent[u] = (k + 4 * u < n) ? lst[k + 4 * u] : 0u;
     // the cell's window = rows x = 2px-1 .. 2px+2, y = 2py-1 .. 2py+2 (staged with a halo: row (x,y) at [(x+1)*PITCH + y+1]),
     // bits z = 2pz-1 .. 2pz+2; nibble (ix,iy) at bits 16*ix + 4*iy.  This lane loads rows (ix = sub>>1, iy = 2*(sub&1), +1).
-    const int ix = sub >> 1, yh = sub & 1;
-    const unsigned v = *reinterpret_cast<const unsigned *>(pk + pp * PK_BYTES + ((2 * px + ix) * PK_PITCH + 2 * py + 2 * yh) * 2);
-    const unsigned n01 = ((((v & 0xFFFFu) << 1) >> (2 * pz)) & 0xFu) | (((((v >> 16) << 1) >> (2 * pz)) & 0xFu) << 4);
-    const unsigned sh = n01 << (16 * (ix & 1) + 8 * yh);
-    unsigned wlo = ix < 2 ? sh : 0u, whi = ix < 2 ? 0u : sh;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int pp = (ent[u] >> 16) & 1, px = (ent[u] >> 20) & 7, py = (ent[u] >> 24) & 7;
+        v[u] = *reinterpret_cast<const unsigned *>(pk + pp * PK_BYTES + ((2 * px + ix) * PK_PITCH + 2 * py + 2 * yh) * 2);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int pz = ent[u] >> 28;
+        const unsigned n01 = ((((v[u] & 0xFFFFu) << 1) >> (2 * pz)) & 0xFu) | (((((v[u] >> 16) << 1) >> (2 * pz)) & 0xFu) << 4);
+        const unsigned sh = n01 << (16 * (ix & 1) + 8 * yh);
+        wlo[u] = ix < 2 ? sh : 0u;
+        whi[u] = ix < 2 ? 0u : sh;
+    }
 #pragma unroll
     for (int d = 1; d < 8; d <<= 1) {
-        wlo |= __shfl_xor_sync(0xffffffffu, wlo, d);
-        whi |= __shfl_xor_sync(0xffffffffu, whi, d);
-    }
-    const int sx = sub >> 2, sy = (sub >> 1) & 1, sz = sub & 1;
-    const unsigned long long w2 = (((unsigned long long)whi << 32) | wlo) >> (16 * sx + 4 * sy + sz);
-    float2 acc2[4];
-    {
-        const float4 c0 = *reinterpret_cast<const float4 *>(b1s), c1 = *reinterpret_cast<const float4 *>(b1s + 4);
-        acc2[0] = make_float2(c0.x, c0.y); acc2[1] = make_float2(c0.z, c0.w);
-        acc2[2] = make_float2(c1.x, c1.y); acc2[3] = make_float2(c1.z, c1.w);
-    }
+        unsigned rl[U], rh[U];
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-        const unsigned g = (unsigned)(w2 >> (16 * dx)) & 0x777u;                       // (dy,dz) bits at 4*dy + dz
-        const unsigned idx = (g & 7u) | ((g >> 1) & 0x38u) | ((g >> 2) & 0x1C0u);
-        if (idx) {   // the empty pattern's row is all zeros; most patterns of a sparse patch are empty
-            const float4 w0 = *reinterpret_cast<const float4 *>(t3 + (dx * 512 + idx) * 16);
-            const float4 w1 = *reinterpret_cast<const float4 *>(t3 + P2_T3_HALF + (dx * 512 + idx) * 16);
-            acc2[0] = __fadd2_rn(acc2[0], make_float2(w0.x, w0.y));
-            acc2[1] = __fadd2_rn(acc2[1], make_float2(w0.z, w0.w));
-            acc2[2] = __fadd2_rn(acc2[2], make_float2(w1.x, w1.y));
-            acc2[3] = __fadd2_rn(acc2[3], make_float2(w1.z, w1.w));
+        for (int u = 0; u < U; ++u) {
+            rl[u] = __shfl_xor_sync(0xffffffffu, wlo[u], d);
+            rh[u] = __shfl_xor_sync(0xffffffffu, whi[u], d);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { wlo[u] |= rl[u]; whi[u] |= rh[u]; }
+    }
+    float2 acc2[U][4];
+    float4 w0[U][3], w1[U][3];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const unsigned long long w2 = (((unsigned long long)whi[u] << 32) | wlo[u]) >> (16 * sx + 4 * sy + sz);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const unsigned g = (unsigned)(w2 >> (16 * dx)) & 0x777u;                       // (dy,dz) bits at 4*dy + dz
+            const unsigned idx = (g & 7u) | ((g >> 1) & 0x38u) | ((g >> 2) & 0x1C0u);
+            // the empty pattern's row is all zeros (x + 0 = x exactly) and most patterns of a sparse patch are empty: those lanes
+            // skip the loads
+            w0[u][dx] = w1[u][dx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx) {
+                const unsigned slot = t3_slot(idx);
+                w0[u][dx] = *reinterpret_cast<const float4 *>(t3 + (dx * 512 + slot) * 16);
+                w1[u][dx] = *reinterpret_cast<const float4 *>(t3 + P2_T3_HALF + (dx * 512 + slot) * 16);
+            }
         }
     }
-    const float acc[8] = {acc2[0].x, acc2[0].y, acc2[1].x, acc2[1].y, acc2[2].x, acc2[2].y, acc2[3].x, acc2[3].y};
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        acc2[u][0] = make_float2(bias_lo.x, bias_lo.y); acc2[u][1] = make_float2(bias_lo.z, bias_lo.w);
+        acc2[u][2] = make_float2(bias_hi.x, bias_hi.y); acc2[u][3] = make_float2(bias_hi.z, bias_hi.w);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            acc2[u][0] = __fadd2_rn(acc2[u][0], make_float2(w0[u][dx].x, w0[u][dx].y));
+            acc2[u][1] = __fadd2_rn(acc2[u][1], make_float2(w0[u][dx].z, w0[u][dx].w));
+            acc2[u][2] = __fadd2_rn(acc2[u][2], make_float2(w1[u][dx].x, w1[u][dx].y));
+            acc2[u][3] = __fadd2_rn(acc2[u][3], make_float2(w1[u][dx].z, w1[u][dx].w));
+        }
+    }
     // max over the eight sub-position lanes, halving the channel set a lane carries at each exchange: lane `sub` ends with
     // channel 4*sx + 2*sy + sz = sub
-    float h4[4], h2[2];
+    float h4[U][4], h2[U][2], o[U];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const float recv = __shfl_xor_sync(0xffffffffu, sx ? acc[c] : acc[4 + c], 4);
-        h4[c] = fmaxf(sx ? acc[4 + c] : acc[c], recv);
+    for (int u = 0; u < U; ++u) {
+        const float acc[8] = {acc2[u][0].x, acc2[u][0].y, acc2[u][1].x, acc2[u][1].y, acc2[u][2].x, acc2[u][2].y, acc2[u][3].x, acc2[u][3].y};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float recv = __shfl_xor_sync(0xffffffffu, sx ? acc[c] : acc[4 + c], 4);
+            h4[u][c] = fmaxf(sx ? acc[4 + c] : acc[c], recv);
+        }
     }
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const float recv = __shfl_xor_sync(0xffffffffu, sy ? h4[c] : h4[2 + c], 2);
-        h2[c] = fmaxf(sy ? h4[2 + c] : h4[c], recv);
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float recv = __shfl_xor_sync(0xffffffffu, sy ? h4[u][c] : h4[u][2 + c], 2);
+            h2[u][c] = fmaxf(sy ? h4[u][2 + c] : h4[u][c], recv);
+        }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const float recv = __shfl_xor_sync(0xffffffffu, sz ? h2[u][0] : h2[u][1], 1);
+        o[u] = fmaxf(sz ? h2[u][1] : h2[u][0], recv);
     }
-    const float recv = __shfl_xor_sync(0xffffffffu, sz ? h2[0] : h2[1], 1);
-    const float o = fmaxf(sz ? h2[1] : h2[0], recv);
-    if (valid) {
-        const int pi = ent & 0xFFFFu;
-        __half h, l;
-        umma::split_f16(fast_tanh(o), h, l);
-        *reinterpret_cast<__half *>(a_hi + pi * 16 + sub * 2) = h;
-        *reinterpret_cast<__half *>(a_lo + pi * 16 + sub * 2) = l;
-    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (k + 4 * u < n) {
+            const int pi = ent[u] & 0xFFFFu;
+            __half h, l;
+            umma::split_f16(fast_tanh(o[u]), h, l);
+            *reinterpret_cast<__half *>(a_hi + pi * 16 + sub * 2) = h;
+            *reinterpret_cast<__half *>(a_lo + pi * 16 + sub * 2) = l;
+        }
 }
 
 __global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12Args a)
@@ -592,7 +642,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12
         float s = 0.f;
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) s += a.tables[((dx * 3 + dy) * 8 + ((idx >> (3 * dy)) & 7)) * 8 + c];
-        *reinterpret_cast<float *>(sm + P2_SM_T3 + (c >> 2) * P2_T3_HALF + (dx * 512 + idx) * 16 + (c & 3) * 4) = s;
+        *reinterpret_cast<float *>(sm + P2_SM_T3 + (c >> 2) * P2_T3_HALF + (dx * 512 + t3_slot(idx)) * 16 + (c & 3) * 4) = s;
     }
     for (int e = tid; e < 27 * 16; e += P2_THREADS) reinterpret_cast<float *>(sm + P2_SM_BGP)[e] = a.tables[576 + e];
     if (tid < 8) {
@@ -695,7 +745,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12
                 if (act) umma::mma_f16(d0, a_base | (1ull << 16), z_desc, id256, 0u);   // clear the pair's accumulators
 #pragma unroll 1
                 for (int x = 0; x < 8; ++x) {
-                    if (!((need >> x) & 1u)) continue;
+                    if (!((need >> x) & 1u) || (a.dbg & 1)) continue;
                     const uint32_t d = d0 + (x == 0 ? 0 : x - 1) * 32;
                     const uint32_t idesc = (x == 0 || x == 7) ? id64 : id96;
                     const uint64_t bx = b_base + (uint64_t)(x == 0 ? (32 * 16) >> 4 : 0);   // slab 0: rows 32..95 (dx = 1, 0)
@@ -729,6 +779,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12
         int *lcnt = reinterpret_cast<int *>(sm + P2_SM_LCNT);
         unsigned pk_next = 0u;
         int n_dirty0 = 0, n_dirty1 = 0;
+        const float4 bias_lo = *reinterpret_cast<const float4 *>(b1s), bias_hi = *reinterpret_cast<const float4 *>(b1s + 4);
         auto fetch = [&](int i) {
             if (i < n_my) {
                 int p = patch_of(i, g);
@@ -803,12 +854,11 @@ __global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12
             asm volatile("bar.sync 1, 512;" ::: "memory");
             if (tl && tid == 0) tl[7] = clock64();
             // ---- pass 2: eight listed cells per warp and round, as two independent groups of four ----
-            const int n = lcnt[b];
+            const int n = (a.dbg & 2) ? 0 : lcnt[b];
             if (b) n_dirty1 = n; else n_dirty0 = n;
             const int sub = lane & 7;
             for (int k0 = warp * 8 + (lane >> 3); k0 - (lane >> 3) < n; k0 += P2_PROD_WARPS * 8) {
-                conv1_cells(lst, k0, n, sm + P2_SM_PK + 2 * b * PK_BYTES, sm + P2_SM_T3, b1s, a_hi, a_lo, sub);
-                conv1_cells(lst, k0 + 4, n, sm + P2_SM_PK + 2 * b * PK_BYTES, sm + P2_SM_T3, b1s, a_hi, a_lo, sub);
+                conv1_cells<2>(lst, k0, n, sm + P2_SM_PK + 2 * b * PK_BYTES, sm + P2_SM_T3, bias_lo, bias_hi, a_hi, a_lo, sub);
             }
             if (tl && tid == 0) tl[8] = clock64();
             umma::fence_proxy_async();
@@ -1509,6 +1559,8 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
     {
         const char *e = getenv("CAELO_CONV12_SKIP_BG");   // debug switch for A/B timing; default on
         c.skip_bg = !(e && e[0] == '0');
+        e = getenv("CAELO_CONV12_DBG");
+        c.dbg = e ? atoi(e) : 0;
     }
     {
         const char *e = getenv("CAELO_CONV12_PAIR");      // switch for A/B timing: "0" = the one-patch-per-MMA kernel (M = 64)

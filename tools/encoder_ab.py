@@ -14,7 +14,11 @@ flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
 ref = None
 for name, env in (("conv12 pair (default)", {}), ("conv12 one patch", {"CAELO_CONV12_PAIR": "0"}),
                   ("conv12 pair, no bg skip", {"CAELO_CONV12_SKIP_BG": "0"}),
-                  ("conv12 one patch, no bg skip", {"CAELO_CONV12_PAIR": "0", "CAELO_CONV12_SKIP_BG": "0"})):
+                  ("conv3 pair, 3 stages", {"CAELO_CONV3_PAIR": "1"}),
+                  ("conv3 pair, 9 stages", {"CAELO_CONV3_PAIR": "19"}),
+                  ("conv12 pair, no MMAs (wrong results)", {"CAELO_CONV12_DBG": "1"}),
+                  ("conv12 pair, no conv1 pass 2 (wrong results)", {"CAELO_CONV12_DBG": "2"}),
+                  ("conv12 pair, neither (wrong results)", {"CAELO_CONV12_DBG": "3"})):
     os.environ.update(env)
     for _ in range(3):
         feat = ctx.encode_frames(packed)

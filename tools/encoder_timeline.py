@@ -31,6 +31,15 @@ print("  pass 1         7-2 :", stat(t[..., 7] - t[..., 2]))
 print("  pass 2         8-7 :", stat(t[..., 8] - t[..., 7]))
 print("  fence + arrive 1-8 :", stat(t[..., 1] - t[..., 8]))
 
+if t[..., 13].max() > 0:
+    sel = t[..., 14] > 0
+    print("  pass 2, warp 0's first round (pairs with listed cells: %.0f %%, mean n %.0f):" % (100 * sel.mean(), t[..., 14][sel].mean()))
+    for a, b, name in ((7, 9, "list entry + row loads"), (9, 10, "window (nibbles + 6 shuffles)"), (10, 11, "3 table rows + adds"),
+                       (11, 12, "max over 8 lanes (7 shuffles)"), (12, 13, "tanh + split + stores"), (13, 8, "later rounds")):
+        print("    %-32s %s" % (name, stat((t[..., b] - t[..., a])[sel])))
+    for lo, hi in ((1, 64), (65, 128), (129, 256), (257, 1024)):
+        m = (t[..., 14] >= lo) & (t[..., 14] <= hi)
+        if m.any(): print("    n in [%4d, %4d]: %4.1f %% of pairs, pass 2 mean %6.0f" % (lo, hi, 100 * m.mean(), (t[..., 8] - t[..., 7])[m].mean()))
 print("mma issue        6-5 :", stat(t[..., 6] - t[..., 5]))
 print("mbar wait        3-1 :", stat(t[..., 3] - t[..., 1]))
 print("epilogue         4-3 :", stat(t[..., 4] - t[..., 3]))
