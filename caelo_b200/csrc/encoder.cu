@@ -653,6 +653,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12
         reinterpret_cast<__half *>(sm + P2_SM_BG + 16)[tid] = l;
     }
     if (tid < 16) b2s[tid] = a.b2[tid];
+    if (tid < 2) reinterpret_cast<int *>(sm + P2_SM_LCNT)[tid] = 0;
     __syncthreads();
     for (int e = tid; e < 4 * 1024; e += P2_THREADS) {     // interior cells start as the background value tanh(b1)
         const int vol = e >> 10, c = e & 1023;
@@ -812,8 +813,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12
                 dst[1] = (unsigned short)(pk_next >> 16);
             }
             fetch(i + 1);
-            asm volatile("bar.sync 1, 512;" ::: "memory");   // rows staged, restore done, the previous pass 2 has left the list
-            if (tid == 0) lcnt[b] = 0;                     // (the other buffer's counter is the one pass 2 just read)
+            asm volatile("bar.sync 1, 512;" ::: "memory");   // rows staged (lcnt[b] was reset during the previous pair's pass 2)
             long long *tl = (a.timeline && i < 64) ? a.timeline + ((size_t)blockIdx.x * 64 + i) * 16 : nullptr;
             if (tl && tid == 0) tl[2] = clock64();
             // ---- pass 1: list the cells with a non-empty window ----
@@ -834,7 +834,6 @@ __global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12
                     cells |= found[half];
                 }
                 if (lane == 0) sm[P2_SM_XS + 16 * (i & 3) + 8 * g + (t >> 5)] = cells != 0u;   // the warp = x-slice px of patch g
-                asm volatile("bar.sync 2, 512;" ::: "memory");                                   // counter reset visible
                 const int cnt = __popc(found[0]) + __popc(found[1]);
                 if (cnt) {
                     int base = 0;
@@ -855,6 +854,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12
             if (tl && tid == 0) tl[7] = clock64();
             // ---- pass 2: eight listed cells per warp and round, as two independent groups of four ----
             const int n = (a.dbg & 2) ? 0 : lcnt[b];
+            if (tid == 0) lcnt[b ^ 1] = 0;   // the next pair's counter: last read before this pair's first barrier, next used after its own
             if (b) n_dirty1 = n; else n_dirty0 = n;
             const int sub = lane & 7;
             for (int k0 = warp * 8 + (lane >> 3); k0 - (lane >> 3) < n; k0 += P2_PROD_WARPS * 8) {
