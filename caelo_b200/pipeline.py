@@ -53,6 +53,8 @@ class OdometryPipeline:
         self.dev = self.ctx.device
         self.keep_details = False      # True: keep the batch's keypoints / descriptors / matches / inlier masks
         self.last_details = None       # (device tensors) for the Features / InliersIdx files of odometry.py
+        self.tail_overlap = os.environ.get("CAELO_TAIL_STREAM", "1") != "0"
+        self.last_done = None          # event of the most recent batch's pairs stage
 
     # ---- device-resident stages ---------------------------------------------------------
     def frames_to_descriptors(self, ring: torch.Tensor, counter: torch.Tensor, vox: torch.Tensor,
@@ -82,24 +84,50 @@ class OdometryPipeline:
         stream; nothing here waits for the device.  ``samples`` is [P,500,4] (first round; failures go through a
         host-driven ladder in ``_collect``) or [3,P,500,4]: then the 0.8 and 1.6 rounds are queued on the device
         right away and skip every pair that already has a model (no host round trip)."""
-        P = kpts.shape[0] - 1
         pc0, pc1 = kpts[:-1], kpts[1:]
-        pair_idx = self.ctx.nn_match(feat[:-1], feat[1:])
         rounds = (samples if samples.dim() == 4 else samples[None]).contiguous()
-        state, mask_acc, rt, thr_used = self.ctx.ransac_ladder(pc0, pc1, pair_idx, rounds, LADDER[:rounds.shape[0]])
-        details = None
-        if self.keep_details:
-            details = dict(kpts=kpts, feat=feat, pair_idx=pair_idx, mask=mask_acc, ok=state[:, 12] != 0)
-        nf = n.to(torch.float32)
-        bad = torch.zeros_like(nf) if status is None else (status != 0).to(torch.float32)
-        packed = torch.cat([state, rt, thr_used[:, None], nf[:-1, None], nf[1:, None],
-                            torch.maximum(bad[:-1], bad[1:])[:, None]], 1)
-        host = self._result_slot(packed.shape)
-        host.copy_(packed, non_blocking=True)
-        done = torch.cuda.Event()
-        done.record()
+        # The pairs stage is ~25 small latency-bound launches (0.3 ms per 32-pair batch at < 10 % of the SMs' issue slots).
+        # It goes on its own stream behind an event, so that the NEXT batch's frame stages — queued on the caller's stream
+        # right after this returns — run next to it instead of behind it.  Its scratch (misc, match_ops, pose_ws, seed_ws)
+        # is disjoint from the frame stages' (cand, bricks, scan_ws, enc_ws), its inputs are this batch's own tensors, and
+        # consecutive batches' pairs stages stay ordered on the one tail stream.  CAELO_TAIL_STREAM=0: everything on the
+        # caller's stream.
+        cur = torch.cuda.current_stream(self.dev)
+        tail = self._tail_stream_() if self.tail_overlap else cur
+        if tail is not cur:
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            tail.wait_event(ready)
+            for t in (kpts, feat, n, rounds) + (() if status is None else (status,)):
+                t.record_stream(tail)                   # allocated under the caller's stream, read under the tail stream
+        with torch.cuda.stream(tail):
+            pair_idx = self.ctx.nn_match(feat[:-1], feat[1:])
+            state, mask_acc, rt, thr_used = self.ctx.ransac_ladder(pc0, pc1, pair_idx, rounds, LADDER[:rounds.shape[0]])
+            details = None
+            if self.keep_details:
+                details = dict(kpts=kpts, feat=feat, pair_idx=pair_idx, mask=mask_acc, ok=state[:, 12] != 0)
+            nf = n.to(torch.float32)
+            bad = torch.zeros_like(nf) if status is None else (status != 0).to(torch.float32)
+            packed = torch.cat([state, rt, thr_used[:, None], nf[:-1, None], nf[1:, None],
+                                torch.maximum(bad[:-1], bad[1:])[:, None]], 1)
+            host = self._result_slot(packed.shape)
+            host.copy_(packed, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(tail)
+        self.last_done = done
         return dict(host=host, done=done, kpts=kpts, feat=feat, pair_idx=pair_idx, pair_ids=list(pair_ids),
                     rounds=rounds.shape[0], details=details)
+
+    def _tail_stream_(self):
+        if not hasattr(self, "_tail_stream"):
+            self._tail_stream = torch.cuda.Stream(self.dev)
+        return self._tail_stream
+
+    def join(self):
+        """Makes the caller's stream wait for every pairs stage queued so far (they run on the tail stream): call before
+        recording an event that is meant to cover whole batches."""
+        if self.last_done is not None:
+            torch.cuda.current_stream(self.dev).wait_event(self.last_done)
 
     def _result_slot(self, shape):
         """Pinned host buffer for one batch's result rows, from a free list that ``_collect`` refills — no pinned
@@ -131,14 +159,16 @@ class OdometryPipeline:
         poses[:, 14] = host[:, 28]
         poses[:, 15] = res[:, 13]
         failed = np.flatnonzero(res[:, 12] == 0)
-        if failed.size and h["rounds"] < len(LADDER):
-            self._ladder(failed, h["kpts"], h["pair_idx"], h["pair_ids"], poses, h["rounds"])
-        elif failed.size:                               # total failure: R=I, T=0 (Match.py:277-278)
-            poses[failed, :12] = [1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]
-            poses[failed, 13] = 0
         short = np.flatnonzero((host[:, 29] != self.K) | (host[:, 30] != self.K))
-        if short.size:
-            self._short_pairs(short, host[:, 29].astype(int), host[:, 30].astype(int), h, poses)
+        # the rare host-driven fallbacks use the pairs stage's scratch: they run where the pairs stages run
+        with torch.cuda.stream(self._tail_stream_() if self.tail_overlap else torch.cuda.current_stream(self.dev)):
+            if failed.size and h["rounds"] < len(LADDER):
+                self._ladder(failed, h["kpts"], h["pair_idx"], h["pair_ids"], poses, h["rounds"])
+            elif failed.size:                               # total failure: R=I, T=0 (Match.py:277-278)
+                poses[failed, :12] = [1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]
+                poses[failed, 13] = 0
+            if short.size:
+                self._short_pairs(short, host[:, 29].astype(int), host[:, 30].astype(int), h, poses)
         return poses
 
     def _short_pairs(self, short, n0s, n1s, h, poses):
