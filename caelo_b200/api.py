@@ -96,6 +96,7 @@ class Context:
         assert a[0].shape == (3, 3, 3, 32) and a[2].size == 256
         self.check(self.lib.caelo_set_respond_weights(self.h, *[_np_ptr(x) for x in a]), "set_respond_weights")
         self.has_respond = True
+        self.__dict__.setdefault("_weight_owner", {}).pop("respond", None)      # see B200Model._bind
 
     def set_encoder_weights(self, w):
         keys = ("conv3d_1/kernel:0", "conv3d_1/bias:0", "conv3d_2/kernel:0", "conv3d_2/bias:0",
@@ -105,6 +106,7 @@ class Context:
         assert a[0].shape == (3, 3, 3, 1, 8) and a[6].shape == (2048, 200) and a[8].shape == (200, 20)
         self.check(self.lib.caelo_set_encoder_weights(self.h, *[_np_ptr(x) for x in a]), "set_encoder_weights")
         self.has_encoder = True
+        self.__dict__.setdefault("_weight_owner", {}).pop("encoder", None)
 
     @property
     def launches(self) -> int:
@@ -297,7 +299,9 @@ class Context:
             self.check(rc, "caelo_gather_patches_scans")
         return packed, f32, trunc, nvox, status
 
-    # a6 in two steps (the index of a batch can be built on a second stream while its key points are selected)
+    # a6 in two steps.  The brick tables are ONE scratch region of the context: a build overwrites the index that
+    # ``bricks_gather`` reads.  ``stream`` lets a caller build on another stream, but then the caller has to order the
+    # build after the previous batch's gather and before this batch's gather with events — the library does not.
     def bricks_build(self, vox: torch.Tensor, vox_offsets: np.ndarray, stream=None):
         off = np.ascontiguousarray(vox_offsets, np.int64)
         F = (off.shape[0] - 1) // 3
@@ -475,16 +479,24 @@ class B200Model:
     """What ``keras.models.load_model`` returns here: ``predict(ndarray) -> ndarray``."""
 
     def __init__(self, kind: str, weights: dict, ctx: Optional[Context] = None):
+        if kind not in ("respond", "encoder"):
+            raise ValueError(kind)
         self.kind = kind
         self.ctx = ctx or default_context()
-        if kind == "respond":
-            self.ctx.set_respond_weights(weights)
-        elif kind == "encoder":
-            self.ctx.set_encoder_weights(weights)
-        else:
-            raise ValueError(kind)
+        self.weights = weights
+        self._bind()
+
+    def _bind(self):
+        """The weights are state of the (shared) context: a model loaded later replaces them.  Every model remembers its
+        own and puts them back before it predicts, so two models of one kind can coexist (the setter waits for queued
+        work that still reads the old ones)."""
+        owners = self.ctx.__dict__.setdefault("_weight_owner", {})
+        if owners.get(self.kind) is not self:
+            (self.ctx.set_respond_weights if self.kind == "respond" else self.ctx.set_encoder_weights)(self.weights)
+            owners[self.kind] = self
 
     def predict(self, x, batch_size=None, verbose=0):
+        self._bind()
         x = np.asarray(x, dtype=np.float32)
         if self.kind == "respond":
             if x.ndim != 4 or x.shape[3] != 3:

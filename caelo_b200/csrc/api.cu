@@ -194,6 +194,8 @@ extern "C" int caelo_set_encoder_weights(caelo_ctx *ctx, const float *k1, const 
     size_t total = 0, off[10];
     for (int i = 0; i < 10; ++i) { off[i] = total; total += (n[i] + 63) / 64 * 64; }
     CAELO_CUDA(ctx, cudaSetDevice(ctx->device));
+    // the weights are context state: kernels still queued on any stream read the old ones — let them finish first
+    if (ctx->have_encoder) CAELO_CUDA(ctx, cudaDeviceSynchronize());
     if (!ctx->enc_blob) CAELO_CUDA(ctx, cudaMalloc(&ctx->enc_blob, total * 4));
     for (int i = 0; i < 10; ++i)
         CAELO_CUDA(ctx, cudaMemcpy(ctx->enc_blob + off[i], src[i], n[i] * 4, cudaMemcpyHostToDevice));

@@ -58,7 +58,10 @@ struct PoseArgs {
 
 __device__ __forceinline__ void load_pair(const PoseArgs &a, int pair, int i, float p0[3], float p1[3])
 {
+    // indices come from the caller (sample_idx, pair_idx): out-of-range values are clamped, never dereferenced
+    i = i < 0 ? 0 : (i >= a.N ? a.N - 1 : i);
     long long j = a.pair_idx ? a.pair_idx[(size_t)pair * a.N + i] : i;
+    j = j < 0 ? 0 : (j >= a.N0 ? a.N0 - 1 : j);
     const float *q0 = a.pc0 + ((size_t)pair * a.N0 + j) * 3;
     const float *q1 = a.pc1 + ((size_t)pair * a.N + i) * 3;
     p0[0] = q0[0]; p0[1] = q0[1]; p0[2] = q0[2];
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(HS_THREADS) hyp_score_kernel(const PoseArgs a)
     }
 }
 
+static_assert(CAELO_MAX_TRIALS <= 2 * 256, "replay_mask_kernel covers two trials per thread of its 256-thread CTA");
 __global__ void __launch_bounds__(256) replay_mask_kernel(const PoseArgs a)
 {
     __shared__ int s_bt, s_bn, s_ok, s_it, s_more, s_first;

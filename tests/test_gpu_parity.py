@@ -239,6 +239,21 @@ def test_conv12_pair_kernel_matches_single_patch_kernel(api, oracle_mod):
         assert got.shape == (F, K, 60) and np.abs(got - old).max() < 4e-6, (F, K)
 
 
+def test_two_models_of_one_kind_keep_their_own_weights(api):
+    """The weights live in the shared context; a model loaded later replaces them — every model puts its own back before
+    it predicts (B200Model._bind), so the Keras shim may hand out several."""
+    rng = np.random.default_rng(5)
+    x = (rng.random((9, 16, 16, 16, 1)) < 0.02).astype(np.float32)
+    a = api.load_model(api.WEIGHT_DIR + "/encoder.npz")
+    ya = a.predict(x)
+    w = dict(a.weights)
+    w["dense_2/bias:0"] = np.asarray(w["dense_2/bias:0"], np.float32) + 0.25
+    b = api.B200Model("encoder", w)
+    yb = b.predict(x)
+    assert np.abs(yb - ya).max() > 1e-2
+    assert np.array_equal(a.predict(x), ya) and np.array_equal(b.predict(x), yb) and np.array_equal(a.predict(x), ya)
+
+
 def test_encoder_rejects_non_binary(api):
     from caelo_b200._lib import CaeloError
     x = np.zeros((2, 16, 16, 16, 1), np.float32)
