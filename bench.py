@@ -648,6 +648,7 @@ def run_ours(args, rank, local_rank, world):
                     "frac": ach / peak}
 
         kernels = [k for k in (
+            kern("conv12_pair_kernel", FLOP_CONV12_PER_PATCH * n_patches, peaks["tf_sustained"], "TFLOP/s", 1e12),
             kern("conv12_tc_kernel", FLOP_CONV12_PER_PATCH * n_patches, peaks["tf_sustained"], "TFLOP/s", 1e12),
             kern("conv3_tc_kernel", FLOP_CONV3_PER_PATCH * n_patches, peaks["tf_sustained"], "TFLOP/s", 1e12),
             kern("dense_tc_kernel", FLOP_DENSE_PER_PATCH * n_patches, peaks["tf_sustained"], "TFLOP/s", 1e12),
@@ -670,6 +671,9 @@ def run_ours(args, rank, local_rank, world):
                         "frac_of_burst_peak": dom["achieved"] / peaks["tf_burst"] if dom["unit"] == "TFLOP/s" else None,
                         "traffic_source": "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of the "
                                           "round's ncu --set full capture of this kernel, per launch)",
+                        "note": "per-kernel times are CUDA-event intervals on the launching stream; the pairs stage (draw_samples "
+                                "... kabsch) runs on the pipeline's tail stream NEXT TO the following step's frame stages, so its "
+                                "intervals include waiting for SMs and the per-kernel times add up to more than the step",
                         "all_kernels": kernels,
                         "time_by_kernel_ms_per_step": {k: v[1] / K for k, v in prof.items()}}
         e2e_best = min(e2e_rings_s, e2e_scans_s)

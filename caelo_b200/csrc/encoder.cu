@@ -1564,8 +1564,9 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
     }
     {
         const char *e = getenv("CAELO_CONV12_PAIR");      // switch for A/B timing: "0" = the one-patch-per-MMA kernel (M = 64)
-        ProfScope ps_(ctx, "conv12_tc_kernel", st);
-        if (e && e[0] == '0') {
+        const bool one_patch = e && e[0] == '0';
+        ProfScope ps_(ctx, one_patch ? "conv12_tc_kernel" : "conv12_pair_kernel", st);
+        if (one_patch) {
             int grid = 2 * ctx->num_sms < P ? 2 * ctx->num_sms : P;
             conv12_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(c);
         } else {
