@@ -1292,6 +1292,210 @@ __global__ void __launch_bounds__(C3P_THREADS, 1) conv3_pair_kernel(const Conv3A
     if (warp == C3P_ISSUER) umma::tmem_dealloc(tbase, 128);
 }
 
+// ---- conv3, eight patches per MMA (M = 128) and dx folded into N ---------------------------------------------------------
+// conv3_tc_kernel is bound by the tensor core's shared-memory operand fetch (80 % of the shared-memory pipe at 189 KB per
+// patch: an M = 64 MMA fetches 2 KB of A for 2 or 1 KB of B).  The same two moves as in conv12_pair_kernel cut that to 90 KB:
+//   * rows = (patch 8, y 4, z 4) of ONE x slab: M = 128, all TMEM lanes used.  For tap (dy,dz) the slab is stored as the
+//     (dy,dz)-shifted compact copy [row 128][16 B] per channel half (zero where the shifted position leaves the 4 x 4 plane),
+//     so every tap's A operand is one contiguous canonical K-major block;
+//   * the three dx taps are folded into N: slab x is multiplied once per (dy,dz) by B = [dx=2 | dx=1 | dx=0] x [W_hi | W_lo]
+//     (N = 192) and accumulates into the 64-column blocks of the output slices x-1, x, x+1 (slabs 0 and 3: the N = 128
+//     sub-matrix).  A_hi and A_lo go through the same B: D[:, hi] + D[:, lo] = (A_hi + A_lo)(W_hi + W_lo).
+// 72 MMAs of 10 KB per eight patches.  One slab of one part (hi or lo) with its nine copies is a 36 KB STAGE; four stages form
+// a ring that the producers refill (hi part of slabs 0-3, then the lo part) as the MMAs release them.  The group's 256
+// accumulator columns are cleared by one N = 256 MMA against a zero B operand; two groups' accumulators fit the 512 TMEM
+// columns, so the epilogue of group g runs under the MMAs of group g+1.
+constexpr int C8_PROD_WARPS = 8;                       // warps 0-7: thread = (patch 8, position-in-slab 16, channel half 2)
+constexpr int C8_ISSUER = 8;
+constexpr int C8_EPI0 = 9, C8_EPI_WARPS = 8;           // warps 9-16: (lane quarter = warp % 4) x (output slices 0-1 / 2-3)
+constexpr int C8_THREADS = (C8_EPI0 + C8_EPI_WARPS) * 32;
+constexpr int C8_COPY = 2 * 128 * 16;                  // one (dy,dz) copy of a slab: [channel half 2][row 128][16 B]
+constexpr int C8_STAGE = 9 * C8_COPY;                  // 36864 B
+constexpr int C8_SM_W = 4 * C8_STAGE;                  // B: [tap 9][chunk 2][row 192][16 B]
+constexpr int C8_W_TAP = 2 * 192 * 16;
+constexpr int C8_SM_Z = C8_SM_W + 9 * C8_W_TAP;        // zero B operand [chunk 2][row 256][16 B]
+constexpr int C8_SM_B3 = C8_SM_Z + 2 * 256 * 16;
+constexpr int C8_SM_BAR = C8_SM_B3 + 128;              // full[4] empty[4] tfull[2] tempty[2] + tmem slot
+constexpr int C8_SMEM = C8_SM_BAR + 12 * 8 + 16;
+static_assert(C8_SMEM <= 227 * 1024, "conv3_oct_kernel shared memory");
+
+__global__ void __launch_bounds__(C8_THREADS, 1) conv3_oct_kernel(const Conv3Args a)
+{
+    extern __shared__ __align__(128) unsigned char sm[];
+    float *b3s = reinterpret_cast<float *>(sm + C8_SM_B3);
+    uint64_t *full = reinterpret_cast<uint64_t *>(sm + C8_SM_BAR), *empty = full + 4, *tfull = full + 8, *tempty = full + 10;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + C8_SM_BAR + 12 * 8);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+    // stages and the zero operand start as zeros (rows a copy never writes are its zero padding); B = the weights
+    for (int i = tid; i < C8_SM_W / 16; i += C8_THREADS) reinterpret_cast<uint4 *>(sm)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 2 * 256 * 16 / 16; i += C8_THREADS) reinterpret_cast<uint4 *>(sm + C8_SM_Z)[i] = make_uint4(0, 0, 0, 0);
+    // B row n = blk*64 + h*32 + co with blk = 2 - dx (output slice x + 1 - dx ascending), h = 0: W_hi, 1: W_lo; chunk = ci/8
+    for (int e = tid; e < 27 * 16 * 32; e += C8_THREADS) {
+        const int t = e / 512, ci = (e / 32) % 16, co = e % 32;
+        const int dx = t / 9, c = t % 9, blk = 2 - dx;
+        __half h, l;
+        umma::split_f16(a.k3[e], h, l);
+        unsigned char *w = sm + C8_SM_W + c * C8_W_TAP + (ci >> 3) * (192 * 16) + (ci & 7) * 2;
+        const int nh = blk * 64 + co, nl = nh + 32;
+        *reinterpret_cast<__half *>(w + (nh >> 3) * 128 + (nh & 7) * 16) = h;
+        *reinterpret_cast<__half *>(w + (nl >> 3) * 128 + (nl & 7) * 16) = l;
+    }
+    if (tid < 32) b3s[tid] = a.b3[tid];
+    if (warp == C8_ISSUER) umma::tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        for (int s = 0; s < 4; ++s) {
+            umma::mbar_init(&full[s], C8_PROD_WARPS * 32);
+            umma::mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            umma::mbar_init(&tfull[b], 1);
+            umma::mbar_init(&tempty[b], C8_EPI_WARPS * 32);
+        }
+        umma::fence_mbar_init();
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t sS = umma::smem_u32(sm), sW = umma::smem_u32(sm + C8_SM_W), sZ = umma::smem_u32(sm + C8_SM_Z);
+    const int n_groups = (a.P + 7) / 8;
+    const int n_my = (n_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // groups of this CTA
+    auto group_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
+
+    if (warp == C8_ISSUER) {
+        const uint32_t id192 = umma::idesc_f16_f32(128, 192), id128 = umma::idesc_f16_f32(128, 128), id256 = umma::idesc_f16_f32(128, 256);
+        const uint64_t a_base = umma::smem_desc(sS, 128 * 16, 128), b_base = umma::smem_desc(sW, 192 * 16, 128);
+        const uint64_t z_desc = umma::smem_desc(sZ, 256 * 16, 128);
+        for (int j = 0; j < n_my; ++j) {
+            const int b = j & 1;
+            if (j >= 2) umma::mbar_wait(&tempty[b], (uint32_t)(((j >> 1) - 1) & 1));
+            const uint32_t d0 = tbase + b * 256;
+#pragma unroll
+            for (int f = 0; f < 8; ++f) {            // fill f = (part = f / 4, slab x = f % 4) of this group
+                const int x = f & 3;
+                umma::mbar_wait(&full[x], (uint32_t)((2 * j + (f >> 2)) & 1));
+                umma::fence_after_thread_sync();
+                if (umma::elect_one()) {
+                    if (f == 0) umma::mma_f16(d0, a_base, z_desc, id256, 0u);   // clear the group's accumulators
+                    const uint32_t d = d0 + (x == 0 ? 0 : x - 1) * 64;
+                    const uint32_t idesc = (x == 0 || x == 3) ? id128 : id192;
+                    const uint64_t bx = b_base + (uint64_t)(x == 0 ? (64 * 16) >> 4 : 0);   // slab 0: rows 64..191 (dx = 1, 0)
+                    const uint64_t ax = a_base + (uint64_t)((x * C8_STAGE) >> 4);
+#pragma unroll
+                    for (int c = 0; c < 9; ++c)
+                        umma::mma_f16(d, ax + (uint64_t)((c * C8_COPY) >> 4), bx + (uint64_t)((c * C8_W_TAP) >> 4), idesc, 1u);
+                    umma::commit(&empty[x]);
+                    if (f == 7) umma::commit(&tfull[b]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < C8_ISSUER) {
+        // ===== producers: thread = (patch p of the group, position yz of a slab, channel half).  Per group it loads its eight
+        // floats of every slab (the next group's loads are issued before this group's stores), splits them once, and writes
+        // the hi part of slabs 0-3 and then the lo part into the nine shifted copies of the slab's stage, each time after the
+        // MMAs that read the stage's previous content have completed =====
+        const int p8 = tid >> 5, yz = (tid >> 1) & 15, half = tid & 1;
+        const int y = yz >> 2, z = yz & 3;
+        float4 nv[4][2];
+        auto fetch = [&](int i) {
+            if (i >= n_my) return;
+            int p = group_of(i) * 8 + p8;
+            if (p >= a.P) p = a.P - 1;                 // a short last group repeats its last patch (never stored)
+            const float4 *src = reinterpret_cast<const float4 *>(a.act2 + (size_t)p * 1024 + yz * 16 + half * 8);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                nv[x][0] = __ldg(src + x * 64);        // slab x: positions x*16 + yz, 16 floats each
+                nv[x][1] = __ldg(src + x * 64 + 1);
+            }
+        };
+        fetch(0);
+        // destination rows of this thread's value in the nine copies: copy (dy,dz) holds input (y,z) at row (y+1-dy, z+1-dz)
+        for (int i = 0; i < n_my; ++i) {
+            uint4 vh[4], vl[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const float f[8] = {nv[x][0].x, nv[x][0].y, nv[x][0].z, nv[x][0].w, nv[x][1].x, nv[x][1].y, nv[x][1].z, nv[x][1].w};
+                __half2 hv[4], lv[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) umma::split_f16x2(f[2 * c], f[2 * c + 1], hv[c], lv[c]);
+                vh[x] = *reinterpret_cast<uint4 *>(hv);
+                vl[x] = *reinterpret_cast<uint4 *>(lv);
+            }
+            fetch(i + 1);
+#pragma unroll
+            for (int f = 0; f < 8; ++f) {
+                const int x = f & 3, part = f >> 2;
+                const int fill = 2 * i + part;           // how many times stage x has been filled before
+                if (fill >= 1) {
+                    umma::mbar_wait(&empty[x], (uint32_t)((fill - 1) & 1));
+                    umma::fence_after_thread_sync();
+                }
+                const uint4 v = part ? vl[x] : vh[x];
+                unsigned char *st = sm + x * C8_STAGE + half * (128 * 16);
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dz = 0; dz < 3; ++dz) {
+                        const int ys = y + 1 - dy, zs = z + 1 - dz;
+                        if ((unsigned)ys < 4u && (unsigned)zs < 4u)
+                            *reinterpret_cast<uint4 *>(st + (dy * 3 + dz) * C8_COPY + (p8 * 16 + ys * 4 + zs) * 16) = v;
+                    }
+                umma::fence_proxy_async();
+                umma::mbar_arrive(&full[x]);
+            }
+        }
+    } else {
+        // ===== epilogue (8 warps): TMEM lane = (patch, y, z); warp -> lane quarter q (patches 2q, 2q+1) and two output slices =====
+        const int q = warp & 3, xh = (warp - C8_EPI0) >> 2;
+        const int pl = 2 * q + (lane >> 4), yz = lane & 15;
+        for (int i = 0; i < n_my; ++i) {
+            const int b = i & 1;
+            umma::mbar_wait(&tfull[b], (uint32_t)((i >> 1) & 1));
+            umma::fence_after_thread_sync();
+            const int p = group_of(i) * 8 + pl;
+            const size_t row8 = ((size_t)(p >> 8) * 256 * 256 + (size_t)(p & 255)) * 8;   // halves (tile-major act3)
+#pragma unroll 1
+            for (int x = 2 * xh; x < 2 * xh + 2; ++x) {
+                const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16) + b * 256 + x * 64;
+                const int pos = x * 16 + yz;
+#pragma unroll
+                for (int hc = 0; hc < 2; ++hc) {          // 16 channels at a time
+                    uint32_t v0[16], v1[16];
+                    umma::tmem_ld_x16(trow + hc * 16, v0);        // W_hi columns
+                    umma::tmem_ld_x16(trow + 32 + hc * 16, v1);   // W_lo columns
+                    umma::tmem_ld_wait();
+                    if (p < a.P) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            __half2 hh[4], ll[4];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const int ch = 8 * g + 2 * c;
+                                const float o0 = fast_tanh((__uint_as_float(v0[ch]) + __uint_as_float(v1[ch])) + b3s[hc * 16 + ch]);
+                                const float o1 = fast_tanh((__uint_as_float(v0[ch + 1]) + __uint_as_float(v1[ch + 1])) + b3s[hc * 16 + ch + 1]);
+                                umma::split_f16x2(o0, o1, hh[c], ll[c]);
+                            }
+                            const size_t o = row8 + (size_t)(pos * 4 + hc * 2 + g) * 256 * 8;
+                            *reinterpret_cast<uint4 *>(a.act3_hi + o) = *reinterpret_cast<uint4 *>(hh);
+                            *reinterpret_cast<uint4 *>(a.act3_lo + o) = *reinterpret_cast<uint4 *>(ll);
+                        }
+                    }
+                }
+            }
+            umma::fence_before_thread_sync();
+            umma::mbar_arrive(&tempty[b]);
+        }
+    }
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    if (warp == C8_ISSUER) umma::tmem_dealloc(tbase, 512);
+}
+
 // ---- dense1 (tcgen05) + tanh + dense2 + tanh ---------------------------------------------------
 // One CTA = 256 patches (two M = 128 tiles) x 208 outputs (N = 200 padded) x K = 2048, split-fp16 operands:
 //   D_t += A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T   (one fp32 accumulator per tile in TMEM, 2 x 208 columns),
@@ -1579,8 +1783,14 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
     c3.act2 = act2; c3.k3 = ctx->enc.k3; c3.b3 = ctx->enc.b3; c3.act3_hi = act3_hi; c3.act3_lo = act3_lo; c3.P = P;
     {
         const char *e = getenv("CAELO_CONV3_PAIR");      // switch for A/B timing: "1" = the two-patches-per-MMA kernel
-        ProfScope ps_(ctx, "conv3_tc_kernel", st);
-        if (!(e && e[0] == '1')) {
+        const char *e8 = getenv("CAELO_CONV3_OCT");      // "0" = not the eight-patches-per-MMA kernel (the default)
+        const bool oct = !(e8 && e8[0] == '0') && !(e && e[0] == '1');
+        ProfScope ps_(ctx, oct ? "conv3_oct_kernel" : "conv3_tc_kernel", st);
+        if (oct) {
+            int grid3 = ctx->num_sms;                    // persistent: one CTA per SM walks the groups of eight patches
+            if (grid3 > (P + 7) / 8) grid3 = (P + 7) / 8;
+            conv3_oct_kernel<<<grid3, C8_THREADS, C8_SMEM, st>>>(c3);
+        } else if (!(e && e[0] == '1')) {
             // one CTA per SM with two operand buffers (two single-buffer CTAs per SM measured slower: 0.95 vs 0.89 ms)
             int grid3 = ctx->num_sms;
             if (grid3 > P) grid3 = P;
@@ -1610,6 +1820,7 @@ int caelo_encoder_init(caelo_ctx *ctx)
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv12_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv12_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem(2)));
+    CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_oct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C8_SMEM));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_pair_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));

@@ -180,24 +180,32 @@ def test_encoder_dense_random_patches(api, oracle_mod):
     assert enc.predict(x[:0]).shape == (0, 20)
 
 
-def test_conv3_pair_kernel_matches_single_patch_kernel(api, oracle_mod):
-    """conv3 with two patches per MMA (M = 128, CAELO_CONV3_PAIR=1) against the one-patch kernel (M = 64, the default) and
-    the oracle, on odd and tiny patch counts (the last pair of an odd count is half empty)."""
+def test_conv3_kernels_agree(api, oracle_mod):
+    """conv3 with eight patches per MMA and dx folded into N (the default), with two patches per MMA (M = 128,
+    CAELO_CONV3_PAIR=1) and the one-patch kernel (M = 64, CAELO_CONV3_OCT=0) against each other and the oracle, on patch
+    counts that leave the last group of eight / the last pair partly empty."""
     import os
     rng = np.random.default_rng(17)
     enc = api.load_model(api.WEIGHT_DIR + "/encoder.npz")
-    for n in (1, 2, 3, 255, 257, 600):
-        x = (rng.random((n, 16, 16, 16, 1)) < rng.choice([0.002, 0.02, 0.2])).astype(np.float32)
-        old = enc.predict(x)
-        os.environ["CAELO_CONV3_PAIR"] = "1"
+
+    def run(env):
+        os.environ.update(env)
         try:
-            got = enc.predict(x)
+            return enc.predict(x)
         finally:
-            del os.environ["CAELO_CONV3_PAIR"]
-        assert np.abs(got - old).max() < 2e-6, n                 # same products, another accumulation order
+            for k in env:
+                del os.environ[k]
+
+    for n in (1, 2, 3, 7, 8, 9, 255, 257, 600):
+        x = (rng.random((n, 16, 16, 16, 1)) < rng.choice([0.002, 0.02, 0.2])).astype(np.float32)
+        got = enc.predict(x)
+        m64 = run({"CAELO_CONV3_OCT": "0"})
+        pair = run({"CAELO_CONV3_PAIR": "1"})
+        assert np.abs(got - m64).max() < 3e-6, n                 # one more product (A_lo W_lo), another accumulation order
+        assert np.abs(pair - m64).max() < 2e-6, n
         if n <= 257:
             assert_descriptors_close(got, oracle_mod.encoder_predict(x))
-        assert np.array_equal(old, enc.predict(x))               # deterministic
+        assert np.array_equal(got, enc.predict(x))               # deterministic
 
 
 def test_conv12_pair_kernel_matches_single_patch_kernel(api, oracle_mod):

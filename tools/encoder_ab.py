@@ -12,8 +12,9 @@ kpts, _, n = ctx.select_keypoints(ring, cnt, None)
 packed, _, _ = ctx.gather_patches(kpts, api._dev(d["vox"]), d["vox_offsets"], n)
 flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
 ref = None
-for name, env in (("conv12 pair (default)", {}), ("conv12 one patch", {"CAELO_CONV12_PAIR": "0"}),
+for name, env in (("defaults (conv12 pair, conv3 oct)", {}), ("conv12 one patch", {"CAELO_CONV12_PAIR": "0"}),
                   ("conv12 pair, no bg skip", {"CAELO_CONV12_SKIP_BG": "0"}),
+                  ("conv3 one patch (M=64)", {"CAELO_CONV3_OCT": "0"}),
                   ("conv3 pair, 3 stages", {"CAELO_CONV3_PAIR": "1"}),
                   ("conv3 pair, 9 stages", {"CAELO_CONV3_PAIR": "19"}),
                   ("conv12 pair, no MMAs (wrong results)", {"CAELO_CONV12_DBG": "1"}),
