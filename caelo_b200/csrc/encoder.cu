@@ -958,6 +958,8 @@ struct Conv3Args {
     const float *k3, *b3;  // (27,16,32), (32)
     __half *act3_hi, *act3_lo;  // split fp16 dense1 operands, tile-major: [ceil(P/256)][256 chunks][256 patches][8]
     int P;
+    int dbg;                    // measurement only (CAELO_CONV3_DBG, conv3_oct_kernel): bit 0 = producers write nothing, bit 1 = the
+                                // epilogue only drains, bit 2 = no MMAs (results are wrong)
 };
 
 template <int NBUF>
@@ -1307,7 +1309,7 @@ __global__ void __launch_bounds__(C3P_THREADS, 1) conv3_pair_kernel(const Conv3A
 // columns, so the epilogue of group g runs under the MMAs of group g+1.
 constexpr int C8_PROD_WARPS = 8;                       // warps 0-7: thread = (patch 8, position-in-slab 16, channel half 2)
 constexpr int C8_ISSUER = 8;
-constexpr int C8_EPI0 = 9, C8_EPI_WARPS = 8;           // warps 9-16: (lane quarter = warp % 4) x (output slices 0-1 / 2-3)
+constexpr int C8_EPI0 = 9, C8_EPI_WARPS = 16;          // warps 9-24: (lane quarter = warp % 4) x (output slice)
 constexpr int C8_THREADS = (C8_EPI0 + C8_EPI_WARPS) * 32;
 constexpr int C8_COPY = 2 * 128 * 16;                  // one (dy,dz) copy of a slab: [channel half 2][row 128][16 B]
 constexpr int C8_STAGE = 9 * C8_COPY;                  // 36864 B
@@ -1316,7 +1318,8 @@ constexpr int C8_W_TAP = 2 * 192 * 16;
 constexpr int C8_SM_Z = C8_SM_W + 9 * C8_W_TAP;        // zero B operand [chunk 2][row 256][16 B]
 constexpr int C8_SM_B3 = C8_SM_Z + 2 * 256 * 16;
 constexpr int C8_SM_BAR = C8_SM_B3 + 128;              // full[4] empty[4] tfull[2] tempty[2] + tmem slot
-constexpr int C8_SMEM = C8_SM_BAR + 12 * 8 + 16;
+constexpr int C8_SM_STG = C8_SM_BAR + 12 * 8 + 16;     // epilogue store staging [slice team 4][hi, lo][position 16][patch 8][16 B]
+constexpr int C8_SMEM = C8_SM_STG + 4 * 4096;
 static_assert(C8_SMEM <= 227 * 1024, "conv3_oct_kernel shared memory");
 
 __global__ void __launch_bounds__(C8_THREADS, 1) conv3_oct_kernel(const Conv3Args a)
@@ -1384,6 +1387,7 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3_oct_kernel(const Conv3Arg
                     const uint32_t idesc = (x == 0 || x == 3) ? id128 : id192;
                     const uint64_t bx = b_base + (uint64_t)(x == 0 ? (64 * 16) >> 4 : 0);   // slab 0: rows 64..191 (dx = 1, 0)
                     const uint64_t ax = a_base + (uint64_t)((x * C8_STAGE) >> 4);
+                    if (!(a.dbg & 4))
 #pragma unroll
                     for (int c = 0; c < 9; ++c)
                         umma::mma_f16(d, ax + (uint64_t)((c * C8_COPY) >> 4), bx + (uint64_t)((c * C8_W_TAP) >> 4), idesc, 1u);
@@ -1398,7 +1402,7 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3_oct_kernel(const Conv3Arg
         // floats of every slab (the next group's loads are issued before this group's stores), splits them once, and writes
         // the hi part of slabs 0-3 and then the lo part into the nine shifted copies of the slab's stage, each time after the
         // MMAs that read the stage's previous content have completed =====
-        const int p8 = tid >> 5, yz = (tid >> 1) & 15, half = tid & 1;
+        const int p8 = tid >> 5, yz = tid & 15, half = (tid >> 4) & 1;   // a quarter warp = 8 consecutive rows of one half: no bank conflicts
         const int y = yz >> 2, z = yz & 3;
         float4 nv[4][2];
         auto fetch = [&](int i) {
@@ -1436,6 +1440,7 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3_oct_kernel(const Conv3Arg
                 }
                 const uint4 v = part ? vl[x] : vh[x];
                 unsigned char *st = sm + x * C8_STAGE + half * (128 * 16);
+                if (!(a.dbg & 1))
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
@@ -1449,42 +1454,54 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3_oct_kernel(const Conv3Arg
             }
         }
     } else {
-        // ===== epilogue (8 warps): TMEM lane = (patch, y, z); warp -> lane quarter q (patches 2q, 2q+1) and two output slices =====
-        const int q = warp & 3, xh = (warp - C8_EPI0) >> 2;
+        // ===== epilogue (16 warps): TMEM lane = (patch, y, z); warp -> lane quarter q (patches 2q, 2q+1) and ONE output slice.
+        // act3 is tile-major for dense1 ([tile of 256 patches][chunk of 8 k][patch][16 B]): for one chunk the group's eight
+        // patches are one 128-byte line, but a warp holds 2 patches x 16 positions, i.e. 32 lines.  Written straight from the
+        // registers that is 32 partial sectors per store instruction, and with the operands cheap those stores bounded the
+        // kernel (0.34 ms with the epilogue only draining, 0.53 ms with it, whether 8 or 16 warps).  So the four warps of a
+        // slice exchange their 16-byte pieces through shared memory (swizzled by position: conflict-free both ways) and every
+        // quarter warp writes one full line. =====
+        const int q = warp & 3, x = (warp - C8_EPI0) >> 2;
         const int pl = 2 * q + (lane >> 4), yz = lane & 15;
+        unsigned char *stg = sm + C8_SM_STG + x * 4096;
+        unsigned char *my_slot = stg + yz * 128 + ((pl ^ (yz & 7)) << 4);
+        const int tt = q * 32 + lane;                          // thread of the slice team: writes line tt/8, patch tt%8
+        const int wl = tt >> 3, wj = tt & 7;
+        const unsigned char *rd_slot = stg + wl * 128 + ((wj ^ (wl & 7)) << 4);
+        const int barid = 1 + x;
         for (int i = 0; i < n_my; ++i) {
             const int b = i & 1;
             umma::mbar_wait(&tfull[b], (uint32_t)((i >> 1) & 1));
             umma::fence_after_thread_sync();
-            const int p = group_of(i) * 8 + pl;
-            const size_t row8 = ((size_t)(p >> 8) * 256 * 256 + (size_t)(p & 255)) * 8;   // halves (tile-major act3)
-#pragma unroll 1
-            for (int x = 2 * xh; x < 2 * xh + 2; ++x) {
-                const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16) + b * 256 + x * 64;
-                const int pos = x * 16 + yz;
+            const int pw = group_of(i) * 8 + wj;               // the patch this thread writes out
+            const size_t row8 = ((size_t)(pw >> 8) * 256 * 256 + (size_t)(pw & 255)) * 8;   // halves (tile-major act3)
+            const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16) + b * 256 + x * 64;
 #pragma unroll
-                for (int hc = 0; hc < 2; ++hc) {          // 16 channels at a time
-                    uint32_t v0[16], v1[16];
-                    umma::tmem_ld_x16(trow + hc * 16, v0);        // W_hi columns
-                    umma::tmem_ld_x16(trow + 32 + hc * 16, v1);   // W_lo columns
-                    umma::tmem_ld_wait();
-                    if (p < a.P) {
+            for (int g = 0; g < 4; ++g) {                 // 8 channels at a time: chunk pos*4 + g of the dense1 K axis
+                uint32_t v0[8], v1[8];
+                umma::tmem_ld_x8(trow + g * 8, v0);        // W_hi columns
+                umma::tmem_ld_x8(trow + 32 + g * 8, v1);   // W_lo columns
+                umma::tmem_ld_wait();
+                __half2 hh[4], ll[4];
+                if (!(a.dbg & 2)) {
+                    const float4 c0 = *reinterpret_cast<const float4 *>(b3s + 8 * g), c1 = *reinterpret_cast<const float4 *>(b3s + 8 * g + 4);
+                    const float bb[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            __half2 hh[4], ll[4];
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const int ch = 8 * g + 2 * c;
-                                const float o0 = fast_tanh((__uint_as_float(v0[ch]) + __uint_as_float(v1[ch])) + b3s[hc * 16 + ch]);
-                                const float o1 = fast_tanh((__uint_as_float(v0[ch + 1]) + __uint_as_float(v1[ch + 1])) + b3s[hc * 16 + ch + 1]);
-                                umma::split_f16x2(o0, o1, hh[c], ll[c]);
-                            }
-                            const size_t o = row8 + (size_t)(pos * 4 + hc * 2 + g) * 256 * 8;
-                            *reinterpret_cast<uint4 *>(a.act3_hi + o) = *reinterpret_cast<uint4 *>(hh);
-                            *reinterpret_cast<uint4 *>(a.act3_lo + o) = *reinterpret_cast<uint4 *>(ll);
-                        }
+                    for (int c = 0; c < 4; ++c) {
+                        const float o0 = fast_tanh((__uint_as_float(v0[2 * c]) + __uint_as_float(v1[2 * c])) + bb[2 * c]);
+                        const float o1 = fast_tanh((__uint_as_float(v0[2 * c + 1]) + __uint_as_float(v1[2 * c + 1])) + bb[2 * c + 1]);
+                        umma::split_f16x2(o0, o1, hh[c], ll[c]);
                     }
+                    *reinterpret_cast<uint4 *>(my_slot) = *reinterpret_cast<uint4 *>(hh);
+                    *reinterpret_cast<uint4 *>(my_slot + 2048) = *reinterpret_cast<uint4 *>(ll);
                 }
+                asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
+                if (pw < a.P && !(a.dbg & 2)) {
+                    const size_t o = row8 + (size_t)((x * 16 + wl) * 4 + g) * 256 * 8;
+                    *reinterpret_cast<uint4 *>(a.act3_hi + o) = *reinterpret_cast<const uint4 *>(rd_slot);
+                    *reinterpret_cast<uint4 *>(a.act3_lo + o) = *reinterpret_cast<const uint4 *>(rd_slot + 2048);
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
             }
             umma::fence_before_thread_sync();
             umma::mbar_arrive(&tempty[b]);
@@ -1781,6 +1798,7 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
     CAELO_LAUNCH_CHECK(ctx);
     Conv3Args c3;
     c3.act2 = act2; c3.k3 = ctx->enc.k3; c3.b3 = ctx->enc.b3; c3.act3_hi = act3_hi; c3.act3_lo = act3_lo; c3.P = P;
+    { const char *e = getenv("CAELO_CONV3_DBG"); c3.dbg = e ? atoi(e) : 0; }
     {
         const char *e = getenv("CAELO_CONV3_PAIR");      // switch for A/B timing: "1" = the two-patches-per-MMA kernel
         const char *e8 = getenv("CAELO_CONV3_OCT");      // "0" = not the eight-patches-per-MMA kernel (the default)

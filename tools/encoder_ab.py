@@ -15,6 +15,10 @@ ref = None
 for name, env in (("defaults (conv12 pair, conv3 oct)", {}), ("conv12 one patch", {"CAELO_CONV12_PAIR": "0"}),
                   ("conv12 pair, no bg skip", {"CAELO_CONV12_SKIP_BG": "0"}),
                   ("conv3 one patch (M=64)", {"CAELO_CONV3_OCT": "0"}),
+                  ("conv3 oct, producers write nothing (wrong)", {"CAELO_CONV3_DBG": "1"}),
+                  ("conv3 oct, epilogue only drains (wrong)", {"CAELO_CONV3_DBG": "2"}),
+                  ("conv3 oct, no MMAs (wrong)", {"CAELO_CONV3_DBG": "4"}),
+                  ("conv3 oct, MMAs only (wrong)", {"CAELO_CONV3_DBG": "3"}),
                   ("conv3 pair, 3 stages", {"CAELO_CONV3_PAIR": "1"}),
                   ("conv3 pair, 9 stages", {"CAELO_CONV3_PAIR": "19"}),
                   ("conv12 pair, no MMAs (wrong results)", {"CAELO_CONV12_DBG": "1"}),
