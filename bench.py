@@ -268,8 +268,8 @@ def _config(args, world):
                         "1024 keypts/frame, 3x16^3 voxel patches, 60-D descriptors, 500-trial RANSAC)"
                         % (args.pairs, args.pairs + 1),
             "pairs_per_step_per_gpu": args.pairs, "keypoints": K_PTS, "parallelism": "pairs sharded x%d" % world,
-            "l2": "192 MiB write before every step (on the stream, inside the timed region); per-step intermediates "
-                  "(~0.8 GB) exceed L2 as well"}
+            "l2": "inputs larger than L2: the steps cycle through 3 input sets (3 x 85 MB of ring images + voxel lists / "
+                  "3 x 65 MB of raw scans vs 126 MB of L2); per-step intermediates (~1.7 GB of traffic) exceed L2 as well"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -508,43 +508,51 @@ def run_ours(args, rank, local_rank, world):
     K = args.steps
     # pair ids of this rank inside a notional sequence: rank r owns pairs [r*P, (r+1)*P)
     pair_ids = list(range(rank * P, (rank + 1) * P))
-    data = synth.make_frames(F, seed=1 + rank, first_frame=rank * P, device=dev)
-    host = dict(ring=torch.from_numpy(data["ring3"]).pin_memory(),
-                counter=torch.from_numpy(data["counter"]).pin_memory(),
-                vox=torch.from_numpy(data["vox"]).pin_memory())
-    voff = data["vox_offsets"]
-    d_ring, d_counter, d_vox = (host[k].to(dev) for k in ("ring", "counter", "vox"))
-    soff = np.zeros(F + 1, np.int64)
-    soff[1:] = np.cumsum([s.shape[0] for s in data["scans"]])
-    scans_h = torch.from_numpy(np.concatenate(data["scans"], 0)).pin_memory()
-    d_scans = scans_h.to(dev)
-    flush = torch.empty(48 << 20, dtype=torch.float32, device=dev)       # 192 MiB > the 126 MB L2
+    # INPUTS LARGER THAN L2: the steps cycle through N_SETS different 33-frame stretches of the drive (3 x 85 MB of ring
+    # images + voxel lists, 3 x 65 MB of raw scans, against 126 MB of L2); a set comes round again after the two others and
+    # ~5 GB of intermediate traffic.  Set 0 is the one the parity check, the CPU baseline and the sub-runs use.
+    N_SETS = 3
+
+    def make_set(s):
+        d = synth.make_frames(F, seed=1 + rank + 1000 * s, first_frame=(rank + s * world) * P, device=dev)
+        h = dict(ring=torch.from_numpy(d["ring3"]).pin_memory(), counter=torch.from_numpy(d["counter"]).pin_memory(),
+                 vox=torch.from_numpy(d["vox"]).pin_memory())
+        so = np.zeros(F + 1, np.int64)
+        so[1:] = np.cumsum([x.shape[0] for x in d["scans"]])
+        sh = torch.from_numpy(np.concatenate(d["scans"], 0)).pin_memory()
+        return dict(data=d, host=h, voff=d["vox_offsets"], dev=tuple(h[k].to(dev) for k in ("ring", "counter", "vox")),
+                    soff=so, scans_h=sh, d_scans=sh.to(dev),
+                    pair_ids=list(range((rank + s * world) * P, (rank + s * world + 1) * P)))
+
+    sets = [make_set(s) for s in range(N_SETS)]
+    data, host, voff, soff, scans_h, pair_ids = (sets[0][k] for k in ("data", "host", "voff", "soff", "scans_h", "pair_ids"))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def enqueue_rings():
-        return pipe.enqueue_device(d_ring, d_counter, d_vox, voff, None, pair_ids)
+    def enqueue_rings(k=0):
+        z = sets[k % N_SETS]
+        return pipe.enqueue_device(*z["dev"], z["voff"], None, z["pair_ids"])
 
-    def enqueue_scans():
-        return pipe.enqueue_device_scans(d_scans, soff, None, pair_ids)
+    def enqueue_scans(k=0):
+        z = sets[k % N_SETS]
+        return pipe.enqueue_device_scans(z["d_scans"], z["soff"], None, z["pair_ids"])
 
     def timed_steps(enqueue):
         """K steps queued back to back (nothing waits for the device in between; the pairs stage of step i runs on the
-        pipeline's tail stream next to the frame stages of step i+1), L2 flushed before every step (a 192 MiB write on the
-        stream, INSIDE the timed region), ONE pair of CUDA events around all K steps; then the host reads every step's
-        result rows and ONE gather brings all K x P rows to rank 0.  -> (device time of the K steps + the gather, wall
-        seconds incl. collect + gather, rows on this rank, gathered rows on rank 0)."""
+        pipeline's tail stream next to the frame stages of step i+1), step k on input set k mod 3 (inputs larger than L2),
+        ONE pair of CUDA events around all K steps; then the host reads every step's result rows and ONE gather brings
+        all K x P rows to rank 0.  -> (device time of the K steps + the gather, wall seconds incl. collect + gather, rows
+        on this rank, gathered rows on rank 0)."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t0 = time.perf_counter()
         handles = []
         ev0.record()
-        for _ in range(K):
-            flush.zero_()
-            handles.append(enqueue())
+        for k in range(K):
+            handles.append(enqueue(k))
         pipe.join()                  # the pairs stages run on the pipeline's tail stream: the end event covers them too
         ev1.record()
         rows = [pipe.collect(h) for h in handles]
@@ -601,9 +609,10 @@ def run_ours(args, rank, local_rank, world):
     # ---- end to end: host (pinned) inputs, H2D + kernels + D2H of every step's rows, one gather at the end ----
     def e2e_run(kind):
         def steps(n):
-            for _ in range(n):
-                yield (("rings", host["ring"], host["counter"], host["vox"], voff, pair_ids) if kind == "rings"
-                       else ("scans", scans_h, soff, pair_ids))
+            for k in range(n):
+                z = sets[k % N_SETS]
+                yield (("rings", z["host"]["ring"], z["host"]["counter"], z["host"]["vox"], z["voff"], z["pair_ids"])
+                       if kind == "rings" else ("scans", z["scans_h"], z["soff"], z["pair_ids"]))
         for _p in pipe.run_host_stream(steps(3)):
             pass
         barrier()
@@ -615,8 +624,11 @@ def run_ours(args, rank, local_rank, world):
 
     e2e_rings_s, e2e_scans_s = reduce_max(e2e_run("rings"), e2e_run("scans"))
     clocks = sampler.stop() if sampler else None
-    h2d_rings = sum(host[k].numel() * host[k].element_size() for k in host) + voff.nbytes + 8 * P
-    h2d_scans = int(scans_h.numel() * 4 + soff.nbytes + 8 * P)
+    # bytes per step, averaged over the steps actually run (the input sets differ a little in voxel / point counts)
+    used = [sets[k % N_SETS] for k in range(K)]
+    h2d_rings = sum(sum(z["host"][k].numel() * z["host"][k].element_size() for k in z["host"]) + z["voff"].nbytes + 8 * P
+                    for z in used) / K
+    h2d_scans = sum(z["scans_h"].numel() * 4 + z["soff"].nbytes + 8 * P for z in used) / K
     d2h = P * 32 * 4
 
     extras = {}
