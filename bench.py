@@ -662,6 +662,7 @@ def run_ours(args, rank, local_rank, world):
         kernels = [k for k in (
             kern("conv12_pair_kernel", FLOP_CONV12_PER_PATCH * n_patches, peaks["tf_sustained"], "TFLOP/s", 1e12),
             kern("conv12_tc_kernel", FLOP_CONV12_PER_PATCH * n_patches, peaks["tf_sustained"], "TFLOP/s", 1e12),
+            kern("conv3_oct_kernel", FLOP_CONV3_PER_PATCH * n_patches, peaks["tf_sustained"], "TFLOP/s", 1e12),
             kern("conv3_tc_kernel", FLOP_CONV3_PER_PATCH * n_patches, peaks["tf_sustained"], "TFLOP/s", 1e12),
             kern("dense_tc_kernel", FLOP_DENSE_PER_PATCH * n_patches, peaks["tf_sustained"], "TFLOP/s", 1e12),
             kern("respond_score_kernel<fused>", BYTES_RESPOND_SELECT_PER_FRAME * F, peaks["hbm"], "GB/s", 1e9),
