@@ -1112,188 +1112,6 @@ __global__ void __launch_bounds__(C3_THREADS, 3 - NBUF) conv3_tc_kernel(const Co
     if (warp == C3_ISSUER) umma::tmem_dealloc(tbase, 128);
 }
 
-// ---- conv3, two patches per MMA (M = 128) ----------------------------------------------------------------------
-// The M = 64 kernel above leaves half of the tensor datapath idle and fetches the 2 KB weight tile of every tap once per
-// patch; an MMA at this size is bound by its shared-memory operand fetch (A 2 KB + B 2 / 1 KB per MMA at ~128 B/clk), so
-// 189 KB of operands per patch cost ~1.5 k cycles.  Here TWO patches share every MMA: each (dy,dz)-shifted compact copy is
-// stored as [xi 6][patch 2][yz 16] x 16 B, so the 128 rows (x, patch, yz) of tap (dx,dy,dz) are again ONE contiguous run
-// (2048 B, SBO = 128 B) starting dx*512 B into the copy.  Operands per patch pair: 27 x (4+2) + 27 x (4+1) KB = 297 KB, i.e.
-// 148 KB per patch (-22 %), half the MMA count, all 128 TMEM lanes used.
-// The pair's operands take 108 KB, so there is ONE operand buffer, pipelined copy by copy: the nine copies are nine
-// stages with their own full / empty mbarriers; the issuer commits after the six MMAs of a stage (3 dx x {hi, lo}), which
-// lets the producers overwrite that copy with the NEXT pair while the later stages of this pair are still being multiplied.
-constexpr int C3P_COPY = 6 * 2 * 16 * 16;             // 3072 B: [xi 6][patch 2][yz 16] x 16 B
-constexpr int C3P_HALF = 9 * C3P_COPY;                // 27648 B: nine copies of one channel half
-constexpr int C3P_PART = 2 * C3P_HALF;                // 55296 B: both halves (the two K chunks)
-constexpr int C3P_BUF = 2 * C3P_PART;                 // 110592 B: hi + lo
-constexpr int C3P_SM_W = C3P_BUF;                     // W3 [kc 54][n 64][16 B]
-constexpr int C3P_SM_B3 = C3P_SM_W + 54 * 1024;
-constexpr int C3P_SM_BAR = C3P_SM_B3 + 128;           // full[9] empty[9] tfull[2] tempty[2] + tmem slot
-constexpr int C3P_SMEM = C3P_SM_BAR + 22 * 8 + 16;
-constexpr int C3P_PROD = 9;                           // warps 0-8 produce: warp c owns the (dy,dz) copy c
-constexpr int C3P_ISSUER = 9;                         // warp 9 issues the MMAs (warps 10, 11 idle: the epilogue warps must start at a multiple of 4)
-constexpr int C3P_EPI0 = 12, C3P_EPI = 8;             // warps 12-19 drain the accumulators (lane quarter x channel half)
-constexpr int C3P_THREADS = (C3P_EPI0 + C3P_EPI) * 32;
-
-template <int NST>   // pipeline stages of the operand ring: 9 (one per copy) or 3 (three copies each)
-__global__ void __launch_bounds__(C3P_THREADS, 1) conv3_pair_kernel(const Conv3Args a)
-{
-    constexpr int CPS = 9 / NST;   // copies per stage
-    extern __shared__ __align__(128) unsigned char sm[];
-    float *b3s = reinterpret_cast<float *>(sm + C3P_SM_B3);
-    uint64_t *full = reinterpret_cast<uint64_t *>(sm + C3P_SM_BAR), *empty = full + 9, *tfull = full + 18, *tempty = full + 20;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + C3P_SM_BAR + 22 * 8);
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-
-    for (int i = tid; i < C3P_BUF / 16; i += C3P_THREADS) reinterpret_cast<uint4 *>(sm)[i] = make_uint4(0, 0, 0, 0);
-    for (int e = tid; e < 27 * 16 * 32; e += C3P_THREADS) {     // B operand as in conv3_tc_kernel
-        int t = e / 512, ci = (e / 32) % 16, co = e % 32;
-        __half h, l;
-        umma::split_f16(a.k3[e], h, l);
-        unsigned char *w = sm + C3P_SM_W + (t * 2 + ci / 8) * 1024 + (ci % 8) * 2;
-        *reinterpret_cast<__half *>(w + (co / 8) * 128 + (co % 8) * 16) = h;
-        *reinterpret_cast<__half *>(w + ((32 + co) / 8) * 128 + (co % 8) * 16) = l;
-    }
-    if (tid < 32) b3s[tid] = a.b3[tid];
-    if (warp == C3P_ISSUER) umma::tmem_alloc(tmem_slot, 128);
-    if (tid == 0) {
-        for (int c = 0; c < NST; ++c) {
-            umma::mbar_init(&full[c], 32 * CPS);   // the producer warps of the stage's copies
-            umma::mbar_init(&empty[c], 1);
-        }
-        for (int b = 0; b < 2; ++b) {
-            umma::mbar_init(&tfull[b], 1);
-            umma::mbar_init(&tempty[b], C3P_EPI * 32);
-        }
-        umma::fence_mbar_init();
-    }
-    umma::fence_proxy_async();
-    umma::fence_before_thread_sync();
-    __syncthreads();
-    umma::fence_after_thread_sync();
-    const uint32_t tbase = *tmem_slot;
-    const uint32_t sC = umma::smem_u32(sm), sW = umma::smem_u32(sm + C3P_SM_W);
-    const int n_pairs = (a.P + 1) / 2;
-    const int n_my = (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // patch pairs of this CTA
-    auto pair_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
-
-    if (warp == C3P_ISSUER) {
-        // Every descriptor is a constant offset from two base descriptors (the loops below are fully unrolled): the issuer
-        // thread's instruction stream must stay well below the tensor core's ~44 cycles per MMA — with run-time (dy,dz) and
-        // descriptors rebuilt per MMA the first version spent ~100 cycles of dependent uniform-datapath code per MMA and the
-        // tensor pipe idled at 25 %.
-        const uint32_t idesc64 = umma::idesc_f16_f32(128, 64), idesc32 = umma::idesc_f16_f32(128, 32);
-        const uint64_t a_base = umma::smem_desc(sC, C3P_HALF, 128), b_base = umma::smem_desc(sW, 1024, 128);
-        for (int j = 0; j < n_my; ++j) {
-            const int b = j & 1;
-            if (j >= 2) umma::mbar_wait(&tempty[b], (uint32_t)(((j >> 1) - 1) & 1));
-            const uint32_t d = tbase + b * 64;
-#pragma unroll
-            for (int sg = 0; sg < NST; ++sg) {
-                umma::mbar_wait(&full[sg], (uint32_t)(j & 1));
-                umma::fence_after_thread_sync();
-                if (umma::elect_one()) {
-#pragma unroll
-                    for (int cc = 0; cc < CPS; ++cc) {
-                        const int c = sg * CPS + cc, dy = c / 3, dz = c % 3;
-#pragma unroll
-                        for (int part = 0; part < 2; ++part)
-#pragma unroll
-                            for (int dx = 0; dx < 3; ++dx) {
-                                const int t = dx * 9 + dy * 3 + dz;
-                                const uint64_t da = a_base + (uint64_t)((part * C3P_PART + c * C3P_COPY + dx * 512) >> 4);
-                                const uint64_t db = b_base + (uint64_t)((t * 2048) >> 4);
-                                umma::mma_f16(d, da, db, part ? idesc32 : idesc64, (c | part | dx) ? 1u : 0u);
-                            }
-                    }
-                    umma::commit(&empty[sg]);
-                    if (sg == NST - 1) umma::commit(&tfull[b]);
-                }
-                __syncwarp();
-            }
-        }
-    } else if (warp < C3P_PROD) {
-        // ===== producers: warp c owns copy c = (dy,dz).  Per pair it loads the pair's whole act2 (2 x 4 KB; eight
-        // (patch, channel half, position) elements per lane, all loads issued before anything waits), and once the previous
-        // pair's MMAs on its copy have completed it writes hi and lo of every position the shifted window holds: one
-        // proxy fence and one arrive per lane and pair.  (A first version had thread = element writing all nine copies:
-        // nine proxy fences per thread and pair made the producers slower than the tensor core, 0.89 ms.) =====
-        const int c = warp, dy = c / 3, dz = c % 3;
-        for (int i = 0; i < n_my; ++i) {
-            float4 v[8][2];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int e = lane + 32 * k, pp = e >> 7, half = (e >> 6) & 1, pos = e & 63;
-                int p = 2 * pair_of(i) + pp;
-                if (p >= a.P) p = a.P - 1;             // odd patch count: the last pair's second half repeats the first
-                const float4 *src = reinterpret_cast<const float4 *>(a.act2 + (size_t)p * 1024 + pos * 16 + half * 8);
-                v[k][0] = __ldg(src);
-                v[k][1] = __ldg(src + 1);
-            }
-            if (i >= 1) {
-                umma::mbar_wait(&empty[c / CPS], (uint32_t)((i - 1) & 1));
-                umma::fence_after_thread_sync();
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int e = lane + 32 * k, pp = e >> 7, half = (e >> 6) & 1, pos = e & 63;
-                const int x = pos >> 4, ys = ((pos >> 2) & 3) + 1 - dy, zs = (pos & 3) + 1 - dz;
-                if ((unsigned)ys < 4u && (unsigned)zs < 4u) {
-                    const float f[8] = {v[k][0].x, v[k][0].y, v[k][0].z, v[k][0].w, v[k][1].x, v[k][1].y, v[k][1].z, v[k][1].w};
-                    __half2 hv[4], lv[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) umma::split_f16x2(f[2 * j], f[2 * j + 1], hv[j], lv[j]);
-                    unsigned char *q = sm + half * C3P_HALF + c * C3P_COPY + ((((x + 1) * 2 + pp) * 4 + ys) * 4 + zs) * 16;
-                    *reinterpret_cast<uint4 *>(q) = *reinterpret_cast<uint4 *>(hv);
-                    *reinterpret_cast<uint4 *>(q + C3P_PART) = *reinterpret_cast<uint4 *>(lv);
-                }
-            }
-            umma::fence_proxy_async();
-            umma::mbar_arrive(&full[c / CPS]);
-        }
-    } else if (warp >= C3P_EPI0) {
-        // ===== epilogue (8 warps = TMEM lane quarter x channel half): lane -> (x = quarter, patch, yz) =====
-        const int q = warp & 3, hc = (warp - C3P_EPI0) >> 2;
-        for (int i = 0; i < n_my; ++i) {
-            const int b = i & 1;
-            umma::mbar_wait(&tfull[b], (uint32_t)((i >> 1) & 1));
-            umma::fence_after_thread_sync();
-            uint32_t v0[16], v1[16];
-            const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16) + b * 64 + hc * 16;
-            umma::tmem_ld_x16(trow, v0);        // columns 0..31: W_hi (A_hi + A_lo products)
-            umma::tmem_ld_x16(trow + 32, v1);   // columns 32..63: W_lo
-            umma::tmem_ld_wait();
-            umma::fence_before_thread_sync();
-            umma::mbar_arrive(&tempty[b]);
-            const int p = 2 * pair_of(i) + (lane >> 4);
-            if (p < a.P) {
-                const int pos = 16 * q + (lane & 15);
-                const size_t row8 = ((size_t)(p >> 8) * 256 * 256 + (size_t)(p & 255)) * 8;   // halves (tile-major act3)
-                const int c0 = pos * 4 + hc * 2;
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    __half2 hh[4], ll[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int ch = 8 * g + 2 * c;
-                        const float o0 = fast_tanh((__uint_as_float(v0[ch]) + __uint_as_float(v1[ch])) + b3s[hc * 16 + ch]);
-                        const float o1 = fast_tanh((__uint_as_float(v0[ch + 1]) + __uint_as_float(v1[ch + 1])) + b3s[hc * 16 + ch + 1]);
-                        umma::split_f16x2(o0, o1, hh[c], ll[c]);
-                    }
-                    const size_t o = row8 + (size_t)(c0 + g) * 256 * 8;
-                    *reinterpret_cast<uint4 *>(a.act3_hi + o) = *reinterpret_cast<uint4 *>(hh);
-                    *reinterpret_cast<uint4 *>(a.act3_lo + o) = *reinterpret_cast<uint4 *>(ll);
-                }
-            }
-        }
-    }
-    umma::fence_before_thread_sync();
-    __syncthreads();
-    umma::fence_after_thread_sync();
-    if (warp == C3P_ISSUER) umma::tmem_dealloc(tbase, 128);
-}
-
 // ---- conv3, eight patches per MMA (M = 128) and dx folded into N ---------------------------------------------------------
 // conv3_tc_kernel is bound by the tensor core's shared-memory operand fetch (80 % of the shared-memory pipe at 189 KB per
 // patch: an M = 64 MMA fetches 2 KB of A for 2 or 1 KB of B).  The same two moves as in conv12_pair_kernel cut that to 90 KB:
@@ -1800,24 +1618,18 @@ int run_encoder(caelo_ctx *ctx, const unsigned *packed, int P, float *feat, int 
     c3.act2 = act2; c3.k3 = ctx->enc.k3; c3.b3 = ctx->enc.b3; c3.act3_hi = act3_hi; c3.act3_lo = act3_lo; c3.P = P;
     { const char *e = getenv("CAELO_CONV3_DBG"); c3.dbg = e ? atoi(e) : 0; }
     {
-        const char *e = getenv("CAELO_CONV3_PAIR");      // switch for A/B timing: "1" = the two-patches-per-MMA kernel
-        const char *e8 = getenv("CAELO_CONV3_OCT");      // "0" = not the eight-patches-per-MMA kernel (the default)
-        const bool oct = !(e8 && e8[0] == '0') && !(e && e[0] == '1');
+        const char *e8 = getenv("CAELO_CONV3_OCT");      // switch for A/B timing: "0" = the one-patch-per-MMA kernel (M = 64)
+        const bool oct = !(e8 && e8[0] == '0');
         ProfScope ps_(ctx, oct ? "conv3_oct_kernel" : "conv3_tc_kernel", st);
         if (oct) {
             int grid3 = ctx->num_sms;                    // persistent: one CTA per SM walks the groups of eight patches
             if (grid3 > (P + 7) / 8) grid3 = (P + 7) / 8;
             conv3_oct_kernel<<<grid3, C8_THREADS, C8_SMEM, st>>>(c3);
-        } else if (!(e && e[0] == '1')) {
+        } else {
             // one CTA per SM with two operand buffers (two single-buffer CTAs per SM measured slower: 0.95 vs 0.89 ms)
             int grid3 = ctx->num_sms;
             if (grid3 > P) grid3 = P;
             conv3_tc_kernel<2><<<grid3, C3_THREADS, c3_smem(2), st>>>(c3);
-        } else {
-            int grid3 = ctx->num_sms;                    // persistent: one CTA per SM walks the patch PAIRS
-            if (grid3 > (P + 1) / 2) grid3 = (P + 1) / 2;
-            if (e[1] == '9') conv3_pair_kernel<9><<<grid3, C3P_THREADS, C3P_SMEM, st>>>(c3);
-            else conv3_pair_kernel<3><<<grid3, C3P_THREADS, C3P_SMEM, st>>>(c3);
         }
     }
     CAELO_LAUNCH_CHECK(ctx);
@@ -1839,8 +1651,6 @@ int caelo_encoder_init(caelo_ctx *ctx)
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv12_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem(2)));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_oct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C8_SMEM));
-    CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_pair_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM));
-    CAELO_CUDA(ctx, cudaFuncSetAttribute(conv3_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM));
     CAELO_CUDA(ctx, cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
     return CAELO_OK;
 }

@@ -1,5 +1,5 @@
 """A/B timing of the encoder kernels on one bench-shaped batch (33 frames x 3 x 1024 patches):
-    python tools/encoder_ab.py            -> per-kernel ms for CAELO_CONV12_PAIR = 1 / 0 (and CAELO_CONV3_PAIR)"""
+    python tools/encoder_ab.py            -> per-kernel ms for CAELO_CONV12_PAIR = 1 / 0 , CAELO_CONV3_OCT = 1 / 0 and with parts of the kernels switched off"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -19,8 +19,6 @@ for name, env in (("defaults (conv12 pair, conv3 oct)", {}), ("conv12 one patch"
                   ("conv3 oct, epilogue only drains (wrong)", {"CAELO_CONV3_DBG": "2"}),
                   ("conv3 oct, no MMAs (wrong)", {"CAELO_CONV3_DBG": "4"}),
                   ("conv3 oct, MMAs only (wrong)", {"CAELO_CONV3_DBG": "3"}),
-                  ("conv3 pair, 3 stages", {"CAELO_CONV3_PAIR": "1"}),
-                  ("conv3 pair, 9 stages", {"CAELO_CONV3_PAIR": "19"}),
                   ("conv12 pair, no MMAs (wrong results)", {"CAELO_CONV12_DBG": "1"}),
                   ("conv12 pair, no conv1 pass 2 (wrong results)", {"CAELO_CONV12_DBG": "2"}),
                   ("conv12 pair, neither (wrong results)", {"CAELO_CONV12_DBG": "3"})):
