@@ -40,6 +40,12 @@ if t[..., 13].max() > 0:
     for lo, hi in ((1, 64), (65, 128), (129, 256), (257, 1024)):
         m = (t[..., 14] >= lo) & (t[..., 14] <= hi)
         if m.any(): print("    n in [%4d, %4d]: %4.1f %% of pairs, pass 2 mean %6.0f" % (lo, hi, 100 * m.mean(), (t[..., 8] - t[..., 7])[m].mean()))
+if t[..., 9].max() > 0:   # epilogue-warp role of the pair kernel: stamps of step j are in row j (restore, listing), of its epilogue in row j-2
+    e = t[:, 2:-2, :]
+    print("epilogue warps, step j: tfull(j-2) -> restore done      :", stat(e[..., 9] - t[:, :-4, 3]))
+    print("                        restore -> cells listed         :", stat(e[..., 10] - e[..., 9]))
+    print("                        listed -> fence + arrive        :", stat(e[..., 2] - e[..., 10]))
+    print("                        epilogue proper of pair j-2     :", stat(t[:, :-4, 4] - t[:, :-4, 11]))
 print("mma issue        6-5 :", stat(t[..., 6] - t[..., 5]))
 print("mbar wait        3-1 :", stat(t[..., 3] - t[..., 1]))
 print("epilogue         4-3 :", stat(t[..., 4] - t[..., 3]))
