@@ -463,8 +463,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
 //     side in TMEM (slabs 0 and 7 use the N = 64 sub-matrix).  The 9 (dy,dz) taps of the hi and of the lo volume are 4 + 4 K-steps
 //     of two taps plus ONE step whose two K chunks are tap 8 of the hi and of the lo volume: 9 MMAs per slab.
 // A_hi and A_lo both go through the same B: D[:, hi columns] + D[:, lo columns] = (A_hi + A_lo)(W_hi + W_lo).
-// Because one MMA now touches three output blocks of which one may be fresh, the pair's 256 accumulator columns are cleared
-// by ONE N = 256 MMA against a zero B operand and everything else accumulates.
+// Because one MMA now touches three output blocks of which one may be fresh, the pair's 256 accumulator columns are
+// initialised by ONE N = 256 MMA (with the background's contribution, see the kernel's set-up) and everything else accumulates.
 // One CTA per SM (all 512 TMEM columns = two pairs in flight): 16 producer warps, 1 issuer warp, 8 epilogue warps.  An output
 // slice pair is skipped when it is background in BOTH patches; a slab is multiplied when one of its three output slices is
 // wanted.
@@ -488,7 +488,7 @@ constexpr int P2_VOL = 8 * 10 * 2 * 10 * 16;          // 25600 B
 constexpr int P2_SM_A = 0;                            // [buf 2][hi, lo][P2_VOL]
 constexpr int P2_W_S = 2 * 96 * 16;                   // one K-step of B: [chunk 2][row 96][16 B]
 constexpr int P2_SM_W = 4 * P2_VOL;
-constexpr int P2_SM_Z = P2_SM_W + 5 * P2_W_S;         // zero B operand [chunk 2][row 256][16 B]
+constexpr int P2_SM_Z = P2_SM_W + 5 * P2_W_S;         // B operand of the accumulator initialisation [chunk 2][row 256][16 B]
 constexpr int P2_SM_T3 = P2_SM_Z + 2 * 256 * 16;      // conv1 partial sums [ch half 2][dx 3][512 (dy,dz) patterns][4] f32
 constexpr int P2_T3_HALF = 3 * 512 * 16;
 constexpr int P2_SM_B12 = P2_SM_T3 + 2 * P2_T3_HALF;
@@ -499,9 +499,10 @@ constexpr int P2_SM_LCNT = P2_SM_LST + 2 * 1024 * 4;  // [buf 2]
 constexpr int P2_SM_XS = P2_SM_LCNT + 16;             // ring of 4 pairs x 2 patches x 8 slice flags
 constexpr int P2_SM_BGP = P2_SM_XS + 64;
 constexpr int P2_SM_BAR = P2_SM_BGP + 27 * 16 * 4;
-constexpr int P2_SMEM = P2_SM_BAR + 64;
+constexpr int P2_SM_AI = (P2_SM_BAR + 64 + 127) / 128 * 128;   // A operand of the accumulator initialisation [chunk 2][row 128][16 B]
+constexpr int P2_SMEM = P2_SM_AI + 2 * 128 * 16;
 static_assert(P2_SM_T3 % 16 == 0 && P2_SM_B12 % 16 == 0 && P2_SM_PK % 16 == 0 && P2_SM_LST % 16 == 0 && P2_SM_XS % 8 == 0 &&
-              P2_SM_BGP % 16 == 0 && P2_SM_BAR % 8 == 0 && P2_SMEM <= 227 * 1024, "smem layout");
+              P2_SM_BGP % 16 == 0 && P2_SM_BAR % 8 == 0 && P2_SM_AI % 128 == 0 && P2_SMEM <= 227 * 1024, "smem layout");
 
 // Row of pattern idx inside a 512-row table.  The eight lanes of a quarter warp (= the eight sub-positions of one cell) read
 // their rows with one 16-byte load each, and the patterns of a sparse patch are mostly single bits: 2^k is a multiple of 8
@@ -518,7 +519,7 @@ __device__ __forceinline__ unsigned t3_slot(unsigned idx) { return idx ^ ((((idx
 template <int U>
 __device__ __forceinline__ void conv1_cells(const unsigned *lst, int k, int n, const unsigned char *pk, const unsigned char *t3,
                                             const float4 &bias_lo, const float4 &bias_hi, unsigned char *a_hi, unsigned char *a_lo,
-                                            int sub)
+                                            int sub, float bgsub)
 {
     const int ix = sub >> 1, yh = sub & 1;
     const int sx = sub >> 2, sy = (sub >> 1) & 1, sz = sub & 1;
@@ -611,7 +612,7 @@ __device__ __forceinline__ void conv1_cells(const unsigned *lst, int k, int n, c
         if (k + 4 * u < n) {
             const int pi = ent[u] & 0xFFFFu;
             __half h, l;
-            umma::split_f16(fast_tanh(o[u]), h, l);
+            umma::split_f16(fast_tanh(o[u]) - bgsub, h, l);   // the volumes hold conv1 minus its background value
             *reinterpret_cast<__half *>(a_hi + pi * 16 + sub * 2) = h;
             *reinterpret_cast<__half *>(a_lo + pi * 16 + sub * 2) = l;
         }
@@ -621,7 +622,6 @@ __global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12
 {
     extern __shared__ __align__(128) unsigned char sm[];
     float *b1s = reinterpret_cast<float *>(sm + P2_SM_B12), *b2s = b1s + 8;
-    const uint4 *bg = reinterpret_cast<const uint4 *>(sm + P2_SM_BG);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(sm + P2_SM_BAR);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + P2_SM_BAR + 48);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -639,20 +639,36 @@ __global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12
         *reinterpret_cast<float *>(sm + P2_SM_T3 + (c >> 2) * P2_T3_HALF + (dx * 512 + t3_slot(idx)) * 16 + (c & 3) * 4) = s;
     }
     for (int e = tid; e < 27 * 16; e += P2_THREADS) reinterpret_cast<float *>(sm + P2_SM_BGP)[e] = a.tables[576 + e];
-    if (tid < 8) {
-        b1s[tid] = a.b1[tid];
-        __half h, l;
-        umma::split_f16(tanhf(a.b1[tid]), h, l);
-        reinterpret_cast<__half *>(sm + P2_SM_BG)[tid] = h;
-        reinterpret_cast<__half *>(sm + P2_SM_BG + 16)[tid] = l;
-    }
+    if (tid < 8) b1s[tid] = a.b1[tid];
     if (tid < 16) b2s[tid] = a.b2[tid];
     if (tid < 2) reinterpret_cast<int *>(sm + P2_SM_LCNT)[tid] = 0;
+    for (int i = tid; i < 2 * 128 * 16 / 16; i += P2_THREADS) reinterpret_cast<uint4 *>(sm + P2_SM_AI)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    for (int e = tid; e < 4 * 1024; e += P2_THREADS) {     // interior cells start as the background value tanh(b1)
-        const int vol = e >> 10, c = e & 1023;
-        const int pi = (((c >> 7) * 10 + ((c >> 4) & 7) + 1) * 2 + ((c >> 3) & 1)) * 10 + (c & 7) + 1;
-        *reinterpret_cast<uint4 *>(sm + P2_SM_A + vol * P2_VOL + pi * 16) = bg[vol & 1];
+    // The operand volumes hold conv1 MINUS its background value tanh(b1): a cell with an empty window is exactly zero, so a
+    // slab without a listed cell contributes nothing and its MMAs are skipped, whatever its neighbours look like.  The
+    // background's own contribution to every conv2 output, sum over the taps that stay inside the volume of tanh(b1) . W2,
+    // only depends on the position's edge class per axis; it is what the accumulators are INITIALISED with, by one K = 16
+    // MMA:  A_init[(y,patch,z)][(dy,dz)] = 1 where tap (dy,dz) stays inside in y and z,  B_init[(dy,dz)][(x, hi|lo, ch)] = the
+    // (hi | lo part of the) sum over ci and over the dx that stay inside in x of tanh(b1[ci]) W2[dx,dy,dz][ci][ch].
+    for (int e = tid; e < 128 * 9; e += P2_THREADS) {
+        const int m = e / 9, t = e % 9, y = m >> 4, z = m & 7, dy = t / 3, dz = t % 3;
+        const bool in = (unsigned)(y + dy - 1) < 8u && (unsigned)(z + dz - 1) < 8u;
+        *reinterpret_cast<__half *>(sm + P2_SM_AI + (t >> 3) * 2048 + (m >> 3) * 128 + (m & 7) * 16 + (t & 7) * 2) =
+            __float2half_rn(in ? 1.0f : 0.0f);
+    }
+    for (int e = tid; e < 8 * 16 * 9; e += P2_THREADS) {
+        const int x = e / 144, ch = (e / 9) % 16, t = e % 9;
+        float sum = 0.f;
+        for (int dx = 0; dx < 3; ++dx) {
+            if ((unsigned)(x + dx - 1) >= 8u) continue;
+            for (int ci = 0; ci < 8; ++ci) sum = fmaf(tanhf(a.b1[ci]), a.k2[((dx * 9 + t) * 8 + ci) * 16 + ch], sum);
+        }
+        __half h, l;
+        umma::split_f16(sum, h, l);
+        unsigned char *w = sm + P2_SM_Z + (t >> 3) * 4096 + (t & 7) * 2;
+        const int nh = x * 32 + ch, nl = nh + 16;
+        *reinterpret_cast<__half *>(w + (nh >> 3) * 128 + (nh & 7) * 16) = h;
+        *reinterpret_cast<__half *>(w + (nl >> 3) * 128 + (nl & 7) * 16) = l;
     }
     // B: K-step s < 4 holds the (dy,dz) taps j = 2s (chunk 0) and 2s+1 (chunk 1); step 4 holds tap 8 in BOTH chunks (its A chunks
     // are tap 8 of the hi and of the lo volume: one MMA serves both parts).  Row n = blk*32 + h*16 + co with blk = 2 - dx (the
@@ -719,11 +735,21 @@ __global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12
         return act;
     };
 
+    auto dirty_slabs = [&](int ord) -> unsigned {
+        if (!a.skip_bg) return 0xFFu;
+        const unsigned long long *fp = reinterpret_cast<const unsigned long long *>(sm + P2_SM_XS + 16 * ord);
+        const unsigned long long f = fp[0] | fp[1];
+        unsigned m = 0;
+#pragma unroll
+        for (int xs = 0; xs < 8; ++xs) m |= (unsigned)((f >> (8 * xs)) & 1ull) << xs;
+        return m;
+    };
+
     if (warp == P2_ISSUER) {
         // ===== MMA issuer =====
         const uint32_t id96 = umma::idesc_f16_f32(128, 96), id64 = umma::idesc_f16_f32(128, 64), id256 = umma::idesc_f16_f32(128, 256);
         const uint64_t a_base = umma::smem_desc(sA, 0, 160), b_base = umma::smem_desc(sW, 96 * 16, 128);
-        const uint64_t z_desc = umma::smem_desc(sZ, 256 * 16, 128);
+        const uint64_t z_desc = umma::smem_desc(sZ, 256 * 16, 128), ai_desc = umma::smem_desc(umma::smem_u32(sm + P2_SM_AI), 128 * 16, 128);
         for (int j = 0; j < n_my; ++j) {
             const int b = j & 1, k = j >> 1;
             umma::mbar_wait(&full[b], (uint32_t)(k & 1));
@@ -731,13 +757,10 @@ __global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12
             umma::fence_after_thread_sync();
             if (lane == 0) stamp(j, 5);
             const unsigned act = active_pairs(j & 3);
-            unsigned need = 0;   // slab x feeds the output slices x-1 .. x+1
-#pragma unroll
-            for (int p = 0; p < 4; ++p)
-                if ((act >> p) & 1u) need |= ((0xFu << (2 * p)) >> 1) & 0xFFu;
+            const unsigned need = dirty_slabs(j & 3);   // slabs with a listed cell in either patch: the others are exactly zero
             if (umma::elect_one()) {
                 const uint32_t d0 = tbase + b * 256;
-                if (act) umma::mma_f16(d0, a_base | (1ull << 16), z_desc, id256, 0u);   // clear the pair's accumulators
+                if (act) umma::mma_f16(d0, ai_desc, z_desc, id256, 0u);   // accumulators := the background's contribution
 #pragma unroll 1
                 for (int x = 0; x < 8; ++x) {
                     if (!((need >> x) & 1u) || (a.dbg & 1)) continue;
@@ -775,6 +798,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12
         unsigned pk_next = 0u;
         int n_dirty0 = 0, n_dirty1 = 0;
         const float4 bias_lo = *reinterpret_cast<const float4 *>(b1s), bias_hi = *reinterpret_cast<const float4 *>(b1s + 4);
+        const float bgsub = tanhf(b1s[lane & 7]);       // background value of the channel this lane finishes in pass 2
         auto fetch = [&](int i) {
             if (i < n_my) {
                 int p = patch_of(i, g);
@@ -792,12 +816,12 @@ __global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12
             }
             unsigned char *a_hi = sm + P2_SM_A + (2 * b) * P2_VOL, *a_lo = a_hi + P2_VOL;
             unsigned *lst = lst_all + b * 1024;
-            // restore the cells the previous pair of this buffer wrote to the background value
+            // the cells the previous pair of this buffer wrote go back to zero (= background)
             const int nd = b ? n_dirty1 : n_dirty0;
             for (int k = tid; k < nd; k += P2_PROD) {
                 const int pi = lst[k] & 0xFFFFu;
-                *reinterpret_cast<uint4 *>(a_hi + pi * 16) = bg[0];
-                *reinterpret_cast<uint4 *>(a_lo + pi * 16) = bg[1];
+                *reinterpret_cast<uint4 *>(a_hi + pi * 16) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4 *>(a_lo + pi * 16) = make_uint4(0, 0, 0, 0);
             }
             // (staged rows are double-buffered like the operands: other warps may still be in pass 2 of the previous pair)
             unsigned short *rows = reinterpret_cast<unsigned short *>(sm + P2_SM_PK + (2 * b + g) * PK_BYTES);
@@ -852,7 +876,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) conv12_pair_kernel(const Conv12
             if (b) n_dirty1 = n; else n_dirty0 = n;
             const int sub = lane & 7;
             for (int k0 = warp * 8 + (lane >> 3); k0 - (lane >> 3) < n; k0 += P2_PROD_WARPS * 8) {
-                conv1_cells<2>(lst, k0, n, sm + P2_SM_PK + 2 * b * PK_BYTES, sm + P2_SM_T3, bias_lo, bias_hi, a_hi, a_lo, sub);
+                conv1_cells<2>(lst, k0, n, sm + P2_SM_PK + 2 * b * PK_BYTES, sm + P2_SM_T3, bias_lo, bias_hi, a_hi, a_lo, sub, bgsub);
             }
             if (tl && tid == 0) tl[8] = clock64();
             umma::fence_proxy_async();
