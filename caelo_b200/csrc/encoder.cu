@@ -465,9 +465,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv12_tc_kernel(const Conv12Ar
 // A_hi and A_lo both go through the same B: D[:, hi columns] + D[:, lo columns] = (A_hi + A_lo)(W_hi + W_lo).
 // Because one MMA now touches three output blocks of which one may be fresh, the pair's 256 accumulator columns are
 // initialised by ONE N = 256 MMA (with the background's contribution, see the kernel's set-up) and everything else accumulates.
-// One CTA per SM (all 512 TMEM columns = two pairs in flight): 16 producer warps, 1 issuer warp, 8 epilogue warps.  An output
-// slice pair is skipped when it is background in BOTH patches; a slab is multiplied when one of its three output slices is
-// wanted.
+// One CTA per SM (all 512 TMEM columns = two pairs in flight): 16 producer warps, 1 issuer warp, 8 epilogue warps.  The
+// volumes hold conv1 minus its background value, so a slab is multiplied only when one of the two patches has a listed cell
+// in it; an output slice pair whose whole neighbourhood is background in both patches is not even read back from TMEM
+// (precomputed constants).
 // conv1 of a pair, by all 16 producer warps (the tensor side above needs ~4 k cycles per pair, so conv1 has to stay below):
 //   pass 1  thread = (patch, (px,py) column, z quarter): ORs the 4x4 occupancy rows around the column and appends the cells
 //           whose 4x4x4 window is non-empty to ONE list for both patches (cell index + coordinates, 4 bytes);
